@@ -1,0 +1,43 @@
+"""pytest configuration: markers, repo root on sys.path, golden-fixture loader."""
+import gzip
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+_CACHE = {}
+
+
+def load_golden(name):
+    """Cases recorded from the unmodified reference by oracle/make_golden.py."""
+    if name not in _CACHE:
+        with gzip.open(os.path.join(GOLDEN_DIR, f"{name}.pt.gz"), "rb") as fh:
+            _CACHE[name] = torch.load(fh, weights_only=False)["cases"]
+    return _CACHE[name]
+
+
+def bits_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
+    """Bit-for-bit equality (distinguishes -0.0 from 0.0, treats equal NaN payloads as equal)."""
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    a, b = a.contiguous().cpu(), b.contiguous().cpu()
+    if a.numel() == 0:
+        return True
+    return torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
