@@ -1,0 +1,169 @@
+"""ctypes binding of the C ABI declared in include/ffq_b200.h.
+
+The shared library is the product's only compute path.  There is no CPU or PyTorch fallback:
+if ``lib/libffq_b200.so`` is missing this module raises at import time, and every op wrapper
+refuses non-CUDA tensors.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import functools
+import os
+from typing import Optional, Sequence
+
+import torch  # imported first on purpose: it loads libcudart.so.12, which the library links against
+
+from .exceptions import QuantizationError  # noqa: F401  (re-exported for callers)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libffq_b200.so")
+
+FFQ_MAX_RANK = 8
+
+# ffq_status_t
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_BITWIDTH, ERR_WORKSPACE = range(6)
+# ffq_ws_kind_t
+WS_QUANTIZE_BWD, WS_MINMAX, WS_PARAMS_FOR_RANGE, WS_DYNAMIC_QUANTIZE = range(4)
+
+# ffq_dtype_t
+DT_NONE = 255
+_DTYPES = {
+    torch.float32: 0,
+    torch.float16: 1,
+    torch.bfloat16: 2,
+    torch.float64: 3,
+    torch.int8: 4,
+    torch.int16: 5,
+    torch.int32: 6,
+    torch.uint8: 7,
+    torch.int64: 8,
+}
+
+
+def dtype_tag(dtype: Optional[torch.dtype]) -> int:
+    if dtype is None:
+        return DT_NONE
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise NotImplementedError(f"fastforward_b200: dtype {dtype} is not supported by the B200 backend") from None
+
+
+class Layout(ctypes.Structure):
+    """ffq_layout_t"""
+
+    _fields_ = [
+        ("rank", ctypes.c_int32),
+        ("dims", ctypes.c_int64 * FFQ_MAX_RANK),
+        ("tile", ctypes.c_int64 * FFQ_MAX_RANK),
+    ]
+
+
+@functools.lru_cache(maxsize=4096)
+def make_layout(shape: tuple, tile: tuple) -> Layout:
+    if len(shape) != len(tile):
+        raise ValueError(
+            f"Input dimensionality must match tile_size dimensionality got {len(shape)} and {len(tile)}"
+        )
+    if len(shape) > FFQ_MAX_RANK:
+        raise NotImplementedError(f"fastforward_b200 supports tensors of rank <= {FFQ_MAX_RANK}")
+    bad = [i for i, (d, t) in enumerate(zip(shape, tile)) if t > 0 and d % t != 0]
+    if bad or any(t <= 0 for t in tile):
+        raise ValueError(
+            "Each dimension of tile_size must divide the corresponding input dimension. Got "
+            + ", ".join(f"{shape[i]} and {tile[i]} for dimension {i}" for i in (bad or range(len(tile))))
+            + "."
+        )
+    lay = Layout()
+    lay.rank = len(shape)
+    for i, (d, t) in enumerate(zip(shape, tile)):
+        lay.dims[i] = d
+        lay.tile[i] = t
+    return lay
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"fastforward_b200: CUDA library not found at {LIB_PATH}. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C fastforward_b200/csrc`). "
+            "There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_size_t
+    lp = ctypes.POINTER(Layout)
+    sig = {
+        "ffq_abi_version": (ctypes.c_int, []),
+        "ffq_last_error": (ctypes.c_char_p, []),
+        "ffq_launch_count": (ctypes.c_uint64, []),
+        "ffq_workspace_bytes": (sz, [i32, lp, i32]),
+        "ffq_num_tiles": (i64, [lp]),
+        "ffq_quantize": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, lp, dbl, vp]),
+        "ffq_dequantize": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, lp, vp]),
+        "ffq_fakequant_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, lp, dbl, vp]),
+        "ffq_quantize_bwd": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, lp, dbl, vp, sz, vp]),
+        "ffq_minmax": (i32, [vp, i32, vp, vp, vp, vp, vp, lp, vp, sz, vp]),
+        "ffq_params_for_range": (i32, [vp, vp, i32, i64, dbl, i32, i32, i32, vp, i32, vp, i32, vp, sz, vp]),
+        "ffq_dynamic_quantize": (i32, [vp, i32, vp, i32, vp, vp, lp, dbl, i32, i32, vp, sz, vp]),
+        "ffq_qlinear_w8a8": (i32, [vp, vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
+        "ffq_rowsum_i8": (i32, [vp, vp, i64, i64, vp]),
+        "ffq_fakequant_fwd_bwd_host": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, lp, dbl, i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ffq_abi_version() != 1:
+        raise ImportError(f"fastforward_b200: ABI version mismatch ({lib.ffq_abi_version()} != 1)")
+    return lib
+
+
+lib = _load()
+EXPORTED = (
+    "ffq_abi_version ffq_last_error ffq_launch_count ffq_workspace_bytes ffq_num_tiles ffq_quantize "
+    "ffq_dequantize ffq_fakequant_fwd ffq_quantize_bwd ffq_minmax ffq_params_for_range "
+    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host"
+).split()
+
+
+def last_error() -> str:
+    msg = lib.ffq_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc: int) -> None:
+    """Map an ffq_status_t to the exception type the reference raises for that condition
+    (SURVEY.md section 8b 'Error conventions')."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(f"fastforward_b200: {msg} (status {rc})")
+
+
+def launch_count() -> int:
+    return int(lib.ffq_launch_count())
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def current_stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"fastforward_b200: '{what}' is on {t.device}; this backend only runs on CUDA (sm_100a) "
+            "and has no CPU fallback."
+        )
+
+
+def workspace_bytes(kind: int, layout: Layout, dtype: torch.dtype) -> int:
+    return int(lib.ffq_workspace_bytes(kind, ctypes.byref(layout), dtype_tag(dtype)))

@@ -1,0 +1,785 @@
+// ffq_reduce.cu -- the kernels with a per-tile reduction (a3, a4, a6, a7):
+//   * straight-through backward: dx + per-tile dscale / doffset sums
+//   * per-tile min/max, merged into running ranges (RunningMinMax calibration step)
+//   * range -> (scale, offset) with the global one-sided decision taken on the device
+//   * dynamic quantize = min/max -> params -> quantize, no host sync
+//
+// All are HBM-bound.  "Row" layouts (contiguous tiles) get two mappings:
+//   - small tiles (tile_numel == LANES*EPT, LANES in 1..32): a LANES-wide sub-warp owns a tile,
+//     the CTA streams a contiguous 16 KB chunk per unrolled step, reduction by shuffles only;
+//   - large tiles: a 256-thread CTA owns a tile segment; few-and-huge tiles (per-tensor) are
+//     split into S segments whose partials are combined by a second tiny kernel.
+// Reductions are fixed trees (thread-serial -> shuffle -> shared memory -> optional second
+// stage): deterministic run to run, no atomics on floating-point data.
+// Algorithmic traffic per element: backward 3s (x, g in; dx out), min/max s.
+#include "ffq_common.cuh"
+
+namespace ffq {
+
+constexpr int RD_THREADS = 256;
+constexpr int RD_UNROLL = 4;
+
+// ------------------------------------------------------------------------------------------
+// backward element math                              quantization/_quantizer_impl.py:203-237
+// ------------------------------------------------------------------------------------------
+struct BParams {
+  float lo, hi;
+  float lo_s, hi_s;   // the bounds as stored in a scale-dtype tensor (scale.new_tensor([lo]))
+  int m_div, m_sub;   // as in the forward
+  int m_s;            // rounding of the scale dtype (dscale chain runs in scale.dtype)
+  int m_sg;           // rounding of promote(scale, grad)
+  int has_offset;
+};
+
+__device__ __forceinline__ void bwd_terms(float x, float g, float s, float o, const BParams& p,
+                                          float& dx, float& dsc, float& doff) {
+  float pre = rnd(__fdiv_rn(x, s), p.m_div);
+  pre = rnd(__fsub_rn(pre, o), p.m_sub);
+  const float q = rintf(pre);
+  const bool below = q < p.lo, above = q > p.hi;
+  const bool clip = below || above;
+  dx = clip ? 0.f : g;
+  doff = clip ? rnd(__fmul_rn(s, g), p.m_sg) : 0.f;
+  const float bound = rnd(__fadd_rn(below ? p.lo_s : p.hi_s, rnd(o, p.m_s)), p.m_s);
+  const float resid = rnd(rnd(__fsub_rn(q, pre), p.m_sub), p.m_s);
+  const float v = clip ? bound : resid;
+  dsc = rnd(rnd(__fmul_rn(v, g), p.m_sg), p.m_s);
+}
+
+struct BwdArgs {
+  const void* x; const void* g; void* dx;
+  int x_dt, g_dt;
+  const void* scale; const void* offset; int s_dt, o_dt;
+  void* dscale; void* doffset; int dsc_dt, doff_dt;   // final outputs (S == 1) ...
+  float* part;                                        // ... or partials [2][num_tiles*S]
+  unsigned long long numel, tile_numel, num_tiles;
+  unsigned long long seg_len; unsigned int S;
+  BParams bp;
+  GenericLayout gl;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  return r;  // valid in warp 0
+}
+
+// --- small tiles: one LANES-wide group per tile -------------------------------------------
+template <typename XT, typename GT, int LANES>
+__global__ void __launch_bounds__(RD_THREADS) bwd_row_group_kernel(const BwdArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  constexpr int GV = (int)(EPT * sizeof(GT)) / 16 > 0 ? (int)(EPT * sizeof(GT)) / 16 : 1;  // 16B chunks of g per vector
+  (void)GV;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const GT* __restrict__ g = static_cast<const GT*>(a.g);
+  GT* __restrict__ dx = static_cast<GT*>(a.dx);
+  const unsigned long long nvec = a.numel / EPT;
+  const unsigned long long vbase = (unsigned long long)blockIdx.x * (RD_THREADS * RD_UNROLL) + threadIdx.x;
+
+  Vec<XT, EPT> xv[RD_UNROLL];
+  Vec<GT, EPT> gv[RD_UNROLL];
+#pragma unroll
+  for (int u = 0; u < RD_UNROLL; ++u) {
+    const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
+    if (v < nvec) {
+      xv[u] = ld_stream<XT, EPT>(x + v * EPT);
+      if constexpr (sizeof(GT) * EPT <= 16) {
+        gv[u] = ld_stream<GT, EPT>(g + v * EPT);
+      } else {
+#pragma unroll
+        for (int c = 0; c < (int)(sizeof(GT) * EPT / 16); ++c) {
+          constexpr int GE = 16 / sizeof(GT);
+          Vec<GT, GE> t = ld_stream<GT, GE>(g + v * EPT + c * GE);
+#pragma unroll
+          for (int i = 0; i < GE; ++i) gv[u].v[c * GE + i] = t.v[i];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < RD_UNROLL; ++u) {
+    const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
+    const bool live = v < nvec;
+    const unsigned long long tile = v / LANES;
+    float sum_sc = 0.f, sum_off = 0.f;
+    if (live) {
+      const float s = load_as_float(a.scale, a.s_dt, tile);
+      const float o = load_offset(a.offset, a.o_dt, tile);
+      Vec<GT, EPT> d;
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) {
+        float dxi, dsc, doff;
+        bwd_terms(Elem<XT>::to_f(xv[u].v[i]), Elem<GT>::to_f(gv[u].v[i]), s, o, a.bp, dxi, dsc, doff);
+        d.v[i] = Elem<GT>::from_f(dxi);
+        sum_sc += dsc;
+        sum_off += doff;
+      }
+      st_vec<GT, EPT>(dx + v * EPT, d);
+    }
+    sum_sc = group_sum<LANES>(sum_sc);
+    if (a.bp.has_offset) sum_off = group_sum<LANES>(sum_off);
+    if (live && (threadIdx.x & (LANES - 1)) == 0) {
+      store_from_float(a.dscale, a.dsc_dt, tile, sum_sc);
+      if (a.bp.has_offset) store_from_float(a.doffset, a.doff_dt, tile, sum_off);
+    }
+  }
+}
+
+// --- large tiles: one CTA per tile segment -------------------------------------------------
+template <typename XT, typename GT, int EPT>
+__global__ void __launch_bounds__(RD_THREADS) bwd_row_cta_kernel(const BwdArgs a) {
+  __shared__ float smem[32];
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const GT* __restrict__ g = static_cast<const GT*>(a.g);
+  GT* __restrict__ dx = static_cast<GT*>(a.dx);
+  const unsigned long long tile = blockIdx.x / a.S;
+  const unsigned int seg = blockIdx.x % a.S;
+  const unsigned long long begin = (unsigned long long)seg * a.seg_len;
+  unsigned long long end = begin + a.seg_len;
+  if (end > a.tile_numel) end = a.tile_numel;
+  const unsigned long long base = tile * a.tile_numel;
+  const float s = load_as_float(a.scale, a.s_dt, tile);
+  const float o = load_offset(a.offset, a.o_dt, tile);
+
+  float sum_sc = 0.f, sum_off = 0.f;
+  const unsigned long long step = (unsigned long long)blockDim.x * EPT;
+  for (unsigned long long i0 = begin + (unsigned long long)threadIdx.x * EPT; i0 < end; i0 += step * RD_UNROLL) {
+    Vec<XT, EPT> xv[RD_UNROLL];
+    Vec<GT, EPT> gv[RD_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RD_UNROLL; ++u) {
+      const unsigned long long i = i0 + u * step;
+      if (i < end) {
+        if constexpr (EPT == 1) {
+          xv[u].v[0] = x[base + i];
+          gv[u].v[0] = g[base + i];
+        } else {
+          xv[u] = ld_stream<XT, EPT>(x + base + i);
+          if constexpr (sizeof(GT) * EPT <= 16) {
+            gv[u] = ld_stream<GT, EPT>(g + base + i);
+          } else {
+#pragma unroll
+            for (int c = 0; c < (int)(sizeof(GT) * EPT / 16); ++c) {
+              constexpr int GE = 16 / sizeof(GT);
+              Vec<GT, GE> t = ld_stream<GT, GE>(g + base + i + c * GE);
+#pragma unroll
+              for (int k = 0; k < GE; ++k) gv[u].v[c * GE + k] = t.v[k];
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RD_UNROLL; ++u) {
+      const unsigned long long i = i0 + u * step;
+      if (i < end) {
+        Vec<GT, EPT> d;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          float dxi, dsc, doff;
+          bwd_terms(Elem<XT>::to_f(xv[u].v[k]), Elem<GT>::to_f(gv[u].v[k]), s, o, a.bp, dxi, dsc, doff);
+          d.v[k] = Elem<GT>::from_f(dxi);
+          sum_sc += dsc;
+          sum_off += doff;
+        }
+        if constexpr (EPT == 1) dx[base + i] = d.v[0];
+        else st_vec<GT, EPT>(dx + base + i, d);
+      }
+    }
+  }
+  sum_sc = block_sum(sum_sc, smem);
+  if (a.bp.has_offset) sum_off = block_sum(sum_off, smem);
+  if (threadIdx.x == 0) {
+    if (a.S == 1) {
+      store_from_float(a.dscale, a.dsc_dt, tile, sum_sc);
+      if (a.bp.has_offset) store_from_float(a.doffset, a.doff_dt, tile, sum_off);
+    } else {
+      a.part[blockIdx.x] = sum_sc;
+      if (a.bp.has_offset) a.part[a.num_tiles * a.S + blockIdx.x] = sum_off;
+    }
+  }
+}
+
+// second stage: one warp per tile folds the S partials in a fixed order
+__global__ void __launch_bounds__(RD_THREADS) bwd_finalize_kernel(const BwdArgs a) {
+  const unsigned long long tile = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tile >= a.num_tiles) return;
+  float sc = 0.f, off = 0.f;
+  for (unsigned int k = lane; k < a.S; k += 32) {
+    sc += a.part[tile * a.S + k];
+    if (a.bp.has_offset) off += a.part[a.num_tiles * a.S + tile * a.S + k];
+  }
+  sc = warp_sum(sc);
+  off = warp_sum(off);
+  if (lane == 0) {
+    store_from_float(a.dscale, a.dsc_dt, tile, sc);
+    if (a.bp.has_offset) store_from_float(a.doffset, a.doff_dt, tile, off);
+  }
+}
+
+// element offset of the k-th element (row-major inside the tile) of tile `t`
+__device__ __forceinline__ unsigned long long tile_elem_offset(unsigned long long t, unsigned long long k,
+                                                               const GenericLayout& gl) {
+  unsigned long long off = 0;
+#pragma unroll 1
+  for (int d = gl.rank - 1; d >= 0; --d) {
+    const unsigned long long tc = t % gl.grid[d]; t /= gl.grid[d];
+    const unsigned long long kc = k % gl.tile[d]; k /= gl.tile[d];
+    off += (tc * gl.tile[d] + kc) * gl.stride[d];
+  }
+  return off;
+}
+
+// any layout, any dtype: one CTA per tile, scalar index math.  Correctness path.
+__global__ void __launch_bounds__(128) bwd_generic_kernel(const BwdArgs a) {
+  __shared__ float smem[32];
+  const unsigned long long tile = blockIdx.x;
+  const float s = load_as_float(a.scale, a.s_dt, tile);
+  const float o = load_offset(a.offset, a.o_dt, tile);
+  float sum_sc = 0.f, sum_off = 0.f;
+  for (unsigned long long k = threadIdx.x; k < a.tile_numel; k += blockDim.x) {
+    const unsigned long long e = a.gl.rank <= 1 ? tile * a.tile_numel + k : tile_elem_offset(tile, k, a.gl);
+    float dxi, dsc, doff;
+    bwd_terms(load_as_float(a.x, a.x_dt, e), load_as_float(a.g, a.g_dt, e), s, o, a.bp, dxi, dsc, doff);
+    store_from_float(a.dx, a.g_dt, e, dxi);
+    sum_sc += dsc;
+    sum_off += doff;
+  }
+  sum_sc = block_sum(sum_sc, smem);
+  sum_off = block_sum(sum_off, smem);
+  if (threadIdx.x == 0) {
+    store_from_float(a.dscale, a.dsc_dt, tile, sum_sc);
+    if (a.bp.has_offset) store_from_float(a.doffset, a.doff_dt, tile, sum_off);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// segmentation shared by backward and min/max
+// ------------------------------------------------------------------------------------------
+struct Segmentation { unsigned int S; unsigned long long seg_len; };
+
+static Segmentation choose_segments(const Plan& plan, int ept) {
+  Segmentation sg{1, (unsigned long long)plan.tile_numel};
+  const long long target = 4ll * sm_count();
+  const unsigned long long quantum = (unsigned long long)RD_THREADS * ept * RD_UNROLL;
+  if (plan.num_tiles >= target || (unsigned long long)plan.tile_numel <= quantum) return sg;
+  unsigned long long want = (unsigned long long)((target + plan.num_tiles - 1) / plan.num_tiles);
+  unsigned long long seg = ((unsigned long long)plan.tile_numel + want - 1) / want;
+  seg = (seg + quantum - 1) / quantum * quantum;
+  sg.seg_len = seg;
+  sg.S = (unsigned int)(((unsigned long long)plan.tile_numel + seg - 1) / seg);
+  if (sg.S <= 1) { sg.S = 1; sg.seg_len = (unsigned long long)plan.tile_numel; }
+  return sg;
+}
+
+static int group_lanes(const Plan& plan, int ept) {
+  // tile_numel == LANES*ept with LANES a power of two <= 32
+  if (plan.tile_numel % ept) return 0;
+  const long long l = plan.tile_numel / ept;
+  if (l >= 1 && l <= 32 && (l & (l - 1)) == 0) return (int)l;
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename XT, typename GT>
+static void launch_bwd_row(const BwdArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
+  constexpr int EPT = 16 / sizeof(XT);
+  const int lanes = vec_ok ? group_lanes(plan, EPT) : 0;
+  if (lanes) {
+    const unsigned long long nvec = a.numel / EPT;
+    const unsigned int blocks = (unsigned int)((nvec + RD_THREADS * RD_UNROLL - 1) / (RD_THREADS * RD_UNROLL));
+    switch (lanes) {
+      case 1: bwd_row_group_kernel<XT, GT, 1><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 2: bwd_row_group_kernel<XT, GT, 2><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 4: bwd_row_group_kernel<XT, GT, 4><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 8: bwd_row_group_kernel<XT, GT, 8><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 16: bwd_row_group_kernel<XT, GT, 16><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      default: bwd_row_group_kernel<XT, GT, 32><<<blocks, RD_THREADS, 0, st>>>(a); break;
+    }
+    return;
+  }
+  const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
+  // shrink the CTA for short tiles so that lanes are not idle
+  const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
+  unsigned long long per_seg = (a.seg_len + ept - 1) / ept;
+  int threads = RD_THREADS;
+  while (threads > 32 && (unsigned long long)threads / 2 >= per_seg) threads /= 2;
+  if (ept == EPT) bwd_row_cta_kernel<XT, GT, EPT><<<blocks, threads, 0, st>>>(a);
+  else bwd_row_cta_kernel<XT, GT, 1><<<blocks, threads, 0, st>>>(a);
+}
+
+template <typename XT>
+static bool dispatch_bwd_g(const BwdArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
+  switch (a.g_dt) {
+    case FFQ_F32: launch_bwd_row<XT, float>(a, plan, vec_ok, st); return true;
+    case FFQ_BF16: launch_bwd_row<XT, __nv_bfloat16>(a, plan, vec_ok, st); return true;
+    case FFQ_F16: launch_bwd_row<XT, __half>(a, plan, vec_ok, st); return true;
+  }
+  return false;
+}
+
+static bool dispatch_bwd(const BwdArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
+  switch (a.x_dt) {
+    case FFQ_F32: return dispatch_bwd_g<float>(a, plan, vec_ok, st);
+    case FFQ_BF16: return dispatch_bwd_g<__nv_bfloat16>(a, plan, vec_ok, st);
+    case FFQ_F16: return dispatch_bwd_g<__half>(a, plan, vec_ok, st);
+  }
+  return false;
+}
+
+static int ept_of(int dt) {
+  const int sz = dt_size(dt);
+  return (sz > 0 && sz <= 4) ? 16 / sz : 4;
+}
+
+// ------------------------------------------------------------------------------------------
+// min / max                                                range_setting/minmax.py:226-237
+// ------------------------------------------------------------------------------------------
+struct MmArgs {
+  const void* x; int x_dt;
+  void* tile_min; void* tile_max;     // optional, dtype x_dt
+  void* run_min; void* run_max;       // optional, dtype x_dt, updated in place
+  int32_t* flags;                     // optional
+  float* part;                        // [2][num_tiles*S] when S > 1
+  unsigned long long numel, tile_numel, num_tiles, seg_len; unsigned int S;
+  GenericLayout gl;
+};
+
+__device__ __forceinline__ void mm_emit(const MmArgs& a, unsigned long long tile, float mn, float mx) {
+  if (a.tile_min) store_from_float(a.tile_min, a.x_dt, tile, mn);
+  if (a.tile_max) store_from_float(a.tile_max, a.x_dt, tile, mx);
+  if (a.run_min) store_from_float(a.run_min, a.x_dt, tile, nan_min(load_as_float(a.run_min, a.x_dt, tile), mn));
+  if (a.run_max) store_from_float(a.run_max, a.x_dt, tile, nan_max(load_as_float(a.run_max, a.x_dt, tile), mx));
+  if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+}
+
+__device__ __forceinline__ void block_minmax(float& mn, float& mx, float* smem) {
+  mn = group_min<32>(mn);
+  mx = group_max<32>(mx);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) { smem[w] = mn; smem[32 + w] = mx; }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (w == 0) {
+    mn = (lane < nw) ? smem[lane] : smem[0];
+    mx = (lane < nw) ? smem[32 + lane] : smem[32];
+    mn = group_min<32>(mn);
+    mx = group_max<32>(mx);
+  }
+}
+
+template <typename XT, int LANES>
+__global__ void __launch_bounds__(RD_THREADS) mm_row_group_kernel(const MmArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const unsigned long long nvec = a.numel / EPT;
+  const unsigned long long vbase = (unsigned long long)blockIdx.x * (RD_THREADS * RD_UNROLL) + threadIdx.x;
+  Vec<XT, EPT> xv[RD_UNROLL];
+#pragma unroll
+  for (int u = 0; u < RD_UNROLL; ++u) {
+    const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
+    if (v < nvec) xv[u] = ld_stream<XT, EPT>(x + v * EPT);
+  }
+#pragma unroll
+  for (int u = 0; u < RD_UNROLL; ++u) {
+    const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
+    const bool live = v < nvec;   // whole groups are live or dead together (nvec % LANES == 0)
+    float mn = INFINITY, mx = -INFINITY;
+    if (live) {
+      mn = mx = Elem<XT>::to_f(xv[u].v[0]);
+#pragma unroll
+      for (int i = 1; i < EPT; ++i) {
+        const float f = Elem<XT>::to_f(xv[u].v[i]);
+        mn = nan_min(mn, f);
+        mx = nan_max(mx, f);
+      }
+    }
+    mn = group_min<LANES>(mn);
+    mx = group_max<LANES>(mx);
+    if (live && (threadIdx.x & (LANES - 1)) == 0) mm_emit(a, v / LANES, mn, mx);
+  }
+}
+
+template <typename XT, int EPT>
+__global__ void __launch_bounds__(RD_THREADS) mm_row_cta_kernel(const MmArgs a) {
+  __shared__ float smem[64];
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  const unsigned long long tile = blockIdx.x / a.S;
+  const unsigned int seg = blockIdx.x % a.S;
+  const unsigned long long begin = (unsigned long long)seg * a.seg_len;
+  unsigned long long end = begin + a.seg_len;
+  if (end > a.tile_numel) end = a.tile_numel;
+  const unsigned long long base = tile * a.tile_numel;
+  // every segment is non-empty, so its first element is a valid identity for every thread
+  float mn = Elem<XT>::to_f(x[base + begin]), mx = mn;
+  const unsigned long long step = (unsigned long long)blockDim.x * EPT;
+  for (unsigned long long i0 = begin + (unsigned long long)threadIdx.x * EPT; i0 < end; i0 += step * RD_UNROLL) {
+    Vec<XT, EPT> xv[RD_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RD_UNROLL; ++u) {
+      const unsigned long long i = i0 + u * step;
+      if (i < end) {
+        if constexpr (EPT == 1) xv[u].v[0] = x[base + i];
+        else xv[u] = ld_stream<XT, EPT>(x + base + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RD_UNROLL; ++u) {
+      const unsigned long long i = i0 + u * step;
+      if (i < end) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          const float f = Elem<XT>::to_f(xv[u].v[k]);
+          mn = nan_min(mn, f);
+          mx = nan_max(mx, f);
+        }
+      }
+    }
+  }
+  block_minmax(mn, mx, smem);
+  if (threadIdx.x == 0) {
+    if (a.S == 1) mm_emit(a, tile, mn, mx);
+    else { a.part[blockIdx.x] = mn; a.part[a.num_tiles * a.S + blockIdx.x] = mx; }
+  }
+}
+
+__global__ void __launch_bounds__(RD_THREADS) mm_finalize_kernel(const MmArgs a) {
+  const unsigned long long tile = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (tile >= a.num_tiles) return;
+  float mn = a.part[tile * a.S], mx = a.part[a.num_tiles * a.S + tile * a.S];
+  for (unsigned int k = lane; k < a.S; k += 32) {
+    mn = nan_min(mn, a.part[tile * a.S + k]);
+    mx = nan_max(mx, a.part[a.num_tiles * a.S + tile * a.S + k]);
+  }
+  mn = group_min<32>(mn);
+  mx = group_max<32>(mx);
+  if (lane == 0) mm_emit(a, tile, mn, mx);
+}
+
+__global__ void __launch_bounds__(128) mm_generic_kernel(const MmArgs a) {
+  __shared__ float smem[64];
+  const unsigned long long tile = blockIdx.x;
+  const unsigned long long e0 = a.gl.rank <= 1 ? tile * a.tile_numel : tile_elem_offset(tile, 0, a.gl);
+  float mn = load_as_float(a.x, a.x_dt, e0), mx = mn;
+  for (unsigned long long k = threadIdx.x; k < a.tile_numel; k += blockDim.x) {
+    const unsigned long long e = a.gl.rank <= 1 ? tile * a.tile_numel + k : tile_elem_offset(tile, k, a.gl);
+    const float f = load_as_float(a.x, a.x_dt, e);
+    mn = nan_min(mn, f);
+    mx = nan_max(mx, f);
+  }
+  block_minmax(mn, mx, smem);
+  if (threadIdx.x == 0) mm_emit(a, tile, mn, mx);
+}
+
+template <typename XT>
+static void launch_mm_row(const MmArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
+  constexpr int EPT = 16 / sizeof(XT);
+  const int lanes = vec_ok ? group_lanes(plan, EPT) : 0;
+  if (lanes) {
+    const unsigned long long nvec = a.numel / EPT;
+    const unsigned int blocks = (unsigned int)((nvec + RD_THREADS * RD_UNROLL - 1) / (RD_THREADS * RD_UNROLL));
+    switch (lanes) {
+      case 1: mm_row_group_kernel<XT, 1><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 2: mm_row_group_kernel<XT, 2><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 4: mm_row_group_kernel<XT, 4><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 8: mm_row_group_kernel<XT, 8><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 16: mm_row_group_kernel<XT, 16><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      default: mm_row_group_kernel<XT, 32><<<blocks, RD_THREADS, 0, st>>>(a); break;
+    }
+    return;
+  }
+  const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
+  const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
+  unsigned long long per_seg = (a.seg_len + ept - 1) / ept;
+  int threads = RD_THREADS;
+  while (threads > 32 && (unsigned long long)threads / 2 >= per_seg) threads /= 2;
+  if (ept == EPT) mm_row_cta_kernel<XT, EPT><<<blocks, threads, 0, st>>>(a);
+  else mm_row_cta_kernel<XT, 1><<<blocks, threads, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// range -> (scale, offset)                                 quantization/affine/range.py:54-122
+// ------------------------------------------------------------------------------------------
+struct PrArgs {
+  const void* mn; const void* mx; int r_dt;
+  unsigned long long n;
+  float int_min_abs, int_max_abs, neg_int_min, steps;
+  int symmetric, allow_one_sided, round_offset;
+  void* scale; int s_dt; void* offset; int o_dt;
+  float* part; unsigned int nparts;
+};
+
+// stage A (only when the one-sided decision is live): per-block min of min_range -> part[]
+__global__ void __launch_bounds__(RD_THREADS) pr_min_kernel(const PrArgs a) {
+  __shared__ float smem[64];
+  float mn = INFINITY, dummy = 0.f;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    mn = nan_min(mn, load_as_float(a.mn, a.r_dt, i));
+  block_minmax(mn, dummy, smem);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = mn;
+}
+
+__global__ void __launch_bounds__(RD_THREADS) pr_apply_kernel(const PrArgs a) {
+  __shared__ float smem[64];
+  __shared__ int s_one_sided;
+  bool one_sided = false;
+  if (a.allow_one_sided && a.symmetric) {   // for asymmetric quantizers the flag changes nothing
+    float mn = INFINITY, dummy = 0.f;
+    for (unsigned int i = threadIdx.x; i < a.nparts; i += blockDim.x) mn = nan_min(mn, a.part[i]);
+    block_minmax(mn, dummy, smem);
+    if (threadIdx.x == 0) s_one_sided = (mn >= 0.f) ? 1 : 0;   // NaN >= 0 is false, as in Python
+    __syncthreads();
+    one_sided = s_one_sided != 0;
+  }
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  float mn = load_as_float(a.mn, a.r_dt, i);
+  const float mx = load_as_float(a.mx, a.r_dt, i);
+  if (a.symmetric && !one_sided) {
+    const float neg = __fdiv_rn(fabsf(mn), a.int_min_abs);
+    const float pos = __fdiv_rn(fabsf(mx), a.int_max_abs);
+    store_from_float(a.scale, a.s_dt, i, nan_max(neg, pos));
+    if (a.offset) store_from_float(a.offset, a.o_dt, i, 0.f);
+    return;
+  }
+  if (a.symmetric) mn = 0.f;
+  float sc = __fdiv_rn(__fsub_rn(mx, mn), a.steps);
+  const float eps = 1.1920928955078125e-07f;
+  sc = (sc != sc) ? sc : fmaxf(sc, eps);
+  float off = __fadd_rn(__fdiv_rn(mn, sc), a.neg_int_min);   // min/scale - int_min
+  if (a.round_offset) off = rintf(off);
+  store_from_float(a.scale, a.s_dt, i, sc);
+  if (a.offset) store_from_float(a.offset, a.o_dt, i, off);
+}
+
+}  // namespace ffq
+
+using namespace ffq;
+
+static size_t seg_workspace(const Plan& plan, int ept) {
+  if (!plan.row) return 0;
+  const Segmentation sg = choose_segments(plan, ept);
+  return sg.S > 1 ? (size_t)2 * plan.num_tiles * sg.S * sizeof(float) : 0;
+}
+
+static const unsigned int PR_MAX_PARTS = 1024;
+
+extern "C" {
+
+size_t ffq_workspace_bytes(int kind, const ffq_layout_t* layout, int data_dtype) {
+  Plan plan;
+  if (make_plan(layout, &plan) != FFQ_OK || plan.numel == 0) return 0;
+  const int ept = ept_of(data_dtype);
+  switch (kind) {
+    case FFQ_WS_QUANTIZE_BWD:
+    case FFQ_WS_MINMAX:
+      return seg_workspace(plan, ept);
+    case FFQ_WS_PARAMS_FOR_RANGE:
+      return PR_MAX_PARTS * sizeof(float);
+    case FFQ_WS_DYNAMIC_QUANTIZE:
+      // [partials for min/max | param partials | tile_min | tile_max] (fp32 holds every data dtype exactly)
+      return seg_workspace(plan, ept) + PR_MAX_PARTS * sizeof(float) + (size_t)2 * plan.num_tiles * 8 + 64;
+  }
+  return 0;
+}
+
+int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dtype, void* dx, void* dscale,
+                     void* doffset, const void* scale, int scale_dtype, const void* offset, int offset_dtype,
+                     const ffq_layout_t* layout, double num_bits, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!(x_dtype == FFQ_F32 || x_dtype == FFQ_F16 || x_dtype == FFQ_BF16) ||
+      !(g_dtype == FFQ_F32 || g_dtype == FFQ_F16 || g_dtype == FFQ_BF16) ||
+      !(scale_dtype == FFQ_F32 || scale_dtype == FFQ_F16 || scale_dtype == FFQ_BF16)) {
+    set_error("quantize_bwd: data, grad and scale must be float32/float16/bfloat16 (got %s, %s, %s)",
+              dt_name(x_dtype), dt_name(g_dtype), dt_name(scale_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (offset == nullptr) offset_dtype = FFQ_NONE;
+  else if (offset_dtype == FFQ_F64 || !(is_float_dt(offset_dtype) || is_int_dt(offset_dtype))) {
+    set_error("quantize_bwd: unsupported offset dtype %s", dt_name(offset_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  Plan plan;
+  int rc = make_plan(layout, &plan);
+  if (rc != FFQ_OK) return rc;
+  if (plan.numel == 0) return FFQ_OK;
+
+  BwdArgs a{};
+  a.x = x; a.g = g; a.dx = dx; a.x_dt = x_dtype; a.g_dt = g_dtype;
+  a.scale = scale; a.offset = offset; a.s_dt = scale_dtype; a.o_dt = offset_dtype;
+  a.dscale = dscale; a.doffset = doffset;
+  a.dsc_dt = scale_dtype; a.doff_dt = promote(scale_dtype, g_dtype);
+  a.numel = plan.numel; a.tile_numel = plan.tile_numel; a.num_tiles = plan.num_tiles;
+  const QParams qp = make_qparams(x_dtype, scale_dtype, offset_dtype, num_bits);
+  a.bp.lo = qp.lo; a.bp.hi = qp.hi; a.bp.m_div = qp.m_div; a.bp.m_sub = qp.m_sub;
+  a.bp.m_s = round_mode_of(scale_dtype);
+  a.bp.m_sg = round_mode_of(promote(scale_dtype, g_dtype));
+  // scale.new_tensor([lo]) : the bound rounded to the scale dtype
+  auto to_s = [&](float v) {
+    if (scale_dtype == FFQ_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+    if (scale_dtype == FFQ_F16) return __half2float(__float2half_rn(v));
+    return v;
+  };
+  a.bp.lo_s = to_s(qp.lo); a.bp.hi_s = to_s(qp.hi);
+  a.bp.has_offset = (offset != nullptr && doffset != nullptr) ? 1 : 0;
+  a.gl = make_generic_layout(plan);
+  a.S = 1; a.seg_len = plan.tile_numel;
+
+  if (plan.row) {
+    const bool vec_ok = aligned16(x) && aligned16(g) && aligned16(dx);
+    const Segmentation sg = choose_segments(plan, ept_of(x_dtype));
+    const bool group = vec_ok && group_lanes(plan, ept_of(x_dtype)) != 0;
+    if (!group && sg.S > 1) {
+      const size_t need = (size_t)2 * plan.num_tiles * sg.S * sizeof(float);
+      if (workspace == nullptr || workspace_bytes < need) {
+        set_error("quantize_bwd: workspace of %zu bytes required, %zu given", need, workspace_bytes);
+        return FFQ_ERR_WORKSPACE;
+      }
+      a.S = sg.S; a.seg_len = sg.seg_len; a.part = static_cast<float*>(workspace);
+    }
+    if (!dispatch_bwd(a, plan, vec_ok, st)) { set_error("quantize_bwd: dtype dispatch failed"); return FFQ_ERR_UNSUPPORTED; }
+    FFQ_LAUNCH_CHECK();
+    if (a.S > 1) {
+      const unsigned long long threads = a.num_tiles * 32;
+      bwd_finalize_kernel<<<(unsigned int)((threads + RD_THREADS - 1) / RD_THREADS), RD_THREADS, 0, st>>>(a);
+      FFQ_LAUNCH_CHECK();
+    }
+    return FFQ_OK;
+  }
+  if (plan.num_tiles > 0x7fffffffll) { set_error("quantize_bwd: too many tiles for the generic kernel"); return FFQ_ERR_UNSUPPORTED; }
+  bwd_generic_kernel<<<(unsigned int)plan.num_tiles, 128, 0, st>>>(a);
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+int ffq_minmax(const void* x, int x_dtype, void* tile_min, void* tile_max, void* run_min, void* run_max,
+               int32_t* flags, const ffq_layout_t* layout, void* workspace, size_t workspace_bytes,
+               void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == FFQ_F64 || !(is_float_dt(x_dtype) || is_int_dt(x_dtype))) {
+    set_error("minmax: unsupported data dtype %s", dt_name(x_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  Plan plan;
+  int rc = make_plan(layout, &plan);
+  if (rc != FFQ_OK) return rc;
+  if (plan.numel == 0) { set_error("minmax: empty tensor"); return FFQ_ERR_INVALID; }
+  MmArgs a{};
+  a.x = x; a.x_dt = x_dtype; a.tile_min = tile_min; a.tile_max = tile_max;
+  a.run_min = run_min; a.run_max = run_max; a.flags = flags;
+  a.numel = plan.numel; a.tile_numel = plan.tile_numel; a.num_tiles = plan.num_tiles;
+  a.gl = make_generic_layout(plan);
+  a.S = 1; a.seg_len = plan.tile_numel;
+  const bool typed = x_dtype == FFQ_F32 || x_dtype == FFQ_F16 || x_dtype == FFQ_BF16;
+  if (plan.row && typed) {
+    const bool vec_ok = aligned16(x);
+    const Segmentation sg = choose_segments(plan, ept_of(x_dtype));
+    const bool group = vec_ok && group_lanes(plan, ept_of(x_dtype)) != 0;
+    if (!group && sg.S > 1) {
+      const size_t need = (size_t)2 * plan.num_tiles * sg.S * sizeof(float);
+      if (workspace == nullptr || workspace_bytes < need) {
+        set_error("minmax: workspace of %zu bytes required, %zu given", need, workspace_bytes);
+        return FFQ_ERR_WORKSPACE;
+      }
+      a.S = sg.S; a.seg_len = sg.seg_len; a.part = static_cast<float*>(workspace);
+    }
+    switch (x_dtype) {
+      case FFQ_F32: launch_mm_row<float>(a, plan, vec_ok, st); break;
+      case FFQ_BF16: launch_mm_row<__nv_bfloat16>(a, plan, vec_ok, st); break;
+      default: launch_mm_row<__half>(a, plan, vec_ok, st); break;
+    }
+    FFQ_LAUNCH_CHECK();
+    if (a.S > 1) {
+      const unsigned long long threads = a.num_tiles * 32;
+      mm_finalize_kernel<<<(unsigned int)((threads + RD_THREADS - 1) / RD_THREADS), RD_THREADS, 0, st>>>(a);
+      FFQ_LAUNCH_CHECK();
+    }
+    return FFQ_OK;
+  }
+  if (plan.num_tiles > 0x7fffffffll) { set_error("minmax: too many tiles for the generic kernel"); return FFQ_ERR_UNSUPPORTED; }
+  mm_generic_kernel<<<(unsigned int)plan.num_tiles, 128, 0, st>>>(a);
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+int ffq_params_for_range(const void* min_range, const void* max_range, int range_dtype, int64_t n,
+                         double num_bits, int symmetric, int allow_one_sided, int round_offset,
+                         void* scale_out, int scale_dtype, void* offset_out, int offset_dtype,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n <= 0) return FFQ_OK;
+  if (range_dtype == FFQ_F64 || !(is_float_dt(range_dtype) || is_int_dt(range_dtype)) ||
+      !(scale_dtype == FFQ_F32 || scale_dtype == FFQ_F16 || scale_dtype == FFQ_BF16)) {
+    set_error("params_for_range: unsupported dtypes (range %s, scale %s)", dt_name(range_dtype), dt_name(scale_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  PrArgs a{};
+  a.mn = min_range; a.mx = max_range; a.r_dt = range_dtype; a.n = (unsigned long long)n;
+  const double lo = -pow(2.0, num_bits - 1.0);
+  a.int_min_abs = (float)fabs(lo);
+  a.int_max_abs = (float)fabs(-lo - 1.0);
+  a.neg_int_min = (float)(-lo);
+  a.steps = (float)(pow(2.0, num_bits) - 1.0);
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided; a.round_offset = round_offset;
+  a.scale = scale_out; a.s_dt = scale_dtype; a.offset = offset_out; a.o_dt = offset_out ? offset_dtype : FFQ_NONE;
+  a.part = static_cast<float*>(workspace);
+  a.nparts = 0;
+  if (symmetric && allow_one_sided) {
+    unsigned long long nb = ((unsigned long long)n + RD_THREADS * 8 - 1) / (RD_THREADS * 8);
+    if (nb > PR_MAX_PARTS) nb = PR_MAX_PARTS;
+    if (nb < 1) nb = 1;
+    if (workspace == nullptr || workspace_bytes < nb * sizeof(float)) {
+      set_error("params_for_range: workspace of %zu bytes required", (size_t)(PR_MAX_PARTS * sizeof(float)));
+      return FFQ_ERR_WORKSPACE;
+    }
+    a.nparts = (unsigned int)nb;
+    pr_min_kernel<<<(unsigned int)nb, RD_THREADS, 0, st>>>(a);
+    FFQ_LAUNCH_CHECK();
+  }
+  pr_apply_kernel<<<(unsigned int)(((unsigned long long)n + RD_THREADS - 1) / RD_THREADS), RD_THREADS, 0, st>>>(a);
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtype, float* scale_out, float* offset_out,
+                         const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  Plan plan;
+  int rc = make_plan(layout, &plan);
+  if (rc != FFQ_OK) return rc;
+  if (plan.numel == 0) { set_error("Cannot dynamically quantize an empty tensor"); return FFQ_ERR_INVALID; }
+  const size_t need = ffq_workspace_bytes(FFQ_WS_DYNAMIC_QUANTIZE, layout, x_dtype);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("dynamic_quantize: workspace of %zu bytes required, %zu given", need, workspace_bytes);
+    return FFQ_ERR_WORKSPACE;
+  }
+  const int ept = ept_of(x_dtype);
+  char* ws = static_cast<char*>(workspace);
+  const size_t seg_bytes = (seg_workspace(plan, ept) + 15) / 16 * 16;
+  float* pr_part = reinterpret_cast<float*>(ws + seg_bytes);
+  // min/max are kept in the data dtype by the reference and only then cast to fp32
+  // (range.py:90); the data dtype embeds exactly in fp32, so fp32 scratch is equivalent
+  // only if we store through the data dtype -- ffq_minmax does (tile_min has dtype x_dtype).
+  char* tmin = ws + seg_bytes + PR_MAX_PARTS * sizeof(float);
+  char* tmax = tmin + (size_t)plan.num_tiles * 8;
+  rc = ffq_minmax(x, x_dtype, tmin, tmax, nullptr, nullptr, nullptr, layout, ws, seg_bytes, stream);
+  if (rc != FFQ_OK) return rc;
+  rc = ffq_params_for_range(tmin, tmax, x_dtype, plan.num_tiles, num_bits, symmetric, allow_one_sided, 1,
+                            scale_out, FFQ_F32, offset_out, FFQ_F32, pr_part, PR_MAX_PARTS * sizeof(float), stream);
+  if (rc != FFQ_OK) return rc;
+  return ffq_quantize(x, x_dtype, q, q_dtype, scale_out, FFQ_F32, offset_out, FFQ_F32, layout, num_bits, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,306 @@
+"""Tensor-level entry points of the hot path: the four ops the reference defines as
+``torch.ops.fastforward.*`` (quantization/_quantizer_impl.py:144,172,193,243), with the same
+argument order, defaults, return conventions and error types -- plus the fused / sync-free
+extras the B200 backend adds (fake_quantize_by_tile, tile_minmax, running_minmax_update_,
+parameters_for_range_).
+
+Everything here is glue: argument validation, output allocation on the input's device and
+current stream, and one C-ABI call.  No arithmetic happens in Python.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi as C
+from .exceptions import QuantizationError
+
+_MANTISSA = {torch.bfloat16: 7, torch.float16: 10, torch.float32: 23, torch.float64: 52}
+
+
+def can_support_bitwidth(dtype: torch.dtype, num_bits: float) -> bool:
+    """quantization/_quantizer_impl.py:44-75."""
+    if dtype.is_floating_point or dtype.is_complex:
+        if dtype in _MANTISSA:
+            avail = _MANTISSA[dtype]
+        elif dtype in (torch.float8_e4m3fn, torch.float8_e4m3fnuz):
+            avail = 3
+        elif dtype in (torch.float8_e5m2, torch.float8_e5m2fnuz):
+            avail = 2
+        else:
+            avail = num_bits
+    else:
+        avail = torch.iinfo(dtype).bits
+    return avail + 2 >= num_bits
+
+
+def _bitwidth_guard(dtype: torch.dtype, num_bits: float) -> None:
+    if not can_support_bitwidth(dtype, num_bits):
+        raise RuntimeError(f"Provided dtype ({dtype}) is not enough to store {num_bits} bits quantized values.")
+
+
+def _tile(data: torch.Tensor, tile_size) -> tuple:
+    if isinstance(tile_size, str):  # "data_shape"
+        return tuple(data.shape)
+    return tuple(int(t) for t in tile_size)
+
+
+def _num_tiles(shape: Sequence[int], tile: Sequence[int]) -> int:
+    n = 1
+    for d, t in zip(shape, tile):
+        n *= d // t if t else 0
+    return n
+
+
+def _param(p: Optional[torch.Tensor], ntiles: int, device: torch.device, what: str) -> Optional[torch.Tensor]:
+    """Flatten a parameter; a one-element parameter broadcasts over the tiles like the
+    reference's ``scale[:, None]`` does; any other size mismatch is the reference's RuntimeError."""
+    if p is None:
+        return None
+    if p.device != device:
+        raise RuntimeError(f"Expected all tensors to be on the same device, but '{what}' is on {p.device} and data on {device}")
+    p = p.detach().reshape(-1)
+    if p.numel() != ntiles:
+        if p.numel() == 1:
+            p = p.expand(ntiles)
+        else:
+            raise RuntimeError(
+                f"The size of '{what}' ({p.numel()}) must match the number of tiles ({ntiles})"
+            )
+    return p.contiguous()
+
+
+def _prep(data: torch.Tensor, tile_size, what: str = "data"):
+    C.require_cuda(data, what)
+    tile = _tile(data, tile_size)
+    shape = tuple(data.shape)
+    layout = C.make_layout(shape, tile)
+    return data.detach().contiguous(), shape, tile, layout
+
+
+# ------------------------------------------------------------------------------------------
+def quantize_by_tile(
+    data: torch.Tensor,
+    scale: torch.Tensor,
+    tile_size,
+    num_bits: float,
+    output_dtype: Optional[torch.dtype],
+    offset: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """``torch.ops.fastforward.quantize_by_tile`` (quantization/_quantizer_impl.py:144-169)."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    promoted = torch.promote_types(x.dtype, scale.dtype)
+    if offset is not None:
+        promoted = torch.promote_types(promoted, offset.dtype)
+    out_dtype = output_dtype or promoted
+    _bitwidth_guard(out_dtype, num_bits)
+    q = torch.empty(shape, dtype=out_dtype, device=x.device)
+    if x.numel() == 0:
+        return q
+    nt = _num_tiles(shape, tile)
+    s = _param(scale, nt, x.device, "scale")
+    o = _param(offset, nt, x.device, "offset")
+    C.check(C.lib.ffq_quantize(
+        x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), C.dtype_tag(out_dtype),
+        s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
+        ctypes.byref(layout), float(num_bits), C.current_stream(x.device)))
+    return q
+
+
+def dequantize_by_tile(
+    data: torch.Tensor,
+    scale: torch.Tensor,
+    tile_size,
+    offset: Optional[torch.Tensor] = None,
+    output_dtype: Optional[torch.dtype] = None,
+) -> torch.Tensor:
+    """``torch.ops.fastforward.dequantize_by_tile`` (quantization/_quantizer_impl.py:172-190)."""
+    q, shape, tile, layout = _prep(data, tile_size)
+    promoted = torch.promote_types(q.dtype, offset.dtype if offset is not None else scale.dtype)
+    promoted = torch.promote_types(promoted, scale.dtype)
+    out_dtype = output_dtype or promoted
+    y = torch.empty(shape, dtype=out_dtype, device=q.device)
+    if q.numel() == 0:
+        return y
+    nt = _num_tiles(shape, tile)
+    s = _param(scale, nt, q.device, "scale")
+    o = _param(offset, nt, q.device, "offset")
+    C.check(C.lib.ffq_dequantize(
+        q.data_ptr(), C.dtype_tag(q.dtype), y.data_ptr(), C.dtype_tag(out_dtype),
+        s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
+        ctypes.byref(layout), C.current_stream(q.device)))
+    return y
+
+
+def fake_quantize_by_tile(
+    data: torch.Tensor,
+    scale: torch.Tensor,
+    tile_size,
+    num_bits: float,
+    quantized_dtype: Optional[torch.dtype] = None,
+    offset: Optional[torch.Tensor] = None,
+    output_dtype: Optional[torch.dtype] = None,
+    return_codes: bool = False,
+):
+    """Fused ``dequantize_by_tile(quantize_by_tile(x))`` in one pass over HBM -- bit-identical to
+    the two-op sequence of affine/function.py:94-121 / quantization/fuse.py:91-121."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    q_dtype = quantized_dtype or x.dtype
+    _bitwidth_guard(q_dtype, num_bits)
+    out_dtype = output_dtype or (x.dtype if x.dtype.is_floating_point else scale.dtype)
+    y = torch.empty(shape, dtype=out_dtype, device=x.device)
+    codes = torch.empty(shape, dtype=q_dtype, device=x.device) if return_codes else None
+    if x.numel() > 0:
+        nt = _num_tiles(shape, tile)
+        s = _param(scale, nt, x.device, "scale")
+        o = _param(offset, nt, x.device, "offset")
+        C.check(C.lib.ffq_fakequant_fwd(
+            x.data_ptr(), C.dtype_tag(x.dtype), y.data_ptr(), C.dtype_tag(out_dtype),
+            C.ptr(codes), C.dtype_tag(q_dtype),
+            s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
+            ctypes.byref(layout), float(num_bits), C.current_stream(x.device)))
+    return (y, codes) if return_codes else y
+
+
+def quantize_by_tile_backward(
+    data: torch.Tensor,
+    output_grad: torch.Tensor,
+    scale: torch.Tensor,
+    tile_size,
+    num_bits: float,
+    offset: Optional[torch.Tensor] = None,
+) -> List[torch.Tensor]:
+    """``torch.ops.fastforward.quantize_by_tile_backward`` (quantization/_quantizer_impl.py:193-237):
+    returns ``[dx, dscale, doffset]``; ``doffset`` is an empty tensor when ``offset`` is None."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    C.require_cuda(output_grad, "output_grad")
+    g = output_grad.detach().contiguous()
+    if tuple(g.shape) != shape:
+        raise RuntimeError(f"output_grad shape {tuple(g.shape)} does not match data shape {shape}")
+    dx = torch.empty(shape, dtype=g.dtype, device=x.device)
+    dscale = torch.empty(scale.shape, dtype=scale.dtype, device=x.device)
+    doff_dtype = torch.promote_types(scale.dtype, g.dtype)
+    doffset = torch.empty(scale.shape, dtype=doff_dtype, device=x.device) if offset is not None else torch.Tensor()
+    if x.numel() == 0:
+        dscale.zero_()
+        if offset is not None:
+            doffset.zero_()
+        return [dx, dscale, doffset]
+    nt = _num_tiles(shape, tile)
+    s = _param(scale, nt, x.device, "scale")
+    o = _param(offset, nt, x.device, "offset")
+    if dscale.numel() != nt:  # one-element scale broadcast over many tiles: reduce afterwards
+        dscale_full = torch.empty(nt, dtype=scale.dtype, device=x.device)
+        doffset_full = torch.empty(nt, dtype=doff_dtype, device=x.device) if offset is not None else None
+    else:
+        dscale_full, doffset_full = dscale, (doffset if offset is not None else None)
+    ws_bytes = C.workspace_bytes(C.WS_QUANTIZE_BWD, layout, x.dtype)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    C.check(C.lib.ffq_quantize_bwd(
+        x.data_ptr(), C.dtype_tag(x.dtype), g.data_ptr(), C.dtype_tag(g.dtype), dx.data_ptr(),
+        dscale_full.data_ptr(), C.ptr(doffset_full),
+        s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
+        ctypes.byref(layout), float(num_bits), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
+    if dscale_full is not dscale:
+        dscale.copy_(dscale_full.sum().reshape(scale.shape))
+        if offset is not None:
+            doffset.copy_(doffset_full.sum().reshape(scale.shape))
+    return [dx, dscale, doffset]
+
+
+def quantize_dynamic_by_tile(
+    data: torch.Tensor,
+    tile_size,
+    num_bits: float,
+    symmetric: bool,
+    allow_one_sided: bool,
+    output_dtype: Optional[torch.dtype],
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """``torch.ops.fastforward.quantize_dynamic_by_tile`` (quantization/_quantizer_impl.py:243-285):
+    returns ``(codes, scale, rounded_offset)``, scale/offset in float32."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    if x.numel() == 0:
+        raise QuantizationError(f"Cannot dynamically quantize an empty tensor of shape {data.shape}")
+    out_dtype = output_dtype or torch.promote_types(x.dtype, torch.float32)
+    _bitwidth_guard(out_dtype, num_bits)
+    nt = _num_tiles(shape, tile)
+    q = torch.empty(shape, dtype=out_dtype, device=x.device)
+    scale = torch.empty(nt, dtype=torch.float32, device=x.device)
+    offset = torch.empty(nt, dtype=torch.float32, device=x.device)
+    ws_bytes = C.workspace_bytes(C.WS_DYNAMIC_QUANTIZE, layout, x.dtype)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    C.check(C.lib.ffq_dynamic_quantize(
+        x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), C.dtype_tag(out_dtype),
+        scale.data_ptr(), offset.data_ptr(), ctypes.byref(layout), float(num_bits),
+        int(bool(symmetric)), int(bool(allow_one_sided)), ws.data_ptr(), ws_bytes, C.current_stream(x.device)))
+    return q, scale, offset
+
+
+# ------------------------------------------------------------------------------------------
+# range estimation pieces (range_setting/minmax.py:226-237, quantization/affine/range.py:54-122)
+# ------------------------------------------------------------------------------------------
+def _minmax_call(x, layout, tile_min, tile_max, run_min, run_max, flags):
+    ws_bytes = C.workspace_bytes(C.WS_MINMAX, layout, x.dtype)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    C.check(C.lib.ffq_minmax(
+        x.data_ptr(), C.dtype_tag(x.dtype), C.ptr(tile_min), C.ptr(tile_max), C.ptr(run_min), C.ptr(run_max),
+        C.ptr(flags), ctypes.byref(layout), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
+
+
+def tile_minmax(data: torch.Tensor, tile_size) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-tile ``(min, max)`` in the data dtype: ``torch.min/max(tiles_to_rows(data), -1).values``."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    if x.numel() == 0:
+        raise IndexError("min(): Expected reduction dim 1 to have non-zero size.")
+    nt = _num_tiles(shape, tile)
+    mn = torch.empty(nt, dtype=x.dtype, device=x.device)
+    mx = torch.empty(nt, dtype=x.dtype, device=x.device)
+    _minmax_call(x, layout, mn, mx, None, None, None)
+    return mn, mx
+
+
+def running_minmax_update_(
+    run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size,
+    flags: Optional[torch.Tensor] = None,
+) -> None:
+    """In-place ``run_min = min(run_min, tile_min(data))`` / ``run_max = max(...)`` in ONE pass
+    over ``data``; ``flags`` (int32[1]) gets bit 0 set if a tile extremum is +-inf
+    (range_setting/minmax.py:229-237, without its host sync)."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    nt = _num_tiles(shape, tile)
+    for t, name in ((run_min, "run_min"), (run_max, "run_max")):
+        C.require_cuda(t, name)
+        if t.numel() != nt or t.dtype != x.dtype or not t.is_contiguous():
+            raise RuntimeError(f"{name} must be a contiguous {x.dtype} tensor with {nt} elements")
+    if flags is not None and (flags.dtype != torch.int32 or not flags.is_cuda):
+        raise RuntimeError("flags must be a CUDA int32 tensor")
+    _minmax_call(x, layout, None, None, run_min, run_max, flags)
+
+
+def parameters_for_range_(
+    min_range: torch.Tensor, max_range: torch.Tensor, num_bits: float, symmetric: bool, allow_one_sided: bool,
+    scale_out: torch.Tensor, offset_out: Optional[torch.Tensor], round_offset: bool = False,
+) -> None:
+    """Device-side, sync-free ``parameters_for_range`` (quantization/affine/range.py:54-122) writing
+    straight into a quantizer's ``scale`` / ``offset`` storage (nn/linear_quantizer.py:347-357)."""
+    C.require_cuda(min_range, "min_range")
+    mn = min_range.detach().reshape(-1).contiguous()
+    mx = max_range.detach().reshape(-1).contiguous()
+    if mn.dtype != mx.dtype:
+        common = torch.promote_types(mn.dtype, mx.dtype)
+        mn, mx = mn.to(common), mx.to(common)
+    n = mn.numel()
+    if mx.numel() != n or scale_out.numel() != n or (offset_out is not None and offset_out.numel() != n):
+        raise RuntimeError("parameters_for_range_: min, max, scale and offset must have the same number of elements")
+    if not scale_out.is_contiguous() or (offset_out is not None and not offset_out.is_contiguous()):
+        raise RuntimeError("parameters_for_range_: outputs must be contiguous")
+    ws = torch.empty(4096, dtype=torch.uint8, device=mn.device)
+    C.check(C.lib.ffq_params_for_range(
+        mn.data_ptr(), mx.data_ptr(), C.dtype_tag(mn.dtype), n, float(num_bits),
+        int(bool(symmetric)), int(bool(allow_one_sided)), int(bool(round_offset)),
+        scale_out.data_ptr(), C.dtype_tag(scale_out.dtype),
+        C.ptr(offset_out), C.dtype_tag(offset_out.dtype if offset_out is not None else None),
+        ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))

@@ -1,0 +1,200 @@
+/*
+ * ffq_b200.h -- C ABI of the B200-native backend for FastForward's quantization hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device
+ * (or, for the *_host variants, host) pointers, dtype tags, a tile-layout descriptor and a CUDA
+ * stream, and returns an int status.  No torch types appear here.  The Python host layer
+ * (fastforward_b200/_cabi.py) binds these with ctypes; INTEGRATION.md shows the stub that
+ * registers them under the reference's own op names.
+ *
+ * All "replaces:" citations are into the reference tree, /root/reference/src/fastforward/.
+ *
+ * Conventions
+ *   - Tensors are dense, row-major ("contiguous" in torch terms).  `layout` gives the data
+ *     shape and the tile shape; parameters (scale/offset/min/max/grads) are flat arrays of
+ *     length num_tiles, tile index row-major over the block grid -- the ordering defined by
+ *     quantization/tiled_tensor.py:71-98.
+ *   - Arithmetic follows PyTorch eager semantics op by op: IEEE division, round-half-even,
+ *     NaN-propagating clamp/min/max, one rounding to the promoted dtype after every op
+ *     (SURVEY.md Appendix B).
+ *   - Functions never allocate device memory and never synchronise the stream (except the
+ *     *_host variants, which own their staging buffers and return after the result is on the
+ *     host).  Scratch space is provided by the caller; ffq_workspace_bytes() sizes it.
+ *   - Thread safety: no global mutable state except a per-thread last-error string and a
+ *     per-device attribute cache.  One process per GPU is the intended deployment.
+ *   - Return value: FFQ_OK or an ffq_status_t error; ffq_last_error() returns the message.
+ */
+#ifndef FFQ_B200_H
+#define FFQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(FFQ_BUILD) && defined(__GNUC__)
+#define FFQ_API __attribute__((visibility("default")))
+#else
+#define FFQ_API
+#endif
+
+#define FFQ_ABI_VERSION 1
+#define FFQ_MAX_RANK 8
+
+typedef enum {
+  FFQ_OK = 0,
+  FFQ_ERR_INVALID = 1,     /* bad argument / tile does not divide shape  -> ValueError        */
+  FFQ_ERR_UNSUPPORTED = 2, /* dtype/layout the backend does not implement -> NotImplementedError */
+  FFQ_ERR_CUDA = 3,        /* CUDA runtime/driver failure                 -> RuntimeError      */
+  FFQ_ERR_BITWIDTH = 4,    /* output dtype cannot hold num_bits           -> RuntimeError
+                              (quantization/_quantizer_impl.py:165-167)                        */
+  FFQ_ERR_WORKSPACE = 5    /* workspace too small                         -> RuntimeError      */
+} ffq_status_t;
+
+typedef enum {
+  FFQ_F32 = 0,
+  FFQ_F16 = 1,
+  FFQ_BF16 = 2,
+  FFQ_F64 = 3, /* accepted in the enum; kernels return FFQ_ERR_UNSUPPORTED for it */
+  FFQ_I8 = 4,
+  FFQ_I16 = 5,
+  FFQ_I32 = 6,
+  FFQ_U8 = 7,
+  FFQ_I64 = 8,
+  FFQ_NONE = 255 /* "this optional tensor is absent" */
+} ffq_dtype_t;
+
+/* Shape of the data tensor and of one tile.  tile[i] must divide dims[i]
+ * (quantization/tiled_tensor.py:19-42). */
+typedef struct {
+  int32_t rank;
+  int64_t dims[FFQ_MAX_RANK];
+  int64_t tile[FFQ_MAX_RANK];
+} ffq_layout_t;
+
+/* Which scratch requirement ffq_workspace_bytes() reports. */
+typedef enum {
+  FFQ_WS_QUANTIZE_BWD = 0,
+  FFQ_WS_MINMAX = 1,
+  FFQ_WS_PARAMS_FOR_RANGE = 2,
+  FFQ_WS_DYNAMIC_QUANTIZE = 3
+} ffq_ws_kind_t;
+
+/* ---- library -------------------------------------------------------------------------- */
+FFQ_API int ffq_abi_version(void);
+FFQ_API const char* ffq_last_error(void);
+/* Number of kernel launches issued by this library since load (all threads).  bench.py reads
+ * it around the timed region to report "gpu_launches". */
+FFQ_API uint64_t ffq_launch_count(void);
+FFQ_API size_t ffq_workspace_bytes(int kind, const ffq_layout_t* layout, int data_dtype);
+/* Number of tiles / parameters implied by a layout; -1 if the tile does not divide the shape. */
+FFQ_API int64_t ffq_num_tiles(const ffq_layout_t* layout);
+
+/* ---- a1: quantize ------------------------------------------------------------------------
+ * q = cast(clamp(rint(x / s_t - rint(o_t)), -2^(b-1), 2^(b-1)-1), q_dtype)
+ * replaces: quantization/_quantizer_impl.py:144-169 (torch.ops.fastforward.quantize_by_tile)
+ * `offset` may be NULL (offset_dtype FFQ_NONE): symmetric, not one-sided. */
+FFQ_API int ffq_quantize(const void* x, int x_dtype, void* q, int q_dtype,
+                 const void* scale, int scale_dtype, const void* offset, int offset_dtype,
+                 const ffq_layout_t* layout, double num_bits, void* stream);
+
+/* ---- a2: dequantize ----------------------------------------------------------------------
+ * y = cast((q + rint(o_t)) * s_t, y_dtype)
+ * replaces: quantization/_quantizer_impl.py:172-190 (torch.ops.fastforward.dequantize_by_tile),
+ *           reached from QuantizedTensor.dequantize, quantized_tensor.py:384-388. */
+FFQ_API int ffq_dequantize(const void* q, int q_dtype, void* y, int y_dtype,
+                   const void* scale, int scale_dtype, const void* offset, int offset_dtype,
+                   const ffq_layout_t* layout, void* stream);
+
+/* ---- a1+a2 fused: fake-quantize ----------------------------------------------------------
+ * y = dequantize(cast(quantize(x), q_dtype)) in ONE pass (x read once, y written once); if
+ * `codes` is non-NULL the integer codes are stored too (dtype q_dtype).  Bit-identical to
+ * ffq_quantize followed by ffq_dequantize.
+ * replaces: the quantize->dequantize pair of affine/function.py:94-121 (export mode) and of
+ *           quantization/fuse.py:91-121 (`weight.copy_(quantizer(weight).dequantize())`). */
+FFQ_API int ffq_fakequant_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* codes, int q_dtype,
+                      const void* scale, int scale_dtype, const void* offset, int offset_dtype,
+                      const ffq_layout_t* layout, double num_bits, void* stream);
+
+/* ---- a3: straight-through backward ------------------------------------------------------
+ * dx = clip ? 0 : g;  dscale_t = sum_tile g*(clip ? bound+rint(o) : q-pre);
+ * doffset_t = sum_tile (clip ? s*g : 0)   (doffset may be NULL when offset is NULL)
+ * dx has the dtype of g; dscale has scale_dtype; doffset has promote(scale_dtype, g_dtype).
+ * Per-tile sums use a fixed reduction tree: deterministic run to run, no atomics.
+ * replaces: quantization/_quantizer_impl.py:193-237 (quantize_by_tile_backward). */
+FFQ_API int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dtype, void* dx,
+                     void* dscale, void* doffset,
+                     const void* scale, int scale_dtype, const void* offset, int offset_dtype,
+                     const ffq_layout_t* layout, double num_bits,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a7: per-tile min/max, optionally merged into running ranges -------------------------
+ * tile_min/tile_max (dtype of x, may be NULL) receive this batch's per-tile extrema.
+ * If run_min/run_max are non-NULL they are updated in place: run_min = min(run_min, tile_min),
+ * run_max = max(run_max, tile_max) (NaN propagates, as torch.min/torch.max do).
+ * If `flags` (int32[1], device) is non-NULL, bit 0 is OR-ed in when any tile extremum of this
+ * batch is +-inf -- the condition for which the reference raises NotImplementedError
+ * (range_setting/minmax.py:233-234); the host checks it at its next sync point.
+ * replaces: range_setting/minmax.py:226-237 (RunningMinMaxEstimator.estimate_step). */
+FFQ_API int ffq_minmax(const void* x, int x_dtype, void* tile_min, void* tile_max,
+               void* run_min, void* run_max, int32_t* flags,
+               const ffq_layout_t* layout, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6: range -> (scale, offset), sync-free ---------------------------------------------
+ * fp32 arithmetic throughout (affine/range.py:89-90).  The global one-sided decision
+ * `min.min() >= 0 and allow_one_sided` (range.py:100, a host sync in the reference) is taken
+ * on the device.  offset_out may be NULL (symmetric and not allow_one_sided); when the
+ * symmetric two-sided branch is taken and offset_out exists it is filled with 0
+ * (nn/linear_quantizer.py:353-357).  round_offset != 0 stores rint(offset) (dynamic path,
+ * _quantizer_impl.py:275).
+ * replaces: quantization/affine/range.py:54-122 + nn/linear_quantizer.py:347-357. */
+FFQ_API int ffq_params_for_range(const void* min_range, const void* max_range, int range_dtype, int64_t n,
+                         double num_bits, int symmetric, int allow_one_sided, int round_offset,
+                         void* scale_out, int scale_dtype, void* offset_out, int offset_dtype,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a4: dynamic quantize -----------------------------------------------------------------
+ * per-tile min/max -> params -> quantize, three launches, no host sync.
+ * scale_out/offset_out are fp32[num_tiles]; offset_out is the rounded offset (zeros when the
+ * symmetric two-sided branch is taken).
+ * replaces: quantization/_quantizer_impl.py:243-285 (quantize_dynamic_by_tile). */
+FFQ_API int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtype,
+                         float* scale_out, float* offset_out,
+                         const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a12: quantized linear (new kernel behind ff.dispatcher "linear") ---------------------
+ * y[m,n] = sx * sw[n] * ( sum_k qx[m,k] qw[n,k] + ox*rowsum_w[n] + ow[n]*rowsum_x[m] + K*ox*ow[n] )
+ *          + bias[n]
+ * qx: int8 [M,K] per-tensor (sx, ox scalars on the device, fp32); qw: int8 [N,K] per-channel
+ * (sw, ow fp32[N]; ow may be NULL).  int32 accumulation on tcgen05 (kind::i8) tensor cores,
+ * dequantisation fused into the epilogue.  y_dtype in {F32, BF16, F16}.
+ * rowsum_w: int32[N] precomputed with ffq_rowsum_i8 (weights are static); rowsum_x may be NULL
+ * when ow is NULL.
+ * replaces: _gen/fallback.py:77-112 (dequantize x2 + torch.nn.functional.linear), selected via
+ *           dispatcher.py:268-283. */
+FFQ_API int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype,
+                     int64_t M, int64_t N, int64_t K,
+                     const float* sx, const float* ox, const float* sw, const float* ow,
+                     const int32_t* rowsum_w, const int32_t* rowsum_x,
+                     const void* bias, int bias_dtype, void* stream);
+
+/* rowsum[r] = sum_k q[r,k]  (int8 [R,K] -> int32[R]) */
+FFQ_API int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream);
+
+/* ---- host-buffer convenience (end-to-end path; copies inside) -----------------------------
+ * Fake-quant forward + STE backward of one tensor whose data lives in HOST memory:
+ * H2D(x, g) -> ffq_fakequant_fwd -> ffq_quantize_bwd -> D2H(y, dx, dscale, doffset).
+ * scale/offset are host arrays too.  All dtypes as in the device entry points.
+ * Returns after the results are in the host buffers. */
+FFQ_API int ffq_fakequant_fwd_bwd_host(const void* x_host, const void* g_host, int dtype,
+                               void* y_host, void* dx_host, float* dscale_host, float* doffset_host,
+                               const float* scale_host, const float* offset_host,
+                               const ffq_layout_t* layout, double num_bits, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFQ_B200_H */
