@@ -2,10 +2,14 @@
 //
 // HBM-bound streaming kernels.  Fast path ("row" layouts: every tile is one contiguous run,
 // which covers per-tensor, per-channel(0) and per-group weights): 16-byte vector loads with
-// L1 no-allocate, 4 vectors in flight per thread, one parameter fetch per vector.  Algorithmic
-// traffic per element: quantize s+c, dequantize c+s, fake-quantize 2s bytes (s = data bytes,
-// c = code bytes).  Everything else (strided tiles, integer inputs, unaligned pointers) runs on
-// a scalar generic kernel: correct for any rank<=8 tiling and any dtype, not tuned.
+// L1 no-allocate, 4 vectors in flight per thread, one parameter fetch and ONE reciprocal per
+// vector; the IEEE-exact quotient costs 3 FMA-pipe instructions per element (shared_div in
+// ffq_common.cuh).  Algorithmic traffic per element: quantize s+c, dequantize c+s,
+// fake-quantize 2s bytes (s = data bytes, c = code bytes).  Everything else (strided tiles,
+// integer inputs, mixed promotion chains, unaligned pointers) runs on a scalar generic kernel:
+// correct for any rank<=8 tiling and any dtype, not tuned.
+#include <type_traits>
+
 #include "ffq_common.cuh"
 
 namespace ffq {
@@ -22,11 +26,13 @@ struct EwArgs {
   int s_dt, o_dt;
   unsigned long long numel;
   unsigned long long tile_numel;
-  FastDiv tdiv;     // valid when numel < 2^32
-  int big;          // numel >= 2^32: 64-bit index math
+  FastDiv tdiv;     // division by tile_numel (fast kernel: numel < 2^31)
   QParams qp;
   DParams dp;
   int q_rt_dt;      // fake-quant: dtype the codes take between quantize and dequantize
+  int rt_needed;    // fake-quant: that round trip can change the value (integer wrap)
+  int q_is_int;     // fake-quant: integer code dtype (drops the sign of a zero)
+  int tiles_aligned; // tile_numel is a multiple of the vector width: no vector straddles tiles
   GenericLayout gl; // generic kernel only
 };
 
@@ -42,6 +48,7 @@ __device__ __forceinline__ float code_roundtrip(float q, int dt) {
   }
 }
 
+// runtime-mode scalar arithmetic (generic kernel, and the slow path of the fast kernel)
 template <int OP>
 __device__ __forceinline__ float ew_apply(float v, float s, float o, const EwArgs& a, float* code_out) {
   if constexpr (OP == OP_QUANT) {
@@ -59,71 +66,147 @@ __device__ __forceinline__ float ew_apply(float v, float s, float o, const EwArg
 constexpr int EW_THREADS = 256;
 constexpr int EW_UNROLL = 4;
 
-template <int OP, typename InT, typename OutT>
-__global__ void __launch_bounds__(EW_THREADS) ew_row_kernel(const EwArgs a) {
-  constexpr int EPT = 16 / sizeof(InT);
+template <typename T, int N>
+__device__ __forceinline__ void unpack(const Vec<T, N>& v, float (&f)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = Elem<T>::to_f(v.v[i]);
+}
+template <typename T, int N>
+__device__ __forceinline__ void pack(const float (&f)[N], Vec<T, N>& v) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value && (N % 2 == 0)) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2)
+      *reinterpret_cast<__nv_bfloat162*>(&v.v[i]) = __floats2bfloat162_rn(f[i], f[i + 1]);
+  } else if constexpr (std::is_same<T, __half>::value && (N % 2 == 0)) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) *reinterpret_cast<__half2*>(&v.v[i]) = __floats2half2_rn(f[i], f[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v.v[i] = Elem<T>::from_f(f[i]);
+  }
+}
+
+template <int RM> struct ParamT { using type = float; };
+template <> struct ParamT<RM_BF16> { using type = __nv_bfloat16; };
+template <> struct ParamT<RM_F16> { using type = __half; };
+
+// Fast kernel.  Preconditions (checked by the host): row layout, numel < 2^31, 16-byte aligned
+// pointers, one promoted dtype RM for the whole chain, scale/offset stored in that dtype.
+template <typename InT, typename OutT> struct EwEpt {
+  static constexpr int value = 16 / (sizeof(InT) > sizeof(OutT) ? sizeof(InT) : sizeof(OutT));
+};
+
+template <int OP, typename InT, typename OutT, int RM>
+__global__ void __launch_bounds__(EW_THREADS, 4) ew_row_kernel(const EwArgs a) {
+  constexpr int EPT = EwEpt<InT, OutT>::value;
+  constexpr bool FLOAT_OUT = std::is_same<OutT, float>::value || std::is_same<OutT, __half>::value ||
+                             std::is_same<OutT, __nv_bfloat16>::value;
+  using PT = typename ParamT<RM>::type;
   const InT* __restrict__ in = static_cast<const InT*>(a.in);
   OutT* __restrict__ out = static_cast<OutT*>(a.out);
-  const unsigned long long nvec = a.numel / EPT;
-  const unsigned long long vbase = (unsigned long long)blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
+  const PT* __restrict__ scale = static_cast<const PT*>(a.scale);
+  const PT* __restrict__ offset = static_cast<const PT*>(a.offset);
+  const unsigned int numel = (unsigned int)a.numel;
+  const unsigned int nvec = numel / EPT;
+  const unsigned int vbase = blockIdx.x * (EW_THREADS * EW_UNROLL) + threadIdx.x;
+  const float lo = a.qp.lo, hi = a.qp.hi;
 
   Vec<InT, EPT> xin[EW_UNROLL];
 #pragma unroll
   for (int u = 0; u < EW_UNROLL; ++u) {
-    const unsigned long long v = vbase + (unsigned long long)u * EW_THREADS;
-    if (v < nvec) xin[u] = ld_stream<InT, EPT>(in + v * EPT);
+    const unsigned int v = vbase + u * EW_THREADS;
+    if (v < nvec) xin[u] = ld_stream<InT, EPT>(in + (size_t)v * EPT);
   }
+  unsigned int pcur = 0xffffffffu;
+  float s = 1.f, o = 0.f;
+  SharedRcp k{};
 #pragma unroll
   for (int u = 0; u < EW_UNROLL; ++u) {
-    const unsigned long long v = vbase + (unsigned long long)u * EW_THREADS;
+    const unsigned int v = vbase + u * EW_THREADS;
     if (v >= nvec) continue;
-    const unsigned long long e0 = v * EPT;
-    unsigned long long p0, p1;
-    if (!a.big) {
-      p0 = fast_div((unsigned int)e0, a.tdiv);
-      p1 = fast_div((unsigned int)e0 + (EPT - 1), a.tdiv);
-    } else {
-      p0 = e0 / a.tile_numel;
-      p1 = (e0 + (EPT - 1)) / a.tile_numel;
+    const unsigned int e0 = v * EPT;
+    const unsigned int p0 = fast_div(e0, a.tdiv);
+    if (p0 != pcur) {   // parameters (and the reciprocal) are fetched once per tile, not per vector
+      pcur = p0;
+      s = Elem<PT>::to_f(scale[p0]);
+      o = offset ? rintf(Elem<PT>::to_f(offset[p0])) : 0.f;
+      if constexpr (OP != OP_DEQUANT) k = make_shared_rcp(s);
     }
-    Vec<OutT, EPT> y;
-    float s = load_as_float(a.scale, a.s_dt, p0);
-    float o = load_offset(a.offset, a.o_dt, p0);
-    if (p0 == p1) {
+    float x[EPT], y[EPT], c[EPT];
+    unpack<InT, EPT>(xin[u], x);
+    const bool straddle = !a.tiles_aligned && fast_div(e0 + (EPT - 1), a.tdiv) != p0;
+    if (!straddle) {
+      if constexpr (OP == OP_DEQUANT) {
 #pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        float c;
-        const float r = ew_apply<OP>(Elem<InT>::to_f(xin[u].v[i]), s, o, a, &c);
-        y.v[i] = Elem<OutT>::from_f(r);
+        for (int i = 0; i < EPT; ++i) y[i] = rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(x[i], o)), s));
+      } else {
+        bool ok = k.ok;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          // float codes expose the sign of a zero quotient: take the strict guard there
+          float t = rndc<RM>(shared_div<(OP == OP_QUANT) && FLOAT_OUT>(x[i], k, ok));
+          t = rndc<RM>(__fsub_rn(t, o));
+          c[i] = nan_clamp(rintf(t), lo, hi);
+        }
+        if (!ok) {   // rare: scale or quotient outside the proven box -> plain IEEE division
+#pragma unroll
+          for (int i = 0; i < EPT; ++i) {
+            float t = rndc<RM>(__fdiv_rn(x[i], s));
+            t = rndc<RM>(__fsub_rn(t, o));
+            c[i] = nan_clamp(rintf(t), lo, hi);
+          }
+        }
         if constexpr (OP == OP_FAKEQUANT) {
-          if (a.codes) store_from_float(a.codes, a.codes_dt, e0 + i, c);
+          if (a.rt_needed) {          // integer code dtype narrower than num_bits: wraps
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) c[i] = code_roundtrip(c[i], a.q_rt_dt);
+          } else if (a.q_is_int) {    // integer codes cannot carry -0
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) c[i] = __fadd_rn(c[i], 0.0f);
+          }
+#pragma unroll
+          for (int i = 0; i < EPT; ++i) y[i] = rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(c[i], o)), s));
+        } else {
+#pragma unroll
+          for (int i = 0; i < EPT; ++i) y[i] = c[i];
         }
       }
-    } else {
+    } else {   // a vector straddling tiles (tile_numel not a multiple of the vector width)
+      unsigned int pp = p0;
+      float ss = s, oo = o;
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
-        const unsigned long long p = a.big ? (e0 + i) / a.tile_numel
-                                           : (unsigned long long)fast_div((unsigned int)e0 + i, a.tdiv);
-        if (p != p0) { p0 = p; s = load_as_float(a.scale, a.s_dt, p); o = load_offset(a.offset, a.o_dt, p); }
-        float c;
-        const float r = ew_apply<OP>(Elem<InT>::to_f(xin[u].v[i]), s, o, a, &c);
-        y.v[i] = Elem<OutT>::from_f(r);
-        if constexpr (OP == OP_FAKEQUANT) {
-          if (a.codes) store_from_float(a.codes, a.codes_dt, e0 + i, c);
+        const unsigned int p = fast_div(e0 + i, a.tdiv);
+        if (p != pp) { pp = p; ss = Elem<PT>::to_f(scale[p]); oo = offset ? rintf(Elem<PT>::to_f(offset[p])) : 0.f; }
+        y[i] = ew_apply<OP>(x[i], ss, oo, a, &c[i]);
+      }
+    }
+    Vec<OutT, EPT> yo;
+    pack<OutT, EPT>(y, yo);
+    st_vec<OutT, EPT>(out + e0, yo);
+    if constexpr (OP == OP_FAKEQUANT) {
+      if (a.codes) {
+        const bool float_codes = a.codes_dt == FFQ_F32 || a.codes_dt == FFQ_F16 || a.codes_dt == FFQ_BF16;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          float ci = c[i];
+          // float codes expose the sign of a zero quotient, which the shared-reciprocal path does
+          // not guarantee for zero / sub-2^-90 dividends: recompute those few exactly
+          if (float_codes && !straddle && !(fabsf(x[i]) >= 0x1p-90f)) ew_apply<OP_FAKEQUANT>(x[i], s, o, a, &ci);
+          store_from_float(a.codes, a.codes_dt, e0 + i, ci);
         }
       }
     }
-    st_vec<OutT, EPT>(out + e0, y);
   }
   // scalar tail (numel % EPT elements), done by the last block's first threads
   if (blockIdx.x == gridDim.x - 1) {
-    const unsigned long long e = nvec * EPT + threadIdx.x;
-    if (e < a.numel) {
-      const unsigned long long p = e / a.tile_numel;
-      const float s = load_as_float(a.scale, a.s_dt, p);
-      const float o = load_offset(a.offset, a.o_dt, p);
+    const unsigned int e = nvec * EPT + threadIdx.x;
+    if (e < numel) {
+      const unsigned int p = fast_div(e, a.tdiv);
+      const float ss = Elem<PT>::to_f(scale[p]);
+      const float oo = offset ? rintf(Elem<PT>::to_f(offset[p])) : 0.f;
       float c;
-      const float r = ew_apply<OP>(Elem<InT>::to_f(in[e]), s, o, a, &c);
+      const float r = ew_apply<OP>(Elem<InT>::to_f(in[e]), ss, oo, a, &c);
       out[e] = Elem<OutT>::from_f(r);
       if constexpr (OP == OP_FAKEQUANT) {
         if (a.codes) store_from_float(a.codes, a.codes_dt, e, c);
@@ -159,37 +242,50 @@ __global__ void __launch_bounds__(256) ew_generic_kernel(const EwArgs a) {
   }
 }
 
-template <int OP, typename InT, typename OutT>
+template <int OP, typename InT, typename OutT, int RM>
 static void launch_row(const EwArgs& a, cudaStream_t st) {
-  constexpr int EPT = 16 / sizeof(InT);
+  constexpr int EPT = EwEpt<InT, OutT>::value;
   const unsigned long long nvec = a.numel / EPT;
   unsigned long long blocks = (nvec + EW_THREADS * EW_UNROLL - 1) / (EW_THREADS * EW_UNROLL);
   if (blocks == 0) blocks = 1;
-  ew_row_kernel<OP, InT, OutT><<<(unsigned int)blocks, EW_THREADS, 0, st>>>(a);
+  ew_row_kernel<OP, InT, OutT, RM><<<(unsigned int)blocks, EW_THREADS, 0, st>>>(a);
+  count_launch();
 }
 
+// Instantiated combinations: every float in/out pair with an fp32 chain; bf16->bf16 with a bf16
+// chain and f16->f16 with an f16 chain (model.to(bfloat16) after the quantizers were created);
+// integer code outputs (quantize) / inputs (dequantize) with an fp32 chain.
 template <int OP, typename InT>
-static bool dispatch_out(const EwArgs& a, cudaStream_t st) {
-  switch (a.out_dt) {
-    case FFQ_F32: launch_row<OP, InT, float>(a, st); return true;
-    case FFQ_BF16: launch_row<OP, InT, __nv_bfloat16>(a, st); return true;
-    case FFQ_F16: launch_row<OP, InT, __half>(a, st); return true;
-    case FFQ_I8: if constexpr (OP == OP_QUANT) { launch_row<OP, InT, int8_t>(a, st); return true; } break;
-    case FFQ_I16: if constexpr (OP == OP_QUANT) { launch_row<OP, InT, int16_t>(a, st); return true; } break;
-    case FFQ_I32: if constexpr (OP == OP_QUANT) { launch_row<OP, InT, int32_t>(a, st); return true; } break;
+static bool dispatch_out(const EwArgs& a, int rm, cudaStream_t st) {
+  if (rm == RM_F32) {
+    switch (a.out_dt) {
+      case FFQ_F32: launch_row<OP, InT, float, RM_F32>(a, st); return true;
+      case FFQ_BF16: launch_row<OP, InT, __nv_bfloat16, RM_F32>(a, st); return true;
+      case FFQ_F16: launch_row<OP, InT, __half, RM_F32>(a, st); return true;
+      case FFQ_I8: if constexpr (OP == OP_QUANT) { launch_row<OP, InT, int8_t, RM_F32>(a, st); return true; } break;
+      case FFQ_I16: if constexpr (OP == OP_QUANT) { launch_row<OP, InT, int16_t, RM_F32>(a, st); return true; } break;
+      case FFQ_I32: if constexpr (OP == OP_QUANT) { launch_row<OP, InT, int32_t, RM_F32>(a, st); return true; } break;
+    }
+    return false;
+  }
+  if constexpr (std::is_same<InT, __nv_bfloat16>::value) {
+    if (rm == RM_BF16 && a.out_dt == FFQ_BF16) { launch_row<OP, InT, __nv_bfloat16, RM_BF16>(a, st); return true; }
+  }
+  if constexpr (std::is_same<InT, __half>::value) {
+    if (rm == RM_F16 && a.out_dt == FFQ_F16) { launch_row<OP, InT, __half, RM_F16>(a, st); return true; }
   }
   return false;
 }
 
 template <int OP>
-static bool dispatch_row(const EwArgs& a, cudaStream_t st) {
+static bool dispatch_row(const EwArgs& a, int rm, cudaStream_t st) {
   switch (a.in_dt) {
-    case FFQ_F32: return dispatch_out<OP, float>(a, st);
-    case FFQ_BF16: return dispatch_out<OP, __nv_bfloat16>(a, st);
-    case FFQ_F16: return dispatch_out<OP, __half>(a, st);
-    case FFQ_I8: if constexpr (OP == OP_DEQUANT) return dispatch_out<OP, int8_t>(a, st); break;
-    case FFQ_I16: if constexpr (OP == OP_DEQUANT) return dispatch_out<OP, int16_t>(a, st); break;
-    case FFQ_I32: if constexpr (OP == OP_DEQUANT) return dispatch_out<OP, int32_t>(a, st); break;
+    case FFQ_F32: return dispatch_out<OP, float>(a, rm, st);
+    case FFQ_BF16: return dispatch_out<OP, __nv_bfloat16>(a, rm, st);
+    case FFQ_F16: return dispatch_out<OP, __half>(a, rm, st);
+    case FFQ_I8: if constexpr (OP == OP_DEQUANT) return dispatch_out<OP, int8_t>(a, rm, st); break;
+    case FFQ_I16: if constexpr (OP == OP_DEQUANT) return dispatch_out<OP, int16_t>(a, rm, st); break;
+    case FFQ_I32: if constexpr (OP == OP_DEQUANT) return dispatch_out<OP, int32_t>(a, rm, st); break;
   }
   return false;
 }
@@ -232,35 +328,79 @@ DParams make_dparams(int q_dt, int s_dt, int o_dt) {
   return dp;
 }
 
-static int run_elementwise(int op, EwArgs& a, const ffq_layout_t* layout, cudaStream_t st) {
+static int param_rm(int dt) { return dt == FFQ_F32 ? RM_F32 : dt == FFQ_BF16 ? RM_BF16 : dt == FFQ_F16 ? RM_F16 : -1; }
+
+static int run_elementwise(int op, EwArgs& a, const ffq_layout_t* layout, double num_bits, cudaStream_t st) {
   Plan plan;
   int rc = make_plan(layout, &plan);
   if (rc != FFQ_OK) return rc;
   if (plan.numel == 0) return FFQ_OK;
   a.numel = (unsigned long long)plan.numel;
   a.tile_numel = (unsigned long long)plan.tile_numel;
-  a.big = plan.numel >= (1ll << 32) ? 1 : 0;
-  a.tdiv = make_fast_div(a.big || plan.tile_numel >= (1ll << 32) ? 1u : (unsigned int)plan.tile_numel);
-  if (!a.big && plan.tile_numel >= (1ll << 32)) a.big = 1;
   a.gl = make_generic_layout(plan);
+  // an integer code dtype narrower than num_bits wraps on the round trip (the reference's
+  // can_support_bitwidth admits iinfo.bits + 2)
+  a.rt_needed = (op == OP_FAKEQUANT && is_int_dt(a.q_rt_dt) && num_bits > dt_size(a.q_rt_dt) * 8) ? 1 : 0;
+  a.q_is_int = (op == OP_FAKEQUANT && is_int_dt(a.q_rt_dt)) ? 1 : 0;
 
-  bool done = false;
-  const bool fast_ok = plan.row && aligned16(a.in) && aligned16(a.out);
-  if (fast_ok) {
-    if (op == OP_QUANT) done = dispatch_row<OP_QUANT>(a, st);
-    else if (op == OP_DEQUANT) done = dispatch_row<OP_DEQUANT>(a, st);
-    else done = dispatch_row<OP_FAKEQUANT>(a, st);
+  // the fast kernel handles chains with a single promoted dtype whose parameters are stored in it
+  int rm = -1;
+  if (op == OP_QUANT) {
+    if (a.qp.m_div == a.qp.m_sub) rm = a.qp.m_div;
+  } else if (op == OP_DEQUANT) {
+    if (a.dp.m_add == a.dp.m_mul && a.dp.int_add_bits == 0) rm = a.dp.m_add;
+  } else {
+    if (a.qp.m_div == a.qp.m_sub && a.dp.m_add == a.dp.m_mul && a.qp.m_div == a.dp.m_add && a.dp.int_add_bits == 0)
+      rm = a.qp.m_div;
   }
-  if (!done) {
-    const unsigned long long blocks = (a.numel + 255) / 256;
-    if (blocks > 0x7fffffffull) {
-      set_error("tensor too large for the generic elementwise kernel");
-      return FFQ_ERR_UNSUPPORTED;
+  if (rm >= 0 && (param_rm(a.s_dt) != rm || (a.offset && param_rm(a.o_dt) != rm))) rm = -1;
+
+  const int in_sz = dt_size(a.in_dt), out_sz = dt_size(a.out_dt), code_sz = a.codes ? dt_size(a.codes_dt) : 0;
+  const int p_sz = dt_size(a.s_dt);
+  if (rm >= 0 && plan.row && aligned16(a.in) && aligned16(a.out) && in_sz > 0 && in_sz <= 4) {
+    // launches of < 2^31 elements each, cut at tile boundaries (a single launch in practice)
+    const int ept = 16 / (in_sz > out_sz ? in_sz : out_sz);
+    const unsigned long long T = a.tile_numel, LIM = 1ull << 31;
+    unsigned long long chunk;        // elements per launch
+    unsigned long long chunk_tiles;  // parameter advance per launch (0: all launches inside one tile)
+    if (a.numel < LIM) { chunk = a.numel; chunk_tiles = 0; }
+    else if (T * 16 <= LIM) { chunk = (LIM / (T * 16)) * (T * 16); chunk_tiles = chunk / T; }
+    else { chunk = 0; chunk_tiles = 0; }   // giant tiles in a giant tensor: handled below
+    if (chunk) {
+      bool ok = true;
+      const EwArgs base = a;
+      for (unsigned long long off = 0; off < base.numel && ok; off += chunk) {
+        EwArgs c = base;
+        c.numel = (base.numel - off < chunk) ? base.numel - off : chunk;
+        c.in = static_cast<const char*>(base.in) + off * in_sz;
+        c.out = static_cast<char*>(base.out) + off * out_sz;
+        if (base.codes) c.codes = static_cast<char*>(base.codes) + off * code_sz;
+        const unsigned long long tile0 = chunk_tiles ? (off / chunk) * chunk_tiles : 0;
+        c.scale = static_cast<const char*>(base.scale) + tile0 * p_sz;
+        if (base.offset) c.offset = static_cast<const char*>(base.offset) + tile0 * p_sz;
+        c.tdiv = make_fast_div((unsigned int)(T < LIM ? T : LIM - 1));
+        if (T >= LIM) c.tdiv = make_fast_div(0x80000000u);   // one tile: every index maps to parameter 0
+        c.tiles_aligned = (T % ept == 0) ? 1 : 0;
+        if (op == OP_QUANT) ok = dispatch_row<OP_QUANT>(c, rm, st);
+        else if (op == OP_DEQUANT) ok = dispatch_row<OP_DEQUANT>(c, rm, st);
+        else ok = dispatch_row<OP_FAKEQUANT>(c, rm, st);
+        if (!ok && off != 0) { set_error("elementwise: dtype dispatch changed between chunks"); return FFQ_ERR_CUDA; }
+      }
+      if (ok) {
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("kernel launch failed: %s", cudaGetErrorString(e)); return FFQ_ERR_CUDA; }
+        return FFQ_OK;
+      }
     }
-    if (op == OP_QUANT) ew_generic_kernel<OP_QUANT><<<(unsigned int)blocks, 256, 0, st>>>(a);
-    else if (op == OP_DEQUANT) ew_generic_kernel<OP_DEQUANT><<<(unsigned int)blocks, 256, 0, st>>>(a);
-    else ew_generic_kernel<OP_FAKEQUANT><<<(unsigned int)blocks, 256, 0, st>>>(a);
   }
+  const unsigned long long blocks = (a.numel + 255) / 256;
+  if (blocks > 0x7fffffffull) {
+    set_error("tensor too large for the generic elementwise kernel");
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (op == OP_QUANT) ew_generic_kernel<OP_QUANT><<<(unsigned int)blocks, 256, 0, st>>>(a);
+  else if (op == OP_DEQUANT) ew_generic_kernel<OP_DEQUANT><<<(unsigned int)blocks, 256, 0, st>>>(a);
+  else ew_generic_kernel<OP_FAKEQUANT><<<(unsigned int)blocks, 256, 0, st>>>(a);
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
 }
@@ -286,7 +426,7 @@ int ffq_quantize(const void* x, int x_dtype, void* q, int q_dtype, const void* s
   a.in_dt = x_dtype; a.out_dt = q_dtype; a.codes_dt = FFQ_NONE;
   a.scale = scale; a.offset = offset; a.s_dt = scale_dtype; a.o_dt = offset_dtype;
   a.qp = make_qparams(x_dtype, scale_dtype, offset_dtype, num_bits);
-  return run_elementwise(OP_QUANT, a, layout, static_cast<cudaStream_t>(stream));
+  return run_elementwise(OP_QUANT, a, layout, num_bits, static_cast<cudaStream_t>(stream));
 }
 
 int ffq_dequantize(const void* q, int q_dtype, void* y, int y_dtype, const void* scale, int scale_dtype,
@@ -303,7 +443,7 @@ int ffq_dequantize(const void* q, int q_dtype, void* y, int y_dtype, const void*
   a.in_dt = q_dtype; a.out_dt = y_dtype; a.codes_dt = FFQ_NONE;
   a.scale = scale; a.offset = offset; a.s_dt = scale_dtype; a.o_dt = offset_dtype;
   a.dp = make_dparams(q_dtype, scale_dtype, offset_dtype);
-  return run_elementwise(OP_DEQUANT, a, layout, static_cast<cudaStream_t>(stream));
+  return run_elementwise(OP_DEQUANT, a, layout, 0.0, static_cast<cudaStream_t>(stream));
 }
 
 int ffq_fakequant_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* codes, int q_dtype,
@@ -323,7 +463,7 @@ int ffq_fakequant_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* co
   a.qp = make_qparams(x_dtype, scale_dtype, offset_dtype, num_bits);
   a.dp = make_dparams(q_dtype, scale_dtype, offset_dtype);
   a.q_rt_dt = q_dtype;
-  return run_elementwise(OP_FAKEQUANT, a, layout, static_cast<cudaStream_t>(stream));
+  return run_elementwise(OP_FAKEQUANT, a, layout, num_bits, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

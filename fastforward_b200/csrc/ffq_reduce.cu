@@ -4,14 +4,18 @@
 //   * range -> (scale, offset) with the global one-sided decision taken on the device
 //   * dynamic quantize = min/max -> params -> quantize, no host sync
 //
-// All are HBM-bound.  "Row" layouts (contiguous tiles) get two mappings:
+// All are HBM-bound.  "Row" layouts (contiguous tiles) get three mappings:
 //   - small tiles (tile_numel == LANES*EPT, LANES in 1..32): a LANES-wide sub-warp owns a tile,
 //     the CTA streams a contiguous 16 KB chunk per unrolled step, reduction by shuffles only;
-//   - large tiles: a 256-thread CTA owns a tile segment; few-and-huge tiles (per-tensor) are
-//     split into S segments whose partials are combined by a second tiny kernel.
+//   - medium tiles (a weight row, up to 64 Ki elements) when there are enough of them: one warp
+//     per tile, shuffle-only reduction, no shared memory and no block barrier;
+//   - large / few tiles: a 256-thread CTA owns a tile segment; few-and-huge tiles (per-tensor)
+//     are split into S segments whose partials are combined by a second tiny kernel.
 // Reductions are fixed trees (thread-serial -> shuffle -> shared memory -> optional second
 // stage): deterministic run to run, no atomics on floating-point data.
 // Algorithmic traffic per element: backward 3s (x, g in; dx out), min/max s.
+#include <type_traits>
+
 #include "ffq_common.cuh"
 
 namespace ffq {
@@ -46,6 +50,63 @@ __device__ __forceinline__ void bwd_terms(float x, float g, float s, float o, co
   dsc = rnd(rnd(__fmul_rn(v, g), p.m_sg), p.m_s);
 }
 
+// fast path: all EPT elements share a tile and the whole chain has one promoted dtype RM
+template <int RM, int EPT>
+__device__ __forceinline__ void bwd_vector(const float (&x)[EPT], const float (&g)[EPT], float (&dx)[EPT], float s,
+                                           float o, const BParams& p, float& sum_sc, float& sum_off) {
+  const SharedRcp k = make_shared_rcp(s);
+  bool ok = k.ok;
+  const float o_s = rndc<RM>(o);
+  const float bound_lo = rndc<RM>(__fadd_rn(p.lo_s, o_s)), bound_hi = rndc<RM>(__fadd_rn(p.hi_s, o_s));
+  float sc = 0.f, off = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    // exactness box of shared_div, plus: a non-zero dividend below 2^-90 leaves the box
+    ok = ok && (fabsf(x[i]) >= 0x1p-90f || x[i] == 0.f);
+    float pre = rndc<RM>(shared_div<false>(x[i], k, ok));
+    pre = rndc<RM>(__fsub_rn(pre, o));
+    const float q = rintf(pre);
+    const bool below = q < p.lo, above = q > p.hi;
+    const bool clip = below || above;
+    dx[i] = clip ? 0.f : g[i];
+    off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
+    const float resid = rndc<RM>(__fsub_rn(q, pre));
+    const float v = clip ? (below ? bound_lo : bound_hi) : resid;
+    sc += rndc<RM>(__fmul_rn(v, g[i]));
+  }
+  if (!ok) {   // rare: recompute the vector with plain IEEE division
+    sc = 0.f; off = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      float dsc, doff;
+      bwd_terms(x[i], g[i], s, o, p, dx[i], dsc, doff);
+      sc += dsc; off += doff;
+    }
+  }
+  sum_sc += sc;
+  sum_off += off;
+}
+
+template <typename T, int N>
+__device__ __forceinline__ void unpack(const Vec<T, N>& v, float (&f)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = Elem<T>::to_f(v.v[i]);
+}
+template <typename T, int N>
+__device__ __forceinline__ void pack(const float (&f)[N], Vec<T, N>& v) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value && (N % 2 == 0)) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2)
+      *reinterpret_cast<__nv_bfloat162*>(&v.v[i]) = __floats2bfloat162_rn(f[i], f[i + 1]);
+  } else if constexpr (std::is_same<T, __half>::value && (N % 2 == 0)) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) *reinterpret_cast<__half2*>(&v.v[i]) = __floats2half2_rn(f[i], f[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v.v[i] = Elem<T>::from_f(f[i]);
+  }
+}
+
 struct BwdArgs {
   const void* x; const void* g; void* dx;
   int x_dt, g_dt;
@@ -70,57 +131,47 @@ __device__ __forceinline__ float block_sum(float v, float* smem) {
   return r;  // valid in warp 0
 }
 
-// --- small tiles: one LANES-wide group per tile -------------------------------------------
-template <typename XT, typename GT, int LANES>
-__global__ void __launch_bounds__(RD_THREADS) bwd_row_group_kernel(const BwdArgs a) {
-  constexpr int EPT = 16 / sizeof(XT);
-  constexpr int GV = (int)(EPT * sizeof(GT)) / 16 > 0 ? (int)(EPT * sizeof(GT)) / 16 : 1;  // 16B chunks of g per vector
-  (void)GV;
-  const XT* __restrict__ x = static_cast<const XT*>(a.x);
-  const GT* __restrict__ g = static_cast<const GT*>(a.g);
-  GT* __restrict__ dx = static_cast<GT*>(a.dx);
-  const unsigned long long nvec = a.numel / EPT;
-  const unsigned long long vbase = (unsigned long long)blockIdx.x * (RD_THREADS * RD_UNROLL) + threadIdx.x;
+// per-type unroll: the same bytes in flight per thread, fewer live registers for 16-bit data
+template <typename T> struct BwdUnroll { static constexpr int value = sizeof(T) >= 4 ? 4 : 2; };
 
-  Vec<XT, EPT> xv[RD_UNROLL];
-  Vec<GT, EPT> gv[RD_UNROLL];
+// --- small tiles: one LANES-wide group per tile -------------------------------------------
+// T is the dtype of x, g and dx (autograd hands back the gradient in the dtype of the output);
+// mixed x/g dtypes take the generic kernel.
+template <typename T, int LANES, int RM>
+__global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_group_kernel(const BwdArgs a) {
+  constexpr int EPT = 16 / sizeof(T);
+  constexpr int U = BwdUnroll<T>::value;
+  const T* __restrict__ x = static_cast<const T*>(a.x);
+  const T* __restrict__ g = static_cast<const T*>(a.g);
+  T* __restrict__ dx = static_cast<T*>(a.dx);
+  const unsigned long long nvec = a.numel / EPT;
+  const unsigned long long vbase = (unsigned long long)blockIdx.x * (RD_THREADS * U) + threadIdx.x;
+
+  Vec<T, EPT> xv[U], gv[U];
 #pragma unroll
-  for (int u = 0; u < RD_UNROLL; ++u) {
+  for (int u = 0; u < U; ++u) {
     const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
     if (v < nvec) {
-      xv[u] = ld_stream<XT, EPT>(x + v * EPT);
-      if constexpr (sizeof(GT) * EPT <= 16) {
-        gv[u] = ld_stream<GT, EPT>(g + v * EPT);
-      } else {
-#pragma unroll
-        for (int c = 0; c < (int)(sizeof(GT) * EPT / 16); ++c) {
-          constexpr int GE = 16 / sizeof(GT);
-          Vec<GT, GE> t = ld_stream<GT, GE>(g + v * EPT + c * GE);
-#pragma unroll
-          for (int i = 0; i < GE; ++i) gv[u].v[c * GE + i] = t.v[i];
-        }
-      }
+      xv[u] = ld_stream<T, EPT>(x + v * EPT);
+      gv[u] = ld_stream<T, EPT>(g + v * EPT);
     }
   }
 #pragma unroll
-  for (int u = 0; u < RD_UNROLL; ++u) {
+  for (int u = 0; u < U; ++u) {
     const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
-    const bool live = v < nvec;
+    const bool live = v < nvec;   // whole groups are live or dead together (nvec % LANES == 0)
     const unsigned long long tile = v / LANES;
     float sum_sc = 0.f, sum_off = 0.f;
     if (live) {
       const float s = load_as_float(a.scale, a.s_dt, tile);
       const float o = load_offset(a.offset, a.o_dt, tile);
-      Vec<GT, EPT> d;
-#pragma unroll
-      for (int i = 0; i < EPT; ++i) {
-        float dxi, dsc, doff;
-        bwd_terms(Elem<XT>::to_f(xv[u].v[i]), Elem<GT>::to_f(gv[u].v[i]), s, o, a.bp, dxi, dsc, doff);
-        d.v[i] = Elem<GT>::from_f(dxi);
-        sum_sc += dsc;
-        sum_off += doff;
-      }
-      st_vec<GT, EPT>(dx + v * EPT, d);
+      float xf[EPT], gf[EPT], df[EPT];
+      unpack<T, EPT>(xv[u], xf);
+      unpack<T, EPT>(gv[u], gf);
+      bwd_vector<RM, EPT>(xf, gf, df, s, o, a.bp, sum_sc, sum_off);
+      Vec<T, EPT> d;
+      pack<T, EPT>(df, d);
+      st_vec<T, EPT>(dx + v * EPT, d);
     }
     sum_sc = group_sum<LANES>(sum_sc);
     if (a.bp.has_offset) sum_off = group_sum<LANES>(sum_off);
@@ -131,68 +182,77 @@ __global__ void __launch_bounds__(RD_THREADS) bwd_row_group_kernel(const BwdArgs
   }
 }
 
-// --- large tiles: one CTA per tile segment -------------------------------------------------
-template <typename XT, typename GT, int EPT>
-__global__ void __launch_bounds__(RD_THREADS) bwd_row_cta_kernel(const BwdArgs a) {
-  __shared__ float smem[32];
-  const XT* __restrict__ x = static_cast<const XT*>(a.x);
-  const GT* __restrict__ g = static_cast<const GT*>(a.g);
-  GT* __restrict__ dx = static_cast<GT*>(a.dx);
-  const unsigned long long tile = blockIdx.x / a.S;
-  const unsigned int seg = blockIdx.x % a.S;
-  const unsigned long long begin = (unsigned long long)seg * a.seg_len;
-  unsigned long long end = begin + a.seg_len;
-  if (end > a.tile_numel) end = a.tile_numel;
-  const unsigned long long base = tile * a.tile_numel;
-  const float s = load_as_float(a.scale, a.s_dt, tile);
-  const float o = load_offset(a.offset, a.o_dt, tile);
-
-  float sum_sc = 0.f, sum_off = 0.f;
-  const unsigned long long step = (unsigned long long)blockDim.x * EPT;
-  for (unsigned long long i0 = begin + (unsigned long long)threadIdx.x * EPT; i0 < end; i0 += step * RD_UNROLL) {
-    Vec<XT, EPT> xv[RD_UNROLL];
-    Vec<GT, EPT> gv[RD_UNROLL];
+// Shared body: `nthreads` cooperating threads (a warp or a CTA), thread `tid` of them, stream
+// elements [0, len) of x/g/dx (already offset to the tile segment) and accumulate the sums.
+template <typename T, int EPT, int RM>
+__device__ __forceinline__ void bwd_stream(const T* __restrict__ x, const T* __restrict__ g, T* __restrict__ dx,
+                                           unsigned int len, unsigned int tid, unsigned int nthreads, float s,
+                                           float o, const BParams& bp, float& sum_sc, float& sum_off) {
+  constexpr int U = BwdUnroll<T>::value;
+  const unsigned int step = nthreads * EPT;
+  for (unsigned int i0 = tid * EPT; i0 < len; i0 += step * U) {
+    Vec<T, EPT> xv[U], gv[U];
 #pragma unroll
-    for (int u = 0; u < RD_UNROLL; ++u) {
-      const unsigned long long i = i0 + u * step;
-      if (i < end) {
-        if constexpr (EPT == 1) {
-          xv[u].v[0] = x[base + i];
-          gv[u].v[0] = g[base + i];
-        } else {
-          xv[u] = ld_stream<XT, EPT>(x + base + i);
-          if constexpr (sizeof(GT) * EPT <= 16) {
-            gv[u] = ld_stream<GT, EPT>(g + base + i);
-          } else {
-#pragma unroll
-            for (int c = 0; c < (int)(sizeof(GT) * EPT / 16); ++c) {
-              constexpr int GE = 16 / sizeof(GT);
-              Vec<GT, GE> t = ld_stream<GT, GE>(g + base + i + c * GE);
-#pragma unroll
-              for (int k = 0; k < GE; ++k) gv[u].v[c * GE + k] = t.v[k];
-            }
-          }
-        }
+    for (int u = 0; u < U; ++u) {
+      const unsigned int i = i0 + u * step;
+      if (i < len) {
+        if constexpr (EPT == 1) { xv[u].v[0] = x[i]; gv[u].v[0] = g[i]; }
+        else { xv[u] = ld_stream<T, EPT>(x + i); gv[u] = ld_stream<T, EPT>(g + i); }
       }
     }
 #pragma unroll
-    for (int u = 0; u < RD_UNROLL; ++u) {
-      const unsigned long long i = i0 + u * step;
-      if (i < end) {
-        Vec<GT, EPT> d;
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-          float dxi, dsc, doff;
-          bwd_terms(Elem<XT>::to_f(xv[u].v[k]), Elem<GT>::to_f(gv[u].v[k]), s, o, a.bp, dxi, dsc, doff);
-          d.v[k] = Elem<GT>::from_f(dxi);
-          sum_sc += dsc;
-          sum_off += doff;
-        }
-        if constexpr (EPT == 1) dx[base + i] = d.v[0];
-        else st_vec<GT, EPT>(dx + base + i, d);
+    for (int u = 0; u < U; ++u) {
+      const unsigned int i = i0 + u * step;
+      if (i < len) {
+        float xf[EPT], gf[EPT], df[EPT];
+        unpack<T, EPT>(xv[u], xf);
+        unpack<T, EPT>(gv[u], gf);
+        bwd_vector<RM, EPT>(xf, gf, df, s, o, bp, sum_sc, sum_off);
+        Vec<T, EPT> d;
+        pack<T, EPT>(df, d);
+        if constexpr (EPT == 1) dx[i] = d.v[0];
+        else st_vec<T, EPT>(dx + i, d);
       }
     }
   }
+}
+
+// --- medium tiles: one warp per tile ---------------------------------------------------------
+template <typename T, int EPT, int RM>
+__global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_warp_kernel(const BwdArgs a) {
+  const unsigned long long tile = (unsigned long long)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
+  if (tile >= a.num_tiles) return;
+  const unsigned int lane = threadIdx.x & 31;
+  const unsigned long long base = tile * a.tile_numel;
+  const float s = load_as_float(a.scale, a.s_dt, tile);
+  const float o = load_offset(a.offset, a.o_dt, tile);
+  float sum_sc = 0.f, sum_off = 0.f;
+  bwd_stream<T, EPT, RM>(static_cast<const T*>(a.x) + base, static_cast<const T*>(a.g) + base,
+                         static_cast<T*>(a.dx) + base, (unsigned int)a.tile_numel, lane, 32u, s, o, a.bp, sum_sc,
+                         sum_off);
+  sum_sc = warp_sum(sum_sc);
+  if (a.bp.has_offset) sum_off = warp_sum(sum_off);
+  if (lane == 0) {
+    store_from_float(a.dscale, a.dsc_dt, tile, sum_sc);
+    if (a.bp.has_offset) store_from_float(a.doffset, a.doff_dt, tile, sum_off);
+  }
+}
+
+// --- large / few tiles: one CTA per tile segment ---------------------------------------------
+template <typename T, int EPT, int RM>
+__global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_cta_kernel(const BwdArgs a) {
+  __shared__ float smem[32];
+  const unsigned long long tile = blockIdx.x / a.S;
+  const unsigned int seg = blockIdx.x % a.S;
+  const unsigned long long begin = (unsigned long long)seg * a.seg_len;
+  const unsigned long long remain = a.tile_numel - begin;
+  const unsigned int len = (unsigned int)(remain < a.seg_len ? remain : a.seg_len);
+  const unsigned long long base = tile * a.tile_numel + begin;
+  const float s = load_as_float(a.scale, a.s_dt, tile);
+  const float o = load_offset(a.offset, a.o_dt, tile);
+  float sum_sc = 0.f, sum_off = 0.f;
+  bwd_stream<T, EPT, RM>(static_cast<const T*>(a.x) + base, static_cast<const T*>(a.g) + base,
+                         static_cast<T*>(a.dx) + base, len, threadIdx.x, blockDim.x, s, o, a.bp, sum_sc, sum_off);
   sum_sc = block_sum(sum_sc, smem);
   if (a.bp.has_offset) sum_off = block_sum(sum_off, smem);
   if (threadIdx.x == 0) {
@@ -265,14 +325,28 @@ __global__ void __launch_bounds__(128) bwd_generic_kernel(const BwdArgs a) {
 // ------------------------------------------------------------------------------------------
 struct Segmentation { unsigned int S; unsigned long long seg_len; };
 
+constexpr long long WARP_TILE_MAX = 1ll << 16;   // largest tile a single warp streams
+
+// One warp per tile pays off when there are enough tiles to fill the machine with warps.
+static bool use_warp_per_tile(const Plan& plan, int ept) {
+  return plan.tile_numel > 32ll * ept && plan.tile_numel <= WARP_TILE_MAX &&
+         plan.num_tiles >= 16ll * sm_count();
+}
+
 static Segmentation choose_segments(const Plan& plan, int ept) {
   Segmentation sg{1, (unsigned long long)plan.tile_numel};
-  const long long target = 4ll * sm_count();
+  if (use_warp_per_tile(plan, ept)) return sg;
+  const long long target = 6ll * sm_count();
   const unsigned long long quantum = (unsigned long long)RD_THREADS * ept * RD_UNROLL;
-  if (plan.num_tiles >= target || (unsigned long long)plan.tile_numel <= quantum) return sg;
+  const unsigned long long max_seg = 1ull << 30;   // in-segment indices are 32-bit
+  if ((plan.num_tiles >= target || (unsigned long long)plan.tile_numel <= quantum) &&
+      (unsigned long long)plan.tile_numel <= max_seg)
+    return sg;
   unsigned long long want = (unsigned long long)((target + plan.num_tiles - 1) / plan.num_tiles);
+  if (want < 1) want = 1;
   unsigned long long seg = ((unsigned long long)plan.tile_numel + want - 1) / want;
   seg = (seg + quantum - 1) / quantum * quantum;
+  if (seg > max_seg) seg = max_seg;
   sg.seg_len = seg;
   sg.S = (unsigned int)(((unsigned long long)plan.tile_numel + seg - 1) / seg);
   if (sg.S <= 1) { sg.S = 1; sg.seg_len = (unsigned long long)plan.tile_numel; }
@@ -289,51 +363,60 @@ static int group_lanes(const Plan& plan, int ept) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <typename XT, typename GT>
+template <typename T, int RM>
 static void launch_bwd_row(const BwdArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
-  constexpr int EPT = 16 / sizeof(XT);
+  constexpr int EPT = 16 / sizeof(T);
   const int lanes = vec_ok ? group_lanes(plan, EPT) : 0;
   if (lanes) {
     const unsigned long long nvec = a.numel / EPT;
-    const unsigned int blocks = (unsigned int)((nvec + RD_THREADS * RD_UNROLL - 1) / (RD_THREADS * RD_UNROLL));
+    constexpr int U = BwdUnroll<T>::value;
+    const unsigned int blocks = (unsigned int)((nvec + RD_THREADS * U - 1) / (RD_THREADS * U));
     switch (lanes) {
-      case 1: bwd_row_group_kernel<XT, GT, 1><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 2: bwd_row_group_kernel<XT, GT, 2><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 4: bwd_row_group_kernel<XT, GT, 4><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 8: bwd_row_group_kernel<XT, GT, 8><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 16: bwd_row_group_kernel<XT, GT, 16><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      default: bwd_row_group_kernel<XT, GT, 32><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 1: bwd_row_group_kernel<T, 1, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 2: bwd_row_group_kernel<T, 2, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 4: bwd_row_group_kernel<T, 4, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 8: bwd_row_group_kernel<T, 8, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 16: bwd_row_group_kernel<T, 16, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      default: bwd_row_group_kernel<T, 32, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
     }
+    return;
+  }
+  const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
+  if (a.S == 1 && use_warp_per_tile(plan, EPT)) {
+    const unsigned int blocks = (unsigned int)((a.num_tiles + RD_THREADS / 32 - 1) / (RD_THREADS / 32));
+    if (ept == EPT) bwd_row_warp_kernel<T, EPT, RM><<<blocks, RD_THREADS, 0, st>>>(a);
+    else bwd_row_warp_kernel<T, 1, RM><<<blocks, RD_THREADS, 0, st>>>(a);
     return;
   }
   const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
   // shrink the CTA for short tiles so that lanes are not idle
-  const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
   unsigned long long per_seg = (a.seg_len + ept - 1) / ept;
   int threads = RD_THREADS;
   while (threads > 32 && (unsigned long long)threads / 2 >= per_seg) threads /= 2;
-  if (ept == EPT) bwd_row_cta_kernel<XT, GT, EPT><<<blocks, threads, 0, st>>>(a);
-  else bwd_row_cta_kernel<XT, GT, 1><<<blocks, threads, 0, st>>>(a);
+  if (ept == EPT) bwd_row_cta_kernel<T, EPT, RM><<<blocks, threads, 0, st>>>(a);
+  else bwd_row_cta_kernel<T, 1, RM><<<blocks, threads, 0, st>>>(a);
 }
 
-template <typename XT>
-static bool dispatch_bwd_g(const BwdArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
-  switch (a.g_dt) {
-    case FFQ_F32: launch_bwd_row<XT, float>(a, plan, vec_ok, st); return true;
-    case FFQ_BF16: launch_bwd_row<XT, __nv_bfloat16>(a, plan, vec_ok, st); return true;
-    case FFQ_F16: launch_bwd_row<XT, __half>(a, plan, vec_ok, st); return true;
-  }
-  return false;
-}
-
+// fast kernels exist for x.dtype == g.dtype with a single promoted dtype for the whole chain
 static bool dispatch_bwd(const BwdArgs& a, const Plan& plan, bool vec_ok, cudaStream_t st) {
+  if (a.x_dt != a.g_dt) return false;
+  const BParams& p = a.bp;
+  if (!(p.m_div == p.m_sub && p.m_sub == p.m_s && p.m_s == p.m_sg)) return false;
+  const int rm = p.m_div;
   switch (a.x_dt) {
-    case FFQ_F32: return dispatch_bwd_g<float>(a, plan, vec_ok, st);
-    case FFQ_BF16: return dispatch_bwd_g<__nv_bfloat16>(a, plan, vec_ok, st);
-    case FFQ_F16: return dispatch_bwd_g<__half>(a, plan, vec_ok, st);
+    case FFQ_F32: if (rm == RM_F32) { launch_bwd_row<float, RM_F32>(a, plan, vec_ok, st); return true; } break;
+    case FFQ_BF16:
+      if (rm == RM_F32) { launch_bwd_row<__nv_bfloat16, RM_F32>(a, plan, vec_ok, st); return true; }
+      if (rm == RM_BF16) { launch_bwd_row<__nv_bfloat16, RM_BF16>(a, plan, vec_ok, st); return true; }
+      break;
+    case FFQ_F16:
+      if (rm == RM_F32) { launch_bwd_row<__half, RM_F32>(a, plan, vec_ok, st); return true; }
+      if (rm == RM_F16) { launch_bwd_row<__half, RM_F16>(a, plan, vec_ok, st); return true; }
+      break;
   }
   return false;
 }
+
 
 static int ept_of(int dt) {
   const int sz = dt_size(dt);
@@ -377,6 +460,34 @@ __device__ __forceinline__ void block_minmax(float& mn, float& mx, float* smem) 
   }
 }
 
+// min and max of one 16-byte vector; 16-bit types use the packed NaN-propagating HMNMX2
+template <typename T, int EPT>
+__device__ __forceinline__ void vec_minmax(const Vec<T, EPT>& v, float& mn, float& mx) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value && EPT >= 2) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+    __nv_bfloat162 lo = h[0], hi = h[0];
+#pragma unroll
+    for (int i = 1; i < EPT / 2; ++i) { lo = __hmin2_nan(lo, h[i]); hi = __hmax2_nan(hi, h[i]); }
+    mn = nan_min(__low2float(lo), __high2float(lo));
+    mx = nan_max(__low2float(hi), __high2float(hi));
+  } else if constexpr (std::is_same<T, __half>::value && EPT >= 2) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    __half2 lo = h[0], hi = h[0];
+#pragma unroll
+    for (int i = 1; i < EPT / 2; ++i) { lo = __hmin2_nan(lo, h[i]); hi = __hmax2_nan(hi, h[i]); }
+    mn = nan_min(__low2float(lo), __high2float(lo));
+    mx = nan_max(__low2float(hi), __high2float(hi));
+  } else {
+    mn = mx = Elem<T>::to_f(v.v[0]);
+#pragma unroll
+    for (int i = 1; i < EPT; ++i) {
+      const float f = Elem<T>::to_f(v.v[i]);
+      mn = nan_min(mn, f);
+      mx = nan_max(mx, f);
+    }
+  }
+}
+
 template <typename XT, int LANES>
 __global__ void __launch_bounds__(RD_THREADS) mm_row_group_kernel(const MmArgs a) {
   constexpr int EPT = 16 / sizeof(XT);
@@ -394,15 +505,7 @@ __global__ void __launch_bounds__(RD_THREADS) mm_row_group_kernel(const MmArgs a
     const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
     const bool live = v < nvec;   // whole groups are live or dead together (nvec % LANES == 0)
     float mn = INFINITY, mx = -INFINITY;
-    if (live) {
-      mn = mx = Elem<XT>::to_f(xv[u].v[0]);
-#pragma unroll
-      for (int i = 1; i < EPT; ++i) {
-        const float f = Elem<XT>::to_f(xv[u].v[i]);
-        mn = nan_min(mn, f);
-        mx = nan_max(mx, f);
-      }
-    }
+    if (live) vec_minmax<XT, EPT>(xv[u], mn, mx);
     mn = group_min<LANES>(mn);
     mx = group_max<LANES>(mx);
     if (live && (threadIdx.x & (LANES - 1)) == 0) mm_emit(a, v / LANES, mn, mx);
@@ -410,41 +513,58 @@ __global__ void __launch_bounds__(RD_THREADS) mm_row_group_kernel(const MmArgs a
 }
 
 template <typename XT, int EPT>
-__global__ void __launch_bounds__(RD_THREADS) mm_row_cta_kernel(const MmArgs a) {
-  __shared__ float smem[64];
-  const XT* __restrict__ x = static_cast<const XT*>(a.x);
-  const unsigned long long tile = blockIdx.x / a.S;
-  const unsigned int seg = blockIdx.x % a.S;
-  const unsigned long long begin = (unsigned long long)seg * a.seg_len;
-  unsigned long long end = begin + a.seg_len;
-  if (end > a.tile_numel) end = a.tile_numel;
-  const unsigned long long base = tile * a.tile_numel;
-  // every segment is non-empty, so its first element is a valid identity for every thread
-  float mn = Elem<XT>::to_f(x[base + begin]), mx = mn;
-  const unsigned long long step = (unsigned long long)blockDim.x * EPT;
-  for (unsigned long long i0 = begin + (unsigned long long)threadIdx.x * EPT; i0 < end; i0 += step * RD_UNROLL) {
-    Vec<XT, EPT> xv[RD_UNROLL];
+__device__ __forceinline__ void mm_stream(const XT* __restrict__ x, unsigned int len, unsigned int tid,
+                                          unsigned int nthreads, float& mn, float& mx) {
+  constexpr int U = RD_UNROLL;
+  const unsigned int step = nthreads * EPT;
+  for (unsigned int i0 = tid * EPT; i0 < len; i0 += step * U) {
+    Vec<XT, EPT> xv[U];
 #pragma unroll
-    for (int u = 0; u < RD_UNROLL; ++u) {
-      const unsigned long long i = i0 + u * step;
-      if (i < end) {
-        if constexpr (EPT == 1) xv[u].v[0] = x[base + i];
-        else xv[u] = ld_stream<XT, EPT>(x + base + i);
+    for (int u = 0; u < U; ++u) {
+      const unsigned int i = i0 + u * step;
+      if (i < len) {
+        if constexpr (EPT == 1) xv[u].v[0] = x[i];
+        else xv[u] = ld_stream<XT, EPT>(x + i);
       }
     }
 #pragma unroll
-    for (int u = 0; u < RD_UNROLL; ++u) {
-      const unsigned long long i = i0 + u * step;
-      if (i < end) {
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-          const float f = Elem<XT>::to_f(xv[u].v[k]);
-          mn = nan_min(mn, f);
-          mx = nan_max(mx, f);
-        }
+    for (int u = 0; u < U; ++u) {
+      const unsigned int i = i0 + u * step;
+      if (i < len) {
+        float vmn, vmx;
+        vec_minmax<XT, EPT>(xv[u], vmn, vmx);
+        mn = nan_min(mn, vmn);
+        mx = nan_max(mx, vmx);
       }
     }
   }
+}
+
+template <typename XT, int EPT>
+__global__ void __launch_bounds__(RD_THREADS) mm_row_warp_kernel(const MmArgs a) {
+  const unsigned long long tile = (unsigned long long)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
+  if (tile >= a.num_tiles) return;
+  const unsigned int lane = threadIdx.x & 31;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x) + tile * a.tile_numel;
+  // a tile is never empty, so its first element is a valid identity for every lane
+  float mn = Elem<XT>::to_f(x[0]), mx = mn;
+  mm_stream<XT, EPT>(x, (unsigned int)a.tile_numel, lane, 32u, mn, mx);
+  mn = group_min<32>(mn);
+  mx = group_max<32>(mx);
+  if (lane == 0) mm_emit(a, tile, mn, mx);
+}
+
+template <typename XT, int EPT>
+__global__ void __launch_bounds__(RD_THREADS) mm_row_cta_kernel(const MmArgs a) {
+  __shared__ float smem[64];
+  const unsigned long long tile = blockIdx.x / a.S;
+  const unsigned int seg = blockIdx.x % a.S;
+  const unsigned long long begin = (unsigned long long)seg * a.seg_len;
+  const unsigned long long remain = a.tile_numel - begin;
+  const unsigned int len = (unsigned int)(remain < a.seg_len ? remain : a.seg_len);
+  const XT* __restrict__ x = static_cast<const XT*>(a.x) + tile * a.tile_numel + begin;
+  float mn = Elem<XT>::to_f(x[0]), mx = mn;
+  mm_stream<XT, EPT>(x, len, threadIdx.x, blockDim.x, mn, mx);
   block_minmax(mn, mx, smem);
   if (threadIdx.x == 0) {
     if (a.S == 1) mm_emit(a, tile, mn, mx);
@@ -498,8 +618,14 @@ static void launch_mm_row(const MmArgs& a, const Plan& plan, bool vec_ok, cudaSt
     }
     return;
   }
-  const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
   const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
+  if (a.S == 1 && use_warp_per_tile(plan, EPT)) {
+    const unsigned int blocks = (unsigned int)((a.num_tiles + RD_THREADS / 32 - 1) / (RD_THREADS / 32));
+    if (ept == EPT) mm_row_warp_kernel<XT, EPT><<<blocks, RD_THREADS, 0, st>>>(a);
+    else mm_row_warp_kernel<XT, 1><<<blocks, RD_THREADS, 0, st>>>(a);
+    return;
+  }
+  const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
   unsigned long long per_seg = (a.seg_len + ept - 1) / ept;
   int threads = RD_THREADS;
   while (threads > 32 && (unsigned long long)threads / 2 >= per_seg) threads /= 2;
@@ -637,7 +763,9 @@ int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dtype, voi
   a.gl = make_generic_layout(plan);
   a.S = 1; a.seg_len = plan.tile_numel;
 
-  if (plan.row) {
+  const bool fast = plan.row && x_dtype == g_dtype && a.bp.m_div == a.bp.m_sub && a.bp.m_sub == a.bp.m_s &&
+                    a.bp.m_s == a.bp.m_sg;
+  if (fast) {
     const bool vec_ok = aligned16(x) && aligned16(g) && aligned16(dx);
     const Segmentation sg = choose_segments(plan, ept_of(x_dtype));
     const bool group = vec_ok && group_lanes(plan, ept_of(x_dtype)) != 0;

@@ -194,6 +194,15 @@ FFQ_API int ffq_fakequant_fwd_bwd_host(const void* x_host, const void* g_host, i
                                const float* scale_host, const float* offset_host,
                                const ffq_layout_t* layout, double num_bits, int device);
 
+/* ---- test hook ---------------------------------------------------------------------------
+ * Sweeps the kernels' shared-reciprocal division against __fdiv_rn over n pseudo-random
+ * (dividend, scale) pairs.  counts_dev: uint64[4], zero-initialised by the caller:
+ * [0] accepted quotients (>= 2^-50 in magnitude) that differ from __fdiv_rn  -- must stay 0
+ * [1] quotients accepted by the magnitude guard   [2] accepted by the strict guard
+ * [3] strict-accepted quotients that differ from __fdiv_rn                   -- must stay 0 */
+FFQ_API int ffq_selftest_shared_div(unsigned long long n, unsigned int seed, unsigned long long* counts_dev,
+                                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

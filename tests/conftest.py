@@ -29,12 +29,19 @@ def load_golden(name):
 
 
 def bits_equal(a: torch.Tensor, b: torch.Tensor) -> bool:
-    """Bit-for-bit equality (distinguishes -0.0 from 0.0, treats equal NaN payloads as equal)."""
+    """Bit-for-bit equality: distinguishes -0.0 from 0.0; NaNs must sit at the same positions
+    (their payload bits are not compared -- GPUs return the canonical NaN)."""
     if a.dtype != b.dtype or a.shape != b.shape:
         return False
-    a, b = a.contiguous().cpu(), b.contiguous().cpu()
+    a, b = a.detach().contiguous().cpu(), b.detach().contiguous().cpu()
     if a.numel() == 0:
         return True
+    if a.dtype.is_floating_point:
+        na, nb = torch.isnan(a), torch.isnan(b)
+        if not torch.equal(na, nb):
+            return False
+        if na.any():
+            a, b = a.masked_fill(na, 0), b.masked_fill(nb, 0)
     return torch.equal(a.view(torch.uint8), b.view(torch.uint8))
 
 

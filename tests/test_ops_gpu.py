@@ -180,7 +180,7 @@ def test_oracle_parity_big(shape, tile, dtype, num_bits, with_offset):
 def test_edge_cases():
     # empty tensor, NaN propagation, inf flag, -0.0, bit-width guard, broadcast scale
     e = torch.empty(0, 4, device=DEV)
-    assert ops.quantize_by_tile(e, torch.ones(1, device=DEV), (0, 4), 8.0, None).shape == (0, 4)
+    assert ops.quantize_by_tile(e, torch.ones(1, device=DEV), (1, 4), 8.0, None).shape == (0, 4)
     x = torch.tensor([float("nan"), -0.3, 0.3, 1e9, -1e9, 2.5, 3.5, -2.5], device=DEV)
     s = torch.ones(1, device=DEV)
     q = ops.quantize_by_tile(x, s, (8,), 4.0, None)
@@ -241,3 +241,14 @@ def test_full_size_properties():
     assert torch.equal(dx, g)
     dx2, dsc2, doff2 = ops.quantize_by_tile_backward(x, 2 * g, scale, tile, 8.0, offset)
     assert torch.equal(dx2, 2 * g) and torch.equal(dsc2, 2 * dsc) and torch.equal(doff2, 2 * doff)
+
+
+def test_shared_reciprocal_division_is_ieee_exact():
+    """The kernels hoist the reciprocal out of the per-element work (ffq_common.cuh: shared_div).
+    Inside its guard the quotient must equal __fdiv_rn bit for bit: sweep 2^30 pairs."""
+    from fastforward_b200 import _cabi as C
+    counts = torch.zeros(4, dtype=torch.int64, device=DEV)
+    C.check(C.lib.ffq_selftest_shared_div(1 << 30, 12345, counts.data_ptr(), C.current_stream(counts.device)))
+    bad, acc, acc_strict, bad_strict = counts.tolist()
+    assert bad == 0 and bad_strict == 0, counts.tolist()
+    assert acc > (1 << 28) and acc_strict > (1 << 28), counts.tolist()   # the guard accepts the bulk
