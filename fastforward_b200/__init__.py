@@ -1,2 +1,40 @@
-"""fastforward_b200 -- B200-native backend for FastForward's quantization hot path."""
-from . import ops  # noqa: F401
+"""fastforward_b200 -- B200-native backend for FastForward's quantization hot path.
+
+The public names mirror ``import fastforward as ff`` for the path this backend covers
+(SURVEY.md section 8): ``quantize_model``, ``find_quantizers(...).initialize``, ``estimate_ranges``,
+``nn.LinearQuantizer``, ``QuantizedTensor``, the dispatcher and the flags.  All arithmetic is
+hand-written CUDA (sm_100a) behind the C ABI in ``include/ffq_b200.h``; importing this package
+fails loudly if that library has not been built, and no op has a CPU fallback."""
+
+from . import _cabi as _cabi          # loads lib/libffq_b200.so (ImportError if missing)
+from . import dispatcher as dispatcher
+from . import exceptions as exceptions
+from . import flags as flags
+from . import mpath as mpath
+from . import nn as nn
+from . import ops as ops
+from . import quantization as quantization
+from . import range_setting as range_setting
+from .dispatcher import Predicate as Predicate
+from .dispatcher import register as register
+from .exceptions import QuantizationError as QuantizationError
+from .flags import (  # noqa: F401
+    compiled_quant_funcs, export_mode, get_compiled_quant_funcs, get_export_mode, get_strict_quantization,
+    set_compiled_quant_funcs, set_export_mode, set_strict_quantization, strict_quantization,
+)
+from .nn.quantized_module import quantize_model as quantize_model
+from .nn.quantized_module import quantized_module_map as quantized_module_map
+from .nn.quantized_module import surrogate_quantized_modules as surrogate_quantized_modules
+from .overrides import disable_quantization as disable_quantization
+from .overrides import enable_quantization as enable_quantization
+from .quant_init import QuantizationConfig as QuantizationConfig
+from .quant_init import QuantizerCollection as QuantizerCollection
+from .quant_init import find_quantizers as find_quantizers
+from .quantization.granularity import PerBlock as PerBlock
+from .quantization.granularity import PerChannel as PerChannel
+from .quantization.granularity import PerTensor as PerTensor
+from .quantization.granularity import PerTile as PerTile
+from .quantized_tensor import QuantizedTensor as QuantizedTensor
+from .range_setting import estimate_ranges as estimate_ranges
+
+__version__ = "0.1.0"

@@ -1,0 +1,178 @@
+"""Running / smoothed min-max range estimators (reference: range_setting/minmax.py:26-303).
+
+What changed for B200 -- behaviour is the same, the schedule is not:
+  * one fused kernel reads the tensor ONCE and merges per-tile min/max into the running range
+    (the reference reads it twice and allocates two temporaries);
+  * the +-inf check (minmax.py:233-234, a host sync per quantizer per forward) is a device flag
+    inspected once when the ``estimate_ranges`` block ends -- pass ``eager_checks=True`` to get
+    the reference's raise-immediately behaviour back (one sync per step);
+  * range -> (scale, offset) is one more kernel writing the quantizer's parameters in place, with
+    the one-sided decision taken on the device (no second host sync);
+  * ``process_group`` (or an initialised default group with ``sync_ranges=True``) all-reduces the
+    running ranges with MIN/MAX at the end of the block: data-parallel calibration.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Iterator, Optional, Sequence
+
+import torch
+
+from .. import ops
+from ..nn.quantized_module import named_quantizers
+from ..nn.quantizer import Quantizer
+from .common import RangeEstimator, RangeSettable, SimpleEstimatorStep
+
+logger = logging.getLogger(__name__)
+
+
+def _param_count(quantizer, data: torch.Tensor) -> int:
+    return quantizer.granularity.parameter_dimensionality(data.shape)
+
+
+class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
+    def __init__(self, quantizer, disable_quantization: bool = False, eager_checks: bool = False) -> None:
+        super().__init__(disable_quantization=disable_quantization)
+        lo, hi = quantizer.quantization_range       # continues from an existing range (minmax.py:198-200)
+        self.register_buffer("min", None if lo is None else lo.detach().clone())
+        self.register_buffer("max", None if hi is None else hi.detach().clone())
+        self.register_buffer("flags", None)
+        self._eager = eager_checks
+
+    def initialize_parameters(self, quantizer, data: torch.Tensor) -> None:
+        n = _param_count(quantizer, data)
+        if self.min is None:
+            self.min = data.new_full((n,), float("inf"))
+        if self.max is None:
+            self.max = data.new_full((n,), float("-inf"))
+        if self.min.dtype != data.dtype or self.min.device != data.device:
+            # torch.min(self.min, data_min) in the reference promotes; keep the running range in the
+            # promoted dtype so that nothing is lost
+            dt = torch.promote_types(self.min.dtype, data.dtype)
+            self.min, self.max = self.min.to(device=data.device, dtype=dt), self.max.to(device=data.device, dtype=dt)
+        if self.flags is None:
+            self.flags = torch.zeros(1, dtype=torch.int32, device=data.device)
+
+    def estimate_step(self, quantizer, data: torch.Tensor) -> None:
+        self.initialize_parameters(quantizer, data)
+        with torch.no_grad():
+            tile = quantizer.granularity.tile_size(data.shape)
+            x = data.detach()
+            if x.dtype != self.min.dtype:
+                x = x.to(self.min.dtype)
+            ops.running_minmax_update_(self.min, self.max, x, tile, self.flags)
+            if self._eager:
+                self.check_finite()
+        quantizer.quantization_range = (self.min, self.max)
+
+    def check_finite(self) -> None:
+        if self.flags is not None and int(self.flags.item()) != 0:
+            raise NotImplementedError("Infinite")
+
+    def extra_repr(self) -> str:
+        return f"min={self.min}, max={self.max}"
+
+
+class SmoothedMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
+    """EMA of the per-batch min/max: ``gamma*batch + (1-gamma)*running``, restarted whenever the
+    running range still contains an infinity (minmax.py:79-90).  The per-tile reduction is the
+    CUDA kernel; the EMA itself is a parameter-sized torch expression."""
+
+    def __init__(self, quantizer, gamma: float = 1.0, disable_quantization: bool = False) -> None:
+        super().__init__(disable_quantization=disable_quantization)
+        lo, hi = quantizer.quantization_range
+        self.gamma = gamma
+        self.register_buffer("min", None if lo is None else lo.detach().clone())
+        self.register_buffer("max", None if hi is None else hi.detach().clone())
+
+    def estimate_step(self, quantizer, data: torch.Tensor) -> None:
+        with torch.no_grad():
+            tile = quantizer.granularity.tile_size(data.shape)
+            batch_min, batch_max = ops.tile_minmax(data.detach(), tile)
+            if self.min is None or self.max is None:
+                self.min, self.max = batch_min, batch_max
+            else:
+                restart = torch.logical_or(self.min.isinf().any(), self.max.isinf().any())
+                new_min = self.gamma * batch_min + (1 - self.gamma) * self.min
+                new_max = self.gamma * batch_max + (1 - self.gamma) * self.max
+                self.min = torch.where(restart, batch_min.to(new_min.dtype), new_min)
+                self.max = torch.where(restart, batch_max.to(new_max.dtype), new_max)
+        quantizer.quantization_range = (self.min, self.max)
+
+    def extra_repr(self) -> str:
+        return f"min={self.min}, max={self.max}"
+
+
+class _MinMaxRangeEstimatorBase(RangeEstimator):
+    skip_unsupported_quantizers = False
+
+    def _check(self, module) -> None:
+        if not isinstance(module, RangeSettable):
+            proto = f"{RangeSettable.__module__}.{RangeSettable.__qualname__}"
+            raise TypeError(f"{type(module).__name__} does not implement {proto}.")
+
+    def cleanup(self, module, metadata) -> None:
+        del module
+        metadata.remove()
+
+    def split_module(self, module: torch.nn.Module) -> Iterator[Quantizer]:
+        quantizers = [("", module)] if isinstance(module, Quantizer) and not module.is_stub() else []
+        quantizers += [(n, q) for n, q in named_quantizers(module, recurse=True) if q is not module]
+        for _, quantizer in quantizers:
+            if isinstance(quantizer, RangeSettable) or not self.skip_unsupported_quantizers:
+                yield quantizer
+            else:
+                logger.warning(f"{type(quantizer).__name__} does not implement RangeSettable. Therefore it is not "
+                               f"included in {type(self).__name__} range setting.")
+
+
+class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
+    def __init__(self, disable_quantization: bool = False, skip_unsupported_quantizers: bool = False, *,
+                 eager_checks: bool = False, sync_ranges: bool = False, process_group=None) -> None:
+        self.disable_quantization = disable_quantization
+        self.skip_unsupported_quantizers = skip_unsupported_quantizers
+        self.eager_checks = eager_checks
+        self.sync_ranges = sync_ranges or process_group is not None
+        self.process_group = process_group
+        self._steps: list = []
+
+    def prepare(self, module):
+        self._check(module)
+        step = RunningMinMaxEstimator(module, disable_quantization=self.disable_quantization,
+                                      eager_checks=self.eager_checks)
+        self._steps.append((module, step))
+        return module.register_override(step)
+
+    def finalize(self, prepared: Sequence[tuple]) -> None:
+        del prepared
+        steps = [(q, s) for q, s in self._steps if s.min is not None]
+        if self.sync_ranges:
+            from ..distributed import all_reduce_ranges
+
+            all_reduce_ranges([(s.min, s.max) for _, s in steps], [s.flags for _, s in steps], group=self.process_group)
+            for quantizer, step in steps:
+                quantizer.quantization_range = (step.min, step.max)
+        # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks
+        flags = [s.flags for _, s in steps if s.flags is not None]
+        if flags and not self.eager_checks:
+            if int(torch.stack([f.reshape(()) for f in flags]).max().item()) != 0:
+                raise NotImplementedError("Infinite")
+        self._steps = []
+
+
+class SmoothedMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
+    def __init__(self, gamma: float = 1.0, disable_quantization: bool = False,
+                 skip_unsupported_quantizers: bool = False) -> None:
+        self.gamma = gamma
+        self.disable_quantization = disable_quantization
+        self.skip_unsupported_quantizers = skip_unsupported_quantizers
+
+    def prepare(self, module):
+        self._check(module)
+        return module.register_override(
+            SmoothedMinMaxEstimator(module, gamma=self.gamma, disable_quantization=self.disable_quantization))
+
+
+running_minmax = RunningMinMaxRangeEstimator
+smoothed_minmax = SmoothedMinMaxRangeEstimator

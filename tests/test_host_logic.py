@@ -1,0 +1,258 @@
+"""Host-side logic of the drop-in layer: no GPU, no compute calls.  Mirrors the reference's own
+tests for these pieces (tests/test_dispatcher.py, tests/quantization/test_tiled_tensor.py,
+tests/quantization/test_granularity.py, tests/nn/test_quantizer.py, tests/test_flags.py)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import fastforward_b200 as ff
+from fastforward_b200 import _cabi, dispatcher
+from fastforward_b200.quantization import granularity as G
+from fastforward_b200.quantization import tiled_tensor as TT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI -----------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ffq_b200.h")).read()
+    declared = sorted(set(re.findall(r"FFQ_API\s+[\w\s\*]+?\b(ffq_\w+)\s*\(", header)))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/ffq_b200.h but not exported"
+    assert sorted(_cabi.EXPORTED) == declared
+    assert lib.ffq_abi_version() == 1
+
+
+def test_layout_planning_through_the_abi():
+    lay = _cabi.make_layout((32, 16, 8), (1, 16, 8))
+    assert _cabi.lib.ffq_num_tiles(ctypes.byref(lay)) == 32
+    lay = _cabi.make_layout((4096, 4096), (1, 128))
+    assert _cabi.lib.ffq_num_tiles(ctypes.byref(lay)) == 4096 * 32
+    assert _cabi.workspace_bytes(_cabi.WS_QUANTIZE_BWD, lay, torch.float32) == 0
+    per_tensor = _cabi.make_layout((4096, 4096), (4096, 4096))
+    assert _cabi.workspace_bytes(_cabi.WS_QUANTIZE_BWD, per_tensor, torch.float32) > 0
+    with pytest.raises(ValueError):
+        _cabi.make_layout((4, 6), (3, 3))
+    with pytest.raises(ValueError):
+        _cabi.make_layout((4, 6), (2,))
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ff.ops.quantize_by_tile(x, torch.ones(1), (4, 4), 8.0, None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ff.ops.tile_minmax(x, (4, 4))
+    q = ff.nn.LinearQuantizer(8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        q.quantization_range = (-1.0, 1.0)
+
+
+# ---- tiles / granularity ------------------------------------------------------------------------
+def test_tile_row_permutation():
+    data = torch.arange(24).reshape(4, 6)
+    rows = TT.tiles_to_rows(data, (2, 3))
+    assert rows.tolist() == [[0, 1, 2, 6, 7, 8], [3, 4, 5, 9, 10, 11], [12, 13, 14, 18, 19, 20], [15, 16, 17, 21, 22, 23]]
+    assert torch.equal(TT.rows_to_tiles(rows, (4, 6), (2, 3)), data)
+    assert torch.equal(TT.tiles_to_rows(data, "data_shape"), data.reshape(1, -1))
+    for bad in ((3, 3), (2,)):
+        with pytest.raises(ValueError):
+            TT.tiles_to_rows(data, bad)
+    with pytest.raises(ValueError):
+        TT.rows_to_tiles(rows[:2], (4, 6), (2, 3))
+
+
+def test_granularities():
+    shape = torch.Size((32, 16, 8))
+    assert G.PerTensor().tile_size(shape) == "data_shape" and G.PerTensor().parameter_dimensionality(shape) == 1
+    assert G.PerChannel(0).tile_size(shape) == (1, 16, 8) and G.PerChannel(0).parameter_dimensionality(shape) == 32
+    assert G.PerChannel((0, 2)).tile_size(shape) == (1, 16, 1)
+    pb = G.PerBlock(block_dims=1, block_sizes=8, per_channel_dims=0)
+    assert pb.tile_size(shape) == (1, 8, 8) and pb.parameter_dimensionality(shape) == 64
+    with pytest.raises(ValueError):
+        G.PerBlock(1, 5, 0).tile_size(shape)
+    with pytest.raises(ValueError):
+        G.PerBlock(1, 32, 0).tile_size(shape)
+    assert G.PerTile((16, 8, 4)).tile_size(shape) == (16, 8, 4)
+    with pytest.raises(ValueError):
+        G.PerTile((5, 8, 4)).tile_size(shape)
+    assert G.PerChannel(1) == G.PerChannel(1) and G.PerChannel(1) != G.PerChannel(0) and G.PerTensor() == G.PerTensor()
+    assert G.granularity_from_sizes(shape, shape) == G.PerTensor()
+    assert G.granularity_from_sizes(shape, torch.Size((1, 16, 8))) == G.PerChannel(0)
+    assert G.granularity_from_sizes(shape, torch.Size((1, 8, 8))).tile_size(shape) == (1, 8, 8)
+
+
+# ---- dispatcher ----------------------------------------------------------------------------------
+@pytest.fixture
+def clean_registry():
+    saved = {k: list(v) for k, v in dispatcher._DISPATCHER.items()}
+    yield
+    dispatcher._DISPATCHER.clear()
+    dispatcher._DISPATCHER.update(saved)
+
+
+def test_dispatcher_order_and_scoping(clean_registry):
+    k1, k2, k3 = (lambda *a, **k: 1), (lambda *a, **k: 2), (lambda *a, **k: 3)
+    P = ff.Predicate
+    dispatcher.register("my_op", P(lambda x: x > 0), k1)
+    dispatcher.register("my_op", P(lambda x: x > 10), k2)
+    assert dispatcher.dispatch("my_op", 5) is k1
+    assert dispatcher.dispatch("my_op", 50) is k2          # newest first within a priority
+    assert dispatcher.dispatch("my_op", -1) is None
+    with dispatcher.register("my_op", None, k3):
+        assert dispatcher.dispatch("my_op", -1) is k3
+    assert dispatcher.dispatch("my_op", -1) is None        # scoped registration removed
+    dispatcher.register("my_op", None, k3, dispatcher.DispatcherPriority.FALLBACK)
+    assert dispatcher.dispatch("my_op", 50) is k2 and dispatcher.dispatch("my_op", -1) is k3
+
+    @dispatcher.register("other", P(lambda **kw: kw.get("flag", False)))
+    def kern(**kw):
+        return "k"
+
+    assert dispatcher.dispatch("other", flag=True) is kern and dispatcher.dispatch("other", flag=False) is None
+    both = P(lambda x: x > 0) & ~P(lambda x: x > 10)
+    assert both(5) and not both(50) and (P(lambda x: x < 0) | both)(-3)
+
+
+def test_linear_consults_dispatcher_then_fallback(clean_registry):
+    calls = []
+
+    def kernel(input, weight, bias, output_quantizer, strict_quantization):
+        calls.append("kernel")
+        return torch.zeros(1)
+
+    x, w = torch.randn(2, 4), torch.randn(3, 4)
+    with dispatcher.register("linear", ff.Predicate(lambda **kw: kw["bias"] is None), kernel):
+        ff.nn.functional.linear(x, w, None, strict_quantization=False)
+        y = ff.nn.functional.linear(x, w, torch.zeros(3), strict_quantization=False)   # predicate rejects
+    assert calls == ["kernel"] and torch.equal(y, torch.nn.functional.linear(x, w))
+    with pytest.raises(ff.QuantizationError):
+        ff.nn.functional.linear(x, w, None, strict_quantization=True)   # strict: needs output_quantizer
+
+
+# ---- flags -----------------------------------------------------------------------------------------
+def test_flags():
+    assert ff.get_strict_quantization() is True and ff.get_export_mode() is False
+    with ff.strict_quantization(False):
+        assert ff.get_strict_quantization() is False
+    assert ff.get_strict_quantization() is True
+    restore = ff.set_export_mode(True)
+    assert ff.get_export_mode() is True
+    with restore:
+        pass
+    assert ff.get_export_mode() is False
+
+
+# ---- quantizers, overrides, model conversion ----------------------------------------------------------
+def test_override_stack_runs_newest_outermost():
+    q = ff.nn.QuantizerStub()
+    order = []
+
+    def make(tag):
+        def ov(quantizer, nxt, args, kwargs):
+            order.append(tag)
+            return nxt(*args, **kwargs)
+        return ov
+
+    h1, h2 = q.register_override(make("first")), q.register_override(make("second"))
+    x = torch.ones(2)
+    assert q(x) is x and order == ["second", "first"]
+    h2.remove()
+    order.clear()
+    q(x)
+    assert order == ["first"]
+    with q.register_override(make("scoped")):
+        order.clear()
+        q(x)
+        assert order == ["scoped", "first"]
+    h1.remove()
+    assert list(q.overrides) == []
+
+
+def test_tags_and_metadata():
+    T = ff.nn.Tag
+    assert T("a/b") is T("a/b") and str(T("a") / "b") == "#a/b"
+    meta = ff.nn.QuantizerMetadata(weight_quantizer=True, shape=(3, 4))
+    assert meta.weight_quantizer and meta.parameter_quantizer and not meta.input_quantizer
+    assert "parameter/weight" in meta and "parameter" in meta and meta.shape == (3, 4)
+    assert ff.nn.QuantizerMetadata(weight_quantizer=True).is_extension(meta)
+
+
+def test_linear_quantizer_lazy_parameters():
+    q = ff.nn.LinearQuantizer(8, granularity=ff.PerChannel())
+    assert q.symmetric and isinstance(q.scale, torch.nn.UninitializedParameter)
+    assert isinstance(q.offset, torch.nn.UninitializedBuffer) and q.quantization_range == (None, None)
+    assert ff.nn.LinearQuantizer(8, allow_one_sided=False).offset is None
+    asym = ff.nn.LinearQuantizer(4, symmetric=False)
+    assert isinstance(asym.offset, torch.nn.UninitializedParameter) and not asym.symmetric
+    with pytest.raises(ValueError, match="uninitialized quantizer"):
+        q(torch.randn(3, 3))
+    assert q.integer_minimum == -128 and q.integer_maximum == 127 and asym.integer_maximum == 7
+    q._initialize_parameters(5)
+    assert q.scale.shape == (5,) and torch.all(q.scale == 1) and torch.all(q.offset == 0)
+    q.reset_parameters()
+    assert q.has_uninitialized_params
+    sd = {"scale": torch.full((7,), 0.5), "offset": torch.zeros(7)}
+    q.load_state_dict(sd)                       # lazy params take the loaded shape
+    assert q.scale.shape == (7,) and float(q.scale[0]) == 0.5
+
+
+def test_quantize_model_and_find_quantizers():
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = torch.nn.Linear(8, 16), torch.nn.Linear(16, 8, bias=False)
+            self.act = torch.nn.SiLU()
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    model = torch.nn.Sequential(Block(), Block())
+    with pytest.raises(ff.QuantizationError):
+        ff.quantize_model(model)                 # Block has no quantized counterpart
+    extra = ff.surrogate_quantized_modules(model)
+    ff.quantize_model(model, extra_conversion=extra)
+    assert isinstance(model[0].fc1, ff.nn.QuantizedLinear) and type(model[0]).__name__ == "QuantizedBlockSurrogate"
+    assert model[0].fc2.bias_quantizer is None
+    assert list(ff.nn.named_quantizers(model)) == []          # stubs are skipped
+    weights = ff.find_quantizers(model, "**/[quantizer:parameter/weight]")
+    assert sorted(r.full_name for r in weights) == ["0.fc1.weight_quantizer", "0.fc2.weight_quantizer",
+                                                    "1.fc1.weight_quantizer", "1.fc2.weight_quantizer"]
+    weights.initialize(ff.nn.LinearQuantizer, num_bits=8, granularity=ff.PerChannel())
+    assert isinstance(model[1].fc2.weight_quantizer, ff.nn.LinearQuantizer)
+    assert model[1].fc2.weight_quantizer.quant_metadata.weight_quantizer      # slot metadata re-attached
+    with pytest.raises(ff.QuantizationError):
+        ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(ff.nn.LinearQuantizer, num_bits=4)
+    ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
+        ff.nn.LinearQuantizer, num_bits=4, overwrite_policy="skip")
+    assert model[0].fc1.weight_quantizer.num_bits == 8
+    ff.find_quantizers(model, "0/fc1/[quantizer:activation/input]").initialize(
+        lambda name, cur: ff.nn.LinearQuantizer(8, symmetric=False))
+    assert len(list(ff.nn.named_quantizers(model))) == 5
+    assert len(ff.find_quantizers(model, "*/[cls:torch.nn.Linear]/[quantizer:activation]")) == 8
+    assert len(ff.find_quantizers(model, "**/[re:fc\\d]/weight_quantizer")) == 4
+    assert len(ff.find_quantizers(model, "**/~[quantizer:parameter]")) == 10
+
+    cfg = ff.QuantizationConfig()
+    cfg.add_rule("**/[quantizer:activation/output]", ff.nn.LinearQuantizer, num_bits=8)
+    cfg.add_rule("1/**/[quantizer:activation/output]", ff.nn.LinearQuantizer, num_bits=4)   # last rule wins
+    cfg.initialize(model)
+    assert model[0].fc1.output_quantizer.num_bits == 8 and model[1].fc1.output_quantizer.num_bits == 4
+
+
+def test_disable_quantization_restores_flags_and_overrides():
+    model = torch.nn.Sequential(torch.nn.Linear(4, 4))
+    ff.quantize_model(model)
+    ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(ff.nn.LinearQuantizer, num_bits=8)
+    x = torch.randn(2, 4)
+    with ff.disable_quantization(model):
+        assert ff.get_strict_quantization() is False
+        y = model(x)                              # quantizers bypassed: plain float linear, no CUDA needed
+    assert torch.allclose(y, torch.nn.functional.linear(x, model[0].weight, model[0].bias))
+    assert ff.get_strict_quantization() is True
+    assert list(model[0].weight_quantizer.overrides) == []
