@@ -1,12 +1,412 @@
-// placeholder until the tcgen05 kernel lands
+// ffq_qlinear.cu -- W8A8 quantized linear on Blackwell tensor cores (a12).
+//
+//   y[m,n] = sx*sw[n] * ( sum_k qx[m,k]*qw[n,k] + ox*rowsum_w[n] + ow[n]*rowsum_x[m] + K*ox*ow[n] ) + bias[n]
+//
+// int8 x int8 -> int32 on tcgen05 (kind::i8), accumulators in TMEM, operands staged by TMA into
+// 128B-swizzled shared memory, dequantisation fused into the epilogue.  The reference has no
+// such kernel: it dequantises both operands to float tensors in HBM and calls a float GEMM
+// (_gen/fallback.py:94-108).  int32 accumulation is exact, so this path is *more* accurate than
+// the fallback it replaces.
+//
+// Structure (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0     : TMA producer   -- cp.async.bulk.tensor of the A (128 x 128B) and B (256 x 128B)
+//                                  k-blocks into a 4-stage ring, completion on mbarriers
+//   warp 1     : MMA issuer     -- one elected lane issues 4 x tcgen05.mma (K=32 each) per k-block
+//                                  into one of two 128x256 fp32-column TMEM accumulators;
+//                                  tcgen05.commit releases the smem stage / publishes the tile
+//   warps 2..5 : epilogue       -- tcgen05.ld 32 columns at a time, y = alpha[n]*float(acc + c[n] +
+//                                  ow[n]*rowsum_x[m]) + bias[n], vector stores; overlaps the next tile's
+//                                  MMAs through the second accumulator.  All offset corrections are
+//                                  added in int32 (exact); one int->float conversion and one FMA
+//                                  per output follow
+// Roofline: tensor pipe; 2*M*N*K ops.  A 128x256 tile needs 96 B/clk/SM of operand traffic at the
+// full MMA rate, so L2->SM bandwidth is the secondary bound.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "ffq_common.cuh"
-extern "C" int ffq_qlinear_w8a8(const int8_t*, const int8_t*, void*, int, int64_t, int64_t, int64_t, const float*,
-                                const float*, const float*, const float*, const int32_t*, const int32_t*,
-                                const void*, int, void*) {
-  ffq::set_error("qlinear_w8a8: not built yet");
-  return FFQ_ERR_UNSUPPORTED;
+
+namespace ffq {
+
+constexpr int BM = 128, BN = 256, BK = 128;      // BK in bytes == int8 elements: one 128B swizzle atom
+constexpr int UMMA_K = 32;                       // int8 elements per tcgen05.mma
+constexpr int STAGES = 4;
+constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;
+constexpr int STAGE_BYTES = A_STAGE + B_STAGE;   // 48 KB
+constexpr int GEMM_THREADS = 192;                // 6 warps
+constexpr int TMEM_COLS = 512;                   // 2 accumulators x 256 columns
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * BN * 4 + 256 + 1024;   // + column params + barriers + align
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-extern "C" int ffq_rowsum_i8(const int8_t*, int32_t*, int64_t, int64_t, void*) {
-  ffq::set_error("rowsum_i8: not built yet");
-  return FFQ_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
+      "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in 128B-swizzled smem (rows of 128 bytes, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);          // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+struct GemmArgs {
+  int M, N, K;
+  void* y; int y_dt;
+  const float* alpha; const float* bias;        // per output column: sx*sw[n], bias[n] (as float)
+  const int32_t* cnst; const int32_t* own;      // per output column: ox*rowsum_w[n] + K*ox*ow[n], ow[n] (own may be null)
+  const int32_t* rowsum_x;                      // per output row; used with own
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_chunk(OutT* dst, const float (&v)[32], int ncols) {
+  // dst: 32 consecutive output columns of one row (16-byte aligned when N % 8 == 0)
+  if (ncols == 32 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    constexpr int PER = 16 / sizeof(OutT);
+#pragma unroll
+    for (int j = 0; j < 32; j += PER) {
+      Vec<OutT, PER> o;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) o.v[i] = Elem<OutT>::from_f(v[j + i]);
+      st_vec<OutT, PER>(dst + j, o);
+    }
+  } else {
+    for (int j = 0; j < ncols; ++j) dst[j] = Elem<OutT>::from_f(v[j]);
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* col_params = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [4][BN]
+  int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * BN * 4);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;   // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // consecutive CTAs share the same N panel of B (tile index runs fastest over m)
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
+          tma_load_2d(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=S32, A=B=signed int8, both K-major, N=256, M=128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);            // how many times this buffer was used before
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing K inside the swizzle atom: +32 bytes == +2 in the (>>4) start-address field
+            umma_i8(tmem_d, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), idesc,
+                    (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                    // frees the smem stage when the MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tmem_full[buf]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5): TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    const int ep_tid = threadIdx.x - 64;                     // 0..127
+    OutT* __restrict__ y = static_cast<OutT*>(g.y);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      // stage this tile's column parameters in shared memory (named barrier over the 4 epilogue warps)
+      asm volatile("bar.sync 1, 128;" ::: "memory");         // previous tile's readers are done
+      for (int c = ep_tid; c < BN; c += 128) {
+        const int n = tn * BN + c;
+        const bool in = n < g.N;
+        col_params[c] = in ? g.alpha[n] : 0.f;
+        col_params[BN + c] = in ? g.bias[n] : 0.f;
+        col_ints[2 * BN + c] = in ? g.cnst[n] : 0;
+        col_ints[3 * BN + c] = (in && g.own) ? g.own[n] : 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int row = tm * BM + quad * 32 + lane;
+      const int32_t rx = (g.own && row < g.M) ? g.rowsum_x[row] : 0;
+
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)c0, acc);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int32_t t = (int32_t)acc[j] + col_ints[2 * BN + c0 + j] + col_ints[3 * BN + c0 + j] * rx;
+          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[BN + c0 + j]);
+        }
+        const int n0 = tn * BN + c0;
+        if (row < g.M && n0 < g.N) {
+          const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
+          store_chunk<OutT>(y + (size_t)row * g.N + n0, v, ncols);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);          // 4 arrivals (one per epilogue warp) free the accumulator
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---- small helper kernels ------------------------------------------------------------------------
+// rowsum[r] = sum_k q[r,k]   (one warp per row, 16-byte loads, dp4a against ones)
+__global__ void __launch_bounds__(256) rowsum_i8_kernel(const int8_t* __restrict__ q, int32_t* __restrict__ out,
+                                                        long long R, long long K) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31;
+  const int8_t* p = q + row * K;
+  int acc = 0;
+  const bool vec = (K % 16 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0);
+  if (vec) {
+    for (long long i = lane * 16; i < K; i += 32 * 16) {
+      const int4 v = *reinterpret_cast<const int4*>(p + i);
+      acc = __dp4a(v.x, 0x01010101, acc);
+      acc = __dp4a(v.y, 0x01010101, acc);
+      acc = __dp4a(v.z, 0x01010101, acc);
+      acc = __dp4a(v.w, 0x01010101, acc);
+    }
+  } else {
+    for (long long i = lane; i < K; i += 32) acc += p[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = acc;
+}
+
+// alpha[n] = sx*sw[n];  cnst[n] = ox*rowsum_w[n] + K*ox*ow[n];  own[n] = ow[n];  bias as float
+__global__ void __launch_bounds__(256) col_params_kernel(int N, int K, const float* sx, const float* ox, const float* sw,
+                                                         const float* ow, const int32_t* rowsum_w, const void* bias,
+                                                         int bias_dt, float* alpha, float* biasf, int32_t* cnst,
+                                                         int32_t* own) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int o_x = ox ? __float2int_rn(rintf(ox[0])) : 0;
+  const int o_w = ow ? __float2int_rn(rintf(ow[n])) : 0;
+  alpha[n] = sx[0] * sw[n];
+  biasf[n] = bias ? load_as_float(bias, bias_dt, n) : 0.f;
+  cnst[n] = o_x * rowsum_w[n] + K * o_x * o_w;
+  if (own) own[n] = o_w;
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("qlinear: cuTensorMapEncodeTiled is not available from the driver"); return FFQ_ERR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("qlinear: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FFQ_ERR_CUDA; }
+  return FFQ_OK;
+}
+
+}  // namespace ffq
+
+using namespace ffq;
+
+extern "C" {
+
+size_t ffq_qlinear_workspace_bytes(int64_t N) { return (size_t)(4 * N) * sizeof(float); }
+
+int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream) {
+  if (R <= 0) return FFQ_OK;
+  rowsum_i8_kernel<<<(unsigned int)((R + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, rowsum, R, K);
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
+                     const float* sx, const float* ox, const float* sw, const float* ow, const int32_t* rowsum_w,
+                     const int32_t* rowsum_x, const void* bias, int bias_dtype, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= 0 || N <= 0) return FFQ_OK;
+  if (K <= 0 || K % 16 != 0) { set_error("qlinear_w8a8: K must be a positive multiple of 16 (got %lld)", (long long)K); return FFQ_ERR_UNSUPPORTED; }
+  if ((reinterpret_cast<uintptr_t>(qx) & 15u) || (reinterpret_cast<uintptr_t>(qw) & 15u)) {
+    set_error("qlinear_w8a8: operand pointers must be 16-byte aligned"); return FFQ_ERR_UNSUPPORTED;
+  }
+  if (!(y_dtype == FFQ_F32 || y_dtype == FFQ_BF16 || y_dtype == FFQ_F16)) {
+    set_error("qlinear_w8a8: output dtype must be float32/bfloat16/float16"); return FFQ_ERR_UNSUPPORTED;
+  }
+  if (M > 0x7fffffffll || N > 0x7fffffffll || K > 0x7fffffffll) { set_error("qlinear_w8a8: dimension too large"); return FFQ_ERR_UNSUPPORTED; }
+  if (ow != nullptr && rowsum_x == nullptr) { set_error("qlinear_w8a8: rowsum_x is required when the weight has an offset"); return FFQ_ERR_INVALID; }
+  if (workspace == nullptr || workspace_bytes < ffq_qlinear_workspace_bytes(N)) {
+    set_error("qlinear_w8a8: workspace of %zu bytes required", ffq_qlinear_workspace_bytes(N)); return FFQ_ERR_WORKSPACE;
+  }
+  float* alpha = static_cast<float*>(workspace);
+  float* biasf = alpha + N;
+  int32_t* cnst = reinterpret_cast<int32_t*>(biasf + N);
+  int32_t* own = ow ? cnst + N : nullptr;
+  col_params_kernel<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>((int)N, (int)K, sx, ox, sw, ow, rowsum_w, bias,
+                                                                     bias_dtype, alpha, biasf, cnst, own);
+  FFQ_LAUNCH_CHECK();
+
+  CUtensorMap map_a, map_b;
+  int rc;
+  if ((rc = make_map(&map_a, qx, M, K, BM)) != FFQ_OK) return rc;
+  if ((rc = make_map(&map_b, qw, N, K, BN)) != FFQ_OK) return rc;
+  GemmArgs g{};
+  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.y_dt = y_dtype;
+  g.alpha = alpha; g.bias = biasf; g.cnst = cnst; g.own = own; g.rowsum_x = rowsum_x;
+  const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e1 = cudaFuncSetAttribute(w8a8_gemm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(w8a8_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e3 = cudaFuncSetAttribute(w8a8_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  });
+  if (attr_err != cudaSuccess) { set_error("qlinear_w8a8: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
+  switch (y_dtype) {
+    case FFQ_F32: w8a8_gemm_kernel<float><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
+    case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
+    default: w8a8_gemm_kernel<__half><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
+  }
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+"""W8A8 quantized linear on tcgen05 tensor cores, plugged in through the operator dispatcher
+(seam 2 of SURVEY.md section 8b: ``ff.dispatcher.register("linear", predicate, kernel)``).
+
+``install()`` registers the kernel; the predicate accepts exactly the case the kernel implements
+(int8 per-tensor activations x int8 per-channel weights on CUDA) and everything else keeps taking
+the reference's dequantize-then-float fallback (_gen/fallback.py:77-112)."""
+
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+
+from .. import _cabi as C
+from ..dispatcher import Predicate, register
+from ..quantization import granularity as G
+from ..quantization.affine.function import StaticAffineQuantParams
+from ..quantized_tensor import QuantizedTensor
+
+_hook = None
+_stats: Dict[str, Any] = {"calls": 0}
+_rowsum_cache: Dict[Any, torch.Tensor] = {}
+
+
+def _params(t) -> Optional[StaticAffineQuantParams]:
+    if not isinstance(t, QuantizedTensor):
+        return None
+    p = t.quant_args()
+    return p if isinstance(p, StaticAffineQuantParams) else None
+
+
+def _accepts(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None) -> bool:
+    px, pw = _params(input), _params(weight)
+    if px is None or pw is None or not input.is_cuda or not weight.is_cuda:
+        return False
+    if input.raw_data.dtype != torch.int8 or weight.raw_data.dtype != torch.int8:
+        return False
+    if px.num_bits > 8 or pw.num_bits > 8 or weight.dim() != 2 or input.dim() < 2:
+        return False
+    if not G.is_per_tensor(px.granularity):
+        return False
+    if not (G.is_per_channel(pw.granularity) and tuple(pw.granularity.channel_dims) == (0,)):
+        return False
+    if not all(isinstance(v, torch.Tensor) and v.dtype == torch.float32 for v in (px.scale, pw.scale)):
+        return False
+    for off in (px.offset, pw.offset):
+        if off is not None and not (isinstance(off, torch.Tensor) and off.dtype == torch.float32):
+            return False
+    if isinstance(bias, QuantizedTensor):
+        return False
+    k = weight.shape[1]
+    return input.shape[-1] == k and k % 16 == 0 and (px.dequantize_dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+
+def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None):
+    px, pw = input.quant_args(), weight.quant_args()
+    qx = input.raw_data
+    lead = qx.shape[:-1]
+    k = qx.shape[-1]
+    qx2 = qx.reshape(-1, k).contiguous()
+    qw = weight.raw_data.contiguous()
+    m, n = qx2.shape[0], qw.shape[0]
+    out_dtype = px.dequantize_dtype or torch.float32
+    y = torch.empty((m, n), dtype=out_dtype, device=qx.device)
+    stream = C.current_stream(qx.device)
+    rowsum_w = torch.empty(n, dtype=torch.int32, device=qx.device)
+    C.check(C.lib.ffq_rowsum_i8(qw.data_ptr(), rowsum_w.data_ptr(), n, k, stream))
+    rowsum_x = None
+    if pw.offset is not None:
+        rowsum_x = torch.empty(m, dtype=torch.int32, device=qx.device)
+        C.check(C.lib.ffq_rowsum_i8(qx2.data_ptr(), rowsum_x.data_ptr(), m, k, stream))
+    sx = px.scale.detach().reshape(-1)
+    ox = None if px.offset is None else px.offset.detach().reshape(-1)
+    sw = pw.scale.detach().reshape(-1).contiguous()
+    ow = None if pw.offset is None else pw.offset.detach().reshape(-1).contiguous()
+    b = None if bias is None else bias.detach().contiguous()
+    ws = torch.empty(4 * n, dtype=torch.float32, device=qx.device)
+    C.check(C.lib.ffq_qlinear_w8a8(
+        qx2.data_ptr(), qw.data_ptr(), y.data_ptr(), C.dtype_tag(out_dtype), m, n, k,
+        sx.data_ptr(), C.ptr(ox), sw.data_ptr(), C.ptr(ow), rowsum_w.data_ptr(), C.ptr(rowsum_x),
+        C.ptr(b), C.dtype_tag(b.dtype if b is not None else None), ws.data_ptr(), ws.numel() * 4, stream))
+    _stats["calls"] += 1
+    y = y.reshape(*lead, n)
+    if output_quantizer is not None:
+        y = output_quantizer(y)
+    return y
+
+
+def install() -> None:
+    """Register the kernel (idempotent)."""
+    global _hook
+    if _hook is None:
+        _hook = register("linear", Predicate(_accepts), w8a8_linear)
+
+
+def uninstall() -> None:
+    global _hook
+    if _hook is not None:
+        _hook.remove()
+        _hook = None
+
+
+def stats() -> Dict[str, Any]:
+    return dict(_stats)

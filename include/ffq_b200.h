@@ -172,14 +172,17 @@ FFQ_API int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtyp
  * (sw, ow fp32[N]; ow may be NULL).  int32 accumulation on tcgen05 (kind::i8) tensor cores,
  * dequantisation fused into the epilogue.  y_dtype in {F32, BF16, F16}.
  * rowsum_w: int32[N] precomputed with ffq_rowsum_i8 (weights are static); rowsum_x may be NULL
- * when ow is NULL.
+ * when ow is NULL.  K must be a multiple of 16 (TMA row pitch); M and N are arbitrary.
  * replaces: _gen/fallback.py:77-112 (dequantize x2 + torch.nn.functional.linear), selected via
  *           dispatcher.py:268-283. */
 FFQ_API int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype,
                      int64_t M, int64_t N, int64_t K,
                      const float* sx, const float* ox, const float* sw, const float* ow,
                      const int32_t* rowsum_w, const int32_t* rowsum_x,
-                     const void* bias, int bias_dtype, void* stream);
+                     const void* bias, int bias_dtype,
+                     void* workspace, size_t workspace_bytes, void* stream);
+/* scratch for ffq_qlinear_w8a8: four 4-byte[N] column-parameter vectors */
+FFQ_API size_t ffq_qlinear_workspace_bytes(int64_t N);
 
 /* rowsum[r] = sum_k q[r,k]  (int8 [R,K] -> int32[R]) */
 FFQ_API int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream);
