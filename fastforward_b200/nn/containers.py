@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import torch
 
+from ..quantized_tensor import QuantizedTensor
 from .quantized_module import QuantizedModule
 from .quantizer import QuantizerStub
 
@@ -28,7 +29,7 @@ class QuantizedSiLU(QuantizedModule, torch.nn.SiLU):
         self.output_quantizer = QuantizerStub(output_quantizer=True)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        x = input.dequantize() if hasattr(input, "dequantize") else input
+        x = input.dequantize() if isinstance(input, QuantizedTensor) else input
         return self.output_quantizer(torch.nn.functional.silu(x))
 
 
@@ -40,7 +41,7 @@ class QuantizedEmbedding(QuantizedModule, torch.nn.Embedding):
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         weight = self.weight_quantizer(self.weight)
-        weight = weight.dequantize() if hasattr(weight, "dequantize") else weight
+        weight = weight.dequantize() if isinstance(weight, QuantizedTensor) else weight
         out = torch.nn.functional.embedding(input, weight, self.padding_idx, self.max_norm, self.norm_type,
                                             self.scale_grad_by_freq, self.sparse)
         return self.output_quantizer(out)
