@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="run the steps eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-layers", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true")
     return ap.parse_args()
 
 
@@ -149,6 +150,109 @@ class OpTimer:
                              gbps=(sum(by) / (sum(ms) * 1e-3) / 1e9) if sum(ms) > 0 else 0.0,
                              avg_us=1e3 * sum(ms) / max(1, len(ms)))
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the other two pieces of BASELINE.json's metric, measured in isolation on this rank's GPU
+# ---------------------------------------------------------------------------------------------
+def _time_cuda(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
+    return ts[len(ts) // 2] * 1e-3
+
+
+def measure_extras(ff, dev, hbm_peak, int8_peak):
+    """fake-quant fwd+bwd GB/s (configs[0]/cfg1 shape and a weight-sized bf16 tensor), W8A8 linear TOPS
+    (configs[3]) and W4 g=128 weight QDQ GB/s (configs[2], one Llama-3-8B gate_proj).  Inputs exceed L2
+    or are cycled so that no iteration re-reads L2-resident data."""
+    import ctypes
+    from fastforward_b200 import _cabi as C, ops
+    out = {}
+    for name, shape, dt in (("cfg1_4096x4096_fp32_perchannel8", (4096, 4096), torch.float32),
+                            ("16384x4096_fp32_perchannel8", (16384, 4096), torch.float32),
+                            ("14336x4096_bf16_perchannel8", (14336, 4096), torch.bfloat16)):
+        torch.manual_seed(0)
+        nbuf = max(1, int(400e6 // (shape[0] * shape[1] * torch.empty(0, dtype=dt).element_size() * 3)) + 1)
+        xs = [torch.randn(shape, device=dev, dtype=dt) for _ in range(nbuf)]
+        gs = [torch.randn(shape, device=dev, dtype=dt) for _ in range(nbuf)]
+        tile = (1, shape[1])
+        mn, mx = ops.tile_minmax(xs[0], tile)
+        scale = torch.empty(shape[0], device=dev); offset = torch.empty(shape[0], device=dev)
+        ops.parameters_for_range_(mn, mx, 8, True, True, scale, offset)
+        it = [0]
+
+        def step():
+            i = it[0] % nbuf; it[0] += 1
+            ops.fake_quantize_by_tile(xs[i], scale, tile, 8.0, None, offset)
+            ops.quantize_by_tile_backward(xs[i], gs[i], scale, tile, 8.0, offset)
+        t = _time_cuda(step)
+        by = 5 * xs[0].numel() * xs[0].element_size()
+        out[name] = {"fwd_bwd_us": round(t * 1e6, 1), "GBps": round(by / t / 1e9, 1), "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3),
+                     "algorithmic_MB": round(by / 1e6, 1), "buffers_cycled": nbuf}
+        if name.startswith("cfg1"):
+            # end to end with HOST buffers through the C ABI (H2D + kernels + D2H inside the call)
+            xh, gh = xs[0].cpu().pin_memory(), gs[0].cpu().pin_memory()
+            yh, dxh = torch.empty_like(xh).pin_memory(), torch.empty_like(xh).pin_memory()
+            sh_, oh_ = scale.cpu(), offset.cpu()
+            dsc, dof = torch.empty(shape[0]), torch.empty(shape[0])
+            lay = C.make_layout(shape, tile)
+
+            def host_step():
+                C.check(C.lib.ffq_fakequant_fwd_bwd_host(xh.data_ptr(), gh.data_ptr(), C.dtype_tag(dt), yh.data_ptr(), dxh.data_ptr(),
+                                                          dsc.data_ptr(), dof.data_ptr(), sh_.data_ptr(), oh_.data_ptr(),
+                                                          ctypes.byref(lay), 8.0, dev.index or 0))
+            host_step()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                host_step()
+            th = (time.perf_counter() - t0) / 5
+            out[name]["e2e_host_buffers"] = {"ms": round(th * 1e3, 2), "GBps_algorithmic": round(by / th / 1e9, 1),
+                                             "h2d_bytes": 2 * xh.numel() * 4, "d2h_bytes": 2 * xh.numel() * 4}
+        del xs, gs
+    # W8A8 linear, configs[3]
+    M, N, K = 8192, 14336, 4096
+    qx = torch.randint(-128, 128, (M, K), dtype=torch.int8, device=dev)
+    qw = torch.randint(-128, 128, (N, K), dtype=torch.int8, device=dev)
+    y = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    sx = torch.tensor([0.01], device=dev); ox = torch.tensor([3.0], device=dev); sw = torch.rand(N, device=dev) * 0.01
+    rs = torch.empty(N, dtype=torch.int32, device=dev); ws = torch.empty(4 * N, device=dev)
+    st = C.current_stream(dev)
+    C.check(C.lib.ffq_rowsum_i8(qw.data_ptr(), rs.data_ptr(), N, K, st))
+
+    def gemm():
+        C.check(C.lib.ffq_qlinear_w8a8(qx.data_ptr(), qw.data_ptr(), y.data_ptr(), 2, M, N, K, sx.data_ptr(), ox.data_ptr(), sw.data_ptr(),
+                                       None, rs.data_ptr(), None, None, 255, ws.data_ptr(), ws.numel() * 4, st))
+    t = _time_cuda(gemm)
+    t_lib = _time_cuda(lambda: torch._int_mm(qx, qw.t()))
+    out["w8a8_linear_8192x14336x4096"] = {"us": round(t * 1e6, 1), "TOPS": round(2 * M * N * K / t / 1e12, 1),
+                                          "frac_of_int8_peak": round(2 * M * N * K / t / 1e12 / int8_peak, 3),
+                                          "context_cublaslt_int_mm_TOPS": round(2 * M * N * K / t_lib / 1e12, 1)}
+    del qx, qw, y
+    # W4 g=128 weight QDQ of one 14336x4096 bf16 weight (configs[2] unit of work): min/max + params + fused QDQ in place
+    w = [torch.randn(14336, 4096, device=dev, dtype=torch.bfloat16) * 0.02 for _ in range(3)]
+    tile = (1, 128)
+    nt = w[0].numel() // 128
+    scale = torch.empty(nt, device=dev); offset = torch.empty(nt, device=dev)
+    it = [0]
+
+    def qdq():
+        i = it[0] % 3; it[0] += 1
+        mn, mx = ops.tile_minmax(w[i], tile)
+        ops.parameters_for_range_(mn, mx, 4, True, True, scale, offset)
+        ops.fake_quantize_by_tile(w[i], scale, tile, 4.0, None, offset)
+    t = _time_cuda(qdq)
+    by = 3 * w[0].numel() * 2    # read (min/max) + read + write
+    out["w4_g128_weight_qdq_14336x4096_bf16"] = {"us": round(t * 1e6, 1), "GBps": round(by / t / 1e9, 1),
+                                                  "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3)}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -275,9 +379,15 @@ def run_ours(args):
             roofline = dict(bound="hbm", kernel=dominant[0], achieved=round(d["gbps"], 1), peak=hbm_peak, unit="GB/s",
                             frac=round(d["gbps"] / hbm_peak, 4), traffic=None, peak_source=peak_src,
                             avg_launch_us=round(d["avg_us"], 2), launches_timed=d["launches"])
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        int8_peak = 2.0 * bf16_peak      # kind::i8 issues at twice the kind::f16 rate on sm_100
+        extras = None
+        if not args.skip_extras:
+            torch.cuda.empty_cache()
+            extras = measure_extras(ff, dev, hbm_peak, int8_peak)
         cpu_baseline = None
         if not args.skip_cpu_baseline:
-            cpu_baseline = run_reference_sample(args, sh, sample_layers=args.cpu_sample_layers, steps=1, warmup=0)
+            cpu_baseline = run_reference_sample(args, sh, sample_layers=args.cpu_sample_layers, steps=3, warmup=1)
         line = {
             "metric": "calib tokens/s (Llama-3-8B-shape W8 per-channel / A8 per-tensor RunningMinMax calibration, seq 2048)"
             if args.shape == "8b" else f"calib tokens/s ({sh.name})",
@@ -296,7 +406,8 @@ def run_ours(args):
             "gpu_launches_per_step": round(launches_per_step, 1),
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "kernels": {k: {kk: (round(vv, 2) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in per_op.items()},
-            "qlinear": qlin,
+            "qlinear": qlin, "extras": extras,
+            "peaks": {"hbm_GBps": hbm_peak, "int8_TOPS": int8_peak, "note": "hbm and bf16 from MEASURED_PEAKS.json; int8 = 2 x measured bf16 burst"},
             "wall_s_timed_region": round(wall, 3),
         }
         print(json.dumps(line))

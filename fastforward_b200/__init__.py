@@ -36,5 +36,7 @@ from .quantization.granularity import PerTensor as PerTensor
 from .quantization.granularity import PerTile as PerTile
 from .quantized_tensor import QuantizedTensor as QuantizedTensor
 from .range_setting import estimate_ranges as estimate_ranges
+from .quantization import fuse as _fuse  # noqa: E402  (after nn: it needs LinearQuantizer)
+from .quantization.fuse import fuse_qdq_weights as fuse_qdq_weights
 
 __version__ = "0.1.0"

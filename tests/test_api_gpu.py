@@ -213,3 +213,42 @@ def test_functional_frontends_and_dynamic():
     assert bits_equal(lq(x).dequantize(), qd.dequantize())
     # python-scalar scale: converted to the data dtype (affine/_autograd.py:35-37)
     assert bits_equal(A.quantize_per_tensor(x, 0.05, None, 4).raw_data, A.quantize_per_tensor(x, torch.tensor(0.05, device=DEV), None, 4).raw_data)
+
+
+def test_fuse_qdq_weights_matches_two_step_and_is_idempotent():
+    """reference tests/quantization/test_fuse.py:51-117: fused weights == quantizer(w).dequantize(), idempotent."""
+    from fastforward_b200.quantization.fuse import calibrate_weight_quantizers, fuse_qdq_weights
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(256, 128, bias=False), torch.nn.Linear(128, 64)).to(torch.bfloat16)
+    ff.quantize_model(model)
+    ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
+        ff.nn.LinearQuantizer, num_bits=4, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+    model.to(DEV)
+    assert calibrate_weight_quantizers(model) == 2
+    expect = []
+    for lin in model:
+        w = lin.weight.detach().cpu()
+        rows = R.tile_rows(w, (1, 128))
+        s, o = R.parameters_for_range(rows.min(1).values, rows.max(1).values, 4, True, True)
+        o = torch.zeros_like(s) if o is None else o
+        assert bits_equal(lin.weight_quantizer.scale.detach(), s)
+        expect.append(R.dequantize_by_tile(R.quantize_by_tile(w, s, (1, 128), 4, w.dtype, o), s, (1, 128), o, w.dtype))
+    two_step = [lin.weight_quantizer(lin.weight).dequantize() for lin in model]
+    assert fuse_qdq_weights(model) == 2
+    for lin, want, ts in zip(model, expect, two_step):
+        assert bits_equal(lin.weight.detach(), want) and bits_equal(lin.weight.detach(), ts)
+    before = [lin.weight.detach().clone() for lin in model]
+    fuse_qdq_weights(model, stub_quantizers=True)
+    for lin, b in zip(model, before):
+        assert bits_equal(lin.weight.detach(), b) and lin.weight_quantizer.is_stub()
+    # sharding: rank r of 2 touches only its targets
+    m2 = torch.nn.Sequential(*[torch.nn.Linear(128, 128, bias=False) for _ in range(4)])
+    ff.quantize_model(m2)
+    ff.find_quantizers(m2, "**/[quantizer:parameter/weight]").initialize(ff.nn.LinearQuantizer, num_bits=4, granularity=ff.PerChannel(0))
+    m2.to(DEV)
+    calibrate_weight_quantizers(m2)
+    orig = [lin.weight.detach().clone() for lin in m2]
+    assert fuse_qdq_weights(m2, rank=1, world_size=2) == 2
+    changed = [not torch.equal(lin.weight.detach(), o) for lin, o in zip(m2, orig)]
+    assert changed == [False, True, False, True]
