@@ -103,52 +103,77 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# per-kernel timing (CUDA events on the launching stream) for the roofline object
+# per-kernel timing for the roofline object
 # ---------------------------------------------------------------------------------------------
-class OpTimer:
-    """Wraps the op entry points with CUDA events; algorithmic bytes are computed from the
-    tensors each call touches (DESIGN.md section 'algorithmic bytes')."""
+class KernelCensus:
+    """Records every hot-path launch of ONE eager step (the callable and its live arguments), then
+    replays each kind of launch back to back from a CUDA graph bracketed by CUDA events on the
+    launching stream.  Eager per-launch events would time the host (the eager step is
+    dispatch-bound); the graph replay keeps the device busy, so total/launches is the kernel's
+    average duration at exactly the shapes and operands of the timed step."""
 
-    def __init__(self, ops):
-        self.ops = ops
-        self.records = {}   # name -> list of (start, end, bytes)
-        self._orig = {}
+    def __init__(self, ff):
+        from fastforward_b200 import _cabi
+        from fastforward_b200.nn import qlinear
+        self.ff, self.C, self.qlinear = ff, _cabi, qlinear
+        self.calls = {}     # kind -> list of (closure, algorithmic units)
+        self._undo = []
 
-    @staticmethod
-    def _nbytes(*tensors):
-        return sum(t.numel() * t.element_size() for t in tensors if isinstance(t, torch.Tensor))
+    def _nbytes(self, *ts):
+        return sum(t.numel() * t.element_size() for t in ts if isinstance(t, torch.Tensor))
 
     def install(self):
-        ops = self.ops
+        ops, C = self.ff.ops, self.C
+        self.qlinear.keepalive = []          # recorded C-ABI pointers must outlive the replay
 
-        def wrap(name, fn, bytes_fn):
-            def timed(*a, **k):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                out = fn(*a, **k)
-                e.record()
-                self.records.setdefault(name, []).append((s, e, bytes_fn(a, k, out)))
+        def wrap(obj, name, kind, units_fn, c_abi=False):
+            orig = getattr(obj, name)
+
+            def rec(*a, **k):
+                out = orig(*a, **k)
+                if c_abi:     # last argument is the stream: re-resolve it at replay time (graph capture stream)
+                    call = lambda: orig(*a[:-1], torch.cuda.current_stream().cuda_stream)
+                else:
+                    call = lambda: orig(*a, **k)
+                self.calls.setdefault(kind, []).append((call, units_fn(a, k, out)))
                 return out
-            self._orig[name] = fn
-            setattr(ops, name, timed)
+            setattr(obj, name, rec)
+            self._undo.append((obj, name, orig))
 
-        wrap("quantize_by_tile", ops.quantize_by_tile, lambda a, k, o: self._nbytes(a[0], o))
-        wrap("dequantize_by_tile", ops.dequantize_by_tile, lambda a, k, o: self._nbytes(a[0], o))
-        wrap("running_minmax_update_", ops.running_minmax_update_, lambda a, k, o: self._nbytes(a[2]))
-        wrap("fake_quantize_by_tile", ops.fake_quantize_by_tile, lambda a, k, o: self._nbytes(a[0], o))
+        wrap(ops, "quantize_by_tile", "quantize (ew_row_kernel<QUANT>)", lambda a, k, o: self._nbytes(a[0], o))
+        wrap(ops, "running_minmax_update_", "running min/max (mm_row_*_kernel)", lambda a, k, o: self._nbytes(a[2]))
+        wrap(ops, "dequantize_by_tile", "dequantize (ew_row_kernel<DEQUANT>)", lambda a, k, o: self._nbytes(a[0], o))
+        # the GEMM at C-ABI level: args 4..6 are M, N, K
+        wrap(C.lib, "ffq_qlinear_w8a8", "w8a8 linear (w8a8_gemm_kernel)", lambda a, k, o: 2.0 * a[4] * a[5] * a[6], c_abi=True)
+        wrap(C.lib, "ffq_rowsum_i8", "rowsum (rowsum_i8_kernel)", lambda a, k, o: float(a[2] * a[3]), c_abi=True)
 
     def remove(self):
-        for name, fn in self._orig.items():
-            setattr(self.ops, name, fn)
+        for obj, name, orig in self._undo:
+            setattr(obj, name, orig)
+        self._undo = []
+        self._alive, self.qlinear.keepalive = self.qlinear.keepalive, None
 
-    def summary(self):
+    def replay(self, reps=3):
         out = {}
-        for name, recs in self.records.items():
-            ms = [s.elapsed_time(e) for s, e, _ in recs]
-            by = [b for _, _, b in recs]
-            out[name] = dict(launches=len(recs), total_ms=sum(ms), bytes=sum(by),
-                             gbps=(sum(by) / (sum(ms) * 1e-3) / 1e9) if sum(ms) > 0 else 0.0,
-                             avg_us=1e3 * sum(ms) / max(1, len(ms)))
+        for kind, calls in self.calls.items():
+            for fn, _ in calls[:3]:
+                fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for fn, _ in calls:
+                    fn()
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            units = sum(u for _, u in calls)
+            out[kind] = dict(launches=len(calls), total_ms=round(ms, 3), avg_us=round(1e3 * ms / len(calls), 2),
+                             units=units, rate=units / (ms * 1e-3))
+            del g
         return out
 
 
@@ -346,13 +371,16 @@ def run_ours(args):
     dt_e2e, _ = region(args.steps, host_tokens, e2e=True, graph=use_graph)
     # ---- instrumented eager pass for the roofline of the dominant kernel ------------------------
     reset_quantizers()
-    timer = OpTimer(ff.ops)
-    timer.install()
     lc0 = _cabi.launch_count()
-    region(2, dev_tokens, e2e=False, graph=False)
-    launches_per_step = (_cabi.launch_count() - lc0) / (2 + args.warmup)
-    timer.remove()
-    per_op = timer.summary()
+    region(1, dev_tokens, e2e=False, graph=False)
+    launches_per_step = (_cabi.launch_count() - lc0) / (1 + args.warmup)
+    census = KernelCensus(ff)
+    census.install()
+    with torch.no_grad(), ff.estimate_ranges(model, ff.range_setting.running_minmax()):
+        static_tokens.copy_(dev_tokens[0])
+        model(static_tokens)                      # ONE recorded eager step (ranges already initialised)
+    census.remove()
+    per_op = census.replay()
     qlin = qlinear.stats()
 
     def allmax(v):
@@ -372,15 +400,22 @@ def run_ours(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+        int8_peak = 2.0 * bf16_peak      # kind::i8 issues at twice the kind::f16 rate on sm_100
         dominant = max(per_op.items(), key=lambda kv: kv[1]["total_ms"]) if per_op else (None, None)
         roofline = None
         if dominant[0]:
             d = dominant[1]
-            roofline = dict(bound="hbm", kernel=dominant[0], achieved=round(d["gbps"], 1), peak=hbm_peak, unit="GB/s",
-                            frac=round(d["gbps"] / hbm_peak, 4), traffic=None, peak_source=peak_src,
-                            avg_launch_us=round(d["avg_us"], 2), launches_timed=d["launches"])
-        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-        int8_peak = 2.0 * bf16_peak      # kind::i8 issues at twice the kind::f16 rate on sm_100
+            if dominant[0].startswith("w8a8"):
+                roofline = dict(bound="tensor", kernel=dominant[0], achieved=round(d["rate"] / 1e12, 1), peak=int8_peak,
+                                unit="TOP/s", frac=round(d["rate"] / 1e12 / int8_peak, 4), traffic=None,
+                                peak_source="2 x MEASURED_PEAKS.json bf16_tflops (burst): int8 MMA issues at twice the bf16 rate",
+                                algorithmic="2*M*N*K ops per launch, M=2048 (the step's 224 linears)")
+            else:
+                roofline = dict(bound="hbm", kernel=dominant[0], achieved=round(d["rate"] / 1e9, 1), peak=hbm_peak, unit="GB/s",
+                                frac=round(d["rate"] / 1e9 / hbm_peak, 4), traffic=None, peak_source=peak_src)
+            roofline.update(avg_launch_us=d["avg_us"], launches_per_step=d["launches"], kernel_ms_per_step=d["total_ms"],
+                            method="all launches of this kind in one step replayed back to back from a CUDA graph, CUDA events on the launching stream")
         extras = None
         if not args.skip_extras:
             torch.cuda.empty_cache()
@@ -405,7 +440,9 @@ def run_ours(args):
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "gpu_launches_per_step": round(launches_per_step, 1),
             "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernels": {k: {kk: (round(vv, 2) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in per_op.items()},
+            "kernels": {k: dict(launches=v["launches"], ms_per_step=v["total_ms"], avg_us=v["avg_us"],
+                                rate=(f"{v['rate'] / 1e12:.0f} TOP/s" if k.startswith("w8a8") else f"{v['rate'] / 1e9:.0f} G(B|elem)/s"))
+                        for k, v in per_op.items()},
             "qlinear": qlin, "extras": extras,
             "peaks": {"hbm_GBps": hbm_peak, "int8_TOPS": int8_peak, "note": "hbm and bf16 from MEASURED_PEAKS.json; int8 = 2 x measured bf16 burst"},
             "wall_s_timed_region": round(wall, 3),

@@ -23,6 +23,8 @@
 // full MMA rate, so L2->SM bandwidth is the secondary bound.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -268,6 +270,185 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ================================================================================================
+// 2-CTA variant: a CTA pair (cluster 2x1x1, two SMs of one TPC) owns a 256x256 output tile.
+// Each CTA stages its own 128 rows of A and its own 128-row half of B (32 KB per k-block instead of
+// 48 KB: the operand traffic per MMA drops by a third, which is what bounds the 1-CTA kernel), the
+// leader CTA issues tcgen05.mma.cta_group::2 (M=256) reading both CTAs' shared memory, and each
+// CTA's TMEM holds its 128 accumulator rows.  TMA completions of both CTAs land on the leader's
+// "full" barrier (cta_group::2 loads), tcgen05.commit multicasts "slot free" / "tile ready" to both
+// CTAs, and the peer's epilogue warps release the accumulator on the leader's barrier.
+// ================================================================================================
+constexpr int STAGES2 = 6;
+constexpr int HALF_STAGE = A_STAGE + BM * BK;      // A 128x128B + B half 128x128B = 32 KB
+constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + 4 * BN * 4 + 256 + 1024;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // shared::cluster address of the same offset in the pair's CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
+      "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+
+template <typename OutT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE);       // [4][BN]
+  int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + 4 * BN * 4);
+  uint64_t* full_bar = bars;                  // [STAGES2]  (the leader's copy is the one in use)
+  uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  (each CTA waits on its own copy)
+  uint64_t* tmem_full = bars + 2 * STAGES2;   // [2]        (each CTA waits on its own copy)
+  uint64_t* tmem_empty = bars + 2 * STAGES2 + 2;   // [2]   (leader's copy, 8 arrivals)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  constexpr int TM = 2 * BM;                  // 256 rows per pair tile
+  const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int k_blocks = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();                         // barriers of BOTH CTAs are initialised before any remote use
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; completions count on the leader's full barrier) =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * HALF_STAGE;
+          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * HALF_STAGE);
+          tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
+          tma_load_2d_pair(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * BN + (int)cta * (BN / 2));
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (cta == 0 && lane == 0) {
+      // D=S32, A=B=signed int8, K-major, N=256, M=256 (128 rows in each CTA)
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * HALF_STAGE);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_STAGE);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_i8_pair(tmem_d, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), idesc,
+                         (kb | k) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);               // both CTAs' producers may refill the slot
+          if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[buf]);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5 of both CTAs): this CTA's 128 rows =====
+    const int quad = warp & 3;
+    const int ep_tid = threadIdx.x - 64;
+    OutT* __restrict__ y = static_cast<OutT*>(g.y);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = ep_tid; c < BN; c += 128) {
+        const int n = tn * BN + c;
+        const bool in = n < g.N;
+        col_params[c] = in ? g.alpha[n] : 0.f;
+        col_params[BN + c] = in ? g.bias[n] : 0.f;
+        col_ints[2 * BN + c] = in ? g.cnst[n] : 0;
+        col_ints[3 * BN + c] = (in && g.own) ? g.own[n] : 0;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
+      const int32_t rx = (g.own && row < g.M) ? g.rowsum_x[row] : 0;
+
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)c0, acc);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int32_t t = (int32_t)acc[j] + col_ints[2 * BN + c0 + j] + col_ints[3 * BN + c0 + j] * rx;
+          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[BN + c0 + j]);
+        }
+        const int n0 = tn * BN + c0;
+        if (row < g.M && n0 < g.N) {
+          const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
+          store_chunk<OutT>(y + (size_t)row * g.N + n0, v, ncols);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);   // 8 arrivals (4 warps x 2 CTAs) free the accumulator
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                         // nobody leaves while the peer may still touch its smem / barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
 // ---- small helper kernels ------------------------------------------------------------------------
 // rowsum[r] = sum_k q[r,k]   (one warp per row, 16-byte loads, dp4a against ones)
 __global__ void __launch_bounds__(256) rowsum_i8_kernel(const int8_t* __restrict__ q, int32_t* __restrict__ out,
@@ -391,6 +572,10 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   g.alpha = alpha; g.bias = biasf; g.cnst = cnst; g.own = own; g.rowsum_x = rowsum_x;
   const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const long long pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  // the pair kernel needs M > 128 to have work for both CTAs; FFQ_GEMM_1CTA=1 forces the single-CTA kernel
+  static const bool force_1cta = getenv("FFQ_GEMM_1CTA") != nullptr;
+  const bool use_pair = !force_1cta && M > BM;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -398,8 +583,25 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
     cudaError_t e2 = cudaFuncSetAttribute(w8a8_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     cudaError_t e3 = cudaFuncSetAttribute(w8a8_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_err = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    cudaError_t f1 = cudaFuncSetAttribute(w8a8_gemm2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    cudaError_t f2 = cudaFuncSetAttribute(w8a8_gemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    cudaError_t f3 = cudaFuncSetAttribute(w8a8_gemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (attr_err == cudaSuccess) attr_err = f1 != cudaSuccess ? f1 : (f2 != cudaSuccess ? f2 : f3);
   });
   if (attr_err != cudaSuccess) { set_error("qlinear_w8a8: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
+  if (use_pair) {
+    CUtensorMap map_b2;     // B box = this CTA's 128-row half
+    if ((rc = make_map(&map_b2, qw, N, K, BN / 2)) != FFQ_OK) return rc;
+    const int max_pairs = sm_count() / 2;
+    const int grid2 = 2 * (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    switch (y_dtype) {
+      case FFQ_F32: w8a8_gemm2_kernel<float><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
+      case FFQ_BF16: w8a8_gemm2_kernel<__nv_bfloat16><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
+      default: w8a8_gemm2_kernel<__half><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
+    }
+    FFQ_LAUNCH_CHECK();
+    return FFQ_OK;
+  }
   switch (y_dtype) {
     case FFQ_F32: w8a8_gemm_kernel<float><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
     case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;

@@ -19,7 +19,9 @@ from ..quantized_tensor import QuantizedTensor
 
 _hook = None
 _stats: Dict[str, Any] = {"calls": 0}
-_rowsum_cache: Dict[Any, torch.Tensor] = {}
+# bench.py's kernel census replays recorded C-ABI launches: while this list is not None the
+# temporaries of every call are kept alive so that the recorded device pointers stay valid.
+keepalive: Optional[list] = None
 
 
 def _params(t) -> Optional[StaticAffineQuantParams]:
@@ -80,6 +82,8 @@ def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, stric
         sx.data_ptr(), C.ptr(ox), sw.data_ptr(), C.ptr(ow), rowsum_w.data_ptr(), C.ptr(rowsum_x),
         C.ptr(b), C.dtype_tag(b.dtype if b is not None else None), ws.data_ptr(), ws.numel() * 4, stream))
     _stats["calls"] += 1
+    if keepalive is not None:
+        keepalive.append((qx2, qw, y, rowsum_w, rowsum_x, sx, ox, sw, ow, b, ws))
     y = y.reshape(*lead, n)
     if output_quantizer is not None:
         y = output_quantizer(y)
