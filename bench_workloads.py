@@ -50,20 +50,28 @@ class RMSNorm(torch.nn.Module):
         self.eps = eps
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        v = x.float()
-        v = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)
-        return (v.to(x.dtype)) * self.weight
+        return torch.nn.functional.rms_norm(x, (x.shape[-1],), self.weight, self.eps)   # one library kernel
 
 
-def rope(x: torch.Tensor, theta: float = 500000.0) -> torch.Tensor:
-    # x: [B, H, S, D]
-    b, h, s, d = x.shape
-    pos = torch.arange(s, device=x.device, dtype=torch.float32)
-    inv = 1.0 / (theta ** (torch.arange(0, d, 2, device=x.device, dtype=torch.float32) / d))
-    ang = pos[:, None] * inv[None, :]
-    cos, sin = ang.cos().to(x.dtype), ang.sin().to(x.dtype)
-    x1, x2 = x[..., 0::2], x[..., 1::2]
-    return torch.stack((x1 * cos - x2 * sin, x1 * sin + x2 * cos), dim=-1).flatten(-2)
+_ROPE_CACHE: dict = {}
+
+
+def rope_tables(s: int, d: int, device, dtype, theta: float = 500000.0):
+    key = (s, d, str(device), dtype)
+    if key not in _ROPE_CACHE:
+        pos = torch.arange(s, device=device, dtype=torch.float32)
+        inv = 1.0 / (theta ** (torch.arange(0, d, 2, device=device, dtype=torch.float32) / d))
+        ang = torch.cat((pos[:, None] * inv[None, :],) * 2, dim=-1)          # [S, D], half-split layout
+        _ROPE_CACHE[key] = (ang.cos().to(dtype), ang.sin().to(dtype))
+    return _ROPE_CACHE[key]
+
+
+def rope(x: torch.Tensor) -> torch.Tensor:
+    # x: [B, H, S, D]; rotate-half formulation with tables computed once per (S, D)
+    cos, sin = rope_tables(x.shape[-2], x.shape[-1], x.device, x.dtype)
+    half = x.shape[-1] // 2
+    rot = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
+    return x * cos + rot * sin
 
 
 class Attention(torch.nn.Module):

@@ -58,6 +58,19 @@ def all_reduce_ranges(ranges: Sequence[Tuple[torch.Tensor, torch.Tensor]],
             f.copy_(v.reshape(f.shape))
 
 
+def all_reduce_minmax_buffers(buffers: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+                              flags: Optional[Sequence[torch.Tensor]] = None, group=None) -> None:
+    """In-place all-reduce of contiguous (min_buffer, max_buffer) pairs: one MIN and one MAX collective
+    per pair (the estimator keeps all running ranges of a dtype in one pair), plus one MAX for the flags."""
+    if not _active(group):
+        return
+    for mn, mx in buffers:
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    for f in flags or []:
+        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=group)
+
+
 def shard_units(num_units: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> List[int]:
     """Indices of the independent units (layers, weight tensors) this rank owns: ``i % world == rank``."""
     if world_size is None:

@@ -31,9 +31,45 @@ def _param_count(quantizer, data: torch.Tensor) -> int:
     return quantizer.granularity.parameter_dimensionality(data.shape)
 
 
+class _RangeArena:
+    """Running ranges of ALL quantizers of one estimate_ranges block live in a few flat buffers
+    (one min and one max buffer per dtype/device), so the data-parallel exchange at the end of the
+    block is two collectives on contiguous memory -- no packing of hundreds of tiny tensors -- and
+    one flag word serves every quantizer."""
+
+    CHUNK = 1 << 21
+
+    def __init__(self) -> None:
+        self.chunks: dict = {}     # (device, dtype) -> list of [min_buf, max_buf, used]
+        self.flags: dict = {}      # device -> int32[1]
+
+    def take(self, n: int, like: torch.Tensor):
+        key = (like.device, like.dtype)
+        chunks = self.chunks.setdefault(key, [])
+        if not chunks or chunks[-1][2] + n > chunks[-1][0].numel():
+            size = max(self.CHUNK, n)
+            chunks.append([like.new_full((size,), float("inf")), like.new_full((size,), float("-inf")), 0])
+        mn, mx, used = chunks[-1]
+        chunks[-1][2] = used + n
+        return mn[used:used + n], mx[used:used + n]
+
+    def flag(self, device: torch.device) -> torch.Tensor:
+        if device not in self.flags:
+            self.flags[device] = torch.zeros(1, dtype=torch.int32, device=device)
+        return self.flags[device]
+
+    def buffers(self):
+        for chunks in self.chunks.values():
+            for mn, mx, used in chunks:
+                if used:
+                    yield mn[:used], mx[:used]
+
+
 class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
-    def __init__(self, quantizer, disable_quantization: bool = False, eager_checks: bool = False) -> None:
+    def __init__(self, quantizer, disable_quantization: bool = False, eager_checks: bool = False,
+                 arena: Optional[_RangeArena] = None) -> None:
         super().__init__(disable_quantization=disable_quantization)
+        self._arena = arena
         lo, hi = quantizer.quantization_range       # continues from an existing range (minmax.py:198-200)
         self.register_buffer("min", None if lo is None else lo.detach().clone())
         self.register_buffer("max", None if hi is None else hi.detach().clone())
@@ -42,6 +78,8 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
 
     def initialize_parameters(self, quantizer, data: torch.Tensor) -> None:
         n = _param_count(quantizer, data)
+        if self.min is None and self.max is None and self._arena is not None:
+            self.min, self.max = self._arena.take(n, data)
         if self.min is None:
             self.min = data.new_full((n,), float("inf"))
         if self.max is None:
@@ -52,7 +90,8 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             dt = torch.promote_types(self.min.dtype, data.dtype)
             self.min, self.max = self.min.to(device=data.device, dtype=dt), self.max.to(device=data.device, dtype=dt)
         if self.flags is None:
-            self.flags = torch.zeros(1, dtype=torch.int32, device=data.device)
+            self.flags = self._arena.flag(data.device) if self._arena is not None else \
+                torch.zeros(1, dtype=torch.int32, device=data.device)
 
     def estimate_step(self, quantizer, data: torch.Tensor) -> None:
         self.initialize_parameters(quantizer, data)
@@ -136,29 +175,34 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
         self.sync_ranges = sync_ranges or process_group is not None
         self.process_group = process_group
         self._steps: list = []
+        self._arena = _RangeArena()
 
     def prepare(self, module):
         self._check(module)
         step = RunningMinMaxEstimator(module, disable_quantization=self.disable_quantization,
-                                      eager_checks=self.eager_checks)
+                                      eager_checks=self.eager_checks, arena=self._arena)
         self._steps.append((module, step))
         return module.register_override(step)
 
     def finalize(self, prepared: Sequence[tuple]) -> None:
         del prepared
         steps = [(q, s) for q, s in self._steps if s.min is not None]
+        flags = list({id(s.flags): s.flags for _, s in steps if s.flags is not None}.values())
         if self.sync_ranges:
-            from ..distributed import all_reduce_ranges
+            from ..distributed import all_reduce_minmax_buffers, all_reduce_ranges
 
-            all_reduce_ranges([(s.min, s.max) for _, s in steps], [s.flags for _, s in steps], group=self.process_group)
+            arena_ids = {id(mn.untyped_storage()) for mn, _ in self._arena.buffers()}
+            loose = [(s.min, s.max) for _, s in steps if id(s.min.untyped_storage()) not in arena_ids]
+            all_reduce_minmax_buffers(list(self._arena.buffers()), flags, group=self.process_group)
+            all_reduce_ranges(loose, None, group=self.process_group)
             for quantizer, step in steps:
                 quantizer.quantization_range = (step.min, step.max)
         # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks
-        flags = [s.flags for _, s in steps if s.flags is not None]
         if flags and not self.eager_checks:
             if int(torch.stack([f.reshape(()) for f in flags]).max().item()) != 0:
                 raise NotImplementedError("Infinite")
         self._steps = []
+        self._arena = _RangeArena()
 
 
 class SmoothedMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
