@@ -33,6 +33,10 @@ struct EwArgs {
   int rt_needed;    // fake-quant: that round trip can change the value (integer wrap)
   int q_is_int;     // fake-quant: integer code dtype (drops the sign of a zero)
   int tiles_aligned; // tile_numel is a multiple of the vector width: no vector straddles tiles
+  int sat8;          // bounds are exactly [-128, 127]: integer codes use the saturating conversion
+  unsigned long long total_segs;   // tile-streaming kernel: number of (tile, segment) work units
+  unsigned int segs_per_tile;
+  unsigned int seg_vecs;           // vectors per segment (multiple of 32 * EW_UNROLL)
   GenericLayout gl; // generic kernel only
 };
 
@@ -117,7 +121,17 @@ __global__ void __launch_bounds__(EW_THREADS, 4) ew_row_kernel(const EwArgs a) {
     const unsigned int v = vbase + u * EW_THREADS;
     if (v < nvec) xin[u] = ld_stream<InT, EPT>(in + (size_t)v * EPT);
   }
-  unsigned int pcur = 0xffffffffu;
+  // parameters of every vector are requested right behind the data loads, so their latency
+  // overlaps the stream instead of stalling the arithmetic
+  unsigned int pv[EW_UNROLL];
+  float sv[EW_UNROLL], ov[EW_UNROLL];
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; ++u) {
+    const unsigned int v = vbase + u * EW_THREADS;
+    pv[u] = fast_div((v < nvec ? v : 0u) * EPT, a.tdiv);
+    sv[u] = Elem<PT>::to_f(scale[pv[u]]);
+    ov[u] = offset ? Elem<PT>::to_f(offset[pv[u]]) : 0.f;
+  }
   float s = 1.f, o = 0.f;
   SharedRcp k{};
 #pragma unroll
@@ -125,11 +139,10 @@ __global__ void __launch_bounds__(EW_THREADS, 4) ew_row_kernel(const EwArgs a) {
     const unsigned int v = vbase + u * EW_THREADS;
     if (v >= nvec) continue;
     const unsigned int e0 = v * EPT;
-    const unsigned int p0 = fast_div(e0, a.tdiv);
-    if (p0 != pcur) {   // parameters (and the reciprocal) are fetched once per tile, not per vector
-      pcur = p0;
-      s = Elem<PT>::to_f(scale[p0]);
-      o = offset ? rintf(Elem<PT>::to_f(offset[p0])) : 0.f;
+    const unsigned int p0 = pv[u];
+    if (u == 0 || pv[u] != pv[u > 0 ? u - 1 : 0]) {   // the reciprocal is formed once per tile change
+      s = sv[u];
+      o = rintf(ov[u]);
       if constexpr (OP != OP_DEQUANT) k = make_shared_rcp(s);
     }
     float x[EPT], y[EPT], c[EPT];
@@ -141,12 +154,26 @@ __global__ void __launch_bounds__(EW_THREADS, 4) ew_row_kernel(const EwArgs a) {
         for (int i = 0; i < EPT; ++i) y[i] = rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(x[i], o)), s));
       } else {
         bool ok = k.ok;
+        if (a.sat8 && !FLOAT_OUT) {
+          // 8-bit codes into an integer container: rint + clamp(-128, 127) is ONE saturating
+          // conversion (cvt.rni.sat.s8.f32).  NaN would convert to 0, so NaN inputs fail the
+          // magnitude guard below and take the exact path.
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-          // float codes expose the sign of a zero quotient: take the strict guard there
-          float t = rndc<RM>(shared_div<(OP == OP_QUANT) && FLOAT_OUT>(x[i], k, ok));
-          t = rndc<RM>(__fsub_rn(t, o));
-          c[i] = nan_clamp(rintf(t), lo, hi);
+          for (int i = 0; i < EPT; ++i) {
+            float t = rndc<RM>(shared_div<false>(x[i], k, ok));
+            t = rndc<RM>(__fsub_rn(t, o));
+            int ci;
+            asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ci) : "f"(t));
+            c[i] = (float)ci;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < EPT; ++i) {
+            // float codes expose the sign of a zero quotient: take the strict guard there
+            float t = rndc<RM>(shared_div<(OP == OP_QUANT) && FLOAT_OUT>(x[i], k, ok));
+            t = rndc<RM>(__fsub_rn(t, o));
+            c[i] = nan_clamp(rintf(t), lo, hi);
+          }
         }
         if (!ok) {   // rare: scale or quotient outside the proven box -> plain IEEE division
 #pragma unroll
@@ -215,6 +242,117 @@ __global__ void __launch_bounds__(EW_THREADS, 4) ew_row_kernel(const EwArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile-streaming kernel: the tuned path for tiles of at least 32 vectors whose length is a multiple
+// of the vector width (weight rows, whole activations).  One warp owns one (tile, segment): the
+// parameters are fetched and the reciprocal is formed ONCE per warp, then the warp streams up to
+// SEG_VECS 16-byte vectors with UNROLL loads in flight per lane.  No per-vector index division, no
+// parameter reload inside the stream, 64-bit addressing only in the prologue.
+// ------------------------------------------------------------------------------------------------
+constexpr int SEG_VECS_MAX = 1024;   // per-warp segment: up to 16 KB of input, shrunk for small tensors
+
+// exact recomputation of one vector (scale or quotient outside the guard of shared_div)
+template <int OP, int RM, int EPT>
+__device__ __forceinline__ void ew_vector_exact(const float (&x)[EPT], float (&y)[EPT], float s, float o, float lo, float hi) {
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    float t = rndc<RM>(__fdiv_rn(x[i], s));
+    t = rndc<RM>(__fsub_rn(t, o));
+    const float c = nan_clamp(rintf(t), lo, hi);
+    y[i] = (OP == OP_FAKEQUANT) ? rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(c, o)), s)) : c;
+  }
+}
+
+template <int OP, typename InT, typename OutT, int RM>
+__global__ void __launch_bounds__(EW_THREADS, 4) ew_tile_kernel(const EwArgs a) {
+  constexpr int EPT = EwEpt<InT, OutT>::value;
+  constexpr int U = EW_UNROLL;
+  constexpr bool FLOAT_OUT = std::is_same<OutT, float>::value || std::is_same<OutT, __half>::value ||
+                             std::is_same<OutT, __nv_bfloat16>::value;
+  using PT = typename ParamT<RM>::type;
+  const unsigned int lane = threadIdx.x & 31;
+  const unsigned long long seg_id = (unsigned long long)blockIdx.x * (EW_THREADS / 32) + (threadIdx.x >> 5);
+  if (seg_id >= a.total_segs) return;
+  const unsigned long long tile = seg_id / a.segs_per_tile;
+  const unsigned int seg = (unsigned int)(seg_id - tile * a.segs_per_tile);
+  const unsigned int tvec = (unsigned int)(a.tile_numel / EPT);
+  const unsigned int vec0 = seg * a.seg_vecs;
+  const unsigned int nv = (tvec - vec0) < a.seg_vecs ? (tvec - vec0) : a.seg_vecs;
+  const unsigned long long base = tile * a.tile_numel + (unsigned long long)vec0 * EPT;
+  const InT* __restrict__ in = static_cast<const InT*>(a.in) + base;
+  OutT* __restrict__ out = static_cast<OutT*>(a.out) + base;
+
+  const float s = Elem<PT>::to_f(static_cast<const PT*>(a.scale)[tile]);
+  const float o = a.offset ? rintf(Elem<PT>::to_f(static_cast<const PT*>(a.offset)[tile])) : 0.f;
+  const float lo = a.qp.lo, hi = a.qp.hi;
+  SharedRcp k{};
+  if constexpr (OP != OP_DEQUANT) k = make_shared_rcp(s);
+  // integer codes of exactly 8 bits: rint + clamp is one saturating conversion (NaN fails the guard)
+  const bool sat8 = a.sat8 != 0;
+  const bool int_zero = a.q_is_int != 0;       // fake-quant through integer codes: -0 becomes +0
+
+  for (unsigned int j0 = lane; j0 < nv; j0 += 32 * U) {
+    Vec<InT, EPT> xin[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned int j = j0 + u * 32;
+      if (j < nv) xin[u] = ld_stream<InT, EPT>(in + (size_t)j * EPT);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned int j = j0 + u * 32;
+      if (j >= nv) continue;
+      float x[EPT], y[EPT];
+      unpack<InT, EPT>(xin[u], x);
+      if constexpr (OP == OP_DEQUANT) {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) y[i] = rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(x[i], o)), s));
+      } else {
+        float t[EPT];
+        float amax = 0.f, amin = INFINITY;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+          const float q0 = __fmul_rn(x[i], k.r);
+          const float e = __fmaf_rn(-k.s, q0, x[i]);
+          const float q = __fmaf_rn(k.r, e, q0);
+          amax = nan_max(amax, fabsf(q));                    // NaN-propagating: a NaN quotient fails the guard
+          if constexpr (OP == OP_QUANT && FLOAT_OUT) amin = fminf(amin, fabsf(q));
+          t[i] = rndc<RM>(__fsub_rn(rndc<RM>(q), o));
+        }
+        bool ok = k.ok && (amax <= 0x1p60f);
+        if constexpr (OP == OP_QUANT && FLOAT_OUT) ok = ok && (amin >= 0x1p-50f);   // float codes expose the sign of zero
+        if (ok) {
+          if (sat8 && (OP == OP_FAKEQUANT || !FLOAT_OUT)) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+              int ci;
+              asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(ci) : "f"(t[i]));
+              const float c = (float)ci;
+              y[i] = (OP == OP_FAKEQUANT) ? rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(c, o)), s)) : c;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+              float c = nan_clamp(rintf(t[i]), lo, hi);
+              if constexpr (OP == OP_FAKEQUANT) {
+                if (int_zero) c = __fadd_rn(c, 0.0f);
+                y[i] = rndc<RM>(__fmul_rn(rndc<RM>(__fadd_rn(c, o)), s));
+              } else {
+                y[i] = c;
+              }
+            }
+          }
+        } else {
+          ew_vector_exact<OP, RM, EPT>(x, y, s, o, lo, hi);
+        }
+      }
+      Vec<OutT, EPT> yo;
+      pack<OutT, EPT>(y, yo);
+      st_vec<OutT, EPT>(out + (size_t)j * EPT, yo);
+    }
+  }
+}
+
 // tile index of a linear element index under a collapsed layout of any rank
 __device__ __forceinline__ unsigned long long tile_of(unsigned long long e, const GenericLayout& g) {
   unsigned long long p = 0;
@@ -243,8 +381,16 @@ __global__ void __launch_bounds__(256) ew_generic_kernel(const EwArgs a) {
 }
 
 template <int OP, typename InT, typename OutT, int RM>
+static void launch_tile(const EwArgs& a, cudaStream_t st) {
+  const unsigned long long blocks = (a.total_segs + EW_THREADS / 32 - 1) / (EW_THREADS / 32);
+  ew_tile_kernel<OP, InT, OutT, RM><<<(unsigned int)blocks, EW_THREADS, 0, st>>>(a);
+  count_launch();
+}
+
+template <int OP, typename InT, typename OutT, int RM>
 static void launch_row(const EwArgs& a, cudaStream_t st) {
   constexpr int EPT = EwEpt<InT, OutT>::value;
+  if (a.total_segs) { launch_tile<OP, InT, OutT, RM>(a, st); return; }
   const unsigned long long nvec = a.numel / EPT;
   unsigned long long blocks = (nvec + EW_THREADS * EW_UNROLL - 1) / (EW_THREADS * EW_UNROLL);
   if (blocks == 0) blocks = 1;
@@ -342,6 +488,8 @@ static int run_elementwise(int op, EwArgs& a, const ffq_layout_t* layout, double
   // can_support_bitwidth admits iinfo.bits + 2)
   a.rt_needed = (op == OP_FAKEQUANT && is_int_dt(a.q_rt_dt) && num_bits > dt_size(a.q_rt_dt) * 8) ? 1 : 0;
   a.q_is_int = (op == OP_FAKEQUANT && is_int_dt(a.q_rt_dt)) ? 1 : 0;
+  a.sat8 = (op != OP_DEQUANT && a.qp.lo == -128.f && a.qp.hi == 127.f &&
+            (op == OP_QUANT ? is_int_dt(a.out_dt) : (is_int_dt(a.q_rt_dt) && !a.rt_needed))) ? 1 : 0;
 
   // the fast kernel handles chains with a single promoted dtype whose parameters are stored in it
   int rm = -1;
@@ -357,6 +505,36 @@ static int run_elementwise(int op, EwArgs& a, const ffq_layout_t* layout, double
 
   const int in_sz = dt_size(a.in_dt), out_sz = dt_size(a.out_dt), code_sz = a.codes ? dt_size(a.codes_dt) : 0;
   const int p_sz = dt_size(a.s_dt);
+  a.total_segs = 0;
+  if (rm >= 0 && plan.row && aligned16(a.in) && aligned16(a.out) && in_sz > 0 && in_sz <= 4 &&
+      !(op == OP_FAKEQUANT && a.codes != nullptr) && !a.rt_needed) {
+    // tile-streaming kernel: tiles of >= 128 whole vectors (64-bit addressing in its prologue: any size)
+    const int ept = 16 / (in_sz > out_sz ? in_sz : out_sz);
+    const unsigned long long T = a.tile_numel;
+    if (T % ept == 0 && T / ept >= 128 && T / ept < (1ull << 31)) {
+      EwArgs c = a;
+      // enough warps to fill the machine (>= 32 per SM) while keeping >= one full unrolled step per warp
+      const unsigned long long total_vecs = a.numel / ept, quantum = 32ull * EW_UNROLL;
+      unsigned long long sv = total_vecs / (32ull * sm_count());
+      sv = sv / quantum * quantum;
+      if (sv < quantum) sv = quantum;
+      if (sv > (unsigned long long)SEG_VECS_MAX) sv = SEG_VECS_MAX;
+      c.seg_vecs = (unsigned int)sv;
+      c.segs_per_tile = (unsigned int)((T / ept + sv - 1) / sv);
+      c.total_segs = (unsigned long long)plan.num_tiles * c.segs_per_tile;
+      if (c.total_segs / (EW_THREADS / 32) < 0x7fffffffull) {
+        bool ok;
+        if (op == OP_QUANT) ok = dispatch_row<OP_QUANT>(c, rm, st);
+        else if (op == OP_DEQUANT) ok = dispatch_row<OP_DEQUANT>(c, rm, st);
+        else ok = dispatch_row<OP_FAKEQUANT>(c, rm, st);
+        if (ok) {
+          cudaError_t e = cudaPeekAtLastError();
+          if (e != cudaSuccess) { cudaGetLastError(); set_error("kernel launch failed: %s", cudaGetErrorString(e)); return FFQ_ERR_CUDA; }
+          return FFQ_OK;
+        }
+      }
+    }
+  }
   if (rm >= 0 && plan.row && aligned16(a.in) && aligned16(a.out) && in_sz > 0 && in_sz <= 4) {
     // launches of < 2^31 elements each, cut at tile boundaries (a single launch in practice)
     const int ept = 16 / (in_sz > out_sz ? in_sz : out_sz);
