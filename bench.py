@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-layers", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--workload", default="calib", choices=["calib", "w4a16-calib", "wq4"],
+                    help="calib: configs[1] (default, W8A8 8B-shape).  w4a16-calib: configs[4] recipe (W4 g=128 / A16) on "
+                         "--shape.  wq4: configs[2], W4 g=128 weight fake-quant of all linears sharded by layer")
     return ap.parse_args()
 
 
@@ -304,7 +307,18 @@ def run_ours(args):
     torch.manual_seed(0)
     model = bw.DecoderStack(sh, layers=layers, dtype=torch.bfloat16, device=dev)
     bw.init_weights_(model, seed=0)
-    bw.quantize_for_w8a8(ff, model)
+    if args.workload == "w4a16-calib":
+        # W4 per-group (g=128) symmetric weights in an int8 container, A16 per-tensor asymmetric (fp32 codes:
+        # bf16 cannot hold 16 bits, _quantizer_impl.py:44-75); the linear takes the dequantize fallback
+        extra = ff.surrogate_quantized_modules(model)
+        ff.quantize_model(model, extra_conversion=extra)
+        ff.find_quantizers(model, "**/layers/**/[quantizer:parameter/weight]").initialize(
+            ff.nn.LinearQuantizer, num_bits=4, quantized_dtype=torch.int8,
+            granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+        ff.find_quantizers(model, "**/layers/**/[quantizer:activation/input]").initialize(
+            ff.nn.LinearQuantizer, num_bits=16, symmetric=False, granularity=ff.PerTensor(), quantized_dtype=torch.float32)
+    else:
+        bw.quantize_for_w8a8(ff, model)
     model.to(dev)
     from fastforward_b200.nn import qlinear
     qlinear.install()            # W8A8 tcgen05 kernel behind dispatcher "linear"
@@ -503,9 +517,81 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_wq4(args):
+    """configs[2]: W4 per-group (g=128) weight fake-quant of every decoder linear of the 8B-shape model,
+    sharded by layer across the ranks (layer i -> rank i mod N), no data-path collective.  A step = calibrate
+    each owned weight quantizer on its weight (min/max + range->params) and snap the weight in place with the
+    fused QDQ kernel (fuse_qdq_weights).  Reports GB/s of algorithmic traffic (3 x 2 bytes per weight)."""
+    import torch.distributed as dist
+
+    import bench_workloads as bw
+    import fastforward_b200 as ff
+    from fastforward_b200 import _cabi
+    from fastforward_b200.quantization.fuse import calibrate_weight_quantizers, fuse_qdq_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sh = shape_of(args.shape)
+    layers = args.layers or sh.layers
+    mine = list(range(rank, layers, world))
+    model = torch.nn.ModuleList(bw.DecoderLayer(sh, torch.bfloat16, dev) for _ in mine)   # only this rank's layers
+    bw.init_weights_(model, seed=rank)
+    ff.quantize_model(model, extra_conversion=ff.surrogate_quantized_modules(model))
+    ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
+        ff.nn.LinearQuantizer, num_bits=4, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+    model.to(dev)
+    n_weights = sum(m.weight.numel() for m in model.modules() if isinstance(m, torch.nn.Linear))
+
+    def step():
+        calibrate_weight_quantizers(model)
+        fuse_qdq_weights(model)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _cabi.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = t0.elapsed_time(t1) * 1e-3
+    launches = _cabi.launch_count() - l0
+    tot = torch.tensor([dt, float(n_weights)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dt, n_all = float(mx[0]), float(sm[1])
+    else:
+        n_all = float(n_weights)
+    if rank == 0:
+        by = 3 * 2 * n_all * args.steps
+        print(json.dumps({
+            "metric": "W4 g=128 weight fake-quant GB/s (Llama-3-8B-shape, all decoder linears, sharded by layer)",
+            "value": round(by / dt / 1e9, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{sh.name}: {layers} layers x 7 linears = {n_all / 1e9:.2f} G weights, LinearQuantizer(4, PerBlock g=128), "
+                                   "calibrate on the weight + fuse_qdq_weights in place; layer i -> rank i mod N"},
+            "gpu_launches": int(launches), "per_gpu_GBps": round(by / dt / 1e9 / world, 1)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "wq4":
+        run_wq4(a)
     else:
         run_ours(a)

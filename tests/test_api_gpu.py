@@ -252,3 +252,20 @@ def test_fuse_qdq_weights_matches_two_step_and_is_idempotent():
     assert fuse_qdq_weights(m2, rank=1, world_size=2) == 2
     changed = [not torch.equal(lin.weight.detach(), o) for lin, o in zip(m2, orig)]
     assert changed == [False, True, False, True]
+
+
+def test_dynamic_linear_quantizer_module():
+    """reference tests/nn/test_dynamic_linear_quantizer.py: dynamic == static with the exact per-call range."""
+    torch.manual_seed(3)
+    x = torch.randn(4, 8, 32, device=DEV, dtype=torch.bfloat16)
+    dq = ff.nn.DynamicLinearQuantizer(8, granularity=ff.PerChannel(2), symmetric=False)
+    out = dq(x)
+    assert isinstance(out, ff.QuantizedTensor)
+    rq, rs, ro = R.quantize_dynamic_by_tile(x.cpu(), (4, 8, 1), 8.0, False, True, x.dtype)
+    assert bits_equal(out.raw_data, rq) and bits_equal(out.quant_args().scale, rs) and bits_equal(out.quant_args().offset, ro)
+    assert bits_equal(out.dequantize(), R.dequantize_by_tile(rq, rs, (4, 8, 1), ro, x.dtype))
+    xg = torch.randn(16, 16, device=DEV, requires_grad=True)
+    ff.nn.DynamicLinearQuantizer(4)(xg).dequantize().sum().backward()
+    assert torch.equal(xg.grad, torch.ones_like(xg))          # identity backward (affine/_autograd.py:125-133)
+    with pytest.raises(ff.QuantizationError):
+        ff.nn.DynamicLinearQuantizer(8)(torch.empty(0, 4, device=DEV))

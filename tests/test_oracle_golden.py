@@ -164,3 +164,31 @@ def test_bitwidth_guard():
     assert R.can_support_bitwidth(torch.int8, 8) and R.can_support_bitwidth(torch.float16, 12)
     with pytest.raises(RuntimeError):
         R.quantize_by_tile(torch.randn(4), torch.tensor(1.0), (4,), 16, torch.bfloat16)
+
+
+# ---- the plain-C restatement (oracle/ffq_oracle.c) against the same reference vectors -----------------
+def test_c_oracle_matches_reference_vectors():
+    from oracle import c_oracle as CO
+
+    lib = CO.load()
+    n = 0
+    for c in STATIC:
+        if not (c["x"].dtype is torch.float32 and c["scale"].dtype is torch.float32 and c["qdtype"] is torch.float32
+                and (c["offset"] is None or c["offset"].dtype is torch.float32)):
+            continue
+        n += 1
+        q = CO.quantize(lib, c["x"], c["scale"], c["tile"], c["num_bits"], c["offset"])
+        assert bits_equal(q, c["q"])
+        assert bits_equal(CO.dequantize(lib, q, c["scale"], c["tile"], c["offset"]), c["y"])
+        dx, dscale, doffset = CO.backward(lib, c["x"], c["grad"], c["scale"], c["tile"], c["num_bits"], c["offset"])
+        assert bits_equal(dx, c["dx"])
+        torch.testing.assert_close(dscale.float().reshape(c["dscale"].shape), c["dscale"], rtol=1e-5, atol=1e-5)
+        mn, mx = CO.minmax(lib, c["x"], c["tile"], c["scale"].numel())
+        rmn, rmx = R.tile_minmax(c["x"], c["tile"])
+        assert bits_equal(mn, rmn) and bits_equal(mx, rmx)
+    assert n > 100
+    for c in QUANTIZER:
+        s, o = CO.params_for_range(lib, c["range_min"], c["range_max"], c["num_bits"], c["symmetric"], c["allow_one_sided"])
+        assert bits_equal(s, c["scale"])
+        if c["offset"] is not None:
+            assert bits_equal(o if o is not None else torch.zeros_like(s), c["offset"])
