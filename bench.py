@@ -395,12 +395,14 @@ def run_ours(args):
     lc0 = _cabi.launch_count()
     region(1, dev_tokens, e2e=False, graph=False)
     launches_per_step = (_cabi.launch_count() - lc0) / (1 + args.warmup)
+    reset_quantizers()
     census = KernelCensus(ff)
-    census.install()
     with torch.no_grad(), ff.estimate_ranges(model, ff.range_setting.running_minmax()):
         static_tokens.copy_(dev_tokens[0])
-        model(static_tokens)                      # ONE recorded eager step (ranges already initialised)
-    census.remove()
+        model(static_tokens)                      # first forward of a block materialises the lazy parameters
+        census.install()
+        model(static_tokens)                      # ONE recorded steady-state eager step
+        census.remove()
     per_op = census.replay()
     qlin = qlinear.stats()
 

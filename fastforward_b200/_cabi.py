@@ -103,7 +103,7 @@ def _load() -> ctypes.CDLL:
         "ffq_dequantize": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, lp, vp]),
         "ffq_fakequant_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, lp, dbl, vp]),
         "ffq_quantize_bwd": (i32, [vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, i32, lp, dbl, vp, sz, vp]),
-        "ffq_minmax": (i32, [vp, i32, vp, vp, vp, vp, vp, lp, vp, sz, vp]),
+        "ffq_minmax": (i32, [vp, i32, vp, vp, vp, vp, i32, vp, lp, vp, sz, vp]),
         "ffq_params_for_range": (i32, [vp, vp, i32, i64, dbl, i32, i32, i32, vp, i32, vp, i32, vp, sz, vp]),
         "ffq_dynamic_quantize": (i32, [vp, i32, vp, i32, vp, vp, lp, dbl, i32, i32, vp, sz, vp]),
         "ffq_qlinear_w8a8": (i32, [vp, vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]),

@@ -429,7 +429,8 @@ static int ept_of(int dt) {
 struct MmArgs {
   const void* x; int x_dt;
   void* tile_min; void* tile_max;     // optional, dtype x_dt
-  void* run_min; void* run_max;       // optional, dtype x_dt, updated in place
+  void* run_min; void* run_max;       // optional, dtype run_dt, updated in place
+  int run_dt;
   int32_t* flags;                     // optional
   float* part;                        // [2][num_tiles*S] when S > 1
   unsigned long long numel, tile_numel, num_tiles, seg_len; unsigned int S;
@@ -439,8 +440,8 @@ struct MmArgs {
 __device__ __forceinline__ void mm_emit(const MmArgs& a, unsigned long long tile, float mn, float mx) {
   if (a.tile_min) store_from_float(a.tile_min, a.x_dt, tile, mn);
   if (a.tile_max) store_from_float(a.tile_max, a.x_dt, tile, mx);
-  if (a.run_min) store_from_float(a.run_min, a.x_dt, tile, nan_min(load_as_float(a.run_min, a.x_dt, tile), mn));
-  if (a.run_max) store_from_float(a.run_max, a.x_dt, tile, nan_max(load_as_float(a.run_max, a.x_dt, tile), mx));
+  if (a.run_min) store_from_float(a.run_min, a.run_dt, tile, nan_min(load_as_float(a.run_min, a.run_dt, tile), mn));
+  if (a.run_max) store_from_float(a.run_max, a.run_dt, tile, nan_max(load_as_float(a.run_max, a.run_dt, tile), mx));
   if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
 }
 
@@ -793,7 +794,7 @@ int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dtype, voi
 }
 
 int ffq_minmax(const void* x, int x_dtype, void* tile_min, void* tile_max, void* run_min, void* run_max,
-               int32_t* flags, const ffq_layout_t* layout, void* workspace, size_t workspace_bytes,
+               int run_dtype, int32_t* flags, const ffq_layout_t* layout, void* workspace, size_t workspace_bytes,
                void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_dtype == FFQ_F64 || !(is_float_dt(x_dtype) || is_int_dt(x_dtype))) {
@@ -807,6 +808,11 @@ int ffq_minmax(const void* x, int x_dtype, void* tile_min, void* tile_max, void*
   MmArgs a{};
   a.x = x; a.x_dt = x_dtype; a.tile_min = tile_min; a.tile_max = tile_max;
   a.run_min = run_min; a.run_max = run_max; a.flags = flags;
+  a.run_dt = (run_min || run_max) ? run_dtype : x_dtype;
+  if ((run_min || run_max) && (run_dtype == FFQ_F64 || !(is_float_dt(run_dtype) || is_int_dt(run_dtype)))) {
+    set_error("minmax: unsupported running-range dtype %s", dt_name(run_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
   a.numel = plan.numel; a.tile_numel = plan.tile_numel; a.num_tiles = plan.num_tiles;
   a.gl = make_generic_layout(plan);
   a.S = 1; a.seg_len = plan.tile_numel;
@@ -902,7 +908,7 @@ int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtype, float
   // only if we store through the data dtype -- ffq_minmax does (tile_min has dtype x_dtype).
   char* tmin = ws + seg_bytes + PR_MAX_PARTS * sizeof(float);
   char* tmax = tmin + (size_t)plan.num_tiles * 8;
-  rc = ffq_minmax(x, x_dtype, tmin, tmax, nullptr, nullptr, nullptr, layout, ws, seg_bytes, stream);
+  rc = ffq_minmax(x, x_dtype, tmin, tmax, nullptr, nullptr, FFQ_NONE, nullptr, layout, ws, seg_bytes, stream);
   if (rc != FFQ_OK) return rc;
   rc = ffq_params_for_range(tmin, tmax, x_dtype, plan.num_tiles, num_bits, symmetric, allow_one_sided, 1,
                             scale_out, FFQ_F32, offset_out, FFQ_F32, pr_part, PR_MAX_PARTS * sizeof(float), stream);

@@ -77,7 +77,8 @@ def _prep(data: torch.Tensor, tile_size, what: str = "data"):
     C.require_cuda(data, what)
     tile = _tile(data, tile_size)
     shape = tuple(data.shape)
-    layout = C.make_layout(shape, tile)
+    # an empty tensor is returned untouched by the reference before any tile check (tiled_tensor.py:85-86)
+    layout = C.make_layout(shape, tile) if data.numel() else None
     return data.detach().contiguous(), shape, tile, layout
 
 
@@ -247,6 +248,7 @@ def _minmax_call(x, layout, tile_min, tile_max, run_min, run_max, flags):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
     C.check(C.lib.ffq_minmax(
         x.data_ptr(), C.dtype_tag(x.dtype), C.ptr(tile_min), C.ptr(tile_max), C.ptr(run_min), C.ptr(run_max),
+        C.dtype_tag(run_min.dtype if run_min is not None else None),
         C.ptr(flags), ctypes.byref(layout), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
 
 
@@ -273,8 +275,9 @@ def running_minmax_update_(
     nt = _num_tiles(shape, tile)
     for t, name in ((run_min, "run_min"), (run_max, "run_max")):
         C.require_cuda(t, name)
-        if t.numel() != nt or t.dtype != x.dtype or not t.is_contiguous():
-            raise RuntimeError(f"{name} must be a contiguous {x.dtype} tensor with {nt} elements")
+        if t.numel() != nt or not t.is_contiguous() or t.dtype != run_min.dtype or \
+                torch.promote_types(t.dtype, x.dtype) != t.dtype:
+            raise RuntimeError(f"{name} must be a contiguous tensor with {nt} elements whose dtype holds {x.dtype}")
     if flags is not None and (flags.dtype != torch.int32 or not flags.is_cuda):
         raise RuntimeError("flags must be a CUDA int32 tensor")
     _minmax_call(x, layout, None, None, run_min, run_max, flags)

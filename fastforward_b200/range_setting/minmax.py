@@ -97,10 +97,9 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         self.initialize_parameters(quantizer, data)
         with torch.no_grad():
             tile = quantizer.granularity.tile_size(data.shape)
-            x = data.detach()
-            if x.dtype != self.min.dtype:
-                x = x.to(self.min.dtype)
-            ops.running_minmax_update_(self.min, self.max, x, tile, self.flags)
+            # the running range may be wider than the data (an fp32 range continued with bf16 data):
+            # the kernel reduces in the data dtype and merges into the range's dtype, as torch.min promotes
+            ops.running_minmax_update_(self.min, self.max, data.detach(), tile, self.flags)
             if self._eager:
                 self.check_finite()
         quantizer.quantization_range = (self.min, self.max)

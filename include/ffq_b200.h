@@ -132,14 +132,16 @@ FFQ_API int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dt
 
 /* ---- a7: per-tile min/max, optionally merged into running ranges -------------------------
  * tile_min/tile_max (dtype of x, may be NULL) receive this batch's per-tile extrema.
- * If run_min/run_max are non-NULL they are updated in place: run_min = min(run_min, tile_min),
- * run_max = max(run_max, tile_max) (NaN propagates, as torch.min/torch.max do).
+ * If run_min/run_max are non-NULL (dtype run_dtype: the data dtype, or a wider float when an
+ * existing fp32 range is being continued with bf16/fp16 data -- torch.min promotes) they are
+ * updated in place: run_min = min(run_min, tile_min), run_max = max(run_max, tile_max) (NaN
+ * propagates, as torch.min/torch.max do).
  * If `flags` (int32[1], device) is non-NULL, bit 0 is OR-ed in when any tile extremum of this
  * batch is +-inf -- the condition for which the reference raises NotImplementedError
  * (range_setting/minmax.py:233-234); the host checks it at its next sync point.
  * replaces: range_setting/minmax.py:226-237 (RunningMinMaxEstimator.estimate_step). */
 FFQ_API int ffq_minmax(const void* x, int x_dtype, void* tile_min, void* tile_max,
-               void* run_min, void* run_max, int32_t* flags,
+               void* run_min, void* run_max, int run_dtype, int32_t* flags,
                const ffq_layout_t* layout, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a6: range -> (scale, offset), sync-free ---------------------------------------------

@@ -269,3 +269,20 @@ def test_dynamic_linear_quantizer_module():
     assert torch.equal(xg.grad, torch.ones_like(xg))          # identity backward (affine/_autograd.py:125-133)
     with pytest.raises(ff.QuantizationError):
         ff.nn.DynamicLinearQuantizer(8)(torch.empty(0, 4, device=DEV))
+
+
+def test_continue_calibration_from_existing_fp32_range():
+    """minmax.py:198-200: an estimator created on an initialised quantizer continues from its (fp32)
+    range; with bf16 data torch.min promotes to fp32 -- no conversion pass over the data here."""
+    torch.manual_seed(5)
+    q = ff.nn.LinearQuantizer(8, symmetric=False, granularity=ff.PerChannel(0), device=DEV)
+    a = torch.randn(8, 64, dtype=torch.bfloat16)
+    b = torch.randn(8, 64, dtype=torch.bfloat16) * 2
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax):
+        q(a.to(DEV))
+    lo0, hi0 = (t.detach().cpu() for t in q.quantization_range)
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax):
+        q(b.to(DEV))
+    mn, mx = R.running_minmax_step(lo0, hi0, b, (1, 64))          # fp32 running range, bf16 data
+    s, o = R.parameters_for_range(mn, mx, 8, False, True)
+    assert bits_equal(q.scale.detach(), s) and bits_equal(q.offset.detach(), o)
