@@ -77,9 +77,14 @@ def make_layout(shape: tuple, tile: tuple) -> Layout:
         )
     lay = Layout()
     lay.rank = len(shape)
+    ntiles = 1
     for i, (d, t) in enumerate(zip(shape, tile)):
         lay.dims[i] = d
         lay.tile[i] = t
+        ntiles *= d // t
+    lay.ref = ctypes.byref(lay)      # cached: the object lives in the lru_cache for the life of the process
+    lay.num_tiles = ntiles
+    lay.ws = {}                      # (kind, dtype) -> workspace bytes
     return lay
 
 
@@ -155,7 +160,12 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def current_stream(device: torch.device) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -168,4 +178,24 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
 
 
 def workspace_bytes(kind: int, layout: Layout, dtype: torch.dtype) -> int:
-    return int(lib.ffq_workspace_bytes(kind, ctypes.byref(layout), dtype_tag(dtype)))
+    key = (kind, dtype)
+    cache = getattr(layout, "ws", None)
+    if cache is not None and key in cache:
+        return cache[key]
+    n = int(lib.ffq_workspace_bytes(kind, ctypes.byref(layout), dtype_tag(dtype)))
+    if cache is not None:
+        cache[key] = n
+    return n
+
+
+_scratch: dict = {}
+
+
+def scratch(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Small persistent per-(device, stream) scratch buffer for parameter-sized kernels."""
+    key = (device.index, current_stream(device))
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 8192), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf

@@ -519,8 +519,12 @@ static int run_elementwise(int op, EwArgs& a, const ffq_layout_t* layout, double
       sv = sv / quantum * quantum;
       if (sv < quantum) sv = quantum;
       if (sv > (unsigned long long)SEG_VECS_MAX) sv = SEG_VECS_MAX;
+      // equal segments within a tile (a 1024-vector row is 2 x 512, not 768 + 256)
+      const unsigned long long tvec = T / ept;
+      const unsigned long long nseg = (tvec + sv - 1) / sv;
+      sv = ((tvec + nseg - 1) / nseg + quantum - 1) / quantum * quantum;
       c.seg_vecs = (unsigned int)sv;
-      c.segs_per_tile = (unsigned int)((T / ept + sv - 1) / sv);
+      c.segs_per_tile = (unsigned int)((tvec + sv - 1) / sv);
       c.total_segs = (unsigned long long)plan.num_tiles * c.segs_per_tile;
       if (c.total_segs / (EW_THREADS / 32) < 0x7fffffffull) {
         bool ok;

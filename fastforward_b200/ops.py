@@ -60,6 +60,8 @@ def _param(p: Optional[torch.Tensor], ntiles: int, device: torch.device, what: s
     reference's ``scale[:, None]`` does; any other size mismatch is the reference's RuntimeError."""
     if p is None:
         return None
+    if p.dim() == 1 and p.numel() == ntiles and p.device == device and p.is_contiguous():
+        return p          # the common case: nothing to reshape, expand or copy
     if p.device != device:
         raise RuntimeError(f"Expected all tensors to be on the same device, but '{what}' is on {p.device} and data on {device}")
     p = p.detach().reshape(-1)
@@ -79,7 +81,7 @@ def _prep(data: torch.Tensor, tile_size, what: str = "data"):
     shape = tuple(data.shape)
     # an empty tensor is returned untouched by the reference before any tile check (tiled_tensor.py:85-86)
     layout = C.make_layout(shape, tile) if data.numel() else None
-    return data.detach().contiguous(), shape, tile, layout
+    return (data if data.is_contiguous() else data.contiguous()), shape, tile, layout
 
 
 # ------------------------------------------------------------------------------------------
@@ -101,13 +103,13 @@ def quantize_by_tile(
     q = torch.empty(shape, dtype=out_dtype, device=x.device)
     if x.numel() == 0:
         return q
-    nt = _num_tiles(shape, tile)
+    nt = layout.num_tiles
     s = _param(scale, nt, x.device, "scale")
     o = _param(offset, nt, x.device, "offset")
     C.check(C.lib.ffq_quantize(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), C.dtype_tag(out_dtype),
         s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
-        ctypes.byref(layout), float(num_bits), C.current_stream(x.device)))
+        layout.ref, float(num_bits), C.current_stream(x.device)))
     return q
 
 
@@ -126,13 +128,13 @@ def dequantize_by_tile(
     y = torch.empty(shape, dtype=out_dtype, device=q.device)
     if q.numel() == 0:
         return y
-    nt = _num_tiles(shape, tile)
+    nt = layout.num_tiles
     s = _param(scale, nt, q.device, "scale")
     o = _param(offset, nt, q.device, "offset")
     C.check(C.lib.ffq_dequantize(
         q.data_ptr(), C.dtype_tag(q.dtype), y.data_ptr(), C.dtype_tag(out_dtype),
         s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
-        ctypes.byref(layout), C.current_stream(q.device)))
+        layout.ref, C.current_stream(q.device)))
     return y
 
 
@@ -155,14 +157,14 @@ def fake_quantize_by_tile(
     y = torch.empty(shape, dtype=out_dtype, device=x.device)
     codes = torch.empty(shape, dtype=q_dtype, device=x.device) if return_codes else None
     if x.numel() > 0:
-        nt = _num_tiles(shape, tile)
+        nt = layout.num_tiles
         s = _param(scale, nt, x.device, "scale")
         o = _param(offset, nt, x.device, "offset")
         C.check(C.lib.ffq_fakequant_fwd(
             x.data_ptr(), C.dtype_tag(x.dtype), y.data_ptr(), C.dtype_tag(out_dtype),
             C.ptr(codes), C.dtype_tag(q_dtype),
             s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
-            ctypes.byref(layout), float(num_bits), C.current_stream(x.device)))
+            layout.ref, float(num_bits), C.current_stream(x.device)))
     return (y, codes) if return_codes else y
 
 
@@ -190,7 +192,7 @@ def quantize_by_tile_backward(
         if offset is not None:
             doffset.zero_()
         return [dx, dscale, doffset]
-    nt = _num_tiles(shape, tile)
+    nt = layout.num_tiles
     s = _param(scale, nt, x.device, "scale")
     o = _param(offset, nt, x.device, "offset")
     if dscale.numel() != nt:  # one-element scale broadcast over many tiles: reduce afterwards
@@ -204,7 +206,7 @@ def quantize_by_tile_backward(
         x.data_ptr(), C.dtype_tag(x.dtype), g.data_ptr(), C.dtype_tag(g.dtype), dx.data_ptr(),
         dscale_full.data_ptr(), C.ptr(doffset_full),
         s.data_ptr(), C.dtype_tag(s.dtype), C.ptr(o), C.dtype_tag(o.dtype if o is not None else None),
-        ctypes.byref(layout), float(num_bits), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
+        layout.ref, float(num_bits), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
     if dscale_full is not dscale:
         dscale.copy_(dscale_full.sum().reshape(scale.shape))
         if offset is not None:
@@ -235,7 +237,7 @@ def quantize_dynamic_by_tile(
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     C.check(C.lib.ffq_dynamic_quantize(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), C.dtype_tag(out_dtype),
-        scale.data_ptr(), offset.data_ptr(), ctypes.byref(layout), float(num_bits),
+        scale.data_ptr(), offset.data_ptr(), layout.ref, float(num_bits),
         int(bool(symmetric)), int(bool(allow_one_sided)), ws.data_ptr(), ws_bytes, C.current_stream(x.device)))
     return q, scale, offset
 
@@ -249,7 +251,7 @@ def _minmax_call(x, layout, tile_min, tile_max, run_min, run_max, flags):
     C.check(C.lib.ffq_minmax(
         x.data_ptr(), C.dtype_tag(x.dtype), C.ptr(tile_min), C.ptr(tile_max), C.ptr(run_min), C.ptr(run_max),
         C.dtype_tag(run_min.dtype if run_min is not None else None),
-        C.ptr(flags), ctypes.byref(layout), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
+        C.ptr(flags), layout.ref, C.ptr(ws), ws_bytes, C.current_stream(x.device)))
 
 
 def tile_minmax(data: torch.Tensor, tile_size) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -290,8 +292,8 @@ def parameters_for_range_(
     """Device-side, sync-free ``parameters_for_range`` (quantization/affine/range.py:54-122) writing
     straight into a quantizer's ``scale`` / ``offset`` storage (nn/linear_quantizer.py:347-357)."""
     C.require_cuda(min_range, "min_range")
-    mn = min_range.detach().reshape(-1).contiguous()
-    mx = max_range.detach().reshape(-1).contiguous()
+    mn = min_range if (min_range.dim() == 1 and min_range.is_contiguous()) else min_range.detach().reshape(-1).contiguous()
+    mx = max_range if (max_range.dim() == 1 and max_range.is_contiguous()) else max_range.detach().reshape(-1).contiguous()
     if mn.dtype != mx.dtype:
         common = torch.promote_types(mn.dtype, mx.dtype)
         mn, mx = mn.to(common), mx.to(common)
@@ -300,7 +302,7 @@ def parameters_for_range_(
         raise RuntimeError("parameters_for_range_: min, max, scale and offset must have the same number of elements")
     if not scale_out.is_contiguous() or (offset_out is not None and not offset_out.is_contiguous()):
         raise RuntimeError("parameters_for_range_: outputs must be contiguous")
-    ws = torch.empty(4096, dtype=torch.uint8, device=mn.device)
+    ws = C.scratch(mn.device, 4096)
     C.check(C.lib.ffq_params_for_range(
         mn.data_ptr(), mx.data_ptr(), C.dtype_tag(mn.dtype), n, float(num_bits),
         int(bool(symmetric)), int(bool(allow_one_sided)), int(bool(round_offset)),

@@ -88,8 +88,15 @@ class FakeQuantizeAffine(torch.autograd.Function):
         return dx, dscale, (doffset if offset is not None else None), None, None, None, None
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
 def quantize_affine(data, scale, offset, tile_size, num_bits: int, quantized_dtype: Optional[torch.dtype]):
     dt = _float_dtype(data)
+    if not _needs_grad(data, scale, offset):      # inference / calibration: no autograd node to build
+        return ops.quantize_by_tile(data, _tensor_or_none(scale, dt, data.device), _resolve_tile(data, tile_size), num_bits,
+                                    quantized_dtype or data.dtype, _tensor_or_none(offset, dt, data.device))
     return QuantizeStaticAffine.apply(
         data, _tensor_or_none(scale, dt, data.device), _tensor_or_none(offset, dt, data.device), tile_size, num_bits,
         quantized_dtype)
@@ -98,6 +105,9 @@ def quantize_affine(data, scale, offset, tile_size, num_bits: int, quantized_dty
 def dequantize_affine(data, scale, offset, tile_size, dtype: Optional[torch.dtype]):
     if dtype is None:
         dtype = _float_dtype(data)
+    if not _needs_grad(data, scale, offset):
+        return ops.dequantize_by_tile(data, _tensor_or_none(scale, dtype, data.device), _resolve_tile(data, tile_size),
+                                      _tensor_or_none(offset, dtype, data.device), dtype)
     return DequantizeAffine.apply(
         data, _tensor_or_none(scale, dtype, data.device), _tensor_or_none(offset, dtype, data.device), tile_size, dtype)
 

@@ -252,3 +252,27 @@ def test_shared_reciprocal_division_is_ieee_exact():
     bad, acc, acc_strict, bad_strict = counts.tolist()
     assert bad == 0 and bad_strict == 0, counts.tolist()
     assert acc > (1 << 28) and acc_strict > (1 << 28), counts.tolist()   # the guard accepts the bulk
+
+
+def test_host_buffer_entry_point():
+    """ffq_fakequant_fwd_bwd_host: the end-to-end C-ABI call with HOST buffers (H2D, two kernels, D2H)."""
+    import ctypes
+    from fastforward_b200 import _cabi as C
+
+    torch.manual_seed(11)
+    shape, tile = (512, 1024), (1, 1024)
+    x, g = torch.randn(shape), torch.randn(shape)
+    scale = (x.abs().amax(1) * 0.6 / 128).contiguous()
+    offset = (torch.randn(shape[0]) * 3).contiguous()
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    dsc, dof = torch.empty(shape[0]), torch.empty(shape[0])
+    lay = C.make_layout(shape, tile)
+    C.check(C.lib.ffq_fakequant_fwd_bwd_host(x.data_ptr(), g.data_ptr(), C.dtype_tag(x.dtype), y.data_ptr(), dx.data_ptr(),
+                                              dsc.data_ptr(), dof.data_ptr(), scale.data_ptr(), offset.data_ptr(),
+                                              ctypes.byref(lay), 8.0, 0))
+    q = R.quantize_by_tile(x, scale, tile, 8, x.dtype, offset)
+    assert bits_equal(y, R.dequantize_by_tile(q, scale, tile, offset, x.dtype))
+    rdx, rdsc, rdof = R.quantize_by_tile_backward_f64(x, g, scale, tile, 8, offset)
+    assert bits_equal(dx, rdx)
+    torch.testing.assert_close(dsc.double(), rdsc, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(dof.double(), rdof, rtol=1e-5, atol=1e-4)
