@@ -51,35 +51,67 @@ __device__ __forceinline__ void bwd_terms(float x, float g, float s, float o, co
 }
 
 // fast path: all EPT elements share a tile and the whole chain has one promoted dtype RM
-template <int RM, int EPT>
-__device__ __forceinline__ void bwd_vector(const float (&x)[EPT], const float (&g)[EPT], float (&dx)[EPT], float s,
-                                           float o, const BParams& p, float& sum_sc, float& sum_off) {
-  const SharedRcp k = make_shared_rcp(s);
-  bool ok = k.ok;
+// per-tile constants of the fast path: formed once per warp / CTA (once per vector for small tiles)
+struct BwdTile {
+  SharedRcp k;
+  float o, bound_lo, bound_hi;
+};
+template <int RM>
+__device__ __forceinline__ BwdTile make_bwd_tile(float s, float o, const BParams& p) {
+  BwdTile t;
+  t.k = make_shared_rcp(s);
+  t.o = o;
   const float o_s = rndc<RM>(o);
-  const float bound_lo = rndc<RM>(__fadd_rn(p.lo_s, o_s)), bound_hi = rndc<RM>(__fadd_rn(p.hi_s, o_s));
-  float sc = 0.f, off = 0.f;
+  t.bound_lo = rndc<RM>(__fadd_rn(p.lo_s, o_s));
+  t.bound_hi = rndc<RM>(__fadd_rn(p.hi_s, o_s));
+  return t;
+}
+
+// exact element (plain IEEE division), single promoted dtype RM
+template <int RM>
+__device__ __forceinline__ void bwd_elem_exact(float x, float g, const BwdTile& t, const BParams& p, float& dx,
+                                               float& dsc, float& doff) {
+  const float s = t.k.s;
+  float pre = rndc<RM>(__fdiv_rn(x, s));
+  pre = rndc<RM>(__fsub_rn(pre, t.o));
+  const float q = rintf(pre);
+  const bool below = q < p.lo, above = q > p.hi, clip = below || above;
+  dx = clip ? 0.f : g;
+  doff = clip ? rndc<RM>(__fmul_rn(s, g)) : 0.f;
+  const float v = clip ? (below ? t.bound_lo : t.bound_hi) : rndc<RM>(__fsub_rn(q, pre));
+  dsc = rndc<RM>(__fmul_rn(v, g));
+}
+
+// fast path: all EPT elements share a tile and the whole chain has one promoted dtype RM.
+// The quotient comes from the shared reciprocal; the vector is redone exactly when the scale or any
+// quotient leaves the box [2^-50, 2^60] in which that quotient is proven to equal __fdiv_rn (this
+// includes vectors containing exact zeros -- rare in dense weights/activations).
+template <int RM, int EPT>
+__device__ __forceinline__ void bwd_vector(const float (&x)[EPT], const float (&g)[EPT], float (&dx)[EPT],
+                                           const BwdTile& t, const BParams& p, float& sum_sc, float& sum_off) {
+  const float s = t.k.s, r = t.k.r;
+  float sc = 0.f, off = 0.f, amax = 0.f, amin = INFINITY;
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    // exactness box of shared_div, plus: a non-zero dividend below 2^-90 leaves the box
-    ok = ok && (fabsf(x[i]) >= 0x1p-90f || x[i] == 0.f);
-    float pre = rndc<RM>(shared_div<false>(x[i], k, ok));
-    pre = rndc<RM>(__fsub_rn(pre, o));
+    const float q0 = __fmul_rn(x[i], r);
+    const float e = __fmaf_rn(-s, q0, x[i]);
+    const float quo = __fmaf_rn(r, e, q0);
+    amax = nan_max(amax, fabsf(quo));
+    amin = fminf(amin, fabsf(quo));
+    const float pre = rndc<RM>(__fsub_rn(rndc<RM>(quo), t.o));
     const float q = rintf(pre);
-    const bool below = q < p.lo, above = q > p.hi;
-    const bool clip = below || above;
+    const bool below = q < p.lo, above = q > p.hi, clip = below || above;
     dx[i] = clip ? 0.f : g[i];
-    off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
-    const float resid = rndc<RM>(__fsub_rn(q, pre));
-    const float v = clip ? (below ? bound_lo : bound_hi) : resid;
+    if (p.has_offset) off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
+    const float v = clip ? (below ? t.bound_lo : t.bound_hi) : rndc<RM>(__fsub_rn(q, pre));
     sc += rndc<RM>(__fmul_rn(v, g[i]));
   }
-  if (!ok) {   // rare: recompute the vector with plain IEEE division
+  if (!(t.k.ok && amax <= 0x1p60f && amin >= 0x1p-50f)) {
     sc = 0.f; off = 0.f;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
       float dsc, doff;
-      bwd_terms(x[i], g[i], s, o, p, dx[i], dsc, doff);
+      bwd_elem_exact<RM>(x[i], g[i], t, p, dx[i], dsc, doff);
       sc += dsc; off += doff;
     }
   }
@@ -137,10 +169,17 @@ template <typename T> struct BwdUnroll { static constexpr int value = sizeof(T) 
 // --- small tiles: one LANES-wide group per tile -------------------------------------------
 // T is the dtype of x, g and dx (autograd hands back the gradient in the dtype of the output);
 // mixed x/g dtypes take the generic kernel.
+template <int RM> struct RParamT { using type = float; };
+template <> struct RParamT<RM_BF16> { using type = __nv_bfloat16; };
+template <> struct RParamT<RM_F16> { using type = __half; };
+
 template <typename T, int LANES, int RM>
 __global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_group_kernel(const BwdArgs a) {
   constexpr int EPT = 16 / sizeof(T);
   constexpr int U = BwdUnroll<T>::value;
+  using PT = typename RParamT<RM>::type;      // the fast path requires scale/offset stored in the chain's dtype
+  const PT* __restrict__ scale = static_cast<const PT*>(a.scale);
+  const PT* __restrict__ offset = static_cast<const PT*>(a.offset);
   const T* __restrict__ x = static_cast<const T*>(a.x);
   const T* __restrict__ g = static_cast<const T*>(a.g);
   T* __restrict__ dx = static_cast<T*>(a.dx);
@@ -148,12 +187,16 @@ __global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_group_kernel(const BwdA
   const unsigned long long vbase = (unsigned long long)blockIdx.x * (RD_THREADS * U) + threadIdx.x;
 
   Vec<T, EPT> xv[U], gv[U];
+  float sv[U], ov[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const unsigned long long v = vbase + (unsigned long long)u * RD_THREADS;
+    sv[u] = 1.f; ov[u] = 0.f;
     if (v < nvec) {
       xv[u] = ld_stream<T, EPT>(x + v * EPT);
       gv[u] = ld_stream<T, EPT>(g + v * EPT);
+      sv[u] = Elem<PT>::to_f(scale[v / LANES]);          // requested with the data: latency overlaps the stream
+      if (offset) ov[u] = Elem<PT>::to_f(offset[v / LANES]);
     }
   }
 #pragma unroll
@@ -163,12 +206,13 @@ __global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_group_kernel(const BwdA
     const unsigned long long tile = v / LANES;
     float sum_sc = 0.f, sum_off = 0.f;
     if (live) {
-      const float s = load_as_float(a.scale, a.s_dt, tile);
-      const float o = load_offset(a.offset, a.o_dt, tile);
+      const float s = sv[u];
+      const float o = rintf(ov[u]);
       float xf[EPT], gf[EPT], df[EPT];
       unpack<T, EPT>(xv[u], xf);
       unpack<T, EPT>(gv[u], gf);
-      bwd_vector<RM, EPT>(xf, gf, df, s, o, a.bp, sum_sc, sum_off);
+      const BwdTile bt = make_bwd_tile<RM>(s, o, a.bp);
+      bwd_vector<RM, EPT>(xf, gf, df, bt, a.bp, sum_sc, sum_off);
       Vec<T, EPT> d;
       pack<T, EPT>(df, d);
       st_vec<T, EPT>(dx + v * EPT, d);
@@ -190,6 +234,7 @@ __device__ __forceinline__ void bwd_stream(const T* __restrict__ x, const T* __r
                                            float o, const BParams& bp, float& sum_sc, float& sum_off) {
   constexpr int U = BwdUnroll<T>::value;
   const unsigned int step = nthreads * EPT;
+  const BwdTile bt = make_bwd_tile<RM>(s, o, bp);
   for (unsigned int i0 = tid * EPT; i0 < len; i0 += step * U) {
     Vec<T, EPT> xv[U], gv[U];
 #pragma unroll
@@ -207,7 +252,7 @@ __device__ __forceinline__ void bwd_stream(const T* __restrict__ x, const T* __r
         float xf[EPT], gf[EPT], df[EPT];
         unpack<T, EPT>(xv[u], xf);
         unpack<T, EPT>(gv[u], gf);
-        bwd_vector<RM, EPT>(xf, gf, df, s, o, bp, sum_sc, sum_off);
+        bwd_vector<RM, EPT>(xf, gf, df, bt, bp, sum_sc, sum_off);
         Vec<T, EPT> d;
         pack<T, EPT>(df, d);
         if constexpr (EPT == 1) dx[i] = d.v[0];
@@ -765,7 +810,9 @@ int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dtype, voi
   a.S = 1; a.seg_len = plan.tile_numel;
 
   const bool fast = plan.row && x_dtype == g_dtype && a.bp.m_div == a.bp.m_sub && a.bp.m_sub == a.bp.m_s &&
-                    a.bp.m_s == a.bp.m_sg;
+                    a.bp.m_s == a.bp.m_sg && (offset == nullptr || offset_dtype == scale_dtype) &&
+                    round_mode_of(scale_dtype) == a.bp.m_div &&
+                    (scale_dtype == FFQ_F32 || scale_dtype == x_dtype);
   if (fast) {
     const bool vec_ok = aligned16(x) && aligned16(g) && aligned16(dx);
     const Segmentation sg = choose_segments(plan, ept_of(x_dtype));
