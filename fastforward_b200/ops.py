@@ -309,3 +309,36 @@ def parameters_for_range_(
         scale_out.data_ptr(), C.dtype_tag(scale_out.dtype),
         C.ptr(offset_out), C.dtype_tag(offset_out.dtype if offset_out is not None else None),
         ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))
+
+
+# ------------------------------------------------------------------------------------------
+# fused MSE grid search (range_setting/min_error.py:206-216)
+# ------------------------------------------------------------------------------------------
+def grid_mse(
+    data: torch.Tensor, cand_scale: torch.Tensor, cand_offset: Optional[torch.Tensor], tile_size, num_bits: float,
+    quantized_dtype: Optional[torch.dtype] = None,
+) -> torch.Tensor:
+    """``err[c, t] = mean_tile_t((dequantize_c(quantize_c(data)) - data) ** 2)`` for every candidate
+    parameter set ``(cand_scale[c], cand_offset[c])`` in ONE read of ``data`` -- the loop body of
+    ``_MinAvgErrorGridEstimator.estimate_step`` with ``mse_error``.  Returns fp32 ``[C, num_tiles]``.
+    Raises ``NotImplementedError`` for layouts whose tiles are not contiguous runs (the caller then
+    evaluates candidate by candidate)."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    _bitwidth_guard(quantized_dtype or x.dtype, num_bits)
+    if x.numel() == 0:
+        raise ValueError("grid_mse: empty tensor")
+    nt = layout.num_tiles
+    C.require_cuda(cand_scale, "cand_scale")
+    ncand = cand_scale.shape[0]
+    if cand_scale.dtype != torch.float32 or cand_scale.shape != (ncand, nt) or not cand_scale.is_contiguous():
+        raise RuntimeError(f"cand_scale must be a contiguous float32 [C, {nt}] tensor")
+    if cand_offset is not None and (cand_offset.dtype != torch.float32 or cand_offset.shape != cand_scale.shape
+                                    or not cand_offset.is_contiguous()):
+        raise RuntimeError("cand_offset must match cand_scale")
+    err = torch.zeros((ncand, nt), dtype=torch.float32, device=x.device)
+    ws_bytes = int(C.lib.ffq_grid_mse_workspace_bytes(layout.ref, C.dtype_tag(x.dtype), ncand))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+    C.check(C.lib.ffq_grid_mse(
+        x.data_ptr(), C.dtype_tag(x.dtype), cand_scale.data_ptr(), C.ptr(cand_offset), ncand, err.data_ptr(),
+        layout.ref, float(num_bits), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
+    return err

@@ -199,6 +199,17 @@ FFQ_API int ffq_fakequant_fwd_bwd_host(const void* x_host, const void* g_host, i
                                const float* scale_host, const float* offset_host,
                                const ffq_layout_t* layout, double num_bits, int device);
 
+/* ---- f2: fused MSE grid search ---------------------------------------------------------------
+ * err_accum[c][t] += mean over tile t of (dequantize_c(quantize_c(x)) - x)^2 for all C candidate
+ * (scale, offset) sets in ONE pass over x.  cand_scale / cand_offset: fp32 [C][num_tiles]
+ * (cand_offset may be NULL); err_accum: fp32 [C][num_tiles].  Contiguous-tile layouts only
+ * (FFQ_ERR_UNSUPPORTED otherwise: the caller evaluates candidates one by one).
+ * replaces: range_setting/min_error.py:206-221 (_MinAvgErrorGridEstimator.estimate_step). */
+FFQ_API int ffq_grid_mse(const void* x, int x_dtype, const float* cand_scale, const float* cand_offset,
+                 int num_candidates, float* err_accum, const ffq_layout_t* layout, double num_bits,
+                 void* workspace, size_t workspace_bytes, void* stream);
+FFQ_API size_t ffq_grid_mse_workspace_bytes(const ffq_layout_t* layout, int x_dtype, int num_candidates);
+
 /* ---- test hook ---------------------------------------------------------------------------
  * Sweeps the kernels' shared-reciprocal division against __fdiv_rn over n pseudo-random
  * (dividend, scale) pairs.  counts_dev: uint64[4], zero-initialised by the caller:

@@ -277,6 +277,44 @@ def linear_cases(ff):
     return cases
 
 
+def mse_grid_cases(ff):
+    """ff.estimate_ranges(quantizer, mse_grid, num_candidates=C) over 3 batches: the search grid,
+    the accumulated errors and the parameters the estimator leaves in the quantizer
+    (range_setting/min_error.py:64-221; tests/range_setting/test_minerror.py)."""
+    cases = []
+    seed = 18000
+    for (gname, gfn, shape), symmetric, positive, xdt, ncand in itertools.product(
+        [("per_tensor", lambda: ff.PerTensor(), (4, 16, 32)),
+         ("per_channel_last", lambda: ff.PerChannel(2), (2, 16, 24)),
+         ("per_channel0", lambda: ff.PerChannel(0), (24, 64)),
+         ("per_block", lambda: ff.PerBlock(block_dims=1, block_sizes=16, per_channel_dims=0), (24, 64))],
+        [True, False], [False, True], [torch.float32, torch.bfloat16], [7, 20],
+    ):
+        seed += 1
+        g = _gen(seed)
+        quantizer = ff.nn.LinearQuantizer(4, symmetric=symmetric, granularity=gfn())
+        batches = []
+        for i in range(3):
+            b = torch.randn(shape, generator=g) * (1.0 + 0.25 * i)
+            batches.append((b.abs() if positive else b).to(xdt))
+        from fastforward.range_setting.min_error import mse_grid
+
+        estimator = mse_grid(num_candidates=ncand)
+        with torch.no_grad(), ff.estimate_ranges(quantizer, estimator):
+            for b in batches:
+                quantizer(b)
+            step = next(iter(quantizer._quantizer_overrides.values()))
+            grid = (step.min_threshold.clone(), step.max_threshold.clone())
+            cumulative = step.cumulative_error.clone()
+        cases.append(dict(
+            kind="mse_grid", gran=gname, shape=shape, symmetric=symmetric, positive=positive, num_candidates=ncand,
+            num_bits=4, batches=batches, min_threshold=grid[0], max_threshold=grid[1], cumulative_error=cumulative,
+            scale=quantizer.scale.detach().clone(),
+            offset=None if quantizer.offset is None else quantizer.offset.detach().clone(),
+        ))
+    return cases
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)   # reduction order of aten sum is thread-count dependent only above the grain size
@@ -284,8 +322,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for name, fn in [
         ("static", static_cases), ("quantizer", quantizer_cases), ("running_minmax", minmax_cases),
-        ("dynamic", dynamic_cases), ("linear", linear_cases),
+        ("dynamic", dynamic_cases), ("linear", linear_cases), ("mse_grid", mse_grid_cases),
     ]:
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue            # `python oracle/make_golden.py mse_grid` regenerates one fixture only
         cases = fn(ff)
         path = os.path.join(OUT, f"{name}.pt.gz")
         with gzip.open(path, "wb", compresslevel=9) as fh:

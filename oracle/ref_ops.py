@@ -376,3 +376,68 @@ def calibration_quantizer_step(
         offset = torch.zeros_like(scale)
     codes = quantize_by_tile(data, scale, tile, num_bits, quantized_dtype or data.dtype, offset)
     return run_min, run_max, scale, offset, codes
+
+
+# --------------------------------------------------------------------------------------
+# f2  MinErrorGridRangeEstimator (mse_grid)          range_setting/min_error.py:64-221
+# --------------------------------------------------------------------------------------
+def uniform_search_grid(
+    data: Tensor, tile: Sequence[int], symmetric: bool, num_candidates: int,
+    absolute_margin: float = 0.5, relative_margin: float = 1.0,
+) -> Tuple[Tensor, Tensor]:
+    """Candidate (min_threshold, max_threshold), each ``[num_candidates, num_tiles]``
+    (min_error.py:78-146; three branches: non-negative data, asymmetric, symmetric)."""
+    rows = tile_rows(data, tile)
+    max_data = relative_margin * rows.max(dim=1).values + absolute_margin          # :102
+    min_data = relative_margin * rows.min(dim=1).values - absolute_margin          # :103
+    kw = dict(dtype=rows.dtype, device=rows.device)
+    if not bool(min_data.min() < 0):                                               # :110-115
+        lo = torch.zeros((num_candidates, rows.shape[0]), **kw)
+        steps = torch.linspace(1 / num_candidates, 1, num_candidates, **kw)
+        hi = steps.unsqueeze(1) * max_data.unsqueeze(0)
+    elif not symmetric:                                                            # :117-139
+        margin = 0.6
+        n_lo = math.floor(math.sqrt(num_candidates))
+        n_hi = n_lo + num_candidates - n_lo ** 2
+        steps_lo = torch.linspace(1, margin, n_lo, **kw)
+        steps_hi = torch.linspace(margin, 1, n_hi, **kw)
+        lo = steps_lo.unsqueeze(1) * (relative_margin * min_data.unsqueeze(0) + absolute_margin)
+        hi = steps_hi.unsqueeze(1) * (relative_margin * max_data.unsqueeze(0) + absolute_margin)
+        lo = lo.repeat(n_hi, 1)
+        hi = hi.repeat_interleave(n_lo, dim=0)
+    else:                                                                          # :141-146
+        steps = torch.linspace(1 / num_candidates, 1, num_candidates, **kw)
+        hi = steps.unsqueeze(1) * torch.max(torch.abs(min_data), torch.abs(max_data)).unsqueeze(0)
+        lo = -hi
+    return lo, hi
+
+
+def mse_grid_errors(
+    data: Tensor, tile: Sequence[int], lo: Tensor, hi: Tensor, num_bits: float, symmetric: bool,
+    allow_one_sided: bool, quantized_dtype: Optional[torch.dtype] = None, num_candidates: Optional[int] = None,
+) -> Tensor:
+    """Per-candidate, per-tile mean squared error of one batch, ``[len(lo), num_tiles]``
+    (min_error.py:206-216: operator_for_range -> quantize -> dequantize -> mse_error :64-74).
+
+    The reference loops ``range(self.num_candidates)`` (:207) although the asymmetric grid holds
+    ``n_lo * n_hi >= num_candidates`` rows (:121-139): rows past ``num_candidates`` are never
+    evaluated and keep an accumulated error of 0 -- reproduced here, it decides the argmin."""
+    rows = tile_rows(data, tile)
+    errs = []
+    evaluated = lo.shape[0] if num_candidates is None else num_candidates
+    for i in range(lo.shape[0]):
+        if i >= evaluated:
+            errs.append(torch.zeros(rows.shape[0], dtype=data.dtype))
+            continue
+        scale, offset = parameters_for_range(lo[i], hi[i], num_bits, symmetric, allow_one_sided)
+        q = quantize_by_tile(data, scale, tile, num_bits, quantized_dtype or data.dtype, offset)
+        y = dequantize_by_tile(q, scale, tile, offset, data.dtype)
+        errs.append(torch.mean((tile_rows(y, tile) - rows) ** 2, dim=1))
+    return torch.stack(errs)
+
+
+def mse_grid_select(cumulative_error: Tensor, lo: Tensor, hi: Tensor) -> Tuple[Tensor, Tensor]:
+    """Range of the candidate with the smallest accumulated error, per tile (min_error.py:197-204)."""
+    best = cumulative_error.min(dim=0).indices
+    idx = torch.arange(lo.shape[1])
+    return lo[best, idx], hi[best, idx]

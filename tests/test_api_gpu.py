@@ -286,3 +286,83 @@ def test_continue_calibration_from_existing_fp32_range():
     mn, mx = R.running_minmax_step(lo0, hi0, b, (1, 64))          # fp32 running range, bf16 data
     s, o = R.parameters_for_range(mn, mx, 8, False, True)
     assert bits_equal(q.scale.detach(), s) and bits_equal(q.offset.detach(), o)
+
+
+MSE_GRID = load_golden("mse_grid")
+
+
+def _mse_grid_run(c, **estimator_kwargs):
+    q = ff.nn.LinearQuantizer(c["num_bits"], symmetric=c["symmetric"], granularity=GRANS[c["gran"]](), device=DEV)
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.mse_grid, num_candidates=c["num_candidates"],
+                                             **estimator_kwargs):
+        for b in c["batches"]:
+            q(b.to(DEV))
+        step = next(iter(q.overrides))
+    return q, step
+
+
+def _check_mse_grid(c, q, step):
+    f32 = c["batches"][0].dtype is torch.float32
+    # the grid is parameter-sized arithmetic on per-tile extrema: bit-exact
+    assert bits_equal(step.min_threshold, c["min_threshold"]) and bits_equal(step.max_threshold, c["max_threshold"])
+    # accumulated errors: same terms, another summation order (and one bf16 rounding per batch)
+    tol = dict(rtol=2e-5, atol=1e-7) if f32 else dict(rtol=2e-2, atol=1e-3)
+    got, want = step.cumulative_error.cpu(), c["cumulative_error"]
+    torch.testing.assert_close(got, want, **tol)
+    assert bool((got[c["num_candidates"]:] == 0).all())    # rows the reference never evaluates stay 0
+    # selected parameters: bit-exact wherever the arg-min is decided by more than the tolerance
+    best_got, best_want = got.min(0).indices, want.min(0).indices
+    same = best_got == best_want
+    cols = torch.arange(want.shape[1])
+    gap = (want[best_got, cols] - want[best_want, cols]).abs()
+    assert bool((gap[~same] <= tol["rtol"] * want[best_want, cols][~same].abs() + tol["atol"]).all())
+    assert bits_equal(q.scale.detach().cpu()[same], c["scale"][same])
+    assert bits_equal(q.offset.detach().cpu()[same], c["offset"][same])
+
+
+@pytest.mark.parametrize("i", range(len(MSE_GRID)))
+def test_mse_grid_matches_reference(i):
+    """range_setting/min_error.py through estimate_ranges, fused kernel where the tiles are runs."""
+    c = MSE_GRID[i]
+    q, step = _mse_grid_run(c)
+    assert step._fused == (c["gran"] != "per_channel_last")
+    _check_mse_grid(c, q, step)
+
+
+@pytest.mark.parametrize("i", [0, 5, 17, 33, 50, 63])
+def test_mse_grid_custom_error_fn_takes_candidate_loop(i):
+    c = MSE_GRID[i]
+
+    def my_mse(quantized, original):
+        return torch.mean((quantized - original) ** 2, dim=1)
+
+    q, step = _mse_grid_run(c, error_fn=my_mse)
+    assert step._fused is False
+    _check_mse_grid(c, q, step)
+
+
+def test_mse_grid_large_tiles_and_policy():
+    """Tiles longer than one warp segment (two-stage sum) against the oracle; update policy honoured."""
+    g = torch.Generator().manual_seed(5)
+    for dtype, shape, gran, tile in [(torch.float32, (6, 5000), "per_channel0", (1, 5000)),
+                                     (torch.bfloat16, (3, 64, 1000), "per_tensor", (3, 64, 1000)),
+                                     (torch.float16, (16, 4096), "per_block128", (1, 128))]:
+        x = torch.randn(shape, generator=g).to(dtype)
+        for symmetric in (True, False):
+            q = ff.nn.LinearQuantizer(4, symmetric=symmetric, granularity=GRANS[gran](), device=DEV)
+            calls = []
+            ntiles = x.numel() // torch.Size(tile).numel()
+            q.quantization_range = (-torch.ones(ntiles, device=DEV), torch.ones(ntiles, device=DEV))
+            before = q.scale.detach().clone()
+            with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.mse_grid, num_candidates=16,
+                                                     update_range_policy=lambda est, n: calls.append(n) or n == 2):
+                q(x.to(DEV))
+                assert torch.equal(q.scale.detach(), before)      # policy said "not yet"
+                q(x.to(DEV))
+                step = next(iter(q.overrides))
+            assert calls == [1, 2] and step._fused
+            lo, hi = R.uniform_search_grid(x, tile, symmetric, 16)
+            assert bits_equal(step.min_threshold, lo) and bits_equal(step.max_threshold, hi)
+            want = 2 * R.mse_grid_errors(x, tile, lo, hi, 4, symmetric, True, num_candidates=16).float()
+            tol = dict(rtol=1e-4, atol=1e-7) if dtype is torch.float32 else dict(rtol=3e-2, atol=1e-3)
+            torch.testing.assert_close(step.cumulative_error.cpu().float(), want, **tol)

@@ -192,3 +192,37 @@ def test_c_oracle_matches_reference_vectors():
         assert bits_equal(s, c["scale"])
         if c["offset"] is not None:
             assert bits_equal(o if o is not None else torch.zeros_like(s), c["offset"])
+
+
+MSE_GRID = load_golden("mse_grid")
+
+
+def mse_grid_tile(c):
+    shape = c["shape"]
+    return {
+        "per_tensor": tuple(shape),
+        "per_channel_last": tuple(shape[:-1]) + (1,),
+        "per_channel0": (1,) + tuple(shape[1:]),
+        "per_block": (1, 16),
+    }[c["gran"]]
+
+
+@pytest.mark.parametrize("i", range(len(MSE_GRID)))
+def test_mse_grid(i):
+    """min_error.py:64-221: the search grid is bit-exact, the accumulated errors are the same aten
+    mean on the same machine (tolerance is the contract), the selected range gives the recorded
+    parameters."""
+    c = MSE_GRID[i]
+    tile = mse_grid_tile(c)
+    batches = c["batches"]
+    lo, hi = R.uniform_search_grid(batches[0], tile, c["symmetric"], c["num_candidates"])
+    assert bits_equal(lo, c["min_threshold"]) and bits_equal(hi, c["max_threshold"])
+    cumulative = torch.zeros_like(lo)
+    for b in batches:
+        cumulative += R.mse_grid_errors(b, tile, lo, hi, c["num_bits"], c["symmetric"], True,
+                                        num_candidates=c["num_candidates"])
+    torch.testing.assert_close(cumulative, c["cumulative_error"], rtol=1e-5, atol=1e-6)
+    best_lo, best_hi = R.mse_grid_select(c["cumulative_error"], lo, hi)
+    scale, offset = R.parameters_for_range(best_lo, best_hi, c["num_bits"], c["symmetric"], True)
+    assert bits_equal(scale, c["scale"])
+    assert bits_equal(offset if offset is not None else torch.zeros_like(scale), c["offset"])
