@@ -26,24 +26,32 @@ struct GsArgs {
   int m_out;                                    // rounding of the data dtype (y, y - x and its square are data-dtype ops)
 };
 
-template <typename T, int U>
+// G lanes share one unit (a tile, or a 32*U-vector segment of a long tile); 32/G units per warp.
+// Short tiles (per-group quantization, g = 128) take G < 32 so that a lane still holds U vectors
+// and the per-candidate overhead (parameter loads, reciprocal, G-lane sum) is amortised.
+template <typename T, int U, int G>
 __global__ void __launch_bounds__(GS_THREADS) grid_mse_kernel(const GsArgs a) {
   constexpr int EPT = 16 / sizeof(T);
+  // y, y - x and its square are ops of the data dtype: round through it (compile-time mode)
+  constexpr int RM = sizeof(T) == 4 ? RM_F32 : (Elem<T>::dt == FFQ_BF16 ? RM_BF16 : RM_F16);
+  constexpr int UPW = 32 / G;                    // units per warp
   const unsigned int lane = threadIdx.x & 31;
-  const unsigned long long unit = (unsigned long long)blockIdx.x * (GS_THREADS / 32) + (threadIdx.x >> 5);
-  if (unit >= a.total_units) return;
-  const unsigned long long tile = unit / a.segs_per_tile;
-  const unsigned int seg = (unsigned int)(unit - tile * a.segs_per_tile);
+  const unsigned int gl = lane % G;
+  const unsigned long long warp = (unsigned long long)blockIdx.x * (GS_THREADS / 32) + (threadIdx.x >> 5);
+  const unsigned long long unit = warp * UPW + lane / G;
+  const bool unit_ok = unit < a.total_units;     // whole groups go idle together; shuffles stay warp-wide
+  const unsigned long long tile = unit_ok ? unit / a.segs_per_tile : 0;
+  const unsigned int seg = unit_ok ? (unsigned int)(unit - tile * a.segs_per_tile) : 0;
   const unsigned int tvec = (unsigned int)(a.tile_numel / EPT);
   const unsigned int vec0 = seg * a.seg_vecs;
-  const unsigned int nv = (tvec - vec0) < a.seg_vecs ? (tvec - vec0) : a.seg_vecs;
+  const unsigned int nv = unit_ok ? ((tvec - vec0) < a.seg_vecs ? (tvec - vec0) : a.seg_vecs) : 0;
   const T* __restrict__ in = static_cast<const T*>(a.x) + tile * a.tile_numel + (unsigned long long)vec0 * EPT;
 
   float x[U][EPT];
   bool live[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const unsigned int j = lane + u * 32;
+    const unsigned int j = gl + u * G;
     live[u] = j < nv;
     if (live[u]) {
       const Vec<T, EPT> v = ld_stream<T, EPT>(in + (size_t)j * EPT);
@@ -78,13 +86,14 @@ __global__ void __launch_bounds__(GS_THREADS) grid_mse_kernel(const GsArgs a) {
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
         const float q = nan_clamp(rintf(__fsub_rn(t[i], o)), a.lo, a.hi);
-        const float y = rnd(__fmul_rn(__fadd_rn(q, o), s), a.m_out);
-        const float d = rnd(__fsub_rn(y, x[u][i]), a.m_out);
-        err = __fadd_rn(err, rnd(__fmul_rn(d, d), a.m_out));
+        const float y = rnd(__fmul_rn(__fadd_rn(q, o), s), RM);
+        const float d = rnd(__fsub_rn(y, x[u][i]), RM);
+        err = __fadd_rn(err, rnd(__fmul_rn(d, d), RM));
       }
     }
-    err = warp_sum(err);
-    if (lane == 0) {
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) err = __fadd_rn(err, __shfl_xor_sync(0xffffffffu, err, off));
+    if (gl == 0 && unit_ok) {
       if (a.segs_per_tile == 1) a.err[(size_t)c * a.num_tiles + tile] += err * a.inv_tile;
       else a.part[unit * a.C + c] = err;
     }
@@ -105,14 +114,35 @@ __global__ void __launch_bounds__(GS_THREADS) grid_mse_finalize_kernel(const GsA
 
 using namespace ffq;
 
-static int gs_geometry(const Plan& plan, int x_dtype, unsigned int* seg_vecs, unsigned int* segs_per_tile) {
+static int gs_lanes(unsigned long long tvec, int U) {   // lanes per unit: pow2, each lane ~U vectors
+  int g = 1;
+  while (g < 32 && (unsigned long long)g * U < tvec) g <<= 1;
+  return g;
+}
+
+static int gs_geometry(const Plan& plan, int x_dtype, unsigned int* seg_vecs, unsigned int* segs_per_tile, int* lanes) {
   const int sz = dt_size(x_dtype);
   const int ept = 16 / sz;
   const int U = sz == 4 ? 8 : 4;
   if (!plan.row || plan.tile_numel % ept != 0 || plan.tile_numel / ept >= (1ll << 31)) return 0;
-  *seg_vecs = 32u * U;
+  *lanes = gs_lanes((unsigned long long)(plan.tile_numel / ept), U);
+  *seg_vecs = (unsigned int)(*lanes) * U;
   *segs_per_tile = (unsigned int)((plan.tile_numel / ept + *seg_vecs - 1) / *seg_vecs);
   return 1;
+}
+
+template <typename T, int U>
+static void gs_launch(const GsArgs& a, int lanes, cudaStream_t st) {
+  const unsigned long long warps = (a.total_units + (32 / lanes) - 1) / (32 / lanes);
+  const unsigned int blocks = (unsigned int)((warps + GS_THREADS / 32 - 1) / (GS_THREADS / 32));
+  switch (lanes) {
+    case 1: grid_mse_kernel<T, U, 1><<<blocks, GS_THREADS, 0, st>>>(a); break;
+    case 2: grid_mse_kernel<T, U, 2><<<blocks, GS_THREADS, 0, st>>>(a); break;
+    case 4: grid_mse_kernel<T, U, 4><<<blocks, GS_THREADS, 0, st>>>(a); break;
+    case 8: grid_mse_kernel<T, U, 8><<<blocks, GS_THREADS, 0, st>>>(a); break;
+    case 16: grid_mse_kernel<T, U, 16><<<blocks, GS_THREADS, 0, st>>>(a); break;
+    default: grid_mse_kernel<T, U, 32><<<blocks, GS_THREADS, 0, st>>>(a); break;
+  }
 }
 
 extern "C" {
@@ -122,7 +152,8 @@ size_t ffq_grid_mse_workspace_bytes(const ffq_layout_t* layout, int x_dtype, int
   if (make_plan(layout, &plan) != FFQ_OK || plan.numel == 0) return 0;
   if (!(x_dtype == FFQ_F32 || x_dtype == FFQ_F16 || x_dtype == FFQ_BF16)) return 0;
   unsigned int sv, spt;
-  if (!gs_geometry(plan, x_dtype, &sv, &spt) || spt <= 1) return 0;
+  int lanes;
+  if (!gs_geometry(plan, x_dtype, &sv, &spt, &lanes) || spt <= 1) return 0;
   return (size_t)plan.num_tiles * spt * (size_t)num_candidates * sizeof(float);
 }
 
@@ -139,7 +170,8 @@ int ffq_grid_mse(const void* x, int x_dtype, const float* cand_scale, const floa
   if (rc != FFQ_OK) return rc;
   if (plan.numel == 0) { set_error("grid_mse: empty tensor"); return FFQ_ERR_INVALID; }
   GsArgs a{};
-  if (!gs_geometry(plan, x_dtype, &a.seg_vecs, &a.segs_per_tile) || (reinterpret_cast<uintptr_t>(x) & 15u)) {
+  int lanes = 32;
+  if (!gs_geometry(plan, x_dtype, &a.seg_vecs, &a.segs_per_tile, &lanes) || (reinterpret_cast<uintptr_t>(x) & 15u)) {
     set_error("grid_mse: only contiguous-tile layouts with vector-aligned tiles are fused; use the per-candidate path");
     return FFQ_ERR_UNSUPPORTED;
   }
@@ -157,12 +189,11 @@ int ffq_grid_mse(const void* x, int x_dtype, const float* cand_scale, const floa
     }
     a.part = static_cast<float*>(workspace);
   }
-  const unsigned long long blocks = (a.total_units + GS_THREADS / 32 - 1) / (GS_THREADS / 32);
-  if (blocks > 0x7fffffffull) { set_error("grid_mse: tensor too large"); return FFQ_ERR_UNSUPPORTED; }
+  if (a.total_units / (32 / lanes) / (GS_THREADS / 32) > 0x7ffffff0ull) { set_error("grid_mse: tensor too large"); return FFQ_ERR_UNSUPPORTED; }
   switch (x_dtype) {
-    case FFQ_F32: grid_mse_kernel<float, 8><<<(unsigned int)blocks, GS_THREADS, 0, st>>>(a); break;
-    case FFQ_BF16: grid_mse_kernel<__nv_bfloat16, 4><<<(unsigned int)blocks, GS_THREADS, 0, st>>>(a); break;
-    default: grid_mse_kernel<__half, 4><<<(unsigned int)blocks, GS_THREADS, 0, st>>>(a); break;
+    case FFQ_F32: gs_launch<float, 8>(a, lanes, st); break;
+    case FFQ_BF16: gs_launch<__nv_bfloat16, 4>(a, lanes, st); break;
+    default: gs_launch<__half, 4>(a, lanes, st); break;
   }
   FFQ_LAUNCH_CHECK();
   if (a.segs_per_tile > 1) {
