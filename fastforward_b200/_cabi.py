@@ -116,6 +116,7 @@ def _load() -> ctypes.CDLL:
         "ffq_rowsum_i8": (i32, [vp, vp, i64, i64, vp]),
         "ffq_fakequant_fwd_bwd_host": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, lp, dbl, i32]),
         "ffq_selftest_shared_div": (i32, [ctypes.c_uint64, ctypes.c_uint32, vp, vp]),
+        "ffq_qlinear_w4a16": (i32, [vp, i32, vp, vp, i64, i64, i64, vp, vp, i64, vp, i32, vp]),
         "ffq_grid_mse": (i32, [vp, i32, vp, vp, i32, vp, lp, dbl, vp, sz, vp]),
         "ffq_grid_mse_workspace_bytes": (sz, [lp, i32, i32]),
     }
@@ -132,7 +133,7 @@ lib = _load()
 EXPORTED = (
     "ffq_abi_version ffq_last_error ffq_launch_count ffq_workspace_bytes ffq_num_tiles ffq_quantize "
     "ffq_dequantize ffq_fakequant_fwd ffq_quantize_bwd ffq_minmax ffq_params_for_range "
-    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_qlinear_workspace_bytes ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes"
+    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_qlinear_workspace_bytes ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16"
 ).split()
 
 

@@ -1,0 +1,348 @@
+// ffq_qlinear_w4a16.cu -- weight-only quantized linear (W4A16; any <= 8-bit integer weight codes)
+// on Blackwell tensor cores (a12, section 8b "ffq_qlinear_w4a16").
+//
+//   y[m,n] = sum_k x[m,k] * w[n,k] + bias[n],   w[n,k] = round_to_dtype_of_x((qw[n,k] + rint(ow[n,g])) * sw[n,g]),  g = k / group
+//
+// The reference's route for this op is its fallback (_gen/fallback.py:94-108): dequantize the
+// weight into a full bf16 tensor in HBM (1 B/elem read + 2 B/elem written), then F.linear re-reads
+// it (2 B/elem).  Here the int8 codes are the only weight bytes that ever cross HBM: the codes
+// tile is dequantized INSIDE the k-loop into the 128B-swizzled bf16 B operand in shared memory,
+// with exactly dequantize_by_tile's arithmetic (fp32 add, fp32 multiply, one rounding to the
+// 16-bit dtype), and consumed by tcgen05.mma.kind::f16 with fp32 accumulation in TMEM -- so the
+// result equals the fallback's up to the GEMM's accumulation order.
+//
+// One CTA pair (cluster 2x1x1) per 256x256 output tile, persistent, warp-specialised (10 warps):
+//   warp 0      TMA producer: A tile (128 rows x 64 elem, 128B swizzle; completes on the LEADER's
+//               full barrier) and this CTA's raw code tile (128 weight rows x 64 B; local barrier)
+//   warp 1      MMA issuer (leader CTA): 4 x tcgen05.mma.cta_group::2 (K = 16) per k-block
+//   warps 2..5  epilogue: tcgen05.ld, + bias, convert, vector stores; overlaps the next tile's k-loop
+//   warps 6..9  dequantizers: raw codes -> (q + o) * s -> bf16/f16 -> swizzled B stage of this CTA,
+//               fence.proxy.async, then arrive on the leader's full barrier
+// Roofline: tensor pipe (bf16 dense), 2*M*N*K flops; the dequantizers need ~4 issue slots per
+// weight element per M-tile, about half of the issue capacity left beside the MMAs.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <mutex>
+
+#include "ffq_common.cuh"
+#include "ffq_umma.cuh"
+
+namespace ffq {
+namespace w4 {
+
+constexpr int BM = 128, BN = 256, BK = 64;        // BK in 16-bit elements: one 128B swizzle atom
+constexpr int TM = 2 * BM;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 5;
+constexpr int A_BYTES = BM * BK * 2;              // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;        // 16 KB: this CTA's half of B, as 16-bit floats
+constexpr int RAW_BYTES = (BN / 2) * BK;          // 8 KB: the same half as int8 codes
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES + RAW_BYTES;
+constexpr int THREADS = 320;
+constexpr int TMEM_COLS = 512;
+constexpr int DQ_WARPS = 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN * 4 + 256 + 1024;
+
+struct Args {
+  int M, N, K;
+  void* y;
+  const float* sw; const float* ow;     // [N][groups]
+  int group, groups;                     // k elements per parameter; K / group
+  const void* bias; int bias_dt;
+};
+
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc),
+      "r"(acc) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // upper half <- first source operand
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+// 4 signed bytes -> 4 floats holding (q + o) * s.  Fast path: the byte is planted into the mantissa
+// of 2^23 (after flipping its sign bit: u = q + 128), so  as_float(0x4B0000uu) + (o - 2^23 - 128) == q + o
+// exactly (integers below 2^24) with one PRMT and one FADD instead of an int->float conversion.
+__device__ __forceinline__ void dequant4(uint32_t w, float c_fast, float o, float s, bool fast, float (&f)[4]) {
+  if (fast) {
+    const uint32_t u = w ^ 0x80808080u;
+    f[0] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)), c_fast), s);
+    f[1] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)), c_fast), s);
+    f[2] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)), c_fast), s);
+    f[3] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)), c_fast), s);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = __fmul_rn(__fadd_rn((float)(int8_t)(w >> (8 * i)), o), s);
+  }
+}
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_raw, const Args g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;                                                   // [STAGES][A | B | raw]
+  float* col_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BN * 4);
+  uint64_t* full_bar = bars;                     // [STAGES]  leader's copy: A bytes of both CTAs + 8 dequantizer warps
+  uint64_t* raw_full = bars + STAGES;            // [STAGES]  local: this CTA's raw code tile has landed
+  uint64_t* empty_bar = bars + 2 * STAGES;       // [STAGES]  local copy, signalled by the leader's tcgen05.commit multicast
+  uint64_t* tmem_full = bars + 3 * STAGES;       // [2]
+  uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]       leader's copy, 8 arrivals
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int k_blocks = g.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + 2 * DQ_WARPS);
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage_base + stage * STAGE_BYTES;
+          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * A_BYTES);
+          tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
+          mbar_expect_tx(&raw_full[stage], RAW_BYTES);
+          tma_load_2d(sa + A_BYTES + B_BYTES, &map_raw, &raw_full[stage], kb * BK, tn * BN + (int)cta * (BN / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (cta == 0 && lane == 0) {
+      constexpr uint32_t fmt = sizeof(T) == 2 && Elem<T>::dt == FFQ_BF16 ? 1u : 0u;
+      // D = F32, A = B = bf16/f16, both K-major, N = 256, M = 256 (128 rows in each CTA)
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // +16 elements = +32 bytes inside the swizzle atom == +2 in the (>>4) start-address field
+            umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[buf]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue (warps 2..5 of both CTAs): this CTA's 128 rows =====
+    const int quad = warp & 3;
+    const int ep_tid = threadIdx.x - 64;
+    T* __restrict__ y = static_cast<T*>(g.y);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      const int buf = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = ep_tid; c < BN; c += 128) {
+        const int n = tn * BN + c;
+        col_bias[c] = (g.bias && n < g.N) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
+
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + (uint32_t)c0, acc);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(acc[j]), col_bias[c0 + j]);
+        const int n0 = tn * BN + c0;
+        if (row < g.M && n0 < g.N) {
+          const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
+          store_chunk<T>(y + (size_t)row * g.N + n0, v, ncols);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
+    }
+  } else {
+    // ===== dequantizers (warps 6..9): raw int8 codes -> swizzled 16-bit B stage =====
+    const int t = threadIdx.x - 192;               // 0..127
+    const int chunk = t & 3;                       // 16 codes = 16 raw bytes = two 16-byte B chunks
+    const int row0 = t >> 2;                       // rows row0 + 32*i, i = 0..3
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int tn = tile / tiles_m;
+      const int nbase = tn * BN + (int)cta * (BN / 2) + row0;
+      float s_cur[4], o_cur[4], s_nxt[4], o_nxt[4];
+      int cur_g = -1;
+      auto fetch = [&](int gi, float (&s)[4], float (&o)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = nbase + 32 * i;
+          const bool in = n < g.N && gi < g.groups;
+          s[i] = in ? __ldg(g.sw + (size_t)n * g.groups + gi) : 0.f;
+          o[i] = (in && g.ow) ? rintf(__ldg(g.ow + (size_t)n * g.groups + gi)) : 0.f;
+        }
+      };
+      fetch(0, s_nxt, o_nxt);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int gi = (kb * BK) / g.group;
+        if (gi != cur_g) {                          // parameters of the NEXT group are requested one group ahead
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { s_cur[i] = s_nxt[i]; o_cur[i] = o_nxt[i]; }
+          cur_g = gi;
+          fetch(gi + 1, s_nxt, o_nxt);
+        }
+        mbar_wait(&raw_full[stage], phase);
+        uint8_t* sb = stage_base + stage * STAGE_BYTES + A_BYTES;
+        const uint8_t* sr = sb + B_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = row0 + 32 * i;
+          const uint4 v = *reinterpret_cast<const uint4*>(sr + r * BK + chunk * 16);
+          const float o = o_cur[i], s = s_cur[i];
+          const bool fast = fabsf(o) < 4194304.f;
+          const float cf = __fsub_rn(o, 8388736.f);   // o - 2^23 - 128, exact for |o| < 2^22
+          float f[16];
+          { float q[4]; dequant4(v.x, cf, o, s, fast, q); f[0] = q[0]; f[1] = q[1]; f[2] = q[2]; f[3] = q[3]; }
+          { float q[4]; dequant4(v.y, cf, o, s, fast, q); f[4] = q[0]; f[5] = q[1]; f[6] = q[2]; f[7] = q[3]; }
+          { float q[4]; dequant4(v.z, cf, o, s, fast, q); f[8] = q[0]; f[9] = q[1]; f[10] = q[2]; f[11] = q[3]; }
+          { float q[4]; dequant4(v.w, cf, o, s, fast, q); f[12] = q[0]; f[13] = q[1]; f[14] = q[2]; f[15] = q[3]; }
+          uint4 lo, hi;
+          lo.x = pack2<T>(f[0], f[1]);   lo.y = pack2<T>(f[2], f[3]);   lo.z = pack2<T>(f[4], f[5]);   lo.w = pack2<T>(f[6], f[7]);
+          hi.x = pack2<T>(f[8], f[9]);   hi.y = pack2<T>(f[10], f[11]); hi.z = pack2<T>(f[12], f[13]); hi.w = pack2<T>(f[14], f[15]);
+          // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r % 8); rows are 128 B apart
+          uint8_t* rowp = sb + r * 128;
+          const int sw7 = r & 7;
+          *reinterpret_cast<uint4*>(rowp + (((2 * chunk) ^ sw7) << 4)) = lo;
+          *reinterpret_cast<uint4*>(rowp + (((2 * chunk + 1) ^ sw7) << 4)) = hi;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader_release(&full_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+static int make_map2(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int64_t rows, int64_t K,
+                     int box_k, int box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("qlinear_w4a16: cuTensorMapEncodeTiled is not available from the driver"); return FFQ_ERR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * elem_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("qlinear_w4a16: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return FFQ_ERR_CUDA; }
+  return FFQ_OK;
+}
+
+}  // namespace w4
+}  // namespace ffq
+
+using namespace ffq;
+
+extern "C" int ffq_qlinear_w4a16(const void* x, int x_dtype, const int8_t* qw, void* y, int64_t M, int64_t N, int64_t K,
+                                 const float* sw, const float* ow, int64_t group, const void* bias, int bias_dtype,
+                                 void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (M <= 0 || N <= 0) return FFQ_OK;
+  if (!(x_dtype == FFQ_BF16 || x_dtype == FFQ_F16)) {
+    set_error("qlinear_w4a16: activations must be bfloat16 or float16"); return FFQ_ERR_UNSUPPORTED;
+  }
+  if (K <= 0 || K % w4::BK != 0) { set_error("qlinear_w4a16: K must be a positive multiple of %d (got %lld)", w4::BK, (long long)K); return FFQ_ERR_UNSUPPORTED; }
+  if (group <= 0 || K % group != 0 || group % w4::BK != 0) {
+    set_error("qlinear_w4a16: the group size must divide K and be a multiple of %d (got %lld)", w4::BK, (long long)group); return FFQ_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(qw) & 15u) || (reinterpret_cast<uintptr_t>(y) & 15u)) {
+    set_error("qlinear_w4a16: pointers must be 16-byte aligned"); return FFQ_ERR_UNSUPPORTED;
+  }
+  if (M > 0x7fffffffll || N > 0x7fffffffll || K > 0x7fffffffll) { set_error("qlinear_w4a16: dimension too large"); return FFQ_ERR_UNSUPPORTED; }
+  CUtensorMap map_a, map_raw;
+  int rc;
+  const CUtensorMapDataType adt = x_dtype == FFQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  if ((rc = w4::make_map2(&map_a, adt, 2, x, M, K, w4::BK, w4::BM, CU_TENSOR_MAP_SWIZZLE_128B)) != FFQ_OK) return rc;
+  if ((rc = w4::make_map2(&map_raw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, qw, N, K, w4::BK, w4::BN / 2, CU_TENSOR_MAP_SWIZZLE_NONE)) != FFQ_OK) return rc;
+  w4::Args g{};
+  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.sw = sw; g.ow = ow; g.group = (int)group; g.groups = (int)(K / group);
+  g.bias = bias; g.bias_dt = bias_dtype;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e1 = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
+    attr_err = e1 != cudaSuccess ? e1 : e2;
+  });
+  if (attr_err != cudaSuccess) { set_error("qlinear_w4a16: cannot reserve %d bytes of shared memory: %s", w4::SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
+  const long long pair_tiles = ((M + w4::TM - 1) / w4::TM) * ((N + w4::BN - 1) / w4::BN);
+  const int max_pairs = sm_count() / 2;
+  const int grid = 2 * (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+  if (x_dtype == FFQ_BF16) w4::w4a16_gemm2_kernel<__nv_bfloat16><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+  else w4::w4a16_gemm2_kernel<__half><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}

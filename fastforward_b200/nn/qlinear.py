@@ -1,9 +1,10 @@
-"""W8A8 quantized linear on tcgen05 tensor cores, plugged in through the operator dispatcher
-(seam 2 of SURVEY.md section 8b: ``ff.dispatcher.register("linear", predicate, kernel)``).
+"""W8A8 and W4A16 quantized linears on tcgen05 tensor cores, plugged in through the operator
+dispatcher (seam 2 of SURVEY.md section 8b: ``ff.dispatcher.register("linear", predicate, kernel)``).
 
-``install()`` registers the kernel; the predicate accepts exactly the case the kernel implements
-(int8 per-tensor activations x int8 per-channel weights on CUDA) and everything else keeps taking
-the reference's dequantize-then-float fallback (_gen/fallback.py:77-112)."""
+``install()`` registers the kernels; each predicate accepts exactly the case its kernel implements
+(W8A8: int8 per-tensor activations x int8 per-channel weights; W4A16: bf16/f16 activations x
+int8-stored per-group / per-channel / per-tensor weight codes) and everything else keeps taking the
+reference's dequantize-then-float fallback (_gen/fallback.py:77-112)."""
 
 from __future__ import annotations
 
@@ -90,18 +91,102 @@ def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, stric
     return y
 
 
+# ------------------------------------------------------------------------------------------
+# W4A16: 16-bit float activations x integer (<= 8 bit, stored as int8) per-group weights
+# ------------------------------------------------------------------------------------------
+_W4_BK = 64
+
+
+def _w4_group(weight, pw) -> Optional[int]:
+    """Elements of K sharing one weight parameter, or None if the tiling is not [1, g] / per-tensor."""
+    n, k = weight.shape
+    tile = pw.granularity.tile_size(weight.shape)
+    tile = (n, k) if isinstance(tile, str) else tuple(tile)      # PerTensor answers "data_shape"
+    if tile == (n, k):
+        return k                     # per-tensor: one parameter, expanded to [N] by the wrapper
+    if tile[0] != 1 or k % tile[1] != 0:
+        return None
+    return tile[1]
+
+
+def _accepts_w4a16(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None) -> bool:
+    pw = _params(weight)
+    if pw is None or not weight.is_cuda or weight.dim() != 2 or weight.raw_data.dtype != torch.int8 or pw.num_bits > 8:
+        return False
+    if not isinstance(input, torch.Tensor) or not input.is_cuda or input.dim() < 2:
+        return False
+    if isinstance(input, QuantizedTensor):
+        px = _params(input)
+        if px is None or _accepts(input, weight, bias, output_quantizer, strict_quantization):
+            return False             # int8 x int8 belongs to the W8A8 kernel
+        x_dtype = px.dequantize_dtype
+    else:
+        x_dtype = input.dtype
+    if x_dtype not in (torch.bfloat16, torch.float16) or pw.dequantize_dtype != x_dtype:
+        return False
+    if not (isinstance(pw.scale, torch.Tensor) and pw.scale.dtype == torch.float32):
+        return False
+    if pw.offset is not None and not (isinstance(pw.offset, torch.Tensor) and pw.offset.dtype == torch.float32):
+        return False
+    if isinstance(bias, QuantizedTensor):
+        return False
+    k = weight.shape[1]
+    group = _w4_group(weight, pw)
+    return input.shape[-1] == k and k % _W4_BK == 0 and group is not None and group % _W4_BK == 0
+
+
+def w4a16_linear(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None):
+    pw = weight.quant_args()
+    x = input.dequantize() if isinstance(input, QuantizedTensor) else input
+    lead = x.shape[:-1]
+    k = x.shape[-1]
+    x2 = x.detach().reshape(-1, k).contiguous()
+    qw = weight.raw_data.contiguous()
+    m, n = x2.shape[0], qw.shape[0]
+    group = _w4_group(weight, pw)
+    groups = k // group
+    sw = pw.scale.detach().reshape(-1)
+    ow = None if pw.offset is None else pw.offset.detach().reshape(-1)
+    if sw.numel() == 1 and n * groups != 1:            # per-tensor weight parameters
+        sw = sw.expand(n * groups)
+        ow = None if ow is None else ow.expand(n * groups)
+    sw = sw.contiguous()
+    ow = None if ow is None else ow.contiguous()
+    b = None if bias is None else bias.detach().contiguous()
+    y = torch.empty((m, n), dtype=x2.dtype, device=x2.device)
+    C.check(C.lib.ffq_qlinear_w4a16(
+        x2.data_ptr(), C.dtype_tag(x2.dtype), qw.data_ptr(), y.data_ptr(), m, n, k,
+        sw.data_ptr(), C.ptr(ow), group, C.ptr(b), C.dtype_tag(b.dtype if b is not None else None),
+        C.current_stream(x2.device)))
+    _stats["calls_w4a16"] = _stats.get("calls_w4a16", 0) + 1
+    if keepalive is not None:
+        keepalive.append((x2, qw, y, sw, ow, b))
+    y = y.reshape(*lead, n)
+    if output_quantizer is not None:
+        y = output_quantizer(y)
+    return y
+
+
+_hook_w4 = None
+
+
 def install() -> None:
-    """Register the kernel (idempotent)."""
-    global _hook
+    """Register the kernels (idempotent)."""
+    global _hook, _hook_w4
     if _hook is None:
         _hook = register("linear", Predicate(_accepts), w8a8_linear)
+    if _hook_w4 is None:
+        _hook_w4 = register("linear", Predicate(_accepts_w4a16), w4a16_linear)
 
 
 def uninstall() -> None:
-    global _hook
+    global _hook, _hook_w4
     if _hook is not None:
         _hook.remove()
         _hook = None
+    if _hook_w4 is not None:
+        _hook_w4.remove()
+        _hook_w4 = None
 
 
 def stats() -> Dict[str, Any]:

@@ -189,6 +189,20 @@ FFQ_API size_t ffq_qlinear_workspace_bytes(int64_t N);
 /* rowsum[r] = sum_k q[r,k]  (int8 [R,K] -> int32[R]) */
 FFQ_API int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream);
 
+/* ---- a12: weight-only quantized linear (W4A16; any integer weight codes of <= 8 bits) --------
+ * y[m,n] = sum_k x[m,k] * w[n,k] + bias[n],  w[n,k] = cast_x_dtype((qw[n,k] + rint(ow[n,k/group])) * sw[n,k/group])
+ * x, y: bf16 or f16 [M,K] / [M,N]; qw: int8 codes [N,K]; sw, ow: fp32 [N, K/group] (ow may be NULL);
+ * group: elements of K that share one parameter (a multiple of 64 that divides K; group == K is
+ * per-channel).  The codes are dequantized inside the k-loop with dequantize_by_tile's arithmetic
+ * and fed to tcgen05.mma.kind::f16 (fp32 accumulation), so the result equals the reference's
+ * fallback up to the GEMM's accumulation order, without the dequantized weight ever touching HBM.
+ * replaces: _gen/fallback.py:77-112 (dequantize weight + torch.nn.functional.linear), selected via
+ *           dispatcher.py:268-283. */
+FFQ_API int ffq_qlinear_w4a16(const void* x, int x_dtype, const int8_t* qw, void* y,
+                      int64_t M, int64_t N, int64_t K,
+                      const float* sw, const float* ow, int64_t group,
+                      const void* bias, int bias_dtype, void* stream);
+
 /* ---- host-buffer convenience (end-to-end path; copies inside) -----------------------------
  * Fake-quant forward + STE backward of one tensor whose data lives in HOST memory:
  * H2D(x, g) -> ffq_fakequant_fwd -> ffq_quantize_bwd -> D2H(y, dx, dscale, doffset).

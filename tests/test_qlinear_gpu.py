@@ -113,3 +113,103 @@ def test_golden_linear_cases_through_kernel():
         y = qlinear.w8a8_linear(input=xq, weight=wq, bias=b, output_quantizer=None, strict_quantization=False)
         tol = 1e-4 if c["x"].dtype is torch.float32 else 2e-2
         torch.testing.assert_close(y.cpu().float(), c["y"].float(), rtol=tol, atol=tol)
+
+
+# ------------------------------------------------------------------------------------------------
+# W4A16: weight-only quantized linear.  The in-kernel dequantisation is dequantize_by_tile's
+# arithmetic, so (a) with one-hot activations the output IS the dequantized weight, bit for bit, and
+# (b) for real activations the only difference to the reference's fallback (dequantize + F.linear)
+# is the fp32 accumulation order: |y_kernel - y_f64| <= |y_fallback - y_f64| + 2 ulp(dtype) elementwise
+# and rtol 2e-2 against the fallback itself (tolerance stated as BASELINE.json asks).
+# ------------------------------------------------------------------------------------------------
+def _w4_layer(k, n, dt, gran, w_sym, bias, bits=4, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lin = torch.nn.Linear(k, n, bias=bias, dtype=dt)
+    with torch.no_grad():
+        lin.weight.copy_((torch.randn(n, k, generator=g) * 0.05).to(dt))
+        if bias:
+            lin.bias.copy_((torch.randn(n, generator=g) * 0.1).to(dt))
+    ff.quantize_model(lin)
+    lin.weight_quantizer = ff.nn.LinearQuantizer(bits, symmetric=w_sym, granularity=gran, quantized_dtype=torch.int8)
+    lin.to(DEV)
+    with torch.no_grad(), ff.estimate_ranges(lin.weight_quantizer, ff.range_setting.running_minmax):
+        lin.weight_quantizer(lin.weight)
+    return lin
+
+
+def _w4_grans(k):
+    return {
+        "g128": ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0),
+        "g64": ff.PerBlock(block_dims=1, block_sizes=64, per_channel_dims=0),
+        "pc": ff.PerChannel(0),
+        "pt": ff.PerTensor(),
+    }
+
+
+def _dispatch_w4(lin, x):
+    # weight-only quantization: the reference's fallback refuses float inputs under strict mode
+    with torch.no_grad(), ff.strict_quantization(False):
+        before = qlinear.stats().get("calls_w4a16", 0)
+        qlinear.install()
+        try:
+            y = lin(x)
+        finally:
+            qlinear.uninstall()
+        assert qlinear.stats().get("calls_w4a16", 0) == before + 1, "the W4A16 kernel was not dispatched"
+        return y, lin(x)            # (kernel, reference fallback: nothing registered)
+
+
+@pytest.mark.parametrize("k,n,gran", [(128, 256, "g128"), (512, 300, "g64"), (1024, 40, "pc"), (256, 513, "pt"), (4096, 256, "g128")])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16] if torch.cuda.is_available() else [])
+@pytest.mark.parametrize("w_sym", [True, False])
+def test_w4a16_one_hot_activations_give_the_dequantized_weight_bit_exact(k, n, gran, dt, w_sym):
+    lin = _w4_layer(k, n, dt, _w4_grans(k)[gran], w_sym, bias=False)
+    x = torch.eye(k, dtype=dt, device=DEV)
+    y, y_fb = _dispatch_w4(lin, x)
+    with torch.no_grad():
+        w_deq = lin.weight_quantizer(lin.weight).dequantize()
+    assert y.dtype == dt and torch.equal(y, w_deq.t()) and torch.equal(y_fb, y)
+
+
+@pytest.mark.parametrize("m,k,n,gran", [(256, 512, 512, "g128"), (300, 1024, 700, "g64"), (17, 128, 40, "pc"),
+                                        (2048, 4096, 1024, "g128"), (129, 4096 + 64, 257, "pc"), (64, 256, 256, "pt")])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16] if torch.cuda.is_available() else [])
+@pytest.mark.parametrize("w_sym,bias", [(True, False), (False, True)])
+def test_w4a16_linear(m, k, n, gran, dt, w_sym, bias):
+    lin = _w4_layer(k, n, dt, _w4_grans(k)[gran], w_sym, bias, seed=m + n)
+    x = torch.randn(m, k, generator=torch.Generator().manual_seed(7)).to(dt).to(DEV)
+    y, y_fb = _dispatch_w4(lin, x)
+    with torch.no_grad():
+        w_deq = lin.weight_quantizer(lin.weight).dequantize()
+    y64 = torch.nn.functional.linear(x.double(), w_deq.double(), None if lin.bias is None else lin.bias.double()).cpu()
+    assert y.dtype == dt and y.shape == (m, n)
+    yk, yf = y.double().cpu(), y_fb.double().cpu()
+    ulp = torch.finfo(dt).eps * y64.abs().clamp_min(1e-2)
+    err_k, err_f = (yk - y64).abs(), (yf - y64).abs()
+    assert bool((err_k <= err_f + 2 * ulp).all()), f"kernel worse than fallback by {float((err_k - err_f - 2 * ulp).max())}"
+    torch.testing.assert_close(y.float().cpu(), y_fb.float().cpu(), rtol=2e-2, atol=2e-2 * float(y_fb.abs().max()))
+
+
+def test_w4a16_quantized_16bit_activations_3d_input_and_predicate():
+    """cfg5 recipe: A16 per-tensor asymmetric (fp32 codes, bf16 data) x W4 g=128; 3-D input; the
+    predicate leaves everything it does not implement to the fallback."""
+    dt = torch.bfloat16
+    lin = _w4_layer(512, 384, dt, _w4_grans(512)["g128"], False, True)
+    lin.input_quantizer = ff.nn.LinearQuantizer(16, symmetric=False, quantized_dtype=torch.float32).to(DEV)
+    x = torch.randn(2, 50, 512, generator=torch.Generator().manual_seed(3)).to(dt).to(DEV)
+    lin.input_quantizer.quantization_range = (x.min(), x.max())
+    y, y_fb = _dispatch_w4(lin, x)
+    assert y.shape == (2, 50, 384)
+    torch.testing.assert_close(y.float(), y_fb.float(), rtol=2e-2, atol=2e-2 * float(y_fb.abs().max()))
+    with torch.no_grad():
+        wq = lin.weight_quantizer(lin.weight)
+        assert qlinear._accepts_w4a16(input=x, weight=wq, bias=None)
+        assert not qlinear._accepts_w4a16(input=x.float(), weight=wq, bias=None)            # fp32 activations
+        assert not qlinear._accepts_w4a16(input=x[..., :448], weight=wq, bias=None)         # K mismatch
+        odd = ff.nn.LinearQuantizer(4, granularity=ff.PerBlock(block_dims=1, block_sizes=32, per_channel_dims=0),
+                                    quantized_dtype=torch.int8).to(DEV)
+        odd.quantization_range = (-torch.ones(384 * 16, device=DEV), torch.ones(384 * 16, device=DEV))
+        assert not qlinear._accepts_w4a16(input=x, weight=odd(lin.weight), bias=None)       # group of 32 < one k-block
+        pcl = ff.nn.LinearQuantizer(4, granularity=ff.PerChannel(1), quantized_dtype=torch.int8).to(DEV)
+        pcl.quantization_range = (-torch.ones(512, device=DEV), torch.ones(512, device=DEV))
+        assert not qlinear._accepts_w4a16(input=x, weight=pcl(lin.weight), bias=None)       # per input channel
