@@ -284,6 +284,30 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
                                           "frac_of_int8_peak": round(2 * M * N * K / t / 1e12 / int8_peak, 3),
                                           "context_cublaslt_int_mm_TOPS": round(2 * M * N * K / t_lib / 1e12, 1)}
     del qx, qw, y
+    # W4A16 linear (configs[4] recipe at the configs[3] shape): bf16 activations x 4-bit g=128 codes
+    for M in (2048, 8192):
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        qw = torch.randint(-8, 8, (N, K), dtype=torch.int8, device=dev)
+        sw4 = torch.rand(N * (K // 128), device=dev) * 0.01 + 1e-3
+        ow4 = torch.randint(-3, 4, (N * (K // 128),), device=dev).float()
+        y = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+
+        def w4():
+            C.check(C.lib.ffq_qlinear_w4a16(x.data_ptr(), 2, qw.data_ptr(), y.data_ptr(), M, N, K, sw4.data_ptr(), ow4.data_ptr(), 128,
+                                            None, 255, st))
+
+        def w4_fallback():      # the reference's route with our dequantize kernel underneath + the library bf16 GEMM
+            wd = ops.dequantize_by_tile(qw, sw4, (1, 128), ow4, torch.bfloat16)
+            torch.nn.functional.linear(x, wd)
+        t = _time_cuda(w4)
+        t_fb = _time_cuda(w4_fallback)
+        wd = ops.dequantize_by_tile(qw, sw4, (1, 128), ow4, torch.bfloat16)
+        t_mm = _time_cuda(lambda: torch.nn.functional.linear(x, wd))
+        out[f"w4a16_linear_{M}x{N}x{K}_g128"] = {
+            "us": round(t * 1e6, 1), "TFLOPS": round(2 * M * N * K / t / 1e12, 1),
+            "frac_of_bf16_peak": round(2 * M * N * K / t / 1e12 / (int8_peak / 2), 3),
+            "fallback_dequant_plus_cublas_us": round(t_fb * 1e6, 1), "context_cublas_bf16_gemm_only_us": round(t_mm * 1e6, 1)}
+        del x, qw, y, wd
     # W4 g=128 weight QDQ of one 14336x4096 bf16 weight (configs[2] unit of work): min/max + params + fused QDQ in place
     w = [torch.randn(14336, 4096, device=dev, dtype=torch.bfloat16) * 0.02 for _ in range(3)]
     tile = (1, 128)

@@ -11,13 +11,17 @@
 // 16-bit dtype), and consumed by tcgen05.mma.kind::f16 with fp32 accumulation in TMEM -- so the
 // result equals the fallback's up to the GEMM's accumulation order.
 //
-// One CTA pair (cluster 2x1x1) per 256x256 output tile, persistent, warp-specialised (10 warps):
-//   warp 0      TMA producer: A tile (128 rows x 64 elem, 128B swizzle; completes on the LEADER's
-//               full barrier) and this CTA's raw code tile (128 weight rows x 64 B; local barrier)
+// One CTA pair (cluster 2x1x1) per 256x256 output tile, persistent, warp-specialised, with THREE
+// decoupled shared-memory rings so that neither HBM latency nor the dequantisation sits on the MMA's
+// critical path:
+//   warp 0      A producer: TMA of the A tile (128 rows x 64 elem, 128B swizzle) into a 6-deep ring;
+//               completes on the LEADER's barrier, slots freed by tcgen05.commit
+//   warp 2      raw-code producer: TMA of this CTA's 128 weight rows x 64 B into an 8-deep ring,
+//               slots freed by the dequantizers as soon as the codes are in registers
+//   warps 8..15 dequantizers: raw codes -> (q + o) * s -> bf16/f16 -> 3-deep swizzled B ring of this CTA
+//               (slot freed by tcgen05.commit), fence.proxy.async, arrive on the leader's barrier
 //   warp 1      MMA issuer (leader CTA): 4 x tcgen05.mma.cta_group::2 (K = 16) per k-block
-//   warps 2..5  epilogue: tcgen05.ld, + bias, convert, vector stores; overlaps the next tile's k-loop
-//   warps 6..9  dequantizers: raw codes -> (q + o) * s -> bf16/f16 -> swizzled B stage of this CTA,
-//               fence.proxy.async, then arrive on the leader's full barrier
+//   warps 4..7  epilogue: tcgen05.ld, + bias, convert, vector stores; overlaps the next tile's k-loop
 // Roofline: tensor pipe (bf16 dense), 2*M*N*K flops; the dequantizers need ~4 issue slots per
 // weight element per M-tile, about half of the issue capacity left beside the MMAs.
 #include <cuda.h>
@@ -34,27 +38,37 @@ namespace w4 {
 constexpr int BM = 128, BN = 256, BK = 64;        // BK in 16-bit elements: one 128B swizzle atom
 constexpr int TM = 2 * BM;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 5;
+constexpr int SA = 6, SB = 3, SR = 8;             // ring depths: A operand / dequantized B / raw codes
 constexpr int A_BYTES = BM * BK * 2;              // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;        // 16 KB: this CTA's half of B, as 16-bit floats
 constexpr int RAW_BYTES = (BN / 2) * BK;          // 8 KB: the same half as int8 codes
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES + RAW_BYTES;
-constexpr int THREADS = 320;
+constexpr int DQ_WARPS = 8;
+// warp roles (TMEM lane quadrant of an epilogue warp = warp % 4; dequantizers spread 2 per scheduler)
+constexpr int WARP_TMA_A = 0, WARP_MMA = 1, WARP_TMA_RAW = 2, WARP_EPI0 = 4, WARP_DQ0 = 8;
+constexpr int THREADS = (WARP_DQ0 + DQ_WARPS) * 32;   // 512 (warp 3 idles)
 constexpr int TMEM_COLS = 512;
-constexpr int DQ_WARPS = 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BN * 4 + 256 + 1024;
+constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_BYTES + SR * RAW_BYTES + BN * 4 + 512 + 1024;
+
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(500);
+  }
+}
 
 struct Args {
   int M, N, K;
   void* y;
   const float* sw; const float* ow;     // [N][groups]
-  int group, groups;                     // k elements per parameter; K / group
+  int group, groups, kb_per_group;       // k elements per parameter; K / group; group / BK
   const void* bias; int bias_dt;
 };
 
-__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
-}
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -75,20 +89,16 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
   return r;
 }
 
-// 4 signed bytes -> 4 floats holding (q + o) * s.  Fast path: the byte is planted into the mantissa
-// of 2^23 (after flipping its sign bit: u = q + 128), so  as_float(0x4B0000uu) + (o - 2^23 - 128) == q + o
+// 4 signed bytes -> 4 floats holding (q + o) * s.  The byte is planted into the mantissa of 2^23
+// (after flipping its sign bit: u = q + 128), so  as_float(0x4B0000uu) + (o - 2^23 - 128) == q + o
 // exactly (integers below 2^24) with one PRMT and one FADD instead of an int->float conversion.
-__device__ __forceinline__ void dequant4(uint32_t w, float c_fast, float o, float s, bool fast, float (&f)[4]) {
-  if (fast) {
-    const uint32_t u = w ^ 0x80808080u;
-    f[0] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)), c_fast), s);
-    f[1] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)), c_fast), s);
-    f[2] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)), c_fast), s);
-    f[3] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)), c_fast), s);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) f[i] = __fmul_rn(__fadd_rn((float)(int8_t)(w >> (8 * i)), o), s);
-  }
+// Valid for |o| < 2^22; larger offsets take the plain conversion path.
+__device__ __forceinline__ void dequant4_fast(uint32_t w, float c_fast, float s, float (&f)[4]) {
+  const uint32_t u = w ^ 0x80808080u;
+  f[0] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7440)), c_fast), s);
+  f[1] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7441)), c_fast), s);
+  f[2] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7442)), c_fast), s);
+  f[3] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)), c_fast), s);
 }
 
 template <typename T>
@@ -96,15 +106,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_raw, const Args g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;                                                   // [STAGES][A | B | raw]
-  float* col_bias = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);      // [BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + BN * 4);
-  uint64_t* full_bar = bars;                     // [STAGES]  leader's copy: A bytes of both CTAs + 8 dequantizer warps
-  uint64_t* raw_full = bars + STAGES;            // [STAGES]  local: this CTA's raw code tile has landed
-  uint64_t* empty_bar = bars + 2 * STAGES;       // [STAGES]  local copy, signalled by the leader's tcgen05.commit multicast
-  uint64_t* tmem_full = bars + 3 * STAGES;       // [2]
-  uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]       leader's copy, 8 arrivals
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  uint8_t* a_base = smem;                                   // [SA][128 rows x 128 B]   A operand, TMA, 128B swizzle
+  uint8_t* b_base = a_base + SA * A_BYTES;                  // [SB][128 rows x 128 B]   this CTA's half of B, written by the dequantizers
+  uint8_t* r_base = b_base + SB * B_BYTES;                  // [SR][128 rows x 64 B]    raw int8 codes, TMA, unswizzled
+  float* col_bias = reinterpret_cast<float*>(r_base + SR * RAW_BYTES);      // [BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(col_bias + BN);
+  uint64_t* a_full = bars;                       // [SA] leader's copy: A bytes of both CTAs
+  uint64_t* a_empty = a_full + SA;               // [SA] local copy, signalled by the leader's tcgen05.commit multicast
+  uint64_t* b_full = a_empty + SA;               // [SB] leader's copy: 2 x DQ_WARPS dequantizer warps
+  uint64_t* b_empty = b_full + SB;               // [SB] local copy, commit multicast
+  uint64_t* raw_full = b_empty + SB;             // [SR] local: this CTA's raw code tile has landed
+  uint64_t* raw_empty = raw_full + SR;           // [SR] local: DQ_WARPS dequantizer warps have read it
+  uint64_t* tmem_full = raw_empty + SR;          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]  leader's copy, 8 arrivals
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
@@ -114,15 +129,13 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int k_blocks = g.K / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1 + 2 * DQ_WARPS);
-      mbar_init(&raw_full[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 2 * DQ_WARPS); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < SR; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], DQ_WARPS); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
                  "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -132,32 +145,43 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  if (warp == 0) {
-    // ===== TMA producer =====
+  if (warp == WARP_TMA_A) {
+    // ===== A producer (both CTAs; completions count on the leader's barrier) =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        const int tm = tile % tiles_m;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = stage_base + stage * STAGE_BYTES;
-          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * A_BYTES);
-          tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
-          mbar_expect_tx(&raw_full[stage], RAW_BYTES);
-          tma_load_2d(sa + A_BYTES + B_BYTES, &map_raw, &raw_full[stage], kb * BK, tn * BN + (int)cta * (BN / 2));
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (cta == 0) mbar_expect_tx(&a_full[stage], 2 * A_BYTES);
+          tma_load_2d_pair(a_base + stage * A_BYTES, &map_a, &a_full[stage], kb * BK, tm * TM + (int)cta * BM);
+          if (++stage == SA) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_TMA_RAW) {
+    // ===== raw-code producer: its own, deeper ring, released by the dequantizers (not by the MMAs) =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_raw) : "memory");
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int tn = tile / tiles_m;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&raw_empty[stage], phase ^ 1);
+          mbar_expect_tx(&raw_full[stage], RAW_BYTES);
+          tma_load_2d(r_base + stage * RAW_BYTES, &map_raw, &raw_full[stage], kb * BK, tn * BN + (int)cta * (BN / 2));
+          if (++stage == SR) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
     // ===== MMA issuer (leader CTA only) =====
     if (cta == 0 && lane == 0) {
-      constexpr uint32_t fmt = sizeof(T) == 2 && Elem<T>::dt == FFQ_BF16 ? 1u : 0u;
+      constexpr uint32_t fmt = Elem<T>::dt == FFQ_BF16 ? 1u : 0u;
       // D = F32, A = B = bf16/f16, both K-major, N = 256, M = 256 (128 rows in each CTA)
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const int buf = it & 1;
@@ -166,25 +190,28 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&a_full[sa], pa);
+          mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+          const uint64_t da = make_smem_desc(smem_u32(a_base + sa * A_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(b_base + sb * B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +16 elements = +32 bytes inside the swizzle atom == +2 in the (>>4) start-address field
             umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           }
-          umma_commit_pair(&empty_bar[stage]);
+          umma_commit_pair(&a_empty[sa]);
+          umma_commit_pair(&b_empty[sb]);
           if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[buf]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          if (++sb == SB) { sb = 0; pb ^= 1; }
         }
       }
     }
-  } else if (warp < 6) {
-    // ===== epilogue (warps 2..5 of both CTAs): this CTA's 128 rows =====
+  } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + 4) {
+    // ===== epilogue (4 warps of both CTAs): this CTA's 128 rows; TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
-    const int ep_tid = threadIdx.x - 64;
+    const int ep_tid = threadIdx.x - WARP_EPI0 * 32;
     T* __restrict__ y = static_cast<T*>(g.y);
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -199,7 +226,7 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
 
-      mbar_wait(&tmem_full[buf], use & 1);
+      mbar_wait_backoff(&tmem_full[buf], use & 1);           // a whole k-loop away: do not burn issue slots
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
@@ -219,70 +246,100 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);
     }
-  } else {
-    // ===== dequantizers (warps 6..9): raw int8 codes -> swizzled 16-bit B stage =====
-    const int t = threadIdx.x - 192;               // 0..127
-    const int chunk = t & 3;                       // 16 codes = 16 raw bytes = two 16-byte B chunks
-    const int row0 = t >> 2;                       // rows row0 + 32*i, i = 0..3
-    int stage = 0; uint32_t phase = 0;
+  } else if (warp >= WARP_DQ0) {
+    // ===== dequantizers (8 warps): raw int8 codes -> swizzled 16-bit B stage =====
+    // Two warps per scheduler so that one warp's shared-memory / fence latency hides behind the
+    // other's arithmetic.  Thread t owns 16 codes (16 raw bytes -> two 16-byte B chunks) of rows
+    // t/4 and t/4 + 64 of this CTA's 128-row half.
+    constexpr int ITEMS = (BN / 2) * 4 / (DQ_WARPS * 32);     // 2
+    constexpr int ROW_STEP = DQ_WARPS * 8;                      // 64
+    const int t = threadIdx.x - WARP_DQ0 * 32;
+    const int chunk = t & 3;
+    const int row0 = t >> 2;
+    const uint32_t b0 = smem_u32(b_base), r0 = smem_u32(r_base);
+    int sr = 0, sb = 0; uint32_t pr = 0, pb = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int tn = tile / tiles_m;
       const int nbase = tn * BN + (int)cta * (BN / 2) + row0;
-      float s_cur[4], o_cur[4], s_nxt[4], o_nxt[4];
-      int cur_g = -1;
-      auto fetch = [&](int gi, float (&s)[4], float (&o)[4]) {
+      float s_cur[ITEMS], o_cur[ITEMS], s_nxt[ITEMS], o_nxt[ITEMS];
+      bool fast = true;
+      // raw parameter loads only: nothing here may consume the values, or the prefetch turns into a stall
+      auto fetch = [&](int gi, float (&s)[ITEMS], float (&o)[ITEMS]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = nbase + 32 * i;
+        for (int i = 0; i < ITEMS; ++i) {
+          const int n = nbase + ROW_STEP * i;
           const bool in = n < g.N && gi < g.groups;
           s[i] = in ? __ldg(g.sw + (size_t)n * g.groups + gi) : 0.f;
-          o[i] = (in && g.ow) ? rintf(__ldg(g.ow + (size_t)n * g.groups + gi)) : 0.f;
+          o[i] = (in && g.ow) ? __ldg(g.ow + (size_t)n * g.groups + gi) : 0.f;
         }
       };
       fetch(0, s_nxt, o_nxt);
+      int gi = 0, left = 0;                          // k-blocks left in the current group
       for (int kb = 0; kb < k_blocks; ++kb) {
-        const int gi = (kb * BK) / g.group;
-        if (gi != cur_g) {                          // parameters of the NEXT group are requested one group ahead
+        if (left == 0) {                             // parameters of the NEXT group are requested one group ahead
+          bool ok = true;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { s_cur[i] = s_nxt[i]; o_cur[i] = o_nxt[i]; }
-          cur_g = gi;
-          fetch(gi + 1, s_nxt, o_nxt);
+          for (int i = 0; i < ITEMS; ++i) { s_cur[i] = s_nxt[i]; o_cur[i] = rintf(o_nxt[i]); ok = ok && fabsf(o_cur[i]) < 4194304.f; }
+          fast = __all_sync(0xffffffffu, ok);       // warp-uniform: the magic-number path needs |offset| < 2^22
+          fetch(++gi, s_nxt, o_nxt);
+          left = g.kb_per_group;
         }
-        mbar_wait(&raw_full[stage], phase);
-        uint8_t* sb = stage_base + stage * STAGE_BYTES + A_BYTES;
-        const uint8_t* sr = sb + B_BYTES;
+        --left;
+        mbar_wait(&raw_full[sr], pr);
+        uint4 v[ITEMS];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = row0 + 32 * i;
-          const uint4 v = *reinterpret_cast<const uint4*>(sr + r * BK + chunk * 16);
-          const float o = o_cur[i], s = s_cur[i];
-          const bool fast = fabsf(o) < 4194304.f;
-          const float cf = __fsub_rn(o, 8388736.f);   // o - 2^23 - 128, exact for |o| < 2^22
-          float f[16];
-          { float q[4]; dequant4(v.x, cf, o, s, fast, q); f[0] = q[0]; f[1] = q[1]; f[2] = q[2]; f[3] = q[3]; }
-          { float q[4]; dequant4(v.y, cf, o, s, fast, q); f[4] = q[0]; f[5] = q[1]; f[6] = q[2]; f[7] = q[3]; }
-          { float q[4]; dequant4(v.z, cf, o, s, fast, q); f[8] = q[0]; f[9] = q[1]; f[10] = q[2]; f[11] = q[3]; }
-          { float q[4]; dequant4(v.w, cf, o, s, fast, q); f[12] = q[0]; f[13] = q[1]; f[14] = q[2]; f[15] = q[3]; }
-          uint4 lo, hi;
-          lo.x = pack2<T>(f[0], f[1]);   lo.y = pack2<T>(f[2], f[3]);   lo.z = pack2<T>(f[4], f[5]);   lo.w = pack2<T>(f[6], f[7]);
-          hi.x = pack2<T>(f[8], f[9]);   hi.y = pack2<T>(f[10], f[11]); hi.z = pack2<T>(f[12], f[13]); hi.w = pack2<T>(f[14], f[15]);
-          // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r % 8); rows are 128 B apart
-          uint8_t* rowp = sb + r * 128;
-          const int sw7 = r & 7;
-          *reinterpret_cast<uint4*>(rowp + (((2 * chunk) ^ sw7) << 4)) = lo;
-          *reinterpret_cast<uint4*>(rowp + (((2 * chunk + 1) ^ sw7) << 4)) = hi;
+        for (int i = 0; i < ITEMS; ++i) {
+          const int r = row0 + ROW_STEP * i;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                       : "r"(r0 + (uint32_t)(sr * RAW_BYTES + r * BK + chunk * 16)));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05.mma
         __syncwarp();
-        if (lane == 0) mbar_arrive_leader_release(&full_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (lane == 0) mbar_arrive(&raw_empty[sr]);            // the codes are in registers: the raw slot may be refilled
+        if (++sr == SR) { sr = 0; pr ^= 1; }
+        float f[ITEMS][16];
+        if (fast) {                                  // ONE warp-uniform branch per k-block
+#pragma unroll
+          for (int i = 0; i < ITEMS; ++i) {
+            const float cf = __fsub_rn(o_cur[i], 8388736.f);   // o - 2^23 - 128, exact for |o| < 2^22
+            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float q[4]; dequant4_fast(w[j], cf, s_cur[i], q); f[i][4 * j] = q[0]; f[i][4 * j + 1] = q[1]; f[i][4 * j + 2] = q[2]; f[i][4 * j + 3] = q[3]; }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[i][j] = __fmul_rn(__fadd_rn((float)(int8_t)(w[j >> 2] >> (8 * (j & 3))), o_cur[i]), s_cur[i]);
+          }
+        }
+        mbar_wait(&b_empty[sb], pb ^ 1);                        // the MMAs that read this B slot have retired
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+          const int r = row0 + ROW_STEP * i;
+          // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r % 8); rows are 128 B apart
+          const uint32_t rowp = b0 + (uint32_t)(sb * B_BYTES + r * 128);
+          const int sw7 = r & 7;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowp + (uint32_t)(((2 * chunk) ^ sw7) << 4)),
+                       "r"(pack2<T>(f[i][0], f[i][1])), "r"(pack2<T>(f[i][2], f[i][3])), "r"(pack2<T>(f[i][4], f[i][5])),
+                       "r"(pack2<T>(f[i][6], f[i][7])) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowp + (uint32_t)(((2 * chunk + 1) ^ sw7) << 4)),
+                       "r"(pack2<T>(f[i][8], f[i][9])), "r"(pack2<T>(f[i][10], f[i][11])), "r"(pack2<T>(f[i][12], f[i][13])),
+                       "r"(pack2<T>(f[i][14], f[i][15])) : "memory");
+        }
+        // generic-proxy stores -> visible to the async proxy (tcgen05.mma), then a plain remote arrive: a
+        // .release.cluster arrive would lower to MEMBAR.ALL.GPU + ERRBAR per k-block (measured: 4x slower kernel)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&b_full[sb]);
+        if (++sb == SB) { sb = 0; pb ^= 1; }
       }
     }
   }
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
@@ -328,7 +385,7 @@ extern "C" int ffq_qlinear_w4a16(const void* x, int x_dtype, const int8_t* qw, v
   if ((rc = w4::make_map2(&map_a, adt, 2, x, M, K, w4::BK, w4::BM, CU_TENSOR_MAP_SWIZZLE_128B)) != FFQ_OK) return rc;
   if ((rc = w4::make_map2(&map_raw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, qw, N, K, w4::BK, w4::BN / 2, CU_TENSOR_MAP_SWIZZLE_NONE)) != FFQ_OK) return rc;
   w4::Args g{};
-  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.sw = sw; g.ow = ow; g.group = (int)group; g.groups = (int)(K / group);
+  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.sw = sw; g.ow = ow; g.group = (int)group; g.groups = (int)(K / group); g.kb_per_group = (int)(group / w4::BK);
   g.bias = bias; g.bias_dt = bias_dtype;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
