@@ -145,6 +145,8 @@ class KernelCensus:
 
         wrap(ops, "quantize_by_tile", "quantize (ew_row_kernel<QUANT>)", lambda a, k, o: self._nbytes(a[0], o))
         wrap(ops, "running_minmax_update_", "running min/max (mm_row_*_kernel)", lambda a, k, o: self._nbytes(a[2]))
+        wrap(ops, "calibrate_quantize_", "fused calibration step (calq_rows/calq_tensor_kernel)",
+             lambda a, k, o: self._nbytes(a[2], o[0]))
         wrap(ops, "dequantize_by_tile", "dequantize (ew_row_kernel<DEQUANT>)", lambda a, k, o: self._nbytes(a[0], o))
         # the GEMM at C-ABI level: args 4..6 are M, N, K
         wrap(C.lib, "ffq_qlinear_w8a8", "w8a8 linear (w8a8_gemm_kernel)", lambda a, k, o: 2.0 * a[4] * a[5] * a[6], c_abi=True)

@@ -119,6 +119,9 @@ def _load() -> ctypes.CDLL:
         "ffq_qlinear_w4a16": (i32, [vp, i32, vp, vp, i64, i64, i64, vp, vp, i64, vp, i32, vp]),
         "ffq_grid_mse": (i32, [vp, i32, vp, vp, i32, vp, lp, dbl, vp, sz, vp]),
         "ffq_grid_mse_workspace_bytes": (sz, [lp, i32, i32]),
+        "ffq_calibrate_quantize": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, lp, dbl, i32, i32, vp, sz, vp]),
+        "ffq_calibrate_quantize_mode": (i32, [lp, i32]),
+        "ffq_calibrate_quantize_workspace_bytes": (sz, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
@@ -133,7 +136,8 @@ lib = _load()
 EXPORTED = (
     "ffq_abi_version ffq_last_error ffq_launch_count ffq_workspace_bytes ffq_num_tiles ffq_quantize "
     "ffq_dequantize ffq_fakequant_fwd ffq_quantize_bwd ffq_minmax ffq_params_for_range "
-    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_qlinear_workspace_bytes ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16"
+    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_qlinear_workspace_bytes ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16 "
+    "ffq_calibrate_quantize ffq_calibrate_quantize_mode ffq_calibrate_quantize_workspace_bytes"
 ).split()
 
 
@@ -201,4 +205,18 @@ def scratch(device: torch.device, nbytes: int) -> torch.Tensor:
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 8192), dtype=torch.uint8, device=device)
         _scratch[key] = buf
+    return buf
+
+
+_barrier_ws: dict = {}
+
+
+def barrier_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Persistent ZERO-initialised per-(device, stream) workspace for kernels with a grid barrier
+    (ffq_calibrate_quantize): the kernel leaves the barrier words zeroed for its next launch."""
+    key = (device.index, current_stream(device))
+    buf = _barrier_ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _barrier_ws[key] = buf
     return buf

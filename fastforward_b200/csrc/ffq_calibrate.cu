@@ -1,0 +1,638 @@
+// ffq_calibrate.cu -- one RunningMinMax calibration step of one quantizer in ONE pass over HBM
+// (SURVEY.md section 8a rows a7 + a6 + a1, plus the code row sums the W8A8 linear of a12 needs):
+//
+//     tile min/max -> running range update (+-inf flag) -> range -> (scale, offset) -> int8 codes
+//     [-> int32 row sums of the codes]
+//
+// The reference does this as RunningMinMaxEstimator.estimate_step (range_setting/minmax.py:215-239:
+// two full reads + a host sync), the quantization_range setter (nn/linear_quantizer.py:347-357 ->
+// affine/range.py:54-122: a second host sync) and quantize_by_tile (_quantizer_impl.py:144-169: a third
+// read) per quantizer per forward.  The unfused B200 path (ffq_minmax + ffq_params_for_range +
+// ffq_quantize + ffq_rowsum_i8) already has no syncs but still reads the tensor three times and the
+// codes once; here the data crosses HBM once (s + c bytes per element) in a single launch:
+//
+//   * calq_rows_kernel  : per-channel weights (tile = one contiguous row).  One CTA holds a row in
+//     registers (<= 8 x 16 B per thread), reduces it, updates the running range, derives the
+//     parameters and quantizes from the registers.
+//   * calq_tensor_kernel: per-tensor activations.  A co-resident (cooperative) grid; every CTA parks
+//     its first 32 KB chunk in shared memory (148 SMs x 4 CTAs x 32 KB = 19 MB of the tensor never
+//     gets re-read), partial extrema meet at a grid barrier, then every CTA derives the same
+//     parameters and quantizes (remaining chunks are re-read through L2).
+//
+// The symmetric "one-sided" decision of parameters_for_range (`min.min() >= 0`, range.py:100) is global
+// over all tiles.  A row whose running min is negative (or NaN) already proves the answer is "two-sided",
+// so it is finished immediately; rows with a non-negative running min are left to calq_rows_fixup_kernel,
+// which runs right behind, takes the global decision and finishes exactly those rows (normally none).
+//
+// Arithmetic is the same op-by-op sequence as the unfused kernels (ffq_common.cuh), so the results are
+// bit-identical to them and to the reference (tests/test_calibrate_gpu.py).
+#include "ffq_common.cuh"
+
+namespace ffq {
+
+struct CalqArgs {
+  const void* x;
+  int8_t* q;
+  void* run_min; void* run_max; int run_dt;
+  float* scale; float* offset;          // fp32 [tiles]; offset may be null (symmetric, one-sided not allowed)
+  int32_t* rowsum;                      // optional: int32 per code row
+  int32_t* flags;                       // optional: bit 0 = +-inf seen, bit 1 = grid barrier timed out
+  int32_t* settled;                     // optional, rows: set once every running min is negative (sticky)
+  unsigned long long rows;              // rows kernels: number of tiles.  tensor kernel: rows of the rowsum
+  unsigned int row_len;                 // elements per row
+  unsigned long long numel;
+  float int_min_abs, int_max_abs, neg_int_min, steps, lo, hi;
+  int symmetric, allow_one_sided, sat8;
+  // tensor kernel
+  float* part;                          // [2 * gridDim.x]
+  unsigned int* bar;                    // [2] zero between launches
+  unsigned int nchunks;
+  FastDiv rdiv;                         // division by row_len (tensor kernel row sums)
+};
+
+constexpr int CQ_CHUNK_VECS = 2048;     // tensor kernel: 32 KB of input per CTA chunk
+constexpr int CQ_T = 256;
+constexpr int CQ_U = 4;               // 16-byte loads in flight per lane
+
+// parameters_for_range for one tile (affine/range.py:89-122), fp32; `one_sided` is the global decision
+__device__ __forceinline__ void calq_params(const CalqArgs& a, float mn, float mx, bool one_sided, float& sc, float& off) {
+  if (a.symmetric && !one_sided) {
+    const float neg = __fdiv_rn(fabsf(mn), a.int_min_abs);
+    const float pos = __fdiv_rn(fabsf(mx), a.int_max_abs);
+    sc = nan_max(neg, pos);
+    off = 0.f;
+    return;
+  }
+  if (a.symmetric) mn = 0.f;
+  sc = __fdiv_rn(__fsub_rn(mx, mn), a.steps);
+  const float eps = 1.1920928955078125e-07f;
+  sc = (sc != sc) ? sc : fmaxf(sc, eps);
+  off = __fadd_rn(__fdiv_rn(mn, sc), a.neg_int_min);
+}
+
+// quantize one 16-byte vector to int8 codes (quantize_by_tile with an fp32 chain); returns the codes
+// packed little-endian and adds them to `sum`
+template <typename XT, int EPT>
+__device__ __forceinline__ void calq_vec(const Vec<XT, EPT>& xin, const SharedRcp& k, float o, float lo, float hi,
+                                         bool sat8, uint32_t (&packed)[EPT / 4], int& sum) {
+  float x[EPT], t[EPT];
+  int c[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) x[i] = Elem<XT>::to_f(xin.v[i]);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const float q0 = __fmul_rn(x[i], k.r);
+    const float e = __fmaf_rn(-k.s, q0, x[i]);
+    const float q = __fmaf_rn(k.r, e, q0);
+    amax = nan_max(amax, fabsf(q));
+    t[i] = __fsub_rn(q, o);
+  }
+  const bool ok = k.ok && (amax <= 0x1p60f);
+  if (ok && sat8) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(c[i]) : "f"(t[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const float tt = ok ? t[i] : __fsub_rn(__fdiv_rn(x[i], k.s), o);
+      c[i] = (int)(int8_t)__float2int_rz(nan_clamp(rintf(tt), lo, hi));
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < EPT / 4; ++w) {
+    packed[w] = (uint32_t)(c[4 * w] & 0xff) | ((uint32_t)(c[4 * w + 1] & 0xff) << 8) |
+                ((uint32_t)(c[4 * w + 2] & 0xff) << 16) | ((uint32_t)(c[4 * w + 3] & 0xff) << 24);
+    sum += c[4 * w] + c[4 * w + 1] + c[4 * w + 2] + c[4 * w + 3];
+  }
+}
+
+// Fast variant for tiles whose guard was settled ONCE from the running range (which contains every element of
+// the tile): the scale is inside the shared-reciprocal box and max(|min|, |max|) / s <= 2^59, so every quotient
+// passes the magnitude guard and there is no NaN (a NaN element would have made the range NaN).  Per element:
+// unpack, FMUL + 2 FFMA (exact quotient), FADD, F2I; packing saturates to int8 two codes at a time and the row
+// sum is one dp4a per four codes.
+template <typename XT, int EPT, bool SAT8>
+__device__ __forceinline__ void calq_vec_fast(const Vec<XT, EPT>& xin, const SharedRcp& k, float o, int lo, int hi,
+                                              uint32_t (&packed)[EPT / 4], int& sum) {
+  int c[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const float x = Elem<XT>::to_f(xin.v[i]);
+    const float q0 = __fmul_rn(x, k.r);
+    const float e = __fmaf_rn(-k.s, q0, x);
+    const float q = __fmaf_rn(k.r, e, q0);
+    c[i] = __float2int_rn(__fsub_rn(q, o));          // saturates to int32; rint-then-clamp == clamp of this
+    if constexpr (!SAT8) c[i] = min(max(c[i], lo), hi);
+  }
+#pragma unroll
+  for (int w = 0; w < EPT / 4; ++w) {
+    uint32_t hi16, word;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(c[4 * w + 3]), "r"(c[4 * w + 2]), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(word) : "r"(c[4 * w + 1]), "r"(c[4 * w]), "r"(hi16));
+    packed[w] = word;
+    sum = __dp4a((int)word, 0x01010101, sum);
+  }
+}
+
+// guard for calq_vec_fast from the tile's running range
+__device__ __forceinline__ bool calq_fast_ok(const SharedRcp& k, float rmn, float rmx) {
+  const float bound = __fmul_rn(nan_max(fabsf(rmn), fabsf(rmx)), fabsf(k.r));
+  return k.ok && (bound <= 0x1p59f);                 // NaN compares false
+}
+
+template <typename XT, int EPT>
+__device__ __forceinline__ void calq_vec_any(const Vec<XT, EPT>& xin, const SharedRcp& k, float o, const CalqArgs& a,
+                                             bool fast, uint32_t (&packed)[EPT / 4], int& sum) {
+  if (fast) {
+    if (a.sat8) calq_vec_fast<XT, EPT, true>(xin, k, o, 0, 0, packed, sum);
+    else calq_vec_fast<XT, EPT, false>(xin, k, o, (int)a.lo, (int)a.hi, packed, sum);
+  } else {
+    calq_vec<XT, EPT>(xin, k, o, a.lo, a.hi, a.sat8 != 0, packed, sum);
+  }
+}
+
+template <int EPT>
+__device__ __forceinline__ void calq_store(int8_t* q, const uint32_t (&packed)[EPT / 4]) {
+  if constexpr (EPT == 8) *reinterpret_cast<uint2*>(q) = make_uint2(packed[0], packed[1]);
+  else *reinterpret_cast<uint32_t*>(q) = packed[0];
+}
+
+// CTA-wide integer sum (result valid in thread 0); smem: 32 ints
+__device__ __forceinline__ int block_isum(int v, int* smem) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (w == 0) {
+    v = lane < nw ? smem[lane] : 0;
+    v = __reduce_add_sync(0xffffffffu, v);
+  }
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// rows: one CTA per tile, the tile lives in registers
+// ------------------------------------------------------------------------------------------
+template <typename XT, int VPT>
+__global__ void __launch_bounds__(512) calq_rows_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  __shared__ float s_mn[16], s_mx[16];
+  __shared__ int s_i[32];
+  const unsigned long long row = blockIdx.x;
+  const unsigned int nvec = a.row_len / EPT;
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x) + row * a.row_len;
+
+  Vec<XT, EPT> xin[VPT];
+#pragma unroll
+  for (int u = 0; u < VPT; ++u) {
+    const unsigned int j = threadIdx.x + u * blockDim.x;
+    if (j < nvec) xin[u] = ld_stream<XT, EPT>(x + (size_t)j * EPT);
+  }
+  // the old running range is requested behind the data so that its latency hides under the stream; every thread
+  // reads it before the barrier below, thread 0 overwrites it after the barrier
+  const float old_mn = load_as_float(a.run_min, a.run_dt, row);
+  const float old_mx = load_as_float(a.run_max, a.run_dt, row);
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < VPT; ++u) {
+    const unsigned int j = threadIdx.x + u * blockDim.x;
+    if (j < nvec) {
+      float vmn, vmx;
+      vec_minmax<XT, EPT>(xin[u], vmn, vmx);
+      mn = nan_min(mn, vmn);
+      mx = nan_max(mx, vmx);
+    }
+  }
+  mn = group_min<32>(mn);
+  mx = group_max<32>(mx);
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  // every thread finishes the reduction and derives the parameters itself: no second barrier, no broadcast
+  mn = s_mn[0]; mx = s_mx[0];
+  for (unsigned int w = 1; w < nw; ++w) { mn = nan_min(mn, s_mn[w]); mx = nan_max(mx, s_mx[w]); }
+  // running update: torch.min(self.min, data_min) / torch.max(...) in the range's dtype (minmax.py:235-237)
+  const float rmn = nan_min(old_mn, mn);
+  const float rmx = nan_max(old_mx, mx);
+  // a negative (or NaN) running min settles the global one-sided question: two-sided
+  const bool deferred = a.symmetric && a.allow_one_sided && (rmn >= 0.f);
+  float sc = 1.f, off = 0.f;
+  if (!deferred) calq_params(a, rmn, rmx, false, sc, off);
+  if (threadIdx.x == 0) {
+    store_from_float(a.run_min, a.run_dt, row, rmn);
+    store_from_float(a.run_max, a.run_dt, row, rmx);
+    if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+    if (!deferred) {
+      a.scale[row] = sc;
+      if (a.offset) a.offset[row] = off;
+    }
+  }
+  if (deferred) return;                    // finished by calq_rows_fixup_kernel
+  const float o = rintf(off);
+  const SharedRcp k = make_shared_rcp(sc);
+  const bool fast = calq_fast_ok(k, rmn, rmx);
+  int8_t* __restrict__ q = a.q + row * a.row_len;
+  int sum = 0;
+#pragma unroll
+  for (int u = 0; u < VPT; ++u) {
+    const unsigned int j = threadIdx.x + u * blockDim.x;
+    if (j < nvec) {
+      uint32_t packed[EPT / 4];
+      calq_vec_any<XT, EPT>(xin[u], k, o, a, fast, packed, sum);
+      calq_store<EPT>(q + (size_t)j * EPT, packed);
+    }
+  }
+  if (a.rowsum) {
+    sum = block_isum(sum, s_i);
+    if (threadIdx.x == 0) a.rowsum[row] = sum;
+  }
+}
+
+// Finishes the rows calq_rows_kernel left open (running min >= 0): takes the global one-sided decision
+// over ALL running mins and quantizes those rows, streaming them from HBM/L2.  Grid: a few CTAs per SM.
+template <typename XT>
+__global__ void __launch_bounds__(CQ_T) calq_rows_fixup_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  __shared__ float s_f[64];
+  __shared__ int s_i[32];
+  __shared__ float s_g[2];
+  // running mins only ever decrease: once every row has a negative one, no row is deferred again
+  if (a.settled && *reinterpret_cast<const volatile int32_t*>(a.settled) != 0) return;
+  float gmn = INFINITY, any = -INFINITY;
+  for (unsigned long long r = threadIdx.x; r < a.rows; r += blockDim.x) {
+    const float v = load_as_float(a.run_min, a.run_dt, r);
+    gmn = nan_min(gmn, v);
+    any = fmaxf(any, (v >= 0.f) ? 1.f : 0.f);
+  }
+  block_minmax(gmn, any, s_f);
+  if (threadIdx.x == 0) { s_g[0] = gmn; s_g[1] = any; }
+  __syncthreads();
+  if (!(s_g[1] > 0.f)) {                   // nothing was deferred
+    if (a.settled && blockIdx.x == 0 && threadIdx.x == 0 && !(s_g[0] != s_g[0])) *a.settled = 1;
+    return;
+  }
+  const bool one_sided = s_g[0] >= 0.f;    // NaN >= 0 is false, as in Python
+  const unsigned int nvec = a.row_len / EPT;
+  for (unsigned long long row = blockIdx.x; row < a.rows; row += gridDim.x) {
+    const float rmn = load_as_float(a.run_min, a.run_dt, row);
+    if (!(rmn >= 0.f)) continue;
+    const float rmx = load_as_float(a.run_max, a.run_dt, row);
+    float sc, off;
+    calq_params(a, rmn, rmx, one_sided, sc, off);
+    if (threadIdx.x == 0) {
+      a.scale[row] = sc;
+      if (a.offset) a.offset[row] = off;
+    }
+    const float o = rintf(off);
+    const SharedRcp k = make_shared_rcp(sc);
+    const bool fast = calq_fast_ok(k, rmn, rmx);
+    const XT* __restrict__ x = static_cast<const XT*>(a.x) + row * a.row_len;
+    int8_t* __restrict__ q = a.q + row * a.row_len;
+    int sum = 0;
+    for (unsigned int j = threadIdx.x; j < nvec; j += blockDim.x) {
+      const Vec<XT, EPT> xv = ld_stream<XT, EPT>(x + (size_t)j * EPT);
+      uint32_t packed[EPT / 4];
+      calq_vec_any<XT, EPT>(xv, k, o, a, fast, packed, sum);
+      calq_store<EPT>(q + (size_t)j * EPT, packed);
+    }
+    if (a.rowsum) {
+      __syncthreads();
+      sum = block_isum(sum, s_i);
+      if (threadIdx.x == 0) a.rowsum[row] = sum;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-tensor: co-resident grid, first chunk of every CTA parked in shared memory
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  constexpr int VPW = CQ_CHUNK_VECS / (CQ_T / 32);       // vectors of a chunk owned by one warp (contiguous)
+  extern __shared__ uint4 s_chunk[];                      // CQ_CHUNK_VECS vectors
+  __shared__ float s_f[64];
+  __shared__ float s_par[4];
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int G = gridDim.x;
+  const unsigned long long nvec = a.numel / EPT;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+
+  float old_mn = 0.f, old_mx = 0.f;
+  if (threadIdx.x == 0) {
+    old_mn = load_as_float(a.run_min, a.run_dt, 0);
+    old_mx = load_as_float(a.run_max, a.run_dt, 0);
+  }
+  if (a.rowsum)
+    for (unsigned long long r = (unsigned long long)blockIdx.x * CQ_T + threadIdx.x; r < a.rows; r += (unsigned long long)G * CQ_T)
+      a.rowsum[r] = 0;
+
+  // ---- phase 1: extrema of this CTA's chunks; the first chunk stays in shared memory ----
+  float mn = INFINITY, mx = -INFINITY;
+  for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
+    const unsigned long long v0 = (unsigned long long)c * CQ_CHUNK_VECS + warp * VPW + lane;
+    const bool keep = c == blockIdx.x;
+#pragma unroll
+    for (int ub = 0; ub < VPW / 32; ub += CQ_U) {
+      Vec<XT, EPT> xv[CQ_U];
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned long long v = v0 + (ub + u) * 32;
+        if (v < nvec) xv[u] = ld_stream<XT, EPT>(x + v * EPT);
+      }
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned long long v = v0 + (ub + u) * 32;
+        if (v < nvec) {
+          if (keep) s_chunk[warp * VPW + (ub + u) * 32 + lane] = *reinterpret_cast<const uint4*>(&xv[u]);
+          float vmn, vmx;
+          vec_minmax<XT, EPT>(xv[u], vmn, vmx);
+          mn = nan_min(mn, vmn);
+          mx = nan_max(mx, vmx);
+        }
+      }
+    }
+  }
+  block_minmax(mn, mx, s_f);
+  // ---- grid barrier (all CTAs are co-resident: cooperative launch, grid <= occupancy) ----
+  if (threadIdx.x == 0) {
+    a.part[blockIdx.x] = mn;
+    a.part[G + blockIdx.x] = mx;
+    __threadfence();
+    atomicAdd(&a.bar[0], 1u);
+    unsigned int spins = 0;
+    while (ld_acquire_u32(&a.bar[0]) < G) {
+      __nanosleep(32);
+      if (++spins > (1u << 21)) {           // ~1 s: never hang the GPU; the host raises on bit 1
+        if (a.flags) atomicOr(a.flags, 2);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- phase 2: every CTA reduces the partials to the same (min, max) and derives the parameters ----
+  mn = INFINITY; mx = -INFINITY;
+  for (unsigned int i = threadIdx.x; i < G; i += CQ_T) {
+    mn = nan_min(mn, __ldcg(&a.part[i]));
+    mx = nan_max(mx, __ldcg(&a.part[G + i]));
+  }
+  block_minmax(mn, mx, s_f);
+  if (threadIdx.x == 0) {
+    const float rmn = nan_min(old_mn, mn);
+    const float rmx = nan_max(old_mx, mx);
+    float sc, off;
+    calq_params(a, rmn, rmx, a.symmetric && a.allow_one_sided && (rmn >= 0.f), sc, off);
+    if (blockIdx.x == 0) {
+      store_from_float(a.run_min, a.run_dt, 0, rmn);
+      store_from_float(a.run_max, a.run_dt, 0, rmx);
+      if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+      a.scale[0] = sc;
+      if (a.offset) a.offset[0] = off;
+    }
+    s_par[0] = sc; s_par[1] = off; s_par[2] = rmn; s_par[3] = rmx;
+  }
+  __syncthreads();
+  const float s = s_par[0], o = rintf(s_par[1]);
+  const SharedRcp k = make_shared_rcp(s);
+  const bool fast = calq_fast_ok(k, s_par[2], s_par[3]);
+  // ---- phase 3: quantize; a warp owns VPW contiguous vectors, so its codes fall in few rows ----
+  for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
+    const unsigned long long w0 = (unsigned long long)c * CQ_CHUNK_VECS + warp * VPW;   // warp's first vector
+    const bool keep = c == blockIdx.x;
+    unsigned long long row0 = 0;
+    unsigned int rem0 = 0;
+    if (a.rowsum) { row0 = (w0 * EPT) / a.row_len; rem0 = (unsigned int)(w0 * EPT - row0 * a.row_len); }
+    int sum = 0;
+    unsigned int cur = ~0u;                  // row (relative to row0) the running sum belongs to
+#pragma unroll
+    for (int ub = 0; ub < VPW / 32; ub += CQ_U) {
+      Vec<XT, EPT> xv[CQ_U];
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned long long v = w0 + (ub + u) * 32 + lane;
+        if (v < nvec) {
+          if (keep) *reinterpret_cast<uint4*>(&xv[u]) = s_chunk[warp * VPW + (ub + u) * 32 + lane];
+          else xv[u] = ld_stream<XT, EPT>(x + v * EPT);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned long long v = w0 + (ub + u) * 32 + lane;
+        if (w0 + (ub + u) * 32 >= nvec) break;           // the whole warp is past the end
+        const bool live = v < nvec;
+        int vs = 0;
+        if (live) {
+          uint32_t packed[EPT / 4];
+          calq_vec_any<XT, EPT>(xv[u], k, o, a, fast, packed, vs);
+          calq_store<EPT>(a.q + v * EPT, packed);
+        }
+        if (a.rowsum) {
+          // one atomic per (warp, row): sums are carried while the whole warp stays in one row
+          const unsigned int r = fast_div(rem0 + ((ub + u) * 32 + lane) * EPT, a.rdiv);
+          const unsigned int r_first = __shfl_sync(0xffffffffu, r, 0);
+          const unsigned int r_last = __shfl_sync(0xffffffffu, r, 31);
+          if (r_first != cur || r_last != cur) {
+            if (cur != ~0u) {
+              const int tot = __reduce_add_sync(0xffffffffu, sum);
+              if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
+            }
+            sum = 0;
+            cur = (r_first == r_last) ? r_first : ~0u;
+          }
+          if (cur != ~0u) sum += vs;
+          else if (live) atomicAdd(&a.rowsum[row0 + r], vs);
+        }
+      }
+    }
+    if (a.rowsum && cur != ~0u) {
+      const int tot = __reduce_add_sync(0xffffffffu, sum);
+      if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
+    }
+  }
+  // ---- leave the barrier words zeroed for the next launch ----
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(&a.bar[1], 1u);
+    if (done == G - 1) { a.bar[0] = 0; a.bar[1] = 0; __threadfence(); }
+  }
+}
+
+static int g_tensor_occ[3] = {-1, -1, -1};   // CTAs per SM of calq_tensor_kernel<bf16 | f16 | float>
+
+template <typename XT>
+static int tensor_grid_cap(int slot) {
+  if (g_tensor_occ[slot] < 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, calq_tensor_kernel<XT>, CQ_T, CQ_CHUNK_VECS * 16) != cudaSuccess)
+      occ = 1;
+    g_tensor_occ[slot] = occ < 1 ? 1 : occ;
+  }
+  return g_tensor_occ[slot] * sm_count();
+}
+
+template <typename XT>
+static cudaError_t launch_tensor(const CalqArgs& a, unsigned int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CQ_T);
+  cfg.dynamicSmemBytes = CQ_CHUNK_VECS * 16; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, calq_tensor_kernel<XT>, a);
+}
+
+template <typename XT>
+static void launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_t st) {
+  // 4 vectors (64 B) in flight per thread and a CTA sized to the row: no idle slots beyond the last warp
+  const int vpt = nvec > 2048 ? 8 : (nvec >= 256 ? 4 : (nvec >= 128 ? 2 : 1));
+  const unsigned int threads = ((nvec + vpt - 1) / vpt + 31) / 32 * 32;
+  const unsigned int grid = (unsigned int)a.rows;
+  switch (vpt) {
+    case 1: calq_rows_kernel<XT, 1><<<grid, threads, 0, st>>>(a); break;
+    case 2: calq_rows_kernel<XT, 2><<<grid, threads, 0, st>>>(a); break;
+    case 4: calq_rows_kernel<XT, 4><<<grid, threads, 0, st>>>(a); break;
+    default: calq_rows_kernel<XT, 8><<<grid, threads, 0, st>>>(a); break;
+  }
+}
+
+}  // namespace ffq
+
+using namespace ffq;
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// 0: not supported (use the unfused sequence), 1: rows kernel, 2: per-tensor kernel
+static int calq_mode(const Plan& plan, int x_dtype) {
+  if (!(x_dtype == FFQ_F32 || x_dtype == FFQ_F16 || x_dtype == FFQ_BF16)) return 0;
+  if (!plan.row || plan.numel == 0) return 0;
+  const int ept = 16 / dt_size(x_dtype);
+  if (plan.tile_numel % ept != 0) return 0;
+  const long long tvec = plan.tile_numel / ept;
+  if (plan.num_tiles == 1) return (plan.numel < (1ll << 40) && tvec >= 64) ? 2 : 0;
+  if (tvec >= 64 && tvec <= 4096 && plan.num_tiles < (1ll << 31) && plan.tile_numel < (1ll << 31)) return 1;
+  return 0;
+}
+
+extern "C" {
+
+int ffq_calibrate_quantize_mode(const ffq_layout_t* layout, int x_dtype) {
+  Plan plan;
+  if (make_plan(layout, &plan) != FFQ_OK) return 0;
+  return calq_mode(plan, x_dtype);
+}
+
+size_t ffq_calibrate_quantize_workspace_bytes(void) {
+  // [bar0, bar1, pad x2 | partial mins and maxes of up to 148 * 16 CTAs]
+  return 16 + (size_t)2 * 4096 * sizeof(float);
+}
+
+int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min, void* run_max, int run_dtype,
+                           float* scale, float* offset, int32_t* rowsum, int64_t rowsum_row_len, int32_t* flags,
+                           int32_t* settled, const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan plan;
+  int rc = make_plan(layout, &plan);
+  if (rc != FFQ_OK) return rc;
+  const int mode = calq_mode(plan, x_dtype);
+  if (mode == 0 || !aligned16(x) || (reinterpret_cast<uintptr_t>(q) & 7u) != 0) {
+    set_error("calibrate_quantize: layout/dtype/alignment not handled by the fused kernels");
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (num_bits > 8 || num_bits < 1) { set_error("calibrate_quantize: int8 codes hold at most 8 bits"); return FFQ_ERR_BITWIDTH; }
+  if (!(run_dtype == FFQ_F32 || run_dtype == FFQ_F16 || run_dtype == FFQ_BF16) || promote(run_dtype, x_dtype) != run_dtype) {
+    set_error("calibrate_quantize: running-range dtype %s cannot hold %s data", dt_name(run_dtype), dt_name(x_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (run_min == nullptr || run_max == nullptr || scale == nullptr || (offset == nullptr && !(symmetric && !allow_one_sided))) {
+    set_error("calibrate_quantize: run_min, run_max, scale (and offset unless symmetric two-sided only) are required");
+    return FFQ_ERR_INVALID;
+  }
+  CalqArgs a{};
+  a.x = x; a.q = q; a.run_min = run_min; a.run_max = run_max; a.run_dt = run_dtype;
+  a.scale = scale; a.offset = offset; a.rowsum = rowsum; a.flags = flags; a.settled = settled;
+  a.numel = (unsigned long long)plan.numel;
+  const double lo = -pow(2.0, num_bits - 1.0);
+  a.int_min_abs = (float)fabs(lo);
+  a.int_max_abs = (float)fabs(-lo - 1.0);
+  a.neg_int_min = (float)(-lo);
+  a.steps = (float)(pow(2.0, num_bits) - 1.0);
+  a.lo = (float)lo; a.hi = (float)(-lo - 1.0);
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided;
+  a.sat8 = (a.lo == -128.f && a.hi == 127.f) ? 1 : 0;
+  const int ept = 16 / dt_size(x_dtype);
+  if (mode == 1) {
+    a.rows = (unsigned long long)plan.num_tiles;
+    a.row_len = (unsigned int)plan.tile_numel;
+    if (rowsum && rowsum_row_len != plan.tile_numel) {
+      set_error("calibrate_quantize: per-channel row sums need rowsum_row_len == tile length");
+      return FFQ_ERR_INVALID;
+    }
+    const unsigned int nvec = a.row_len / ept;
+    switch (x_dtype) {
+      case FFQ_F32: launch_rows<float>(a, nvec, st); break;
+      case FFQ_BF16: launch_rows<__nv_bfloat16>(a, nvec, st); break;
+      default: launch_rows<__half>(a, nvec, st); break;
+    }
+    FFQ_LAUNCH_CHECK();
+    if (symmetric && allow_one_sided) {
+      unsigned int grid = (unsigned int)(a.rows < (unsigned long long)sm_count() ? a.rows : sm_count());
+      switch (x_dtype) {
+        case FFQ_F32: calq_rows_fixup_kernel<float><<<grid, CQ_T, 0, st>>>(a); break;
+        case FFQ_BF16: calq_rows_fixup_kernel<__nv_bfloat16><<<grid, CQ_T, 0, st>>>(a); break;
+        default: calq_rows_fixup_kernel<__half><<<grid, CQ_T, 0, st>>>(a); break;
+      }
+      FFQ_LAUNCH_CHECK();
+    }
+    return FFQ_OK;
+  }
+  // per-tensor
+  if (workspace == nullptr || workspace_bytes < ffq_calibrate_quantize_workspace_bytes() ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) {
+    set_error("calibrate_quantize: a 16-byte aligned workspace of %zu bytes is required", ffq_calibrate_quantize_workspace_bytes());
+    return FFQ_ERR_WORKSPACE;
+  }
+  if (rowsum) {
+    if (rowsum_row_len <= 0 || plan.numel % rowsum_row_len != 0 || rowsum_row_len % ept != 0 || rowsum_row_len >= (1ll << 31)) {
+      set_error("calibrate_quantize: rowsum_row_len must divide the tensor and be a multiple of the vector width");
+      return FFQ_ERR_INVALID;
+    }
+    a.rows = (unsigned long long)(plan.numel / rowsum_row_len);
+    a.row_len = (unsigned int)rowsum_row_len;
+  } else {
+    a.rows = 0; a.row_len = (unsigned int)ept;
+  }
+  a.rdiv = make_fast_div(a.row_len);
+  a.bar = static_cast<unsigned int*>(workspace);
+  a.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
+  const unsigned long long nvec = a.numel / ept;
+  const unsigned long long nchunks = (nvec + CQ_CHUNK_VECS - 1) / CQ_CHUNK_VECS;
+  if (nchunks >= (1ull << 31)) { set_error("calibrate_quantize: tensor too large"); return FFQ_ERR_UNSUPPORTED; }
+  a.nchunks = (unsigned int)nchunks;
+  int cap = (x_dtype == FFQ_F32) ? tensor_grid_cap<float>(2) : (x_dtype == FFQ_BF16 ? tensor_grid_cap<__nv_bfloat16>(0) : tensor_grid_cap<__half>(1));
+  if (cap > 4096) cap = 4096;
+  const unsigned int grid = (unsigned int)(nchunks < (unsigned long long)cap ? nchunks : (unsigned long long)cap);
+  cudaError_t e;
+  switch (x_dtype) {
+    case FFQ_F32: e = launch_tensor<float>(a, grid, st); break;
+    case FFQ_BF16: e = launch_tensor<__nv_bfloat16>(a, grid, st); break;
+    default: e = launch_tensor<__half>(a, grid, st); break;
+  }
+  if (e != cudaSuccess) {
+    set_error("calibrate_quantize: cooperative launch failed: %s", cudaGetErrorString(e));
+    return FFQ_ERR_CUDA;
+  }
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+}  // extern "C"

@@ -490,50 +490,6 @@ __device__ __forceinline__ void mm_emit(const MmArgs& a, unsigned long long tile
   if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
 }
 
-__device__ __forceinline__ void block_minmax(float& mn, float& mx, float* smem) {
-  mn = group_min<32>(mn);
-  mx = group_max<32>(mx);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) { smem[w] = mn; smem[32 + w] = mx; }
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  if (w == 0) {
-    mn = (lane < nw) ? smem[lane] : smem[0];
-    mx = (lane < nw) ? smem[32 + lane] : smem[32];
-    mn = group_min<32>(mn);
-    mx = group_max<32>(mx);
-  }
-}
-
-// min and max of one 16-byte vector; 16-bit types use the packed NaN-propagating HMNMX2
-template <typename T, int EPT>
-__device__ __forceinline__ void vec_minmax(const Vec<T, EPT>& v, float& mn, float& mx) {
-  if constexpr (std::is_same<T, __nv_bfloat16>::value && EPT >= 2) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-    __nv_bfloat162 lo = h[0], hi = h[0];
-#pragma unroll
-    for (int i = 1; i < EPT / 2; ++i) { lo = __hmin2_nan(lo, h[i]); hi = __hmax2_nan(hi, h[i]); }
-    mn = nan_min(__low2float(lo), __high2float(lo));
-    mx = nan_max(__low2float(hi), __high2float(hi));
-  } else if constexpr (std::is_same<T, __half>::value && EPT >= 2) {
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-    __half2 lo = h[0], hi = h[0];
-#pragma unroll
-    for (int i = 1; i < EPT / 2; ++i) { lo = __hmin2_nan(lo, h[i]); hi = __hmax2_nan(hi, h[i]); }
-    mn = nan_min(__low2float(lo), __high2float(lo));
-    mx = nan_max(__low2float(hi), __high2float(hi));
-  } else {
-    mn = mx = Elem<T>::to_f(v.v[0]);
-#pragma unroll
-    for (int i = 1; i < EPT; ++i) {
-      const float f = Elem<T>::to_f(v.v[i]);
-      mn = nan_min(mn, f);
-      mx = nan_max(mx, f);
-    }
-  }
-}
-
 template <typename XT, int LANES>
 __global__ void __launch_bounds__(RD_THREADS) mm_row_group_kernel(const MmArgs a) {
   constexpr int EPT = 16 / sizeof(XT);

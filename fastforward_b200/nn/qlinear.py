@@ -55,6 +55,13 @@ def _accepts(input=None, weight=None, bias=None, output_quantizer=None, strict_q
     return input.shape[-1] == k and k % 16 == 0 and (px.dequantize_dtype in (torch.float32, torch.bfloat16, torch.float16))
 
 
+def _attached_rowsum(t, rows: int) -> Optional[torch.Tensor]:
+    rs = getattr(t, "_ffq_rowsum", None)
+    if isinstance(rs, torch.Tensor) and rs.dtype == torch.int32 and rs.numel() == rows and rs.device == t.device:
+        return rs
+    return None
+
+
 def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None):
     px, pw = input.quant_args(), weight.quant_args()
     qx = input.raw_data
@@ -66,12 +73,17 @@ def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, stric
     out_dtype = px.dequantize_dtype or torch.float32
     y = torch.empty((m, n), dtype=out_dtype, device=qx.device)
     stream = C.current_stream(qx.device)
-    rowsum_w = torch.empty(n, dtype=torch.int32, device=qx.device)
-    C.check(C.lib.ffq_rowsum_i8(qw.data_ptr(), rowsum_w.data_ptr(), n, k, stream))
+    # row sums of the codes: produced by the fused calibration step when the codes come straight from it
+    rowsum_w = _attached_rowsum(weight, n)
+    if rowsum_w is None:
+        rowsum_w = torch.empty(n, dtype=torch.int32, device=qx.device)
+        C.check(C.lib.ffq_rowsum_i8(qw.data_ptr(), rowsum_w.data_ptr(), n, k, stream))
     rowsum_x = None
     if pw.offset is not None:
-        rowsum_x = torch.empty(m, dtype=torch.int32, device=qx.device)
-        C.check(C.lib.ffq_rowsum_i8(qx2.data_ptr(), rowsum_x.data_ptr(), m, k, stream))
+        rowsum_x = _attached_rowsum(input, m)
+        if rowsum_x is None:
+            rowsum_x = torch.empty(m, dtype=torch.int32, device=qx.device)
+            C.check(C.lib.ffq_rowsum_i8(qx2.data_ptr(), rowsum_x.data_ptr(), m, k, stream))
     sx = px.scale.detach().reshape(-1)
     ox = None if px.offset is None else px.offset.detach().reshape(-1)
     sw = pw.scale.detach().reshape(-1).contiguous()

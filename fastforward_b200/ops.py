@@ -311,6 +311,62 @@ def parameters_for_range_(
         ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))
 
 
+def calibrate_quantize_mode(shape: Sequence[int], tile_size, dtype: torch.dtype) -> int:
+    """0: the fused calibration step does not handle this layout, 1: per-channel rows, 2: per-tensor."""
+    shape = tuple(shape)
+    tile = shape if isinstance(tile_size, str) else tuple(int(t) for t in tile_size)
+    if dtype not in (torch.float32, torch.float16, torch.bfloat16) or len(shape) != len(tile) or 0 in shape:
+        return 0
+    try:
+        layout = C.make_layout(shape, tile)
+    except (ValueError, NotImplementedError):
+        return 0
+    cache = layout.ws
+    key = ("calq", dtype)
+    if key not in cache:
+        cache[key] = int(C.lib.ffq_calibrate_quantize_mode(layout.ref, C.dtype_tag(dtype)))
+    return cache[key]
+
+
+_CALQ_WS = int(C.lib.ffq_calibrate_quantize_workspace_bytes())
+
+
+def calibrate_quantize_(
+    run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size, num_bits: float,
+    symmetric: bool, allow_one_sided: bool, scale_out: torch.Tensor, offset_out: Optional[torch.Tensor],
+    flags: Optional[torch.Tensor] = None, settled: Optional[torch.Tensor] = None, rowsum: bool = False,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """One RunningMinMax calibration step in one pass over ``data``: updates ``run_min``/``run_max`` in place
+    (range_setting/minmax.py:229-237), writes the quantizer's ``scale``/``offset`` for the updated range in place
+    (nn/linear_quantizer.py:347-357) and returns ``(int8 codes, rowsum-or-None)`` -- the codes are what
+    ``quantize_by_tile(data, scale, tile, num_bits, torch.int8, offset)`` returns for those parameters, and
+    ``rowsum`` (int32, one value per row of the last dimension) is what the W8A8 linear needs from them.
+    Raises NotImplementedError for layouts the fused kernels do not cover (see calibrate_quantize_mode)."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    _bitwidth_guard(torch.int8, num_bits)
+    if x.numel() == 0:
+        raise NotImplementedError("calibrate_quantize_: empty tensor")
+    nt = layout.num_tiles
+    for t, name in ((run_min, "run_min"), (run_max, "run_max")):
+        C.require_cuda(t, name)
+        if t.numel() != nt or not t.is_contiguous() or t.dtype != run_min.dtype or \
+                torch.promote_types(t.dtype, x.dtype) != t.dtype:
+            raise RuntimeError(f"{name} must be a contiguous tensor with {nt} elements whose dtype holds {x.dtype}")
+    for t, name in ((scale_out, "scale_out"), (offset_out, "offset_out")):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != nt or not t.is_contiguous() or not t.is_cuda):
+            raise RuntimeError(f"{name} must be a contiguous CUDA float32 tensor with {nt} elements")
+    q = torch.empty(shape, dtype=torch.int8, device=x.device)
+    row_len = shape[-1]
+    rs = torch.empty(x.numel() // row_len, dtype=torch.int32, device=x.device) if rowsum else None
+    ws = C.barrier_workspace(x.device, _CALQ_WS)
+    C.check(C.lib.ffq_calibrate_quantize(
+        x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), run_min.data_ptr(), run_max.data_ptr(), C.dtype_tag(run_min.dtype),
+        scale_out.data_ptr(), C.ptr(offset_out), C.ptr(rs), row_len, C.ptr(flags), C.ptr(settled),
+        layout.ref, float(num_bits), int(bool(symmetric)), int(bool(allow_one_sided)),
+        ws.data_ptr(), ws.numel(), C.current_stream(x.device)))
+    return q, rs
+
+
 # ------------------------------------------------------------------------------------------
 # fused MSE grid search (range_setting/min_error.py:206-216)
 # ------------------------------------------------------------------------------------------

@@ -9,7 +9,11 @@ What changed for B200 -- behaviour is the same, the schedule is not:
   * range -> (scale, offset) is one more kernel writing the quantizer's parameters in place, with
     the one-sided decision taken on the device (no second host sync);
   * ``process_group`` (or an initialised default group with ``sync_ranges=True``) all-reduces the
-    running ranges with MIN/MAX at the end of the block: data-parallel calibration.
+    running ranges with MIN/MAX at the end of the block: data-parallel calibration;
+  * when the step is followed by the quantizer's own int8 quantization (the usual W8A8 calibration
+    forward) and the layout is a per-channel row or a whole tensor, estimate_step + range setter +
+    quantize (+ the code row sums the W8A8 linear needs) are ONE kernel reading the tensor once
+    (``ops.calibrate_quantize_``; pass ``fused=False`` to the estimator to keep the separate kernels).
 """
 
 from __future__ import annotations
@@ -19,7 +23,9 @@ from typing import Iterator, Optional, Sequence
 
 import torch
 
+from .. import flags as _flags
 from .. import ops
+from ..forward_override import _Chain
 from ..nn.quantized_module import named_quantizers
 from ..nn.quantizer import Quantizer
 from .common import RangeEstimator, RangeSettable, SimpleEstimatorStep
@@ -67,9 +73,11 @@ class _RangeArena:
 
 class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
     def __init__(self, quantizer, disable_quantization: bool = False, eager_checks: bool = False,
-                 arena: Optional[_RangeArena] = None) -> None:
+                 arena: Optional[_RangeArena] = None, fused: bool = True) -> None:
         super().__init__(disable_quantization=disable_quantization)
         self._arena = arena
+        self._fused = fused
+        self._settled = None
         lo, hi = quantizer.quantization_range       # continues from an existing range (minmax.py:198-200)
         self.register_buffer("min", None if lo is None else lo.detach().clone())
         self.register_buffer("max", None if hi is None else hi.detach().clone())
@@ -105,11 +113,80 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         quantizer.quantization_range = (self.min, self.max)
 
     def check_finite(self) -> None:
-        if self.flags is not None and int(self.flags.item()) != 0:
-            raise NotImplementedError("Infinite")
+        if self.flags is not None:
+            _raise_for_flags(int(self.flags.item()))
+
+    # ---- fused step: min/max + running update + range->params + int8 quantize in one kernel ----
+    def _fused_mode(self, quantizer, callback, data) -> int:
+        from ..nn.linear_quantizer import LinearQuantizer
+        from ..quantized_tensor import QuantizedTensor
+
+        if not self._fused or self._disable_quantization or type(quantizer) is not LinearQuantizer:
+            return 0
+        if quantizer.quantized_dtype != torch.int8 or quantizer.num_bits > 8 or torch.is_grad_enabled():
+            return 0
+        if not isinstance(data, torch.Tensor) or isinstance(data, QuantizedTensor) or not data.is_cuda:
+            return 0
+        if _flags.get_export_mode():
+            return 0
+        # the quantizer's own quantize must be what runs next (no other overrides in between)
+        if not isinstance(callback, _Chain) or callback._pending or \
+                getattr(callback._fn, "__func__", None) is not LinearQuantizer.quantize:
+            return 0
+        for p in (quantizer.scale, quantizer.offset):
+            if p is not None and (p.dtype != torch.float32 or p.device != data.device):
+                return 0
+        return ops.calibrate_quantize_mode(data.shape, quantizer.granularity.tile_size(data.shape), data.dtype)
+
+    def _fused_step(self, quantizer, data: torch.Tensor, mode: int):
+        from ..quantization.affine.function import AffineQuantizationFunction
+        from ..quantization.function import QuantizationContext
+        from ..quantized_tensor import QuantizedTensor
+
+        self.initialize_parameters(quantizer, data)
+        if quantizer.has_uninitialized_params:
+            quantizer._initialize_parameters(self.min.numel())
+        one_sided_live = quantizer.symmetric and quantizer.allow_one_sided
+        if mode == 1 and one_sided_live and self._settled is None:
+            self._settled = torch.zeros(1, dtype=torch.int32, device=data.device)
+        tile = quantizer.granularity.tile_size(data.shape)
+        want_rowsum = data.dim() >= 2 and (mode == 2 or self.min.numel() * data.shape[-1] == data.numel())
+        codes, rowsum = ops.calibrate_quantize_(
+            self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
+            quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
+            self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum)
+        if self._eager:
+            self.check_finite()
+        params = quantizer.quantization_parameters()
+        params = params.with_changes(dequantize_dtype=params.dequantize_dtype or data.dtype)
+        out = QuantizedTensor(codes, QuantizationContext(AffineQuantizationFunction, params))
+        if rowsum is not None:
+            out._ffq_rowsum = rowsum          # consumed by nn/qlinear.py instead of a separate row-sum pass
+        return out
+
+    def forward(self, quantizer, callback, args: tuple, kwargs: dict):
+        data = args[0] if args else kwargs.get("data", next(iter(kwargs.values()), None))
+        mode = self._fused_mode(quantizer, callback, data)
+        if mode and self.min is not None and (self.min.device != data.device or
+                                              torch.promote_types(self.min.dtype, data.dtype) != self.min.dtype):
+            mode = 0     # a continued range on another device / in a narrower dtype: the plain path converts it
+        if not mode:
+            return super().forward(quantizer, callback, args, kwargs)
+        if not self._initialized:
+            self.setup_estimator(data)
+            self._initialized = True
+        return self._fused_step(quantizer, data, mode)
 
     def extra_repr(self) -> str:
         return f"min={self.min}, max={self.max}"
+
+
+def _raise_for_flags(value: int) -> None:
+    if value & 2:
+        raise RuntimeError("fastforward_b200: the grid barrier of the fused calibration kernel timed out "
+                           "(its workspace was shared between streams?)")
+    if value & 1:
+        raise NotImplementedError("Infinite")
 
 
 class SmoothedMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
@@ -167,19 +244,20 @@ class _MinMaxRangeEstimatorBase(RangeEstimator):
 
 class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
     def __init__(self, disable_quantization: bool = False, skip_unsupported_quantizers: bool = False, *,
-                 eager_checks: bool = False, sync_ranges: bool = False, process_group=None) -> None:
+                 eager_checks: bool = False, sync_ranges: bool = False, process_group=None, fused: bool = True) -> None:
         self.disable_quantization = disable_quantization
         self.skip_unsupported_quantizers = skip_unsupported_quantizers
         self.eager_checks = eager_checks
         self.sync_ranges = sync_ranges or process_group is not None
         self.process_group = process_group
+        self.fused = fused
         self._steps: list = []
         self._arena = _RangeArena()
 
     def prepare(self, module):
         self._check(module)
         step = RunningMinMaxEstimator(module, disable_quantization=self.disable_quantization,
-                                      eager_checks=self.eager_checks, arena=self._arena)
+                                      eager_checks=self.eager_checks, arena=self._arena, fused=self.fused)
         self._steps.append((module, step))
         return module.register_override(step)
 
@@ -198,8 +276,10 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
                 quantizer.quantization_range = (step.min, step.max)
         # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks
         if flags and not self.eager_checks:
-            if int(torch.stack([f.reshape(()) for f in flags]).max().item()) != 0:
-                raise NotImplementedError("Infinite")
+            value = 0
+            for v in torch.stack([f.reshape(()) for f in flags]).tolist():
+                value |= int(v)
+            _raise_for_flags(value)
         self._steps = []
         self._arena = _RangeArena()
 

@@ -167,6 +167,33 @@ FFQ_API int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtyp
                          const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a7 + a6 + a1 fused: one RunningMinMax calibration step of one quantizer -----------------
+ * tile min/max of x -> run_min/run_max updated in place (NaN propagates; bit 0 of *flags is OR-ed in
+ * when a tile extremum is +-inf) -> (scale, offset) for the UPDATED running range -> int8 codes of x
+ * under those parameters [-> rowsum[r] = sum of the codes of row r, rows of rowsum_row_len elements],
+ * with x read from HBM once.  Bit-identical to ffq_minmax + ffq_params_for_range + ffq_quantize
+ * (+ ffq_rowsum_i8).  x: f32/f16/bf16; q: int8, num_bits <= 8; scale/offset: fp32 [num_tiles]
+ * (offset may be NULL only for symmetric && !allow_one_sided; it is filled with 0 on the symmetric
+ * two-sided branch); run_dtype must hold x_dtype.
+ * Layouts: contiguous tiles of 64..4096 16-byte vectors (per-channel weight rows; rowsum_row_len must
+ * equal the tile length) or ONE tile (per-tensor; rowsum_row_len divides numel).  Anything else
+ * returns FFQ_ERR_UNSUPPORTED; ffq_calibrate_quantize_mode() tells in advance (0 unsupported, 1 rows,
+ * 2 per-tensor).  The per-tensor kernel is a cooperative launch with a grid barrier: `workspace`
+ * (ffq_calibrate_quantize_workspace_bytes(), 16-byte aligned) must be ZERO before its first use and
+ * be used by one stream at a time; bit 1 of *flags reports a barrier time-out (never expected).
+ * `settled` (optional int32[1], zero-initialised, one per running range) lets the rows path skip its
+ * one-sided fix-up pass once every running min is negative.
+ * replaces: range_setting/minmax.py:215-239 + nn/linear_quantizer.py:347-357 +
+ *           quantization/affine/range.py:54-122 + quantization/_quantizer_impl.py:144-169. */
+FFQ_API int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q,
+                           void* run_min, void* run_max, int run_dtype,
+                           float* scale, float* offset, int32_t* rowsum, int64_t rowsum_row_len,
+                           int32_t* flags, int32_t* settled,
+                           const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
+                           void* workspace, size_t workspace_bytes, void* stream);
+FFQ_API int ffq_calibrate_quantize_mode(const ffq_layout_t* layout, int x_dtype);
+FFQ_API size_t ffq_calibrate_quantize_workspace_bytes(void);
+
 /* ---- a12: quantized linear (new kernel behind ff.dispatcher "linear") ---------------------
  * y[m,n] = sx * sw[n] * ( sum_k qx[m,k] qw[n,k] + ox*rowsum_w[n] + ow[n]*rowsum_x[m] + K*ox*ow[n] )
  *          + bias[n]

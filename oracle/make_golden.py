@@ -228,6 +228,46 @@ def minmax_cases(ff):
     return cases
 
 
+def calib_int8_cases(ff):
+    """The W8A8 calibration recipe: LinearQuantizer(quantized_dtype=int8) under estimate_ranges(running_minmax) over
+    3 batches, on layouts the fused calibration kernels cover (per-channel rows, whole tensors).  Records the codes
+    of EVERY step (each step quantizes with the range known so far), the final parameters and the running range.
+    Data variants exercise the global one-sided decision: mixed-sign, all rows non-negative, some rows non-negative."""
+    cases = []
+    seed = 12000
+    for gname, gfn, shape in [
+        ("per_tensor", lambda: ff.PerTensor(), (6, 640)),
+        ("per_channel0", lambda: ff.PerChannel(0), (5, 1024)),
+    ]:
+        for (symmetric, one_sided), xdt, variant, bits in itertools.product(
+                [(True, True), (True, False), (False, True)], [torch.float32, torch.bfloat16],
+                ["mixed", "positive", "some_positive"], [8, 4]):
+            if bits == 4 and (variant != "mixed" or xdt != torch.bfloat16):
+                continue
+            seed += 1
+            g = _gen(seed)
+            quantizer = ff.nn.LinearQuantizer(bits, symmetric=symmetric, allow_one_sided=one_sided, granularity=gfn(),
+                                              quantized_dtype=torch.int8)
+            batches = []
+            for i in range(3):
+                b = torch.randn(shape, generator=g) * (0.4 + 0.3 * i)
+                if variant == "positive":
+                    b = b.abs() + 0.01
+                elif variant == "some_positive":
+                    b[::2] = b[::2].abs()
+                batches.append(b.to(xdt))
+            raws = []
+            with torch.no_grad(), ff.estimate_ranges(quantizer, ff.range_setting.running_minmax):
+                for b in batches:
+                    raws.append(quantizer(b).raw_data.clone())
+            rng = tuple(t.detach().clone() for t in quantizer.quantization_range)
+            cases.append(dict(
+                kind="calib_int8", gran=gname, shape=shape, symmetric=symmetric, allow_one_sided=one_sided, num_bits=bits,
+                variant=variant, batches=batches, raws=raws, scale=quantizer.scale.detach().clone(),
+                offset=None if quantizer.offset is None else quantizer.offset.detach().clone(), range=rng))
+    return cases
+
+
 def dynamic_cases(ff):
     ops = torch.ops.fastforward
     cases = []
@@ -323,6 +363,7 @@ def main():
     for name, fn in [
         ("static", static_cases), ("quantizer", quantizer_cases), ("running_minmax", minmax_cases),
         ("dynamic", dynamic_cases), ("linear", linear_cases), ("mse_grid", mse_grid_cases),
+        ("calib_int8", calib_int8_cases),
     ]:
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue            # `python oracle/make_golden.py mse_grid` regenerates one fixture only

@@ -1,0 +1,270 @@
+"""Fused calibration step (ffq_calibrate_quantize): min/max + running-range update + range->params + int8
+quantize (+ code row sums) in one kernel.  Checked bit for bit against (1) vectors recorded from the
+unmodified reference running the W8A8 calibration recipe (tests/golden/calib_int8.pt.gz), (2) the CPU oracle
+and (3) the unfused kernel sequence, including the deferred one-sided rows, NaN/inf data, ragged sizes,
+multi-chunk tensors and CUDA-graph replay."""
+import pytest
+import torch
+
+from conftest import bits_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import fastforward_b200 as ff
+    from fastforward_b200 import ops
+    from oracle import ref_ops as R
+
+DEV = "cuda"
+CALIB8 = load_golden("calib_int8")
+
+
+def _gran(name):
+    return ff.PerTensor() if name == "per_tensor" else ff.PerChannel(0)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("i", range(len(CALIB8)))
+def test_estimate_ranges_int8_matches_reference(i, fused):
+    c = CALIB8[i]
+    q = ff.nn.LinearQuantizer(c["num_bits"], symmetric=c["symmetric"], allow_one_sided=c["allow_one_sided"],
+                              granularity=_gran(c["gran"]), quantized_dtype=torch.int8, device=DEV)
+    launches = []
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax, fused=fused):
+        for b, raw in zip(c["batches"], c["raws"]):
+            before = ff._cabi.launch_count()
+            out = q(b.to(DEV))
+            launches.append(ff._cabi.launch_count() - before)
+            assert isinstance(out, ff.QuantizedTensor) and out.raw_data.dtype == torch.int8
+            assert bits_equal(out.raw_data, raw)
+            assert out.quant_args().dequantize_dtype == b.dtype
+            if fused:
+                assert out._ffq_rowsum.cpu().tolist() == raw.int().sum(-1).reshape(-1).tolist()
+    assert bits_equal(q.scale.detach(), c["scale"])
+    if c["offset"] is None:
+        assert q.offset is None
+    else:
+        assert bits_equal(q.offset.detach(), c["offset"])
+    lo, hi = q.quantization_range
+    assert bits_equal(lo.detach(), c["range"][0]) and bits_equal(hi.detach(), c["range"][1])
+    if fused:   # one kernel (+ the one-sided fix-up pass behind per-channel symmetric quantizers)
+        rows_fixup = c["gran"] == "per_channel0" and c["symmetric"] and c["allow_one_sided"]
+        assert max(launches) <= (2 if rows_fixup else 1)
+    else:
+        assert min(launches) >= 3
+
+
+def _oracle_step(mn, mx, x, tile, bits, symmetric, one_sided):
+    mn, mx = R.running_minmax_step(mn, mx, x, tile)
+    scale, offset = R.parameters_for_range(mn, mx, bits, symmetric, one_sided)
+    q = R.quantize_by_tile(x, scale, tile, bits, torch.int8, offset)
+    return mn, mx, scale, offset, q
+
+
+def _run_fused(xs, tile, bits, symmetric, one_sided, rowsum=True, run_dtype=None):
+    x0 = xs[0]
+    nt = 1
+    for d, t in zip(x0.shape, tile):
+        nt *= d // t
+    rdt = run_dtype or x0.dtype
+    mn = torch.full((nt,), float("inf"), dtype=rdt, device=DEV)
+    mx = torch.full((nt,), float("-inf"), dtype=rdt, device=DEV)
+    scale = torch.empty(nt, device=DEV)
+    offset = None if (symmetric and not one_sided) else torch.empty(nt, device=DEV)
+    flags = torch.zeros(1, dtype=torch.int32, device=DEV)
+    settled = torch.zeros(1, dtype=torch.int32, device=DEV)
+    outs = []
+    for x in xs:
+        q, rs = ops.calibrate_quantize_(mn, mx, x.to(DEV), tile, bits, symmetric, one_sided, scale, offset, flags, settled,
+                                        rowsum=rowsum)
+        outs.append((q.cpu(), None if rs is None else rs.cpu(), scale.cpu().clone(), None if offset is None else offset.cpu().clone(),
+                     mn.cpu().clone(), mx.cpu().clone()))
+    return outs, int(flags.item()), int(settled.item())
+
+
+def _check_against_oracle(xs, tile, bits, symmetric, one_sided):
+    outs, flags, _ = _run_fused(xs, tile, bits, symmetric, one_sided)
+    mn = mx = None
+    for x, (q, rs, scale, offset, rmn, rmx) in zip(xs, outs):
+        mn, mx, s, o, rq = _oracle_step(mn, mx, x, tile, bits, symmetric, one_sided)
+        assert bits_equal(rmn, mn) and bits_equal(rmx, mx)
+        assert bits_equal(scale, s)
+        if offset is not None:
+            assert bits_equal(offset, o if o is not None else torch.zeros_like(s))
+        assert bits_equal(q, rq)
+        assert torch.equal(rs, rq.reshape(-1, rq.shape[-1]).int().sum(1).to(torch.int32))
+    return flags
+
+
+ROW_SHAPES = [((7, 512), torch.bfloat16), ((3, 4096), torch.bfloat16), ((5, 14336), torch.bfloat16), ((4, 1000 * 8), torch.float16),
+              ((9, 256), torch.float32), ((2, 16384), torch.float32), ((3, 5000), torch.float32), ((301, 1024), torch.bfloat16)]
+
+
+@pytest.mark.parametrize("shape,dtype", ROW_SHAPES)
+@pytest.mark.parametrize("symmetric,one_sided", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("variant", ["mixed", "positive", "some_positive"])
+def test_rows_vs_oracle(shape, dtype, symmetric, one_sided, variant):
+    g = torch.Generator().manual_seed(sum(shape) * 8 + symmetric * 4 + one_sided * 2 + len(variant))
+    xs = []
+    for i in range(3):
+        x = torch.randn(shape, generator=g) * (0.02 + 0.5 * i)
+        if variant == "positive":
+            x = x.abs() + 1e-3
+        elif variant == "some_positive":
+            x[::2] = x[::2].abs()
+        xs.append(x.to(dtype))
+    assert _check_against_oracle(xs, (1, shape[1]), 8, symmetric, one_sided) == 0
+
+
+TENSOR_SHAPES = [((8, 512), torch.bfloat16), ((2048, 4096), torch.bfloat16), ((1500, 14336), torch.bfloat16), ((3, 77, 264), torch.float16),
+                 ((64, 256), torch.float32), ((1024, 4096), torch.float32), ((2, 5, 104), torch.float32)]
+
+
+@pytest.mark.parametrize("shape,dtype", TENSOR_SHAPES)
+@pytest.mark.parametrize("symmetric,one_sided", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("variant", ["mixed", "positive"])
+def test_tensor_vs_oracle(shape, dtype, symmetric, one_sided, variant):
+    g = torch.Generator().manual_seed(sum(shape) * 8 + symmetric * 4 + one_sided * 2 + len(variant))
+    xs = []
+    for i in range(2):
+        x = torch.randn(shape, generator=g) * (0.3 + 1.5 * i) + 0.2
+        if variant == "positive":
+            x = x.abs()
+        xs.append(x.to(dtype))
+    assert _check_against_oracle(xs, tuple(shape), 8, symmetric, one_sided) == 0
+
+
+@pytest.mark.parametrize("bits", [2, 4, 7])
+def test_low_bit_widths(bits):
+    g = torch.Generator().manual_seed(bits)
+    xs = [torch.randn(6, 1024, generator=g).bfloat16() for _ in range(2)]
+    _check_against_oracle(xs, (1, 1024), bits, True, True)
+    _check_against_oracle(xs, (6, 1024), bits, False, True)
+
+
+def test_special_values():
+    """NaN propagates into the range and the parameters exactly as torch.min/max do; +-inf sets the flag;
+    huge / tiny magnitudes take the exact-division path."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(6, 1024, generator=g)
+    x[1, 5] = float("nan")
+    x[2, 7] = 3e38
+    x[3, :] = 0.0
+    x[4, 9] = -1e-30
+    for tile in [(1, 1024), (6, 1024)]:
+        for symmetric in (True, False):
+            assert _check_against_oracle([x, x * 0.5], tile, 8, symmetric, True) == 0
+    x[5, 1] = float("inf")
+    outs, flags, _ = _run_fused([x], (1, 1024), 8, False, True)
+    assert flags & 1
+    x[1, 5] = 0.0          # a NaN extremum is not infinite: the reference does not raise for it either
+    outs, flags, _ = _run_fused([x], (6, 1024), 8, False, True)
+    assert flags & 1
+
+
+def test_settled_flag_and_range_dtype():
+    """`settled` latches once every running min is negative; an fp32 running range continued with bf16 data."""
+    g = torch.Generator().manual_seed(11)
+    xs = [torch.randn(8, 2048, generator=g).bfloat16() for _ in range(3)]
+    outs, _, settled = _run_fused(xs, (1, 2048), 8, True, True, run_dtype=torch.float32)
+    assert settled == 1
+    mn = mx = None
+    for x, (q, rs, scale, offset, rmn, rmx) in zip(xs, outs):
+        mn, mx, s, o, rq = _oracle_step(mn, mx, x, (1, 2048), 8, True, True)
+        assert bits_equal(rmn, mn.float()) and bits_equal(scale, s) and bits_equal(q, rq)
+    pos = [x.abs() for x in xs]
+    _, _, settled = _run_fused(pos, (1, 2048), 8, True, True)
+    assert settled == 0
+
+
+def test_matches_unfused_kernels_large():
+    """Llama-3-8B weight / activation shapes: identical bits to minmax + params_for_range + quantize + rowsum."""
+    torch.manual_seed(3)
+    for shape, tile, symmetric in [((4096, 4096), (1, 4096), True), ((14336, 4096), (1, 4096), True), ((4096, 14336), (1, 14336), True),
+                                   ((2048, 4096), (2048, 4096), False), ((2048, 14336), (2048, 14336), False)]:
+        x = (torch.randn(shape, device=DEV) * 0.02).bfloat16()
+        nt = (shape[0] // tile[0]) * (shape[1] // tile[1])
+        mn = torch.full((nt,), float("inf"), dtype=torch.bfloat16, device=DEV); mx = -mn
+        mn2, mx2 = mn.clone(), mx.clone()
+        scale, offset = torch.empty(nt, device=DEV), torch.empty(nt, device=DEV)
+        scale2, offset2 = torch.empty(nt, device=DEV), torch.empty(nt, device=DEV)
+        q, rs = ops.calibrate_quantize_(mn, mx, x, tile, 8, symmetric, True, scale, offset, rowsum=True)
+        ops.running_minmax_update_(mn2, mx2, x, tile)
+        ops.parameters_for_range_(mn2, mx2, 8, symmetric, True, scale2, offset2)
+        q2 = ops.quantize_by_tile(x, scale2, tile, 8.0, torch.int8, offset2)
+        assert torch.equal(mn, mn2) and torch.equal(mx, mx2) and torch.equal(scale, scale2) and torch.equal(offset, offset2)
+        assert torch.equal(q, q2)
+        assert torch.equal(rs, q2.int().sum(1).to(torch.int32))
+
+
+def test_unsupported_layouts_fall_back():
+    assert ops.calibrate_quantize_mode((64, 128), (1, 128), torch.bfloat16) == 0       # rows shorter than 64 vectors
+    assert ops.calibrate_quantize_mode((64, 4096), (64, 1), torch.bfloat16) == 0       # strided tiles
+    assert ops.calibrate_quantize_mode((64, 4096), (1, 4096), torch.int32) == 0
+    assert ops.calibrate_quantize_mode((64, 4096), (1, 4096), torch.bfloat16) == 1
+    assert ops.calibrate_quantize_mode((64, 4096), (64, 4096), torch.bfloat16) == 2
+    # the estimator silently takes the separate kernels there: per-group weights, float codes, grad mode
+    q = ff.nn.LinearQuantizer(8, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0),
+                              quantized_dtype=torch.int8, device=DEV)
+    x = torch.randn(16, 512, device=DEV)
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax):
+        out = q(x)
+    assert not hasattr(out, "_ffq_rowsum")
+    q2 = ff.nn.LinearQuantizer(8, granularity=ff.PerChannel(0), device=DEV)             # float codes
+    with torch.no_grad(), ff.estimate_ranges(q2, ff.range_setting.running_minmax):
+        out = q2(x)
+    assert out.raw_data.dtype == torch.float32 and not hasattr(out, "_ffq_rowsum")
+
+
+def test_quantized_linear_calibration_fused_equals_unfused_and_graph_replay():
+    """A QuantizedLinear calibrated with the fused step gives the same parameters and outputs as with the separate
+    kernels, consumes the attached row sums, and the whole step (cooperative kernel included) replays from a CUDA graph."""
+    from fastforward_b200.nn import qlinear
+    qlinear.install()
+    torch.manual_seed(0)
+
+    def build():
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(1024, 768, bias=True).to(DEV).bfloat16()
+        m = torch.nn.Sequential(lin)
+        ff.quantize_model(m)
+        ff.find_quantizers(m, "**/[quantizer:parameter/weight]").initialize(
+            ff.nn.LinearQuantizer, num_bits=8, granularity=ff.PerChannel(0), quantized_dtype=torch.int8)
+        ff.find_quantizers(m, "**/[quantizer:activation/input]").initialize(
+            ff.nn.LinearQuantizer, num_bits=8, symmetric=False, granularity=ff.PerTensor(), quantized_dtype=torch.int8)
+        return m.to(DEV)
+
+    xs = [(torch.randn(2, 96, 1024, device=DEV) * (1 + i)).bfloat16() for i in range(3)]
+    results = {}
+    for fused in (True, False):
+        m = build()
+        ys = []
+        before = ff._cabi.launch_count()
+        with torch.no_grad(), ff.estimate_ranges(m, ff.range_setting.running_minmax, fused=fused):
+            for x in xs:
+                ys.append(m(x))
+        results[fused] = (ys, [p.detach().clone() for _, q in ff.nn.named_quantizers(m) for p in (q.scale, q.offset)],
+                          ff._cabi.launch_count() - before)
+    for a, b in zip(results[True][0], results[False][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(results[True][1], results[False][1]):
+        assert torch.equal(a, b)
+    assert results[True][2] < results[False][2]
+
+    m = build()
+    static = xs[0].clone()
+    with torch.no_grad(), ff.estimate_ranges(m, ff.range_setting.running_minmax):
+        for _ in range(2):
+            m(static)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = m(static)
+        for x, want in zip(xs, results[True][0]):
+            static.copy_(x)
+            g.replay()
+        torch.cuda.synchronize()
+    # the replays saw xs[0] (x3 incl. warm-up and capture), xs[0..2]: same running range as the eager run
+    assert torch.equal(y, results[True][0][2])
+    for (_, q), want in zip(ff.nn.named_quantizers(m), zip(results[True][1][0::2], results[True][1][1::2])):
+        assert torch.equal(q.scale.detach(), want[0]) and torch.equal(q.offset.detach(), want[1])

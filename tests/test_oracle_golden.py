@@ -96,6 +96,28 @@ def test_running_minmax(i):
         assert bits_equal(q, c["last_raw"])
 
 
+CALIB8 = load_golden("calib_int8")
+
+
+@pytest.mark.parametrize("i", range(len(CALIB8)))
+def test_calibration_int8_recipe(i):
+    """W8A8 calibration recipe (int8 codes): every step's codes, the final parameters and the running range."""
+    c = CALIB8[i]
+    shape = c["shape"]
+    tile = shape if c["gran"] == "per_tensor" else (1,) + tuple(shape[1:])
+    mn = mx = None
+    for b, raw in zip(c["batches"], c["raws"]):
+        mn, mx = R.running_minmax_step(mn, mx, b, tile)
+        scale, offset = R.parameters_for_range(mn, mx, c["num_bits"], c["symmetric"], c["allow_one_sided"])
+        q = R.quantize_by_tile(b, scale, tile, c["num_bits"], torch.int8, offset)
+        assert bits_equal(q, raw)
+    assert bits_equal(scale, c["scale"])
+    if c["offset"] is None:
+        assert offset is None
+    else:
+        assert bits_equal(offset if offset is not None else torch.zeros_like(scale), c["offset"])
+
+
 DYNAMIC = load_golden("dynamic")
 
 
