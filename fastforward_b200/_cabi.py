@@ -119,7 +119,7 @@ def _load() -> ctypes.CDLL:
         "ffq_qlinear_w4a16": (i32, [vp, i32, vp, vp, i64, i64, i64, vp, vp, i64, vp, i32, vp]),
         "ffq_grid_mse": (i32, [vp, i32, vp, vp, i32, vp, lp, dbl, vp, sz, vp]),
         "ffq_grid_mse_workspace_bytes": (sz, [lp, i32, i32]),
-        "ffq_calibrate_quantize": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, lp, dbl, i32, i32, vp, sz, vp]),
+        "ffq_calibrate_quantize": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, i32, lp, dbl, i32, i32, vp, sz, vp]),
         "ffq_calibrate_quantize_mode": (i32, [lp, i32]),
         "ffq_calibrate_quantize_workspace_bytes": (sz, []),
     }

@@ -13,7 +13,9 @@
 //
 //   * calq_rows_kernel  : per-channel weights (tile = one contiguous row).  One CTA holds a row in
 //     registers (<= 8 x 16 B per thread), reduces it, updates the running range, derives the
-//     parameters and quantizes from the registers.
+//     parameters and quantizes from the registers.  (A persistent variant streaming rows through a
+//     3-deep shared-memory ring with 1-D TMA bulk copies measured 15-20 % slower on B200: the kernel is
+//     bound by instruction issue -- exact IEEE division -- not by bytes in flight.)
 //   * calq_tensor_kernel: per-tensor activations.  A co-resident (cooperative) grid; every CTA parks
 //     its first 32 KB chunk in shared memory (148 SMs x 4 CTAs x 32 KB = 19 MB of the tensor never
 //     gets re-read), partial extrema meet at a grid barrier, then every CTA derives the same
@@ -45,7 +47,7 @@ struct CalqArgs {
   int symmetric, allow_one_sided, sat8;
   // tensor kernel
   float* part;                          // [2 * gridDim.x]
-  unsigned int* bar;                    // [2] zero between launches
+  unsigned int* bar;                    // [0] arrivals (wraps to 0), [1] generation; zero before first use
   unsigned int nchunks;
   FastDiv rdiv;                         // division by row_len (tensor kernel row sums)
 };
@@ -362,43 +364,51 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
     }
   }
   block_minmax(mn, mx, s_f);
-  // ---- grid barrier (all CTAs are co-resident: cooperative launch, grid <= occupancy) ----
+  // ---- grid barrier (all CTAs are co-resident: cooperative launch, grid <= occupancy).  Sense-reversing:
+  // bar[0] counts arrivals and wraps to 0 with the last one, which then bumps the generation bar[1]; nothing to
+  // reset between launches, any grid size ----
   if (threadIdx.x == 0) {
     a.part[blockIdx.x] = mn;
     a.part[G + blockIdx.x] = mx;
-    __threadfence();
-    atomicAdd(&a.bar[0], 1u);
-    unsigned int spins = 0;
-    while (ld_acquire_u32(&a.bar[0]) < G) {
-      __nanosleep(32);
-      if (++spins > (1u << 21)) {           // ~1 s: never hang the GPU; the host raises on bit 1
-        if (a.flags) atomicOr(a.flags, 2);
-        break;
+    const unsigned int gen0 = ld_acquire_u32(&a.bar[1]);
+    unsigned int old;
+    asm volatile("atom.inc.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.bar), "r"(G - 1) : "memory");
+    if (old == G - 1) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar + 1) : "memory");
+    } else {
+      unsigned int spins = 0;
+      while (ld_acquire_u32(&a.bar[1]) == gen0) {
+        if (++spins > (1u << 22)) {           // ~1 s: never hang the GPU; the host raises on bit 1
+          if (a.flags) atomicOr(a.flags, 2);
+          break;
+        }
       }
     }
-    __threadfence();
   }
   __syncthreads();
-  // ---- phase 2: every CTA reduces the partials to the same (min, max) and derives the parameters ----
-  mn = INFINITY; mx = -INFINITY;
-  for (unsigned int i = threadIdx.x; i < G; i += CQ_T) {
-    mn = nan_min(mn, __ldcg(&a.part[i]));
-    mx = nan_max(mx, __ldcg(&a.part[G + i]));
-  }
-  block_minmax(mn, mx, s_f);
-  if (threadIdx.x == 0) {
-    const float rmn = nan_min(old_mn, mn);
-    const float rmx = nan_max(old_mx, mx);
-    float sc, off;
-    calq_params(a, rmn, rmx, a.symmetric && a.allow_one_sided && (rmn >= 0.f), sc, off);
-    if (blockIdx.x == 0) {
-      store_from_float(a.run_min, a.run_dt, 0, rmn);
-      store_from_float(a.run_max, a.run_dt, 0, rmx);
-      if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
-      a.scale[0] = sc;
-      if (a.offset) a.offset[0] = off;
+  // ---- phase 2: warp 0 of every CTA reduces the partials to the same (min, max) and derives the parameters ----
+  if (warp == 0) {
+    mn = INFINITY; mx = -INFINITY;
+    for (unsigned int i = lane; i < G; i += 32) {
+      mn = nan_min(mn, __ldcg(&a.part[i]));
+      mx = nan_max(mx, __ldcg(&a.part[G + i]));
     }
-    s_par[0] = sc; s_par[1] = off; s_par[2] = rmn; s_par[3] = rmx;
+    mn = group_min<32>(mn);
+    mx = group_max<32>(mx);
+    if (lane == 0) {
+      const float rmn = nan_min(old_mn, mn);
+      const float rmx = nan_max(old_mx, mx);
+      float sc, off;
+      calq_params(a, rmn, rmx, a.symmetric && a.allow_one_sided && (rmn >= 0.f), sc, off);
+      if (blockIdx.x == 0) {
+        store_from_float(a.run_min, a.run_dt, 0, rmn);
+        store_from_float(a.run_max, a.run_dt, 0, rmx);
+        if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+        a.scale[0] = sc;
+        if (a.offset) a.offset[0] = off;
+      }
+      s_par[0] = sc; s_par[1] = off; s_par[2] = rmn; s_par[3] = rmx;
+    }
   }
   __syncthreads();
   const float s = s_par[0], o = rintf(s_par[1]);
@@ -458,11 +468,6 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
       if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
     }
   }
-  // ---- leave the barrier words zeroed for the next launch ----
-  if (threadIdx.x == 0) {
-    const unsigned int done = atomicAdd(&a.bar[1], 1u);
-    if (done == G - 1) { a.bar[0] = 0; a.bar[1] = 0; __threadfence(); }
-  }
 }
 
 static int g_tensor_occ[3] = {-1, -1, -1};   // CTAs per SM of calq_tensor_kernel<bf16 | f16 | float>
@@ -483,17 +488,24 @@ static cudaError_t launch_tensor(const CalqArgs& a, unsigned int grid, cudaStrea
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CQ_T);
   cfg.dynamicSmemBytes = CQ_CHUNK_VECS * 16; cfg.stream = st;
+  // cooperative: the driver guarantees that the whole grid is co-resident (the barrier cannot starve behind
+  // another kernel).  FFQ_CALQ_COOP=0 launches it as an ordinary kernel (same grid, sized to the occupancy).
+  static const bool coop = []() { const char* e = getenv("FFQ_CALQ_COOP"); return !(e && e[0] == '0'); }();
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = coop ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, calq_tensor_kernel<XT>, a);
 }
 
 template <typename XT>
-static void launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_t st) {
-  // 4 vectors (64 B) in flight per thread and a CTA sized to the row: no idle slots beyond the last warp
-  const int vpt = nvec > 2048 ? 8 : (nvec >= 256 ? 4 : (nvec >= 128 ? 2 : 1));
+static cudaError_t launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_t st) {
+  // one CTA per row, sized to the row (no idle slots beyond the last warp); 8 vectors (128 B) per thread in
+  // flight for rows of >= 512 vectors: half as many warps share the per-row work (reduction, parameters)
+  static const int force = []() { const char* e = getenv("FFQ_CALQ_VPT"); return e ? atoi(e) : 0; }();
+  int vpt = (nvec >= 512 && a.rows >= 2048) ? 8 : (nvec >= 256 ? 4 : (nvec >= 128 ? 2 : 1));
+  if (nvec > 2048) vpt = 8;
+  if ((force == 4 || force == 8) && nvec >= 256 && (unsigned long long)force * 512 >= nvec) vpt = force;
   const unsigned int threads = ((nvec + vpt - 1) / vpt + 31) / 32 * 32;
   const unsigned int grid = (unsigned int)a.rows;
   switch (vpt) {
@@ -502,6 +514,7 @@ static void launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_t st) {
     case 4: calq_rows_kernel<XT, 4><<<grid, threads, 0, st>>>(a); break;
     default: calq_rows_kernel<XT, 8><<<grid, threads, 0, st>>>(a); break;
   }
+  return cudaSuccess;
 }
 
 }  // namespace ffq
@@ -537,8 +550,8 @@ size_t ffq_calibrate_quantize_workspace_bytes(void) {
 
 int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min, void* run_max, int run_dtype,
                            float* scale, float* offset, int32_t* rowsum, int64_t rowsum_row_len, int32_t* flags,
-                           int32_t* settled, const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+                           int32_t* settled, int run_fixup, const ffq_layout_t* layout, double num_bits, int symmetric,
+                           int allow_one_sided, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan plan;
   int rc = make_plan(layout, &plan);
@@ -578,13 +591,15 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
       return FFQ_ERR_INVALID;
     }
     const unsigned int nvec = a.row_len / ept;
+    cudaError_t le;
     switch (x_dtype) {
-      case FFQ_F32: launch_rows<float>(a, nvec, st); break;
-      case FFQ_BF16: launch_rows<__nv_bfloat16>(a, nvec, st); break;
-      default: launch_rows<__half>(a, nvec, st); break;
+      case FFQ_F32: le = launch_rows<float>(a, nvec, st); break;
+      case FFQ_BF16: le = launch_rows<__nv_bfloat16>(a, nvec, st); break;
+      default: le = launch_rows<__half>(a, nvec, st); break;
     }
+    if (le != cudaSuccess) { set_error("calibrate_quantize: %s", cudaGetErrorString(le)); return FFQ_ERR_CUDA; }
     FFQ_LAUNCH_CHECK();
-    if (symmetric && allow_one_sided) {
+    if (symmetric && allow_one_sided && run_fixup) {
       unsigned int grid = (unsigned int)(a.rows < (unsigned long long)sm_count() ? a.rows : sm_count());
       switch (x_dtype) {
         case FFQ_F32: calq_rows_fixup_kernel<float><<<grid, CQ_T, 0, st>>>(a); break;

@@ -335,12 +335,15 @@ def calibrate_quantize_(
     run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size, num_bits: float,
     symmetric: bool, allow_one_sided: bool, scale_out: torch.Tensor, offset_out: Optional[torch.Tensor],
     flags: Optional[torch.Tensor] = None, settled: Optional[torch.Tensor] = None, rowsum: bool = False,
+    run_fixup: bool = True,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """One RunningMinMax calibration step in one pass over ``data``: updates ``run_min``/``run_max`` in place
     (range_setting/minmax.py:229-237), writes the quantizer's ``scale``/``offset`` for the updated range in place
     (nn/linear_quantizer.py:347-357) and returns ``(int8 codes, rowsum-or-None)`` -- the codes are what
     ``quantize_by_tile(data, scale, tile, num_bits, torch.int8, offset)`` returns for those parameters, and
     ``rowsum`` (int32, one value per row of the last dimension) is what the W8A8 linear needs from them.
+    ``settled`` / ``run_fixup``: see include/ffq_b200.h -- only a caller that has read ``settled != 0`` may pass
+    ``run_fixup=False``.
     Raises NotImplementedError for layouts the fused kernels do not cover (see calibrate_quantize_mode)."""
     x, shape, tile, layout = _prep(data, tile_size)
     _bitwidth_guard(torch.int8, num_bits)
@@ -361,7 +364,7 @@ def calibrate_quantize_(
     ws = C.barrier_workspace(x.device, _CALQ_WS)
     C.check(C.lib.ffq_calibrate_quantize(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), run_min.data_ptr(), run_max.data_ptr(), C.dtype_tag(run_min.dtype),
-        scale_out.data_ptr(), C.ptr(offset_out), C.ptr(rs), row_len, C.ptr(flags), C.ptr(settled),
+        scale_out.data_ptr(), C.ptr(offset_out), C.ptr(rs), row_len, C.ptr(flags), C.ptr(settled), int(bool(run_fixup)),
         layout.ref, float(num_bits), int(bool(symmetric)), int(bool(allow_one_sided)),
         ws.data_ptr(), ws.numel(), C.current_stream(x.device)))
     return q, rs

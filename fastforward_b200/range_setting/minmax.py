@@ -77,7 +77,9 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         super().__init__(disable_quantization=disable_quantization)
         self._arena = arena
         self._fused = fused
-        self._settled = None
+        self._settled = None          # device int32[1]: set by the kernel once every running min is negative
+        self._settled_host = None     # pinned mirror, refreshed asynchronously: lets later steps skip the fix-up launch
+        self._settled_seen = False
         lo, hi = quantizer.quantization_range       # continues from an existing range (minmax.py:198-200)
         self.register_buffer("min", None if lo is None else lo.detach().clone())
         self.register_buffer("max", None if hi is None else hi.detach().clone())
@@ -149,12 +151,18 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         one_sided_live = quantizer.symmetric and quantizer.allow_one_sided
         if mode == 1 and one_sided_live and self._settled is None:
             self._settled = torch.zeros(1, dtype=torch.int32, device=data.device)
+            self._settled_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        if self._settled_host is not None and not self._settled_seen:
+            # a plain host read of the pinned mirror: no sync; a stale 0 only costs one more fix-up launch
+            self._settled_seen = bool(self._settled_host[0] != 0)
         tile = quantizer.granularity.tile_size(data.shape)
         want_rowsum = data.dim() >= 2 and (mode == 2 or self.min.numel() * data.shape[-1] == data.numel())
         codes, rowsum = ops.calibrate_quantize_(
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
-            self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum)
+            self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen)
+        if self._settled_host is not None and not self._settled_seen:
+            self._settled_host.copy_(self._settled, non_blocking=True)
         if self._eager:
             self.check_finite()
         params = quantizer.quantization_parameters()

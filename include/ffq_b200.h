@@ -181,14 +181,17 @@ FFQ_API int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtyp
  * 2 per-tensor).  The per-tensor kernel is a cooperative launch with a grid barrier: `workspace`
  * (ffq_calibrate_quantize_workspace_bytes(), 16-byte aligned) must be ZERO before its first use and
  * be used by one stream at a time; bit 1 of *flags reports a barrier time-out (never expected).
- * `settled` (optional int32[1], zero-initialised, one per running range) lets the rows path skip its
- * one-sided fix-up pass once every running min is negative.
+ * Rows path, symmetric && allow_one_sided: the global one-sided decision (range.py:100) is taken by a second,
+ * tiny fix-up launch that finishes exactly the rows whose running min is >= 0 (normally none).  `settled`
+ * (optional int32[1], zero-initialised, one per running range) is set by that launch once every running min
+ * is negative -- permanent, because running mins only decrease; a caller that has OBSERVED *settled != 0 may
+ * pass run_fixup = 0 from then on and save the launch.  run_fixup must be non-zero otherwise.
  * replaces: range_setting/minmax.py:215-239 + nn/linear_quantizer.py:347-357 +
  *           quantization/affine/range.py:54-122 + quantization/_quantizer_impl.py:144-169. */
 FFQ_API int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q,
                            void* run_min, void* run_max, int run_dtype,
                            float* scale, float* offset, int32_t* rowsum, int64_t rowsum_row_len,
-                           int32_t* flags, int32_t* settled,
+                           int32_t* flags, int32_t* settled, int run_fixup,
                            const ffq_layout_t* layout, double num_bits, int symmetric, int allow_one_sided,
                            void* workspace, size_t workspace_bytes, void* stream);
 FFQ_API int ffq_calibrate_quantize_mode(const ffq_layout_t* layout, int x_dtype);
