@@ -472,12 +472,26 @@ def run_ours(args):
         bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
         int8_peak = 2.0 * bf16_peak      # kind::i8 issues at twice the kind::f16 rate on sm_100
         dominant = max(per_op.items(), key=lambda kv: kv[1]["total_ms"]) if per_op else (None, None)
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of one
+        # decoder layer (profiles/r01s3_ncu_full_layer.md) -- a profiler figure, never measured inside this run
+        try:
+            ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except OSError:
+            ncu_traffic = {}
+
+        def traffic_of(kind):
+            key = "w8a8_gemm2_kernel" if kind.startswith("w8a8") else None
+            ent = ncu_traffic.get(key) if key else None
+            return ent["dram_bytes_per_launch"] if ent and layers == sh.layers and seq == SEQ and args.shape == "8b" else None
         roofline = None
         if dominant[0]:
             d = dominant[1]
             if dominant[0].startswith("w8a8"):
                 roofline = dict(bound="tensor", kernel=dominant[0], achieved=round(d["rate"] / 1e12, 1), peak=int8_peak,
-                                unit="TOP/s", frac=round(d["rate"] / 1e12 / int8_peak, 4), traffic=None,
+                                unit="TOP/s", frac=round(d["rate"] / 1e12 / int8_peak, 4), traffic=traffic_of(dominant[0]),
+                                traffic_unit="DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
+                                             "7 linears of a layer; profiles/r01s3_ncu_full_layer.md); int8 operands + bf16 output "
+                                             "are 67.7 MB per launch algorithmic, the rest is served by L2",
                                 peak_source="2 x MEASURED_PEAKS.json bf16_tflops (burst): int8 MMA issues at twice the bf16 rate",
                                 algorithmic="2*M*N*K ops per launch, M=2048 (the step's 224 linears)")
             else:

@@ -254,6 +254,26 @@ FFQ_API int ffq_grid_mse(const void* x, int x_dtype, const float* cand_scale, co
                  void* workspace, size_t workspace_bytes, void* stream);
 FFQ_API size_t ffq_grid_mse_workspace_bytes(const ffq_layout_t* layout, int x_dtype, int num_candidates);
 
+/* ---- f3: GPTQ inner block loop ----------------------------------------------------------------
+ * For the `ncols` (<= 128) columns of one block, in order j = 0..ncols-1 and for every row r independently:
+ *     q[r,j]   = dequantize(quantize(w[r,j]))          parameters of (r, orig_col[j]), see below
+ *     err[r,j] = (w[r,j] - q[r,j]) / hinv[j,j]
+ *     w[r,k]  -= err[r,j] * hinv[j,k]                   for k = j+1 .. ncols-1
+ * w: fp32 [R, ldw] (the block's columns, updated in place -- the reference's `weights_block`); q, err: fp32
+ * outputs with their own leading dimensions; hinv: fp32 [ncols, ldh], the diagonal block of the upper Cholesky
+ * factor of the inverse Hessian.  The parameter of element (r, c) is scale[(r / row_block) * num_col_blocks +
+ * c / col_block] with c = orig_col[j] the column index in the un-permuted weight: per-tensor (row_block = R,
+ * col_block = C), per-channel(0) (1, C), per-channel(1) (R, 1), per-element (1, 1), per-block/tile.
+ * code_dtype: dtype the codes take between quantize and dequantize (the quantizer's quantized_dtype or f32).
+ * Every step is rounded like the reference's separate aten ops (no FMA contraction), so the results are
+ * bit-identical to quantization/gptq.py:100-132 + column_quantizer (:149-235) on the same inputs.
+ * replaces: quantization/gptq.py:106-130 (the `for j in range(block_end - i)` loop). */
+FFQ_API int ffq_gptq_block(float* w, int64_t ldw, float* q, int64_t ldq, float* err, int64_t lde,
+                   const float* hinv, int64_t ldh, int64_t R, int64_t ncols,
+                   const void* scale, int scale_dtype, const void* offset, int offset_dtype,
+                   const int32_t* orig_col, int64_t row_block, int64_t col_block, int64_t num_col_blocks,
+                   double num_bits, int code_dtype, void* stream);
+
 /* ---- test hook ---------------------------------------------------------------------------
  * Sweeps the kernels' shared-reciprocal division against __fdiv_rn over n pseudo-random
  * (dividend, scale) pairs.  counts_dev: uint64[4], zero-initialised by the caller:

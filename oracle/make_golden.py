@@ -268,6 +268,57 @@ def calib_int8_cases(ff):
     return cases
 
 
+def gptq_cases(ff):
+    """fastforward.quantization.gptq.gptq() on seeded QuantizedLinear layers: initial weight, calibration inputs,
+    the calibrated parameters BEFORE the block loop (smoothed_minmax on the fp32 weight), final weight and
+    final parameters (group scales are recomputed for PerBlock without actorder)."""
+    import importlib
+    ref_gptq = importlib.import_module('fastforward.quantization.gptq')
+
+    cases = []
+    seed = 15000
+    grans = {
+        "per_tensor": lambda: ff.PerTensor(),
+        "per_channel0": lambda: ff.PerChannel(0),
+        "per_channel1": lambda: ff.PerChannel(1),
+        "per_block32": lambda: ff.PerBlock(block_dims=1, block_sizes=32, per_channel_dims=0),
+        "per_tile": lambda: ff.PerTile((4, 48)),
+    }
+    for gname, bits, symmetric, actorder, block_size, qdtype in [
+        ("per_channel0", 4, True, False, 64, None), ("per_channel0", 4, False, True, 64, None),
+        ("per_tensor", 8, True, False, 128, torch.int8), ("per_channel1", 4, False, False, 32, None),
+        ("per_block32", 4, True, False, 64, None), ("per_block32", 3, False, False, 48, torch.int8),
+        ("per_block32", 4, True, True, 64, None), ("per_tile", 4, False, False, 128, None),
+        ("per_channel0", 2, True, False, 128, None),
+    ]:
+        seed += 1
+        g = _gen(seed)
+        rows, cols = 24, 192
+        layer = ff.nn.QuantizedLinear(cols, rows, bias=False)
+        with torch.no_grad():
+            layer.weight.copy_(torch.randn(rows, cols, generator=g) * 0.05)
+        layer.weight_quantizer = ff.nn.LinearQuantizer(bits, symmetric=symmetric, granularity=grans[gname](),
+                                                       quantized_dtype=qdtype)
+        acts = [torch.randn(2, 40, cols, generator=g) * (1.0 + 0.5 * torch.rand(cols, generator=g)) for _ in range(3)]
+        w0 = layer.weight.detach().clone()
+        # the parameters the block loop starts from: what gptq() computes first (gptq.py:76-77)
+        probe = ff.nn.LinearQuantizer(bits, symmetric=symmetric, granularity=grans[gname](), quantized_dtype=qdtype)
+        with ff.estimate_ranges(probe, ff.range_setting.smoothed_minmax):
+            probe(w0.clone().float())
+        dataset = [((a.clone(),), {}) for a in acts]
+        with torch.no_grad():
+            ref_gptq.gptq(layer, dataset, block_size=block_size, perc_damp=0.01, actorder=actorder)
+        wq = layer.weight_quantizer
+        cases.append(dict(
+            kind="gptq", gran=gname, num_bits=bits, symmetric=symmetric, actorder=actorder, block_size=block_size,
+            qdtype=qdtype, weight=w0, activations=acts, scale0=probe.scale.detach().clone(),
+            offset0=None if probe.offset is None else probe.offset.detach().clone(),
+            tile=tuple(wq.granularity.tile_size(w0.shape)) if not isinstance(wq.granularity.tile_size(w0.shape), str) else tuple(w0.shape),
+            new_weight=layer.weight.detach().clone(), scale=wq.scale.detach().clone(),
+            offset=None if wq.offset is None else wq.offset.detach().clone()))
+    return cases
+
+
 def dynamic_cases(ff):
     ops = torch.ops.fastforward
     cases = []
@@ -363,7 +414,7 @@ def main():
     for name, fn in [
         ("static", static_cases), ("quantizer", quantizer_cases), ("running_minmax", minmax_cases),
         ("dynamic", dynamic_cases), ("linear", linear_cases), ("mse_grid", mse_grid_cases),
-        ("calib_int8", calib_int8_cases),
+        ("calib_int8", calib_int8_cases), ("gptq", gptq_cases),
     ]:
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue            # `python oracle/make_golden.py mse_grid` regenerates one fixture only

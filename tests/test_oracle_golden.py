@@ -118,6 +118,48 @@ def test_calibration_int8_recipe(i):
         assert bits_equal(offset if offset is not None else torch.zeros_like(scale), c["offset"])
 
 
+GPTQ = load_golden("gptq")
+
+
+@pytest.mark.parametrize("i", range(len(GPTQ)))
+def test_gptq(i):
+    """oracle/gptq_ref.py against the unmodified reference's gptq(): calibrated parameters, final weight and
+    (for grouped quantizers) the recomputed group parameters, bit for bit."""
+    from oracle import gptq_ref as G
+
+    c = GPTQ[i]
+    w = c["weight"]
+    tile = c["tile"]
+    # initial range estimation (gptq.py:76-77): smoothed_minmax of one batch == that batch's min/max
+    mn, mx = R.smoothed_minmax_step(None, None, w.float(), tile, 1.0)
+    scale, offset = R.parameters_for_range(mn, mx, c["num_bits"], c["symmetric"], True)
+    assert bits_equal(scale, c["scale0"])
+    if c["offset0"] is None:
+        assert offset is None
+    else:
+        offset = offset if offset is not None else torch.zeros_like(scale)
+        assert bits_equal(offset, c["offset0"])
+    scale = scale.clone()
+    offset = None if offset is None else offset.clone()
+    # the trailing update between blocks is a library GEMM; its accumulation order depends on the thread count,
+    # and the golden vectors were recorded single-threaded (oracle/make_golden.py)
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        new_w, _ = _run_gptq_oracle(G, c, w, scale, offset, tile)
+    finally:
+        torch.set_num_threads(threads)
+    assert bits_equal(new_w, c["new_weight"])
+    assert bits_equal(scale, c["scale"])
+    if c["offset"] is not None:
+        assert bits_equal(offset, c["offset"])
+
+
+def _run_gptq_oracle(G, c, w, scale, offset, tile):
+    return G.gptq(w, c["activations"], scale, offset, tile, c["num_bits"], c["symmetric"], True, c["qdtype"],
+                  block_size=c["block_size"], actorder=c["actorder"], grouped=c["gran"] in ("per_block32", "per_tile"))
+
+
 DYNAMIC = load_golden("dynamic")
 
 
