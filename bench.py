@@ -273,13 +273,13 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
     qw = torch.randint(-128, 128, (N, K), dtype=torch.int8, device=dev)
     y = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
     sx = torch.tensor([0.01], device=dev); ox = torch.tensor([3.0], device=dev); sw = torch.rand(N, device=dev) * 0.01
-    rs = torch.empty(N, dtype=torch.int32, device=dev); ws = torch.empty(4 * N, device=dev)
+    rs = torch.empty(N, dtype=torch.int32, device=dev)
     st = C.current_stream(dev)
     C.check(C.lib.ffq_rowsum_i8(qw.data_ptr(), rs.data_ptr(), N, K, st))
 
     def gemm():
         C.check(C.lib.ffq_qlinear_w8a8(qx.data_ptr(), qw.data_ptr(), y.data_ptr(), 2, M, N, K, sx.data_ptr(), ox.data_ptr(), sw.data_ptr(),
-                                       None, rs.data_ptr(), None, None, 255, ws.data_ptr(), ws.numel() * 4, st))
+                                       None, rs.data_ptr(), None, None, 255, None, 0, st))
     t = _time_cuda(gemm)
     t_lib = _time_cuda(lambda: torch._int_mm(qx, qw.t()))
     out["w8a8_linear_8192x14336x4096"] = {"us": round(t * 1e6, 1), "TOPS": round(2 * M * N * K / t / 1e12, 1),
@@ -621,20 +621,33 @@ def run_wq4(args):
 
     for _ in range(args.warmup):
         step()
+    l0 = _cabi.launch_count()
+    step()
+    launches = (_cabi.launch_count() - l0) * args.steps
+    # the step has no host sync and only in-place updates of persistent buffers: replay it from a CUDA graph
+    # (--no-graph times the eager step, which is bound by Python/launch overhead: ~900 launches of 5-100 us)
+    cg = None
+    if not args.no_graph:
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            step()
+        cg.replay()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    l0 = _cabi.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        step()
+        if cg is not None:
+            cg.replay()
+        else:
+            step()
     t1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     dt = t0.elapsed_time(t1) * 1e-3
-    launches = _cabi.launch_count() - l0
     tot = torch.tensor([dt, float(n_weights)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -650,7 +663,8 @@ def run_wq4(args):
             "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{sh.name}: {layers} layers x 7 linears = {n_all / 1e9:.2f} G weights, LinearQuantizer(4, PerBlock g=128), "
-                                   "calibrate on the weight + fuse_qdq_weights in place; layer i -> rank i mod N"},
+                                   "calibrate on the weight + fuse_qdq_weights in place; layer i -> rank i mod N",
+                       "cuda_graph": cg is not None},
             "gpu_launches": int(launches), "per_gpu_GBps": round(by / dt / 1e9 / world, 1)}))
     if world > 1:
         dist.destroy_process_group()

@@ -414,6 +414,8 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
   const float s = s_par[0], o = rintf(s_par[1]);
   const SharedRcp k = make_shared_rcp(s);
   const bool fast = calq_fast_ok(k, s_par[2], s_par[3]);
+  // rows that are a whole number of warp spans (VPW vectors): a warp never straddles two rows
+  const bool simple_rows = a.rowsum != nullptr && (a.row_len % (VPW * EPT)) == 0;
   // ---- phase 3: quantize; a warp owns VPW contiguous vectors, so its codes fall in few rows ----
   for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
     const unsigned long long w0 = (unsigned long long)c * CQ_CHUNK_VECS + warp * VPW;   // warp's first vector
@@ -445,7 +447,9 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
           calq_vec_any<XT, EPT>(xv[u], k, o, a, fast, packed, vs);
           calq_store<EPT>(a.q + v * EPT, packed);
         }
-        if (a.rowsum) {
+        if (simple_rows) {
+          sum += vs;                       // the warp's whole span lies in one row: one atomic per chunk
+        } else if (a.rowsum) {
           // one atomic per (warp, row): sums are carried while the whole warp stays in one row
           const unsigned int r = fast_div(rem0 + ((ub + u) * 32 + lane) * EPT, a.rdiv);
           const unsigned int r_first = __shfl_sync(0xffffffffu, r, 0);
@@ -462,6 +466,13 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
           else if (live) atomicAdd(&a.rowsum[row0 + r], vs);
         }
       }
+    }
+    if (simple_rows) {
+      if (w0 < nvec) {
+        const int tot = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) atomicAdd(&a.rowsum[row0], tot);
+      }
+      continue;
     }
     if (a.rowsum && cur != ~0u) {
       const int tot = __reduce_add_sync(0xffffffffu, sum);

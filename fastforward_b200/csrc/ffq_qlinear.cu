@@ -46,10 +46,30 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * BN * 4 + 256 + 1024;   // 
 struct GemmArgs {
   int M, N, K;
   void* y; int y_dt;
-  const float* alpha; const float* bias;        // per output column: sx*sw[n], bias[n] (as float)
-  const int32_t* cnst; const int32_t* own;      // per output column: ox*rowsum_w[n] + K*ox*ow[n], ow[n] (own may be null)
-  const int32_t* rowsum_x;                      // per output row; used with own
+  const float* sx; const float* ox;             // activation scale / offset (one element each; ox may be null)
+  const float* sw; const float* ow;             // per output column (ow may be null)
+  const int32_t* rowsum_w;                      // per output column: sum_k qw[n,k]
+  const void* bias; int bias_dt;                // per output column, optional
+  const int32_t* rowsum_x;                      // per output row; used with ow
 };
+
+// Per-column epilogue parameters of one tile, derived where they are consumed (no separate launch, no scratch):
+//   alpha[n] = sx*sw[n];  bias[n] as float;  cnst[n] = ox*rowsum_w[n] + K*ox*ow[n];  own[n] = ow[n]
+// with ox, ow rounded to integers exactly as dequantize_by_tile rounds them.
+__device__ __forceinline__ void stage_col_params(const GemmArgs& g, int n0, int bn, int tid, int nthreads,
+                                                 float* col_params, int32_t* col_ints) {
+  const float sx = g.sx[0];
+  const int o_x = g.ox ? __float2int_rn(rintf(g.ox[0])) : 0;
+  for (int c = tid; c < bn; c += nthreads) {
+    const int n = n0 + c;
+    const bool in = n < g.N;
+    const int o_w = (in && g.ow) ? __float2int_rn(rintf(g.ow[n])) : 0;
+    col_params[c] = in ? sx * g.sw[n] : 0.f;
+    col_params[bn + c] = (in && g.bias) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
+    col_ints[2 * bn + c] = in ? o_x * g.rowsum_w[n] + g.K * o_x * o_w : 0;
+    col_ints[3 * bn + c] = o_w;
+  }
+}
 
 template <typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -147,17 +167,10 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t use = (uint32_t)(it >> 1);
       // stage this tile's column parameters in shared memory (named barrier over the 4 epilogue warps)
       asm volatile("bar.sync 1, 128;" ::: "memory");         // previous tile's readers are done
-      for (int c = ep_tid; c < BN; c += 128) {
-        const int n = tn * BN + c;
-        const bool in = n < g.N;
-        col_params[c] = in ? g.alpha[n] : 0.f;
-        col_params[BN + c] = in ? g.bias[n] : 0.f;
-        col_ints[2 * BN + c] = in ? g.cnst[n] : 0;
-        col_ints[3 * BN + c] = (in && g.own) ? g.own[n] : 0;
-      }
+      stage_col_params(g, tn * BN, BN, ep_tid, 128, col_params, col_ints);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row = tm * BM + quad * 32 + lane;
-      const int32_t rx = (g.own && row < g.M) ? g.rowsum_x[row] : 0;
+      const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
@@ -299,17 +312,10 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = ep_tid; c < BN; c += 128) {
-        const int n = tn * BN + c;
-        const bool in = n < g.N;
-        col_params[c] = in ? g.alpha[n] : 0.f;
-        col_params[BN + c] = in ? g.bias[n] : 0.f;
-        col_ints[2 * BN + c] = in ? g.cnst[n] : 0;
-        col_ints[3 * BN + c] = (in && g.own) ? g.own[n] : 0;
-      }
+      stage_col_params(g, tn * BN, BN, ep_tid, 128, col_params, col_ints);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
-      const int32_t rx = (g.own && row < g.M) ? g.rowsum_x[row] : 0;
+      const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
@@ -369,21 +375,6 @@ __global__ void __launch_bounds__(256) rowsum_i8_kernel(const int8_t* __restrict
   if (lane == 0) out[row] = acc;
 }
 
-// alpha[n] = sx*sw[n];  cnst[n] = ox*rowsum_w[n] + K*ox*ow[n];  own[n] = ow[n];  bias as float
-__global__ void __launch_bounds__(256) col_params_kernel(int N, int K, const float* sx, const float* ox, const float* sw,
-                                                         const float* ow, const int32_t* rowsum_w, const void* bias,
-                                                         int bias_dt, float* alpha, float* biasf, int32_t* cnst,
-                                                         int32_t* own) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const int o_x = ox ? __float2int_rn(rintf(ox[0])) : 0;
-  const int o_w = ow ? __float2int_rn(rintf(ow[n])) : 0;
-  alpha[n] = sx[0] * sw[n];
-  biasf[n] = bias ? load_as_float(bias, bias_dt, n) : 0.f;
-  cnst[n] = o_x * rowsum_w[n] + K * o_x * o_w;
-  if (own) own[n] = o_w;
-}
-
 // ---- host side -------------------------------------------------------------------------------------
 static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
@@ -405,7 +396,7 @@ using namespace ffq;
 
 extern "C" {
 
-size_t ffq_qlinear_workspace_bytes(int64_t N) { return (size_t)(4 * N) * sizeof(float); }
+size_t ffq_qlinear_workspace_bytes(int64_t N) { (void)N; return 0; }
 
 int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream) {
   if (R <= 0) return FFQ_OK;
@@ -429,16 +420,7 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   }
   if (M > 0x7fffffffll || N > 0x7fffffffll || K > 0x7fffffffll) { set_error("qlinear_w8a8: dimension too large"); return FFQ_ERR_UNSUPPORTED; }
   if (ow != nullptr && rowsum_x == nullptr) { set_error("qlinear_w8a8: rowsum_x is required when the weight has an offset"); return FFQ_ERR_INVALID; }
-  if (workspace == nullptr || workspace_bytes < ffq_qlinear_workspace_bytes(N)) {
-    set_error("qlinear_w8a8: workspace of %zu bytes required", ffq_qlinear_workspace_bytes(N)); return FFQ_ERR_WORKSPACE;
-  }
-  float* alpha = static_cast<float*>(workspace);
-  float* biasf = alpha + N;
-  int32_t* cnst = reinterpret_cast<int32_t*>(biasf + N);
-  int32_t* own = ow ? cnst + N : nullptr;
-  col_params_kernel<<<(unsigned int)((N + 255) / 256), 256, 0, st>>>((int)N, (int)K, sx, ox, sw, ow, rowsum_w, bias,
-                                                                     bias_dtype, alpha, biasf, cnst, own);
-  FFQ_LAUNCH_CHECK();
+  (void)workspace; (void)workspace_bytes;      // kept in the ABI; the column parameters are derived inside the kernel
 
   CUtensorMap map_a, map_b;
   int rc;
@@ -446,13 +428,18 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   if ((rc = make_map(&map_b, qw, N, K, BN)) != FFQ_OK) return rc;
   GemmArgs g{};
   g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.y_dt = y_dtype;
-  g.alpha = alpha; g.bias = biasf; g.cnst = cnst; g.own = own; g.rowsum_x = rowsum_x;
+  g.sx = sx; g.ox = ox; g.sw = sw; g.ow = ow; g.rowsum_w = rowsum_w; g.bias = bias; g.bias_dt = bias_dtype;
+  g.rowsum_x = rowsum_x;
   const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const long long pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   // the pair kernel needs M > 128 to have work for both CTAs; FFQ_GEMM_1CTA=1 forces the single-CTA kernel
   static const bool force_1cta = getenv("FFQ_GEMM_1CTA") != nullptr;
-  const bool use_pair = !force_1cta && M > BM;
+  // ... and when the pair tiles would leave CTA pairs idle while the 128-row tiles still fit in one wave (e.g.
+  // the k/v projections, N = 1024 at M = 2048: 32 pair tiles on 74 pairs vs 64 tiles on 148 SMs), the single-CTA
+  // kernel finishes the same work in half-size tiles, all at once
+  const bool underfilled = pair_tiles < sm_count() / 2 && tiles <= sm_count();
+  const bool use_pair = !force_1cta && M > BM && !underfilled;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

@@ -89,14 +89,13 @@ def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, stric
     sw = pw.scale.detach().reshape(-1).contiguous()
     ow = None if pw.offset is None else pw.offset.detach().reshape(-1).contiguous()
     b = None if bias is None else bias.detach().contiguous()
-    ws = torch.empty(4 * n, dtype=torch.float32, device=qx.device)
     C.check(C.lib.ffq_qlinear_w8a8(
         qx2.data_ptr(), qw.data_ptr(), y.data_ptr(), C.dtype_tag(out_dtype), m, n, k,
         sx.data_ptr(), C.ptr(ox), sw.data_ptr(), C.ptr(ow), rowsum_w.data_ptr(), C.ptr(rowsum_x),
-        C.ptr(b), C.dtype_tag(b.dtype if b is not None else None), ws.data_ptr(), ws.numel() * 4, stream))
+        C.ptr(b), C.dtype_tag(b.dtype if b is not None else None), None, 0, stream))
     _stats["calls"] += 1
     if keepalive is not None:
-        keepalive.append((qx2, qw, y, rowsum_w, rowsum_x, sx, ox, sw, ow, b, ws))
+        keepalive.append((qx2, qw, y, rowsum_w, rowsum_x, sx, ox, sw, ow, b))
     y = y.reshape(*lead, n)
     if output_quantizer is not None:
         y = output_quantizer(y)

@@ -213,7 +213,8 @@ FFQ_API int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_
                      const int32_t* rowsum_w, const int32_t* rowsum_x,
                      const void* bias, int bias_dtype,
                      void* workspace, size_t workspace_bytes, void* stream);
-/* scratch for ffq_qlinear_w8a8: four 4-byte[N] column-parameter vectors */
+/* scratch for ffq_qlinear_w8a8: none since the column parameters are derived inside the kernel (returns 0;
+ * `workspace` may be NULL) -- kept for ABI stability */
 FFQ_API size_t ffq_qlinear_workspace_bytes(int64_t N);
 
 /* rowsum[r] = sum_k q[r,k]  (int8 [R,K] -> int32[R]) */
