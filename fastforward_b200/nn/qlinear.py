@@ -106,6 +106,11 @@ def w8a8_linear(input=None, weight=None, bias=None, output_quantizer=None, stric
 # W4A16: 16-bit float activations x integer (<= 8 bit, stored as int8) per-group weights
 # ------------------------------------------------------------------------------------------
 _W4_BK = 64
+# The fused kernel dequantizes the weight tile once per M tile; beyond ~512 rows dequantizing the weight ONCE
+# (dequantize_by_tile kernel) and running the library bf16 GEMM -- the dispatcher's fallback -- is faster on B200
+# (measured on 14336x4096, g=128: 46 vs 70 us at 256 rows, 83 vs 88 us at 512, 156 vs 126 us at 1024;
+# tools/bench_w4a16.py).  None removes the limit.
+W4A16_MAX_ROWS: Optional[int] = 512
 
 
 def _w4_group(weight, pw) -> Optional[int]:
@@ -142,6 +147,8 @@ def _accepts_w4a16(input=None, weight=None, bias=None, output_quantizer=None, st
     if isinstance(bias, QuantizedTensor):
         return False
     k = weight.shape[1]
+    if W4A16_MAX_ROWS is not None and k > 0 and input.numel() // k > W4A16_MAX_ROWS:
+        return False
     group = _w4_group(weight, pw)
     return input.shape[-1] == k and k % _W4_BK == 0 and group is not None and group % _W4_BK == 0
 

@@ -151,9 +151,11 @@ def _dispatch_w4(lin, x):
     with torch.no_grad(), ff.strict_quantization(False):
         before = qlinear.stats().get("calls_w4a16", 0)
         qlinear.install()
+        limit, qlinear.W4A16_MAX_ROWS = qlinear.W4A16_MAX_ROWS, None     # exercise the kernel at every size
         try:
             y = lin(x)
         finally:
+            qlinear.W4A16_MAX_ROWS = limit
             qlinear.uninstall()
         assert qlinear.stats().get("calls_w4a16", 0) == before + 1, "the W4A16 kernel was not dispatched"
         return y, lin(x)            # (kernel, reference fallback: nothing registered)
@@ -205,6 +207,7 @@ def test_w4a16_quantized_16bit_activations_3d_input_and_predicate():
         wq = lin.weight_quantizer(lin.weight)
         assert qlinear._accepts_w4a16(input=x, weight=wq, bias=None)
         assert not qlinear._accepts_w4a16(input=x.float(), weight=wq, bias=None)            # fp32 activations
+        assert not qlinear._accepts_w4a16(input=x.repeat(8, 1, 1), weight=wq, bias=None)    # 800 rows > W4A16_MAX_ROWS
         assert not qlinear._accepts_w4a16(input=x[..., :448], weight=wq, bias=None)         # K mismatch
         odd = ff.nn.LinearQuantizer(4, granularity=ff.PerBlock(block_dims=1, block_sizes=32, per_channel_dims=0),
                                     quantized_dtype=torch.int8).to(DEV)
