@@ -31,5 +31,33 @@ for m, k, n in [(300, 1040, 700), (128, 128, 256), (17, 96, 40)]:
     qlinear.install()
     with torch.no_grad():
         lin(x)
+# fused calibration step: per-channel rows (all vector-per-thread variants, deferred one-sided rows), per-tensor
+# (single chunk, many chunks, ragged tail, rows straddling warp spans)
+for shape, tile, dt, sym in [((7, 512), (1, 512), torch.bfloat16, True), ((5, 1024), (1, 1024), torch.float32, False),
+                             ((3, 2056), (1, 2056), torch.float16, True), ((2, 4096), (1, 4096), torch.bfloat16, True),
+                             ((2100, 4096), (1, 4096), torch.bfloat16, True), ((3, 20480), (1, 20480), torch.bfloat16, True),
+                             ((8, 512), (8, 512), torch.bfloat16, False), ((3, 77, 264), (3, 77, 264), torch.float16, True),
+                             ((1500, 4096), (1500, 4096), torch.bfloat16, False), ((700, 14336), (700, 14336), torch.bfloat16, False)]:
+    nt = 1
+    for d, t in zip(shape, tile):
+        nt *= d // t
+    for variant in ("mixed", "positive"):
+        x = torch.randn(shape, device=dev).to(dt)
+        x = x.abs() if variant == "positive" else x
+        mn = torch.full((nt,), float("inf"), dtype=dt, device=dev); mx = -mn
+        s = torch.empty(nt, device=dev); o = torch.empty(nt, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev); settled = torch.zeros(1, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            ops.calibrate_quantize_(mn, mx, x, tile, 8, sym, True, s, o, flags, settled, rowsum=True)
+        assert int(flags.item()) == 0
+# GPTQ block kernel: full and ragged blocks, few and many rows
+from fastforward_b200.quantization import gptq as G
+for rows, ncols in [(5, 128), (1000, 37), (33, 64)]:
+    w = torch.randn(rows, 256, device=dev) * 0.1
+    blk = w[:, 64:64 + ncols].contiguous(); q = torch.zeros_like(w); e = torch.zeros_like(w)
+    hinv = torch.eye(256, device=dev) + torch.triu(torch.randn(256, 256, device=dev) * 0.01, 1)
+    sc = torch.rand(rows * 2, device=dev) * 0.02 + 1e-3; of = torch.randn(rows * 2, device=dev)
+    G.gptq_block_(blk, q[:, 64:64 + ncols], e[:, 64:64 + ncols], hinv[64:64 + ncols, 64:64 + ncols], sc, of,
+                  torch.arange(64, 64 + ncols, dtype=torch.int32, device=dev), 1, 128, 2, 4)
 torch.cuda.synchronize()
 print("sanitize pass done")
