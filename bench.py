@@ -329,6 +329,37 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
     return out
 
 
+def measure_reference_eager_cuda(args, sh, dev):
+    """Context baseline (part of the baseline leg, not of the product): the reference's own aten op sequence --
+    oracle/ref_ops.py is that sequence op for op -- executed on CUDA tensors, i.e. what the unmodified reference
+    does on this GPU without the B200 backend ('the real beat-this bars')."""
+    import bench_workloads as bw
+    from oracle import ref_ops as R
+    from oracle import workload as ow
+
+    out = {}
+    torch.manual_seed(0)
+    x = torch.randn(4096, 4096, device=dev); g = torch.randn(4096, 4096, device=dev)
+    tile = (1, 4096)
+    mn, mx = R.tile_minmax(x, tile)
+    scale, offset = R.parameters_for_range(mn, mx, 8, True, True)
+    t = _time_cuda(lambda: R.fake_quant_fwd_bwd(x, g, scale, offset, tile, 8), iters=10, warm=2)
+    out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_us"] = round(t * 1e6, 1)
+    del x, g
+    layers = 2
+    model = bw.DecoderStack(sh, layers=layers, dtype=torch.bfloat16, device=dev)
+    bw.init_weights_(model, seed=0)
+    ow.oracle_calibration_model(model)
+    tok = torch.randint(0, sh.vocab, (1, args.seq), device=dev)
+    with torch.no_grad():
+        t = _time_cuda(lambda: model(tok), iters=5, warm=2)
+    out["calibration_tokens_per_s"] = round(args.seq / (t * sh.layers / layers), 1)
+    out["calibration_sample"] = f"{layers} of {sh.layers} decoder layers at seq {args.seq}, scaled; eager aten ops + float fallback GEMM, host syncs as in the reference"
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------
@@ -504,8 +535,10 @@ def run_ours(args):
             torch.cuda.empty_cache()
             extras = measure_extras(ff, dev, hbm_peak, int8_peak)
         cpu_baseline = None
+        ref_eager_cuda = None
         if not args.skip_cpu_baseline:
             cpu_baseline = run_reference_sample(args, sh, sample_layers=args.cpu_sample_layers, steps=3, warmup=1)
+            ref_eager_cuda = measure_reference_eager_cuda(args, sh, dev)
         line = {
             "metric": "calib tokens/s (Llama-3-8B-shape W8 per-channel / A8 per-tensor RunningMinMax calibration, seq 2048)"
             if args.shape == "8b" else f"calib tokens/s ({sh.name})",
@@ -526,7 +559,7 @@ def run_ours(args):
             "kernels": {k: dict(launches=v["launches"], ms_per_step=v["total_ms"], avg_us=v["avg_us"],
                                 rate=(f"{v['rate'] / 1e12:.0f} TOP/s" if k.startswith("w8a8") else f"{v['rate'] / 1e9:.0f} G(B|elem)/s"))
                         for k, v in per_op.items()},
-            "qlinear": qlin, "extras": extras,
+            "qlinear": qlin, "extras": extras, "reference_eager_cuda": ref_eager_cuda,
             "peaks": {"hbm_GBps": hbm_peak, "int8_TOPS": int8_peak, "note": "hbm and bf16 from MEASURED_PEAKS.json; int8 = 2 x measured bf16 burst"},
             "wall_s_timed_region": round(wall, 3), "block_exit_ms": round(exit_ms, 2),
         }

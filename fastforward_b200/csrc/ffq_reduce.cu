@@ -16,6 +16,8 @@
 // Algorithmic traffic per element: backward 3s (x, g in; dx out), min/max s.
 #include <type_traits>
 
+#include <cstring>
+
 #include "ffq_common.cuh"
 
 namespace ffq {
@@ -691,6 +693,47 @@ __global__ void __launch_bounds__(RD_THREADS) pr_apply_kernel(const PrArgs a) {
   if (a.offset) store_from_float(a.offset, a.o_dt, i, off);
 }
 
+// Batched variant: one CTA per quantizer, all running ranges living in one contiguous buffer (the estimator's
+// arena).  desc[q] = {start, len, scale_ptr, offset_ptr (0: none), c0, c1, cfg, 0} with c0/c1/cfg the words
+// ffq_params_for_ranges_encode() produces (the integer-grid constants as float bits; bit 0 symmetric, bit 1
+// allow_one_sided); scale/offset are fp32.  Same arithmetic as pr_min_kernel + pr_apply_kernel.
+__global__ void __launch_bounds__(RD_THREADS) pr_batched_kernel(const void* mn_base, const void* mx_base, int r_dt,
+                                                                const long long* __restrict__ desc) {
+  __shared__ float smem[64];
+  __shared__ int s_one_sided;
+  const long long* d = desc + (long long)blockIdx.x * 8;
+  const unsigned long long start = (unsigned long long)d[0], len = (unsigned long long)d[1];
+  float* scale = reinterpret_cast<float*>(d[2]);
+  float* offset = reinterpret_cast<float*>(d[3]);
+  const float int_min_abs = __int_as_float((int)(d[4] & 0xffffffffll)), int_max_abs = __int_as_float((int)(d[4] >> 32));
+  const float neg_int_min = __int_as_float((int)(d[5] & 0xffffffffll)), steps = __int_as_float((int)(d[5] >> 32));
+  const bool symmetric = (d[6] & 1) != 0, allow_one_sided = (d[6] & 2) != 0;
+  bool one_sided = false;
+  if (symmetric && allow_one_sided) {
+    float mn = INFINITY, dummy = 0.f;
+    for (unsigned long long i = threadIdx.x; i < len; i += blockDim.x) mn = nan_min(mn, load_as_float(mn_base, r_dt, start + i));
+    block_minmax(mn, dummy, smem);
+    if (threadIdx.x == 0) s_one_sided = (mn >= 0.f) ? 1 : 0;
+    __syncthreads();
+    one_sided = s_one_sided != 0;
+  }
+  for (unsigned long long i = threadIdx.x; i < len; i += blockDim.x) {
+    float mn = load_as_float(mn_base, r_dt, start + i);
+    const float mx = load_as_float(mx_base, r_dt, start + i);
+    if (symmetric && !one_sided) {
+      scale[i] = nan_max(__fdiv_rn(fabsf(mn), int_min_abs), __fdiv_rn(fabsf(mx), int_max_abs));
+      if (offset) offset[i] = 0.f;
+      continue;
+    }
+    if (symmetric) mn = 0.f;
+    float sc = __fdiv_rn(__fsub_rn(mx, mn), steps);
+    const float eps = 1.1920928955078125e-07f;
+    sc = (sc != sc) ? sc : fmaxf(sc, eps);
+    scale[i] = sc;
+    if (offset) offset[i] = __fadd_rn(__fdiv_rn(mn, sc), neg_int_min);
+  }
+}
+
 }  // namespace ffq
 
 using namespace ffq;
@@ -917,6 +960,30 @@ int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtype, float
                             scale_out, FFQ_F32, offset_out, FFQ_F32, pr_part, PR_MAX_PARTS * sizeof(float), stream);
   if (rc != FFQ_OK) return rc;
   return ffq_quantize(x, x_dtype, q, q_dtype, scale_out, FFQ_F32, offset_out, FFQ_F32, layout, num_bits, stream);
+}
+
+void ffq_params_for_ranges_encode(double num_bits, int symmetric, int allow_one_sided, int64_t words[3]) {
+  const double lo = -pow(2.0, num_bits - 1.0);
+  const float f[4] = {(float)fabs(lo), (float)fabs(-lo - 1.0), (float)(-lo), (float)(pow(2.0, num_bits) - 1.0)};
+  uint32_t u[4];
+  memcpy(u, f, sizeof(u));
+  words[0] = (int64_t)(((uint64_t)u[1] << 32) | u[0]);
+  words[1] = (int64_t)(((uint64_t)u[3] << 32) | u[2]);
+  words[2] = (symmetric ? 1 : 0) | (allow_one_sided ? 2 : 0);
+}
+
+int ffq_params_for_ranges_batched(const void* min_base, const void* max_base, int range_dtype, const int64_t* desc_dev,
+                                  int64_t num_quantizers, void* stream) {
+  if (num_quantizers <= 0) return FFQ_OK;
+  if (range_dtype == FFQ_F64 || !(is_float_dt(range_dtype) || is_int_dt(range_dtype))) {
+    set_error("params_for_ranges_batched: unsupported range dtype %s", dt_name(range_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (num_quantizers > 0x7fffffffll || desc_dev == nullptr) { set_error("params_for_ranges_batched: bad descriptor table"); return FFQ_ERR_INVALID; }
+  pr_batched_kernel<<<(unsigned int)num_quantizers, RD_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      min_base, max_base, range_dtype, reinterpret_cast<const long long*>(desc_dev));
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
 }
 
 }  // extern "C"

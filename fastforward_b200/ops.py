@@ -311,6 +311,35 @@ def parameters_for_range_(
         ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))
 
 
+def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor, entries) -> None:
+    """``parameters_for_range_`` for many quantizers in ONE launch.  ``min_buf`` / ``max_buf``: contiguous buffers
+    holding every quantizer's running range; ``entries``: ``(start, length, num_bits, symmetric, allow_one_sided,
+    scale, offset_or_None)`` with fp32 contiguous CUDA ``scale`` / ``offset`` of ``length`` elements."""
+    C.require_cuda(min_buf, "min_buf")
+    if not entries:
+        return
+    if min_buf.dtype != max_buf.dtype or not min_buf.is_contiguous() or not max_buf.is_contiguous():
+        raise RuntimeError("parameters_for_ranges_batched_: range buffers must be contiguous and of one dtype")
+    words = (ctypes.c_int64 * 3)()
+    enc = {}
+    rows = []
+    for start, length, num_bits, symmetric, allow_one_sided, scale, offset in entries:
+        for t in (scale, offset):
+            if t is not None and (t.dtype != torch.float32 or t.numel() != length or not t.is_contiguous() or t.device != min_buf.device):
+                raise RuntimeError("parameters_for_ranges_batched_: scale/offset must be contiguous fp32 tensors of the range's length")
+        if start < 0 or start + length > min_buf.numel():
+            raise RuntimeError("parameters_for_ranges_batched_: range outside the buffers")
+        key = (float(num_bits), bool(symmetric), bool(allow_one_sided))
+        if key not in enc:
+            C.lib.ffq_params_for_ranges_encode(key[0], int(key[1]), int(key[2]), words)
+            enc[key] = (int(words[0]), int(words[1]), int(words[2]))
+        w = enc[key]
+        rows.append((int(start), int(length), scale.data_ptr(), 0 if offset is None else offset.data_ptr(), w[0], w[1], w[2], 0))
+    desc = torch.tensor(rows, dtype=torch.int64).to(min_buf.device, non_blocking=False)
+    C.check(C.lib.ffq_params_for_ranges_batched(min_buf.data_ptr(), max_buf.data_ptr(), C.dtype_tag(min_buf.dtype),
+                                                desc.data_ptr(), len(rows), C.current_stream(min_buf.device)))
+
+
 def calibrate_quantize_mode(shape: Sequence[int], tile_size, dtype: torch.dtype) -> int:
     """0: the fused calibration step does not handle this layout, 1: per-channel rows, 2: per-tensor."""
     shape = tuple(shape)
@@ -335,7 +364,7 @@ def calibrate_quantize_(
     run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size, num_bits: float,
     symmetric: bool, allow_one_sided: bool, scale_out: torch.Tensor, offset_out: Optional[torch.Tensor],
     flags: Optional[torch.Tensor] = None, settled: Optional[torch.Tensor] = None, rowsum: bool = False,
-    run_fixup: bool = True,
+    run_fixup: bool = True, workspace: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """One RunningMinMax calibration step in one pass over ``data``: updates ``run_min``/``run_max`` in place
     (range_setting/minmax.py:229-237), writes the quantizer's ``scale``/``offset`` for the updated range in place
@@ -343,7 +372,9 @@ def calibrate_quantize_(
     ``quantize_by_tile(data, scale, tile, num_bits, torch.int8, offset)`` returns for those parameters, and
     ``rowsum`` (int32, one value per row of the last dimension) is what the W8A8 linear needs from them.
     ``settled`` / ``run_fixup``: see include/ffq_b200.h -- only a caller that has read ``settled != 0`` may pass
-    ``run_fixup=False``.
+    ``run_fixup=False``.  ``workspace``: zero-initialised uint8 buffer of ``_CALQ_WS`` bytes for the per-tensor
+    kernel's grid barrier, owned by the caller and used by one stream at a time (default: a cached per-(device,
+    stream) buffer).
     Raises NotImplementedError for layouts the fused kernels do not cover (see calibrate_quantize_mode)."""
     x, shape, tile, layout = _prep(data, tile_size)
     _bitwidth_guard(torch.int8, num_bits)
@@ -361,7 +392,9 @@ def calibrate_quantize_(
     q = torch.empty(shape, dtype=torch.int8, device=x.device)
     row_len = shape[-1]
     rs = torch.empty(x.numel() // row_len, dtype=torch.int32, device=x.device) if rowsum else None
-    ws = C.barrier_workspace(x.device, _CALQ_WS)
+    ws = workspace if workspace is not None else C.barrier_workspace(x.device, _CALQ_WS)
+    if ws.numel() < _CALQ_WS or ws.dtype != torch.uint8 or ws.device != x.device:
+        raise RuntimeError(f"calibrate_quantize_: workspace must be a uint8 tensor of {_CALQ_WS} bytes on {x.device}")
     C.check(C.lib.ffq_calibrate_quantize(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), run_min.data_ptr(), run_max.data_ptr(), C.dtype_tag(run_min.dtype),
         scale_out.data_ptr(), C.ptr(offset_out), C.ptr(rs), row_len, C.ptr(flags), C.ptr(settled), int(bool(run_fixup)),

@@ -48,6 +48,7 @@ class _RangeArena:
     def __init__(self) -> None:
         self.chunks: dict = {}     # (device, dtype) -> list of [min_buf, max_buf, used]
         self.flags: dict = {}      # device -> int32[1]
+        self.barriers: dict = {}   # device -> zeroed scratch of the fused per-tensor kernel's grid barrier
 
     def take(self, n: int, like: torch.Tensor):
         key = (like.device, like.dtype)
@@ -63,6 +64,13 @@ class _RangeArena:
         if device not in self.flags:
             self.flags[device] = torch.zeros(1, dtype=torch.int32, device=device)
         return self.flags[device]
+
+    def barrier_workspace(self, device: torch.device) -> torch.Tensor:
+        """Owned by the block (like the running ranges), so a CUDA graph captured inside the block never points at
+        scratch that outlives it; one stream per block is assumed, as everywhere in the reference."""
+        if device not in self.barriers:
+            self.barriers[device] = torch.zeros(ops._CALQ_WS, dtype=torch.uint8, device=device)
+        return self.barriers[device]
 
     def buffers(self):
         for chunks in self.chunks.values():
@@ -160,7 +168,8 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         codes, rowsum = ops.calibrate_quantize_(
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
-            self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen)
+            self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen,
+            workspace=self._arena.barrier_workspace(data.device) if (mode == 2 and self._arena is not None) else None)
         if self._settled_host is not None and not self._settled_seen:
             self._settled_host.copy_(self._settled, non_blocking=True)
         if self._eager:
@@ -280,8 +289,7 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
             loose = [(s.min, s.max) for _, s in steps if id(s.min.untyped_storage()) not in arena_ids]
             all_reduce_minmax_buffers(list(self._arena.buffers()), flags, group=self.process_group)
             all_reduce_ranges(loose, None, group=self.process_group)
-            for quantizer, step in steps:
-                quantizer.quantization_range = (step.min, step.max)
+            self._reset_parameters_from_ranges(steps)
         # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks
         if flags and not self.eager_checks:
             value = 0
@@ -290,6 +298,35 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
             _raise_for_flags(value)
         self._steps = []
         self._arena = _RangeArena()
+
+
+    def _reset_parameters_from_ranges(self, steps) -> None:
+        """After the ranges were merged across ranks: every quantizer's (scale, offset) from its merged range.  The
+        quantizers whose running range lives in an arena chunk and whose parameters are materialised fp32 tensors of
+        the right size are done with ONE launch per chunk; the rest go through the ``quantization_range`` setter."""
+        from ..nn.linear_quantizer import LinearQuantizer
+
+        chunks = {}
+        for chunk_list in self._arena.chunks.values():
+            for mn, mx, used in chunk_list:
+                if used:
+                    chunks[mn.untyped_storage().data_ptr()] = (mn, mx, [])
+        for quantizer, step in steps:
+            entry = chunks.get(step.min.untyped_storage().data_ptr())
+            n = step.min.numel()
+            ok = entry is not None and type(quantizer) is LinearQuantizer and not quantizer.has_uninitialized_params \
+                and step.min.is_contiguous() and step.max.storage_offset() == step.min.storage_offset() \
+                and quantizer.scale.dtype == torch.float32 and quantizer.scale.numel() == n \
+                and quantizer.scale.device == step.min.device and quantizer.scale.is_contiguous() \
+                and (quantizer.offset is None or (quantizer.offset.dtype == torch.float32 and quantizer.offset.numel() == n
+                                                  and quantizer.offset.is_contiguous()))
+            if not ok:
+                quantizer.quantization_range = (step.min, step.max)
+                continue
+            entry[2].append((step.min.storage_offset(), n, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
+                             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data))
+        for mn, mx, entries in chunks.values():
+            ops.parameters_for_ranges_batched_(mn, mx, entries)
 
 
 class SmoothedMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):

@@ -157,6 +157,16 @@ FFQ_API int ffq_params_for_range(const void* min_range, const void* max_range, i
                          void* scale_out, int scale_dtype, void* offset_out, int offset_dtype,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched form for MANY quantizers whose ranges live in one contiguous buffer (the calibration block's arena): one
+ * launch, one CTA per quantizer.  desc_dev: device int64 [num_quantizers][8] =
+ * {start element in the range buffers, number of tiles, scale pointer (fp32), offset pointer (fp32, 0 = none),
+ *  words[0], words[1], words[2] of ffq_params_for_ranges_encode(num_bits, symmetric, allow_one_sided), 0}.
+ * Results equal ffq_params_for_range called per quantizer (round_offset = 0).  Used when the data-parallel range
+ * exchange has merged the ranges of all quantizers at the end of an estimate_ranges block. */
+FFQ_API int ffq_params_for_ranges_batched(const void* min_base, const void* max_base, int range_dtype,
+                                  const int64_t* desc_dev, int64_t num_quantizers, void* stream);
+FFQ_API void ffq_params_for_ranges_encode(double num_bits, int symmetric, int allow_one_sided, int64_t words[3]);
+
 /* ---- a4: dynamic quantize -----------------------------------------------------------------
  * per-tile min/max -> params -> quantize, three launches, no host sync.
  * scale_out/offset_out are fp32[num_tiles]; offset_out is the rounded offset (zeros when the

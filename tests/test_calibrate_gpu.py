@@ -268,3 +268,32 @@ def test_quantized_linear_calibration_fused_equals_unfused_and_graph_replay():
     assert torch.equal(y, results[True][0][2])
     for (_, q), want in zip(ff.nn.named_quantizers(m), zip(results[True][1][0::2], results[True][1][1::2])):
         assert torch.equal(q.scale.detach(), want[0]) and torch.equal(q.offset.detach(), want[1])
+
+
+def test_batched_parameters_for_ranges_equals_per_quantizer_calls():
+    """The block-exit path of data-parallel calibration: one launch for all quantizers of an arena chunk."""
+    g = torch.Generator().manual_seed(21)
+    sizes = [1, 4096, 1, 14336, 7, 1, 300]
+    cfgs = [(8, False, True), (8, True, True), (4, True, False), (8, True, True), (2, False, True), (8, True, True), (6, True, True)]
+    total = sum(sizes)
+    for dt in (torch.bfloat16, torch.float32):
+        mn = (torch.randn(total, generator=g) - 0.5).to(dt).to(DEV)
+        mx = (mn.float() + torch.rand(total, generator=g).to(DEV) * 3).to(dt)
+        mn[sizes[0]:sizes[0] + 4096] = mn[sizes[0]:sizes[0] + 4096].abs()        # a one-sided quantizer
+        mn[-300] = float("nan")                                                    # NaN range: never one-sided
+        entries, expect, start = [], [], 0
+        for n, (bits, sym, one_sided) in zip(sizes, cfgs):
+            scale = torch.empty(n, device=DEV)
+            offset = None if (sym and not one_sided) else torch.empty(n, device=DEV)
+            entries.append((start, n, bits, sym, one_sided, scale, offset))
+            s2 = torch.empty(n, device=DEV)
+            o2 = None if offset is None else torch.empty(n, device=DEV)
+            ops.parameters_for_range_(mn[start:start + n], mx[start:start + n], bits, sym, one_sided, s2, o2)
+            expect.append((s2, o2))
+            start += n
+        before = ff._cabi.launch_count()
+        ops.parameters_for_ranges_batched_(mn, mx, entries)
+        assert ff._cabi.launch_count() - before == 1
+        for (_, _, _, _, _, scale, offset), (s2, o2) in zip(entries, expect):
+            assert bits_equal(scale, s2)
+            assert (offset is None) == (o2 is None) and (offset is None or bits_equal(offset, o2))
