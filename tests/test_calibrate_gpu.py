@@ -297,3 +297,67 @@ def test_batched_parameters_for_ranges_equals_per_quantizer_calls():
         for (_, _, _, _, _, scale, offset), (s2, o2) in zip(entries, expect):
             assert bits_equal(scale, s2)
             assert (offset is None) == (o2 is None) and (offset is None or bits_equal(offset, o2))
+
+
+def _unfused(run_mn, run_mx, x, tile, bits, sym, one_sided, flags):
+    nt = run_mn.numel()
+    scale = torch.empty(nt, device=DEV)
+    offset = None if (sym and not one_sided) else torch.empty(nt, device=DEV)
+    ops.running_minmax_update_(run_mn, run_mx, x, tile, flags)
+    ops.parameters_for_range_(run_mn, run_mx, bits, sym, one_sided, scale, offset)
+    q = ops.quantize_by_tile(x, scale, tile, float(bits), torch.int8, offset)
+    return q, scale, offset
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fused_equals_separate_kernels_on_random_configurations(seed):
+    """Property test at sizes the CPU oracle would be slow for: for random shapes / dtypes / bit widths / quantizer
+    kinds / data scales (with NaN, inf, zeros and huge values sprinkled in) three consecutive fused steps produce
+    bit for bit what minmax + params_for_range + quantize (+ row sums) produce."""
+    import random
+    rnd = random.Random(1000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    dt = rnd.choice([torch.bfloat16, torch.float16, torch.float32])
+    ept = 4 if dt == torch.float32 else 8
+    per_tensor = rnd.random() < 0.4
+    if per_tensor:
+        shape = rnd.choice([(rnd.randint(1, 900), ept * rnd.randint(8, 700)), (rnd.randint(1, 5), rnd.randint(1, 60), ept * rnd.randint(8, 300))])
+        tile = shape
+        if shape[-1] * (shape[0] if len(shape) == 2 else shape[0] * shape[1]) < 64 * ept:
+            shape = (8, 64 * ept); tile = shape
+    else:
+        shape = (rnd.randint(1, 400), ept * rnd.randint(64, 2300))
+        tile = (1, shape[1])
+    bits = rnd.choice([8, 8, 8, 4, 3, 7])
+    sym = rnd.random() < 0.5
+    one_sided = rnd.random() < 0.7 or not sym
+    nt = 1 if per_tensor else shape[0]
+    rdt = rnd.choice([dt, torch.float32])
+    mn1 = torch.full((nt,), float("inf"), dtype=rdt, device=DEV); mx1 = -mn1
+    mn2, mx2 = mn1.clone(), mx1.clone()
+    scale = torch.empty(nt, device=DEV)
+    offset = None if (sym and not one_sided) else torch.empty(nt, device=DEV)
+    f1 = torch.zeros(1, dtype=torch.int32, device=DEV); f2 = torch.zeros(1, dtype=torch.int32, device=DEV)
+    settled = torch.zeros(1, dtype=torch.int32, device=DEV)
+    special = rnd.random() < 0.35
+    for step in range(3):
+        x = torch.randn(shape, generator=g) * (10 ** rnd.uniform(-3, 2))
+        kind = rnd.random()
+        if kind < 0.2:
+            x = x.abs()
+        elif kind < 0.35 and not per_tensor:
+            x[::3] = x[::3].abs()
+        if special:
+            flat = x.view(-1)
+            for v in (float("nan"), float("inf"), 0.0, -0.0, 3e38, -1e-38):
+                if rnd.random() < 0.4:
+                    flat[rnd.randrange(flat.numel())] = v
+        x = x.to(dt).to(DEV)
+        q, rs = ops.calibrate_quantize_(mn1, mx1, x, tile, bits, sym, one_sided, scale, offset, f1, settled, rowsum=True)
+        q2, s2, o2 = _unfused(mn2, mx2, x, tile, bits, sym, one_sided, f2)
+        assert bits_equal(mn1, mn2) and bits_equal(mx1, mx2), "running range"
+        assert bits_equal(scale, s2), "scale"
+        assert offset is None or bits_equal(offset, o2), "offset"
+        assert torch.equal(q, q2), "codes"
+        assert torch.equal(rs, q2.reshape(-1, shape[-1]).int().sum(1).to(torch.int32)), "row sums"
+        assert int(f1.item()) == int(f2.item())
