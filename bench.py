@@ -287,7 +287,7 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
                                           "context_cublaslt_int_mm_TOPS": round(2 * M * N * K / t_lib / 1e12, 1)}
     del qx, qw, y
     # W4A16 linear (configs[4] recipe at the configs[3] shape): bf16 activations x 4-bit g=128 codes
-    for M in (2048, 8192):
+    for M in (256, 2048):     # the dispatcher takes the fused kernel up to 512 rows (nn/qlinear.py: W4A16_MAX_ROWS)
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         qw = torch.randint(-8, 8, (N, K), dtype=torch.int8, device=dev)
         sw4 = torch.rand(N * (K // 128), device=dev) * 0.01 + 1e-3

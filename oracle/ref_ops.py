@@ -199,7 +199,7 @@ def backward_terms(
     doff = None
     if offset is not None:
         doff = torch.where(clip, s[:, None] * gr, 0)         # :221
-    dsc = torch.empty(q.shape, dtype=s.dtype)                # :224
+    dsc = torch.empty(q.shape, dtype=s.dtype, device=s.device)   # :224
     torch.where(q < lo, s.new_tensor([lo]), s.new_tensor([hi]), out=dsc)   # :225-227
     dsc.add_(o[:, None].to(dsc.dtype))                       # :228
     torch.where(clip, dsc, (q - pre).to(dsc.dtype), out=dsc)  # :229
