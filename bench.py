@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-layers", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--with-compiled-baseline", action="store_true",
+                    help="also time torch.compile of the reference's op sequence for cfg1 on the GPU (context; ~1 min of compilation)")
     ap.add_argument("--workload", default="calib", choices=["calib", "w4a16-calib", "wq4"],
                     help="calib: configs[1] (default, W8A8 8B-shape).  w4a16-calib: configs[4] recipe (W4 g=128 / A16) on "
                          "--shape.  wq4: configs[2], W4 g=128 weight fake-quant of all linears sharded by layer")
@@ -266,6 +268,12 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
             th = (time.perf_counter() - t0) / 5
             out[name]["e2e_host_buffers"] = {"ms": round(th * 1e3, 2), "GBps_algorithmic": round(by / th / 1e9, 1),
                                              "h2d_bytes": 2 * xh.numel() * 4, "d2h_bytes": 2 * xh.numel() * 4}
+        if name.startswith("cfg1"):
+            # asymmetric (doffset live) and clipping (range = 0.5 x true range: clip branches taken) variant
+            ops.parameters_for_range_(mn * 0.5, mx * 0.5, 8, False, True, scale, offset)
+            t2 = _time_graph(step, calls_per_replay=max(4, 2 * nbuf))
+            out[name]["asymmetric_clipping_variant"] = {"fwd_bwd_us": round(t2 * 1e6, 1), "GBps": round(by / t2 / 1e9, 1),
+                                                        "frac_of_measured_hbm": round(by / t2 / 1e9 / hbm_peak, 3)}
         del xs, gs
     # W8A8 linear, configs[3]
     M, N, K = 8192, 14336, 4096
@@ -345,6 +353,25 @@ def measure_reference_eager_cuda(args, sh, dev):
     scale, offset = R.parameters_for_range(mn, mx, 8, True, True)
     t = _time_cuda(lambda: R.fake_quant_fwd_bwd(x, g, scale, offset, tile, 8), iters=10, warm=2)
     out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_us"] = round(t * 1e6, 1)
+    if args.with_compiled_baseline:
+        # the reference's `compiled_quant_funcs` route: the same op sequence through torch.compile (inductor)
+        try:
+            # (a) forward and backward compiled separately, as autograd runs them (x is read by both: 20 B/element)
+            c_fwd = torch.compile(lambda a: R.dequantize_by_tile(R.quantize_by_tile(a, scale, tile, 8, a.dtype, offset), scale, tile, offset, a.dtype))
+            c_bwd = torch.compile(lambda a, b: R.quantize_by_tile_backward(a, b, scale, tile, 8, offset))
+
+            def sep():
+                c_fwd(x)
+                c_bwd(x, g)
+            t = _time_cuda(sep, iters=10, warm=3)
+            out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_torch_compile_us"] = round(t * 1e6, 1)
+            # (b) both in ONE compiled graph: inductor reads x once (16 B/element) -- not something autograd can do,
+            # the gradient does not exist yet when the forward runs
+            compiled = torch.compile(lambda a, b: R.fake_quant_fwd_bwd(a, b, scale, offset, tile, 8))
+            t = _time_cuda(lambda: compiled(x, g), iters=10, warm=3)
+            out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_torch_compile_single_graph_us"] = round(t * 1e6, 1)
+        except Exception as e:  # noqa: BLE001  (a baseline that cannot be built is reported, not fatal)
+            out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_torch_compile_us"] = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
     del x, g
     layers = 2
     model = bw.DecoderStack(sh, layers=layers, dtype=torch.bfloat16, device=dev)
@@ -415,7 +442,7 @@ def run_ours(args):
 
     def region(steps, tokens_src, e2e, graph):
         """Enter estimate_ranges, warm up, time `steps` steps + block exit.  Returns seconds (device)."""
-        out_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        out_host = torch.empty(max(steps, 1), dtype=torch.float32).pin_memory()    # one pinned slot per step
         with torch.no_grad(), ff.estimate_ranges(model, estimator):
             for i in range(args.warmup):
                 static_tokens.copy_(dev_tokens[i])
@@ -441,11 +468,15 @@ def run_ours(args):
                 else:
                     y = model(static_tokens)
                 if e2e:
-                    out_host.copy_(y.float().abs().mean().reshape(1), non_blocking=False)   # D2H read of the step's result
+                    # D2H read of the step's result into that step's pinned slot; asynchronous like the H2D copy of the
+                    # inputs, all of them complete before the region's closing synchronize
+                    out_host[i:i + 1].copy_(y.float().abs().mean().reshape(1), non_blocking=True)
             tmid.record()
         # leaving the block: +-inf check (one sync) and, for N>1, the MIN/MAX all-reduce of all ranges
         t1.record()
         torch.cuda.synchronize(); barrier()
+        if e2e and not bool(torch.isfinite(out_host[:steps]).all()):
+            raise RuntimeError("bench: a step's result read back from the device is not finite")
         wall = time.perf_counter() - wall0
         dt = t0.elapsed_time(t1) * 1e-3
         region.exit_ms = tmid.elapsed_time(t1)
