@@ -333,7 +333,17 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
     t = _time_graph(qdq, calls_per_replay=6)
     by = 3 * w[0].numel() * 2    # read (min/max) + read + write
     out["w4_g128_weight_qdq_14336x4096_bf16"] = {"us": round(t * 1e6, 1), "GBps": round(by / t / 1e9, 1),
-                                                  "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3)}
+                                                  "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3),
+                                                  "what": "three launches: min/max, params, fused QDQ (3s bytes/element)"}
+
+    def qdq_fused():        # calibrate + snap in ONE launch (ffq_calibrate_fakequant), 2s bytes/element
+        i = it[0] % 3; it[0] += 1
+        ops.calibrate_fake_quantize_(w[i], tile, 4, True, True, scale, offset, None, out=w[i])
+    t = _time_graph(qdq_fused, calls_per_replay=6)
+    by = 2 * w[0].numel() * 2
+    out["w4_g128_weight_qdq_fused_14336x4096_bf16"] = {"us": round(t * 1e6, 1), "GBps": round(by / t / 1e9, 1),
+                                                        "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3),
+                                                        "what": "one launch (+ the early-exit fix-up): read once, write once"}
     return out
 
 
@@ -665,7 +675,7 @@ def run_wq4(args):
     import bench_workloads as bw
     import fastforward_b200 as ff
     from fastforward_b200 import _cabi
-    from fastforward_b200.quantization.fuse import calibrate_weight_quantizers, fuse_qdq_weights
+    from fastforward_b200.quantization.fuse import calibrate_and_fuse_qdq_weights, calibrate_weight_quantizers, fuse_qdq_weights
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -684,9 +694,14 @@ def run_wq4(args):
     model.to(dev)
     n_weights = sum(m.weight.numel() for m in model.modules() if isinstance(m, torch.nn.Linear))
 
+    two_step = os.environ.get("FFQ_WQ4_TWO_STEP") == "1"     # the separate calibrate + fuse launches, for comparison
+
     def step():
-        calibrate_weight_quantizers(model)
-        fuse_qdq_weights(model)
+        if two_step:
+            calibrate_weight_quantizers(model)
+            fuse_qdq_weights(model)
+        else:
+            calibrate_and_fuse_qdq_weights(model)
 
     for _ in range(args.warmup):
         step()
@@ -725,14 +740,16 @@ def run_wq4(args):
     else:
         n_all = float(n_weights)
     if rank == 0:
-        by = 3 * 2 * n_all * args.steps
+        by = (3 if two_step else 2) * 2 * n_all * args.steps     # algorithmic: one read + one write (+ the min/max read)
         print(json.dumps({
             "metric": "W4 g=128 weight fake-quant GB/s (Llama-3-8B-shape, all decoder linears, sharded by layer)",
             "value": round(by / dt / 1e9, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{sh.name}: {layers} layers x 7 linears = {n_all / 1e9:.2f} G weights, LinearQuantizer(4, PerBlock g=128), "
-                                   "calibrate on the weight + fuse_qdq_weights in place; layer i -> rank i mod N",
+                                   + ("calibrate_weight_quantizers + fuse_qdq_weights (3s bytes/element)" if two_step else
+                                    "calibrate_and_fuse_qdq_weights: one fused launch per weight, in place (2s bytes/element)")
+                                   + "; layer i -> rank i mod N",
                        "cuda_graph": cg is not None},
             "gpu_launches": int(launches), "per_gpu_GBps": round(by / dt / 1e9 / world, 1)}))
     if world > 1:

@@ -122,6 +122,7 @@ def _load() -> ctypes.CDLL:
         "ffq_calibrate_quantize": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, vp, i64, vp, vp, i32, lp, dbl, i32, i32, vp, sz, vp]),
         "ffq_calibrate_quantize_mode": (i32, [lp, i32]),
         "ffq_calibrate_quantize_workspace_bytes": (sz, []),
+        "ffq_calibrate_fakequant": (i32, [vp, i32, vp, vp, vp, i32, vp, vp, vp, lp, dbl, i32, i32, i32, vp, sz, vp]),
         "ffq_params_for_ranges_batched": (i32, [vp, vp, i32, vp, i64, vp]),
         "ffq_params_for_ranges_encode": (None, [dbl, i32, i32, ctypes.POINTER(ctypes.c_int64)]),
         "ffq_gptq_block": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp, i32, vp, i32, vp, i64, i64, i64, dbl, i32, vp]),
@@ -141,7 +142,7 @@ EXPORTED = (
     "ffq_dequantize ffq_fakequant_fwd ffq_quantize_bwd ffq_minmax ffq_params_for_range "
     "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_qlinear_workspace_bytes ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16 "
     "ffq_calibrate_quantize ffq_calibrate_quantize_mode ffq_calibrate_quantize_workspace_bytes ffq_gptq_block "
-    "ffq_params_for_ranges_batched ffq_params_for_ranges_encode"
+    "ffq_params_for_ranges_batched ffq_params_for_ranges_encode ffq_calibrate_fakequant"
 ).split()
 
 

@@ -50,6 +50,11 @@ struct CalqArgs {
   unsigned int* bar;                    // [0] arrivals (wraps to 0), [1] generation; zero before first use
   unsigned int nchunks;
   FastDiv rdiv;                         // division by row_len (tensor kernel row sums)
+  // fake-quant output mode (calq_group_kernel / calq_rows_fq_kernel): y = dequantize(quantize(x)), may alias x
+  void* y;
+  int code_is_int;                      // integer code dtype between quantize and dequantize: -0 becomes +0
+  unsigned int* ws_flags;               // [0] some tile was deferred, [1] some (running) tile min is negative/NaN
+  unsigned int lanes;                   // group kernel: 16-byte vectors per tile
 };
 
 constexpr int CQ_CHUNK_VECS = 2048;     // tensor kernel: 32 KB of input per CTA chunk
@@ -308,6 +313,290 @@ __global__ void __launch_bounds__(CQ_T) calq_rows_fixup_kernel(const CalqArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
+// fake-quant output (quantize + dequantize, fp32 chain): the arithmetic of ew_tile_kernel<OP_FAKEQUANT>
+// ------------------------------------------------------------------------------------------
+struct FqConst { float lo, hi; bool int_zero; };    // read once per thread: no per-element constant loads / branches
+
+template <typename XT, int EPT, bool FAST, bool INT_ZERO>
+__device__ __forceinline__ Vec<XT, EPT> calq_vec_fq_impl(const Vec<XT, EPT>& xin, const SharedRcp& k, float o, const FqConst c) {
+  float y[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const float x = Elem<XT>::to_f(xin.v[i]);
+    float t;
+    if constexpr (FAST) {
+      const float q0 = __fmul_rn(x, k.r);
+      const float e = __fmaf_rn(-k.s, q0, x);
+      t = __fsub_rn(__fmaf_rn(k.r, e, q0), o);
+    } else {
+      t = __fsub_rn(__fdiv_rn(x, k.s), o);
+    }
+    float q = nan_clamp(rintf(t), c.lo, c.hi);
+    if constexpr (INT_ZERO) q = __fadd_rn(q, 0.0f);
+    y[i] = __fmul_rn(__fadd_rn(q, o), k.s);
+  }
+  Vec<XT, EPT> out;
+  if constexpr (std::is_same<XT, __nv_bfloat16>::value) {
+#pragma unroll
+    for (int i = 0; i < EPT; i += 2) *reinterpret_cast<__nv_bfloat162*>(&out.v[i]) = __floats2bfloat162_rn(y[i], y[i + 1]);
+  } else if constexpr (std::is_same<XT, __half>::value) {
+#pragma unroll
+    for (int i = 0; i < EPT; i += 2) *reinterpret_cast<__half2*>(&out.v[i]) = __floats2half2_rn(y[i], y[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) out.v[i] = Elem<XT>::from_f(y[i]);
+  }
+  return out;
+}
+
+template <typename XT, int EPT>
+__device__ __forceinline__ Vec<XT, EPT> calq_vec_fq(const Vec<XT, EPT>& xin, const SharedRcp& k, float o, const FqConst c,
+                                                    bool fast) {
+  if (c.int_zero) return fast ? calq_vec_fq_impl<XT, EPT, true, true>(xin, k, o, c) : calq_vec_fq_impl<XT, EPT, false, true>(xin, k, o, c);
+  return fast ? calq_vec_fq_impl<XT, EPT, true, false>(xin, k, o, c) : calq_vec_fq_impl<XT, EPT, false, false>(xin, k, o, c);
+}
+
+constexpr float CQ_DEFERRED = -1.0f;    // scale sentinel: a legitimate scale is never negative
+
+// Short tiles (per-group weights): LANES 16-byte vectors per tile, one vector per lane, the tile's extrema by
+// sub-warp shuffles; four tiles' worth of loads in flight per thread.  FQ: fake-quant output (weight QDQ, may run
+// in place); otherwise int8 codes.  The running range is optional (null: the tile's own min/max is the range).
+// Deferred tiles (symmetric one-sided candidates) get the sentinel scale and are finished by calq_sentinel_fixup.
+template <typename XT, int LANES, bool FQ>
+__global__ void __launch_bounds__(256) calq_group_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  constexpr int U = 4;
+  const unsigned long long nvec = a.numel / EPT;
+  const unsigned long long vbase = (unsigned long long)blockIdx.x * (256 * U) + threadIdx.x;
+  // everything below indexes relative to this thread's first vector with compile-time offsets (u * 256 vectors)
+  const XT* __restrict__ x = static_cast<const XT*>(a.x) + vbase * EPT;
+  const unsigned int remaining = (unsigned int)(nvec > vbase ? (nvec - vbase < 0x7fffffffull ? nvec - vbase : 0x7fffffffull) : 0ull);
+  const unsigned long long tile0 = vbase / LANES;               // tile of vector u: tile0 + u * (256 / LANES)
+  const unsigned int sel = threadIdx.x & (LANES - 1);          // position inside the tile's lane group
+  const bool lead = sel == 0;
+  const bool decide = a.symmetric && a.allow_one_sided;
+  const FqConst fqc{a.lo, a.hi, a.code_is_int != 0};
+  Vec<XT, EPT> xv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if ((unsigned int)(u * 256) < remaining) xv[u] = ld_stream<XT, EPT>(x + u * 256 * EPT);
+  }
+  // ---- extrema and (running) range of the U tiles this lane group touches ----
+  float rmn[U], rmx[U];
+  bool neg_any = false, def_any = false;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const bool live = (unsigned int)(u * 256) < remaining;   // whole groups are live or dead together (nvec % LANES == 0)
+    float mn = INFINITY, mx = -INFINITY;
+    if (live) vec_minmax<XT, EPT>(xv[u], mn, mx);
+    mn = group_min<LANES>(mn);
+    mx = group_max<LANES>(mx);
+    rmn[u] = mn; rmx[u] = mx;
+    if (!live) continue;
+    const unsigned long long tile = tile0 + u * (256 / LANES);
+    if (a.run_min) {
+      rmn[u] = nan_min(load_as_float(a.run_min, a.run_dt, tile), mn);
+      rmx[u] = nan_max(load_as_float(a.run_max, a.run_dt, tile), mx);
+      if (lead) {
+        store_from_float(a.run_min, a.run_dt, tile, rmn[u]);
+        store_from_float(a.run_max, a.run_dt, tile, rmx[u]);
+      }
+    }
+    if (lead && a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+    neg_any = neg_any || !(rmn[u] >= 0.f);
+    def_any = def_any || (decide && rmn[u] >= 0.f);
+  }
+  // ---- parameters: lane `sel` of a group derives them for tile u = sel (once per thread instead of once per
+  // vector), the other lanes fetch them by shuffle.  Groups narrower than U fall back to one derivation per vector. ----
+  constexpr bool SPREAD = LANES >= U;
+  float sc_m = 1.f, off_m = 0.f, r_m = 1.f;
+  int fast_m = 0;
+  if constexpr (SPREAD) {
+    float mn_m = rmn[0], mx_m = rmx[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u)
+      if (sel == (unsigned int)u) { mn_m = rmn[u]; mx_m = rmx[u]; }
+    calq_params(a, mn_m, mx_m, false, sc_m, off_m);
+    const SharedRcp km = make_shared_rcp(sc_m);
+    r_m = km.r;
+    fast_m = (calq_fast_ok(km, mn_m, mx_m) ? 1 : 0) | (km.ok ? 2 : 0);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float sc, off;
+    SharedRcp k;
+    bool fast;
+    if constexpr (SPREAD) {
+      const int src = (int)((threadIdx.x & 31u) - sel) + u;      // lane u of this group
+      sc = __shfl_sync(0xffffffffu, sc_m, src);
+      off = __shfl_sync(0xffffffffu, off_m, src);
+      const int fl = __shfl_sync(0xffffffffu, fast_m, src);
+      k.s = sc; k.r = __shfl_sync(0xffffffffu, r_m, src); k.ok = (fl & 2) != 0;
+      fast = (fl & 1) != 0;
+    }
+    if ((unsigned int)(u * 256) >= remaining) continue;
+    const unsigned long long tile = tile0 + u * (256 / LANES);
+    if (decide && rmn[u] >= 0.f) {         // finished by calq_sentinel_fixup_kernel
+      if (lead) a.scale[tile] = CQ_DEFERRED;
+      continue;
+    }
+    if constexpr (!SPREAD) {
+      calq_params(a, rmn[u], rmx[u], false, sc, off);
+      k = make_shared_rcp(sc);
+      fast = calq_fast_ok(k, rmn[u], rmx[u]);
+    }
+    if (lead) {
+      a.scale[tile] = sc;
+      if (a.offset) a.offset[tile] = off;
+    }
+    const float o = rintf(off);
+    if constexpr (FQ) {
+      const Vec<XT, EPT> yv = calq_vec_fq<XT, EPT>(xv[u], k, o, fqc, fast);
+      st_vec<XT, EPT>(static_cast<XT*>(a.y) + vbase * EPT + u * 256 * EPT, yv);
+    } else {
+      uint32_t packed[EPT / 4];
+      int sum = 0;
+      calq_vec_any<XT, EPT>(xv[u], k, o, a, fast, packed, sum);
+      calq_store<EPT>(a.q + vbase * EPT + u * 256 * EPT, packed);
+    }
+  }
+  if (decide) {
+    // one word each, written at most once per CTA and only while still unset
+    const int neg = __syncthreads_or(neg_any ? 1 : 0);
+    const int def = __syncthreads_or(def_any ? 1 : 0);
+    if (threadIdx.x == 0) {
+      if (neg && *reinterpret_cast<volatile unsigned int*>(a.ws_flags + 1) == 0) a.ws_flags[1] = 1;
+      if (def && *reinterpret_cast<volatile unsigned int*>(a.ws_flags) == 0) a.ws_flags[0] = 1;
+    }
+  }
+}
+
+// Long rows with fake-quant output: calq_rows_kernel's structure (row in registers), the sentinel protocol for
+// deferred rows, optional running range.
+template <typename XT, int VPT>
+__global__ void __launch_bounds__(512) calq_rows_fq_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  __shared__ float s_mn[16], s_mx[16];
+  const unsigned long long row = blockIdx.x;
+  const unsigned int nvec = a.row_len / EPT;
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x) + row * a.row_len;
+  const FqConst fqc{a.lo, a.hi, a.code_is_int != 0};
+  Vec<XT, EPT> xin[VPT];
+#pragma unroll
+  for (int u = 0; u < VPT; ++u) {
+    const unsigned int j = threadIdx.x + u * blockDim.x;
+    if (j < nvec) xin[u] = ld_stream<XT, EPT>(x + (size_t)j * EPT);
+  }
+  float old_mn = INFINITY, old_mx = -INFINITY;
+  if (a.run_min) {
+    old_mn = load_as_float(a.run_min, a.run_dt, row);
+    old_mx = load_as_float(a.run_max, a.run_dt, row);
+  }
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < VPT; ++u) {
+    const unsigned int j = threadIdx.x + u * blockDim.x;
+    if (j < nvec) {
+      float vmn, vmx;
+      vec_minmax<XT, EPT>(xin[u], vmn, vmx);
+      mn = nan_min(mn, vmn);
+      mx = nan_max(mx, vmx);
+    }
+  }
+  mn = group_min<32>(mn);
+  mx = group_max<32>(mx);
+  if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+  __syncthreads();
+  mn = s_mn[0]; mx = s_mx[0];
+  for (unsigned int w = 1; w < nw; ++w) { mn = nan_min(mn, s_mn[w]); mx = nan_max(mx, s_mx[w]); }
+  const float rmn = a.run_min ? nan_min(old_mn, mn) : mn;
+  const float rmx = a.run_min ? nan_max(old_mx, mx) : mx;
+  const bool live_decision = a.symmetric && a.allow_one_sided;
+  const bool deferred = live_decision && (rmn >= 0.f);
+  float sc = CQ_DEFERRED, off = 0.f;
+  if (!deferred) calq_params(a, rmn, rmx, false, sc, off);
+  if (threadIdx.x == 0) {
+    if (a.run_min) {
+      store_from_float(a.run_min, a.run_dt, row, rmn);
+      store_from_float(a.run_max, a.run_dt, row, rmx);
+    }
+    if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+    a.scale[row] = sc;
+    if (!deferred && a.offset) a.offset[row] = off;
+    if (live_decision) {
+      if (!(rmn >= 0.f) && *reinterpret_cast<volatile unsigned int*>(a.ws_flags + 1) == 0) a.ws_flags[1] = 1;
+      if (deferred && *reinterpret_cast<volatile unsigned int*>(a.ws_flags) == 0) a.ws_flags[0] = 1;
+    }
+  }
+  if (deferred) return;
+  const float o = rintf(off);
+  const SharedRcp k = make_shared_rcp(sc);
+  const bool fast = calq_fast_ok(k, rmn, rmx);
+  XT* __restrict__ y = static_cast<XT*>(a.y) + row * a.row_len;
+#pragma unroll
+  for (int u = 0; u < VPT; ++u) {
+    const unsigned int j = threadIdx.x + u * blockDim.x;
+    if (j < nvec) st_vec<XT, EPT>(y + (size_t)j * EPT, calq_vec_fq<XT, EPT>(xin[u], k, o, fqc, fast));
+  }
+}
+
+// Finishes the tiles marked with the sentinel scale: a warp per tile.  Runs right behind calq_group_kernel /
+// calq_rows_fq_kernel and returns after one load unless something was deferred (weights whose tiles are all
+// non-negative are the only case).  The global decision: one-sided unless some tile min was negative or NaN.
+template <typename XT, bool FQ>
+__global__ void __launch_bounds__(256) calq_sentinel_fixup_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  if (*reinterpret_cast<volatile unsigned int*>(a.ws_flags) == 0) return;
+  const bool one_sided = *reinterpret_cast<volatile unsigned int*>(a.ws_flags + 1) == 0;
+  const unsigned int lane = threadIdx.x & 31;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  const unsigned int tvec = a.row_len / EPT;
+  const FqConst fqc{a.lo, a.hi, a.code_is_int != 0};
+  for (unsigned long long tile = warp0; tile < a.rows; tile += nwarps) {
+    if (a.scale[tile] != CQ_DEFERRED) continue;
+    const XT* __restrict__ x = static_cast<const XT*>(a.x) + tile * a.row_len;
+    float rmn, rmx;
+    if (a.run_min) {
+      rmn = load_as_float(a.run_min, a.run_dt, tile);
+      rmx = load_as_float(a.run_max, a.run_dt, tile);
+    } else {
+      float mn = INFINITY, mx = -INFINITY;
+      for (unsigned int j = lane; j < tvec; j += 32) {
+        float vmn, vmx;
+        vec_minmax<XT, EPT>(ld_stream<XT, EPT>(x + (size_t)j * EPT), vmn, vmx);
+        mn = nan_min(mn, vmn);
+        mx = nan_max(mx, vmx);
+      }
+      rmn = group_min<32>(mn);
+      rmx = group_max<32>(mx);
+    }
+    float sc, off;
+    calq_params(a, rmn, rmx, one_sided, sc, off);
+    const float o = rintf(off);
+    const SharedRcp k = make_shared_rcp(sc);
+    const bool fast = calq_fast_ok(k, rmn, rmx);
+    for (unsigned int j = lane; j < tvec; j += 32) {
+      const Vec<XT, EPT> xv = ld_stream<XT, EPT>(x + (size_t)j * EPT);
+      if constexpr (FQ) {
+        st_vec<XT, EPT>(static_cast<XT*>(a.y) + tile * a.row_len + (size_t)j * EPT, calq_vec_fq<XT, EPT>(xv, k, o, fqc, fast));
+      } else {
+        uint32_t packed[EPT / 4];
+        int sum = 0;
+        calq_vec_any<XT, EPT>(xv, k, o, a, fast, packed, sum);
+        calq_store<EPT>(a.q + tile * a.row_len + (size_t)j * EPT, packed);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {          // parameters last: the sentinel is this tile's "still to do" mark
+      a.scale[tile] = sc;
+      if (a.offset) a.offset[tile] = off;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // per-tensor: co-resident grid, first chunk of every CTA parked in shared memory
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -528,13 +817,51 @@ static cudaError_t launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_
   return cudaSuccess;
 }
 
+template <typename XT, bool FQ>
+static void launch_group(const CalqArgs& a, cudaStream_t st) {
+  constexpr int EPT = 16 / sizeof(XT);
+  const unsigned long long nvec = a.numel / EPT;
+  const unsigned int grid = (unsigned int)((nvec + 256 * 4 - 1) / (256 * 4));
+  switch (a.lanes) {
+    case 1: calq_group_kernel<XT, 1, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 2: calq_group_kernel<XT, 2, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 4: calq_group_kernel<XT, 4, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 8: calq_group_kernel<XT, 8, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 16: calq_group_kernel<XT, 16, FQ><<<grid, 256, 0, st>>>(a); break;
+    default: calq_group_kernel<XT, 32, FQ><<<grid, 256, 0, st>>>(a); break;
+  }
+}
+
+template <typename XT>
+static void launch_rows_fq(const CalqArgs& a, unsigned int nvec, cudaStream_t st) {
+  int vpt = (nvec >= 512 && a.rows >= 2048) ? 8 : (nvec >= 256 ? 4 : (nvec >= 128 ? 2 : 1));
+  if (nvec > 2048) vpt = 8;
+  const unsigned int threads = ((nvec + vpt - 1) / vpt + 31) / 32 * 32;
+  const unsigned int grid = (unsigned int)a.rows;
+  switch (vpt) {
+    case 1: calq_rows_fq_kernel<XT, 1><<<grid, threads, 0, st>>>(a); break;
+    case 2: calq_rows_fq_kernel<XT, 2><<<grid, threads, 0, st>>>(a); break;
+    case 4: calq_rows_fq_kernel<XT, 4><<<grid, threads, 0, st>>>(a); break;
+    default: calq_rows_fq_kernel<XT, 8><<<grid, threads, 0, st>>>(a); break;
+  }
+}
+
+template <typename XT, bool FQ>
+static void launch_sentinel_fixup(const CalqArgs& a, cudaStream_t st) {
+  const unsigned long long warps_wanted = a.rows;
+  unsigned long long blocks = (warps_wanted + 7) / 8;
+  const unsigned long long cap = (unsigned long long)4 * sm_count();
+  if (blocks > cap) blocks = cap;
+  calq_sentinel_fixup_kernel<XT, FQ><<<(unsigned int)blocks, 256, 0, st>>>(a);
+}
+
 }  // namespace ffq
 
 using namespace ffq;
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// 0: not supported (use the unfused sequence), 1: rows kernel, 2: per-tensor kernel
+// 0: not supported (use the unfused sequence), 1: rows kernel, 2: per-tensor kernel, 3: sub-warp group kernel
 static int calq_mode(const Plan& plan, int x_dtype) {
   if (!(x_dtype == FFQ_F32 || x_dtype == FFQ_F16 || x_dtype == FFQ_BF16)) return 0;
   if (!plan.row || plan.numel == 0) return 0;
@@ -543,6 +870,7 @@ static int calq_mode(const Plan& plan, int x_dtype) {
   const long long tvec = plan.tile_numel / ept;
   if (plan.num_tiles == 1) return (plan.numel < (1ll << 40) && tvec >= 64) ? 2 : 0;
   if (tvec >= 64 && tvec <= 4096 && plan.num_tiles < (1ll << 31) && plan.tile_numel < (1ll << 31)) return 1;
+  if (tvec <= 32 && (tvec & (tvec - 1)) == 0 && plan.num_tiles < (1ll << 40)) return 3;   // sub-warp groups
   return 0;
 }
 
@@ -594,6 +922,31 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
   a.symmetric = symmetric; a.allow_one_sided = allow_one_sided;
   a.sat8 = (a.lo == -128.f && a.hi == 127.f) ? 1 : 0;
   const int ept = 16 / dt_size(x_dtype);
+  if (mode == 3) {
+    if (rowsum) { set_error("calibrate_quantize: row sums are not produced for per-group tiles"); return FFQ_ERR_UNSUPPORTED; }
+    if (workspace == nullptr || workspace_bytes < 16) { set_error("calibrate_quantize: workspace required"); return FFQ_ERR_WORKSPACE; }
+    a.rows = (unsigned long long)plan.num_tiles;
+    a.row_len = (unsigned int)plan.tile_numel;
+    a.lanes = (unsigned int)(plan.tile_numel / ept);
+    a.ws_flags = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 8);
+    const bool decide = symmetric && allow_one_sided;
+    if (decide) FFQ_CUDA_CHECK(cudaMemsetAsync(a.ws_flags, 0, 8, st));
+    switch (x_dtype) {
+      case FFQ_F32: launch_group<float, false>(a, st); break;
+      case FFQ_BF16: launch_group<__nv_bfloat16, false>(a, st); break;
+      default: launch_group<__half, false>(a, st); break;
+    }
+    FFQ_LAUNCH_CHECK();
+    if (decide) {
+      switch (x_dtype) {
+        case FFQ_F32: launch_sentinel_fixup<float, false>(a, st); break;
+        case FFQ_BF16: launch_sentinel_fixup<__nv_bfloat16, false>(a, st); break;
+        default: launch_sentinel_fixup<__half, false>(a, st); break;
+      }
+      FFQ_LAUNCH_CHECK();
+    }
+    return FFQ_OK;
+  }
   if (mode == 1) {
     a.rows = (unsigned long long)plan.num_tiles;
     a.row_len = (unsigned int)plan.tile_numel;
@@ -658,6 +1011,85 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
     return FFQ_ERR_CUDA;
   }
   FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* run_min, void* run_max, int run_dtype,
+                            float* scale, float* offset, int32_t* flags, const ffq_layout_t* layout, double num_bits,
+                            int symmetric, int allow_one_sided, int code_dtype, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Plan plan;
+  int rc = make_plan(layout, &plan);
+  if (rc != FFQ_OK) return rc;
+  const int mode = calq_mode(plan, x_dtype);
+  if (!(mode == 1 || mode == 3) || !aligned16(x) || !aligned16(y)) {
+    set_error("calibrate_fakequant: layout/dtype/alignment not handled by the fused kernels");
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if ((run_min == nullptr) != (run_max == nullptr)) { set_error("calibrate_fakequant: run_min and run_max go together"); return FFQ_ERR_INVALID; }
+  if (run_min && (!(run_dtype == FFQ_F32 || run_dtype == FFQ_F16 || run_dtype == FFQ_BF16) || promote(run_dtype, x_dtype) != run_dtype)) {
+    set_error("calibrate_fakequant: running-range dtype %s cannot hold %s data", dt_name(run_dtype), dt_name(x_dtype));
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (scale == nullptr || (offset == nullptr && !(symmetric && !allow_one_sided))) {
+    set_error("calibrate_fakequant: scale (and offset unless symmetric two-sided only) are required");
+    return FFQ_ERR_INVALID;
+  }
+  const bool float_codes = code_dtype == FFQ_F32 || code_dtype == FFQ_F16 || code_dtype == FFQ_BF16;
+  const int mant = code_dtype == FFQ_F32 ? 23 : (code_dtype == FFQ_F16 ? 10 : 7);
+  if (float_codes ? (mant + 2 < num_bits) : (!is_int_dt(code_dtype) || code_dtype == FFQ_U8 || 8 * dt_size(code_dtype) < num_bits)) {
+    set_error("calibrate_fakequant: code dtype %s cannot hold %g-bit signed codes exactly", dt_name(code_dtype), num_bits);
+    return FFQ_ERR_BITWIDTH;
+  }
+  if (float_codes && mant + 1 < num_bits) {   // representable by the reference's rule but not exactly: keep the separate kernels
+    set_error("calibrate_fakequant: %s codes round %g-bit values", dt_name(code_dtype), num_bits);
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (workspace == nullptr || workspace_bytes < 16) { set_error("calibrate_fakequant: workspace required"); return FFQ_ERR_WORKSPACE; }
+  CalqArgs a{};
+  a.x = x; a.y = y; a.run_min = run_min; a.run_max = run_max; a.run_dt = run_dtype;
+  a.scale = scale; a.offset = offset; a.flags = flags;
+  a.numel = (unsigned long long)plan.numel;
+  const double lo = -pow(2.0, num_bits - 1.0);
+  a.int_min_abs = (float)fabs(lo);
+  a.int_max_abs = (float)fabs(-lo - 1.0);
+  a.neg_int_min = (float)(-lo);
+  a.steps = (float)(pow(2.0, num_bits) - 1.0);
+  a.lo = (float)lo; a.hi = (float)(-lo - 1.0);
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided;
+  a.sat8 = 0;
+  a.code_is_int = float_codes ? 0 : 1;
+  const int ept = 16 / dt_size(x_dtype);
+  a.rows = (unsigned long long)plan.num_tiles;
+  a.row_len = (unsigned int)plan.tile_numel;
+  a.lanes = (unsigned int)(plan.tile_numel / ept);
+  a.ws_flags = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 8);
+  const bool decide = symmetric && allow_one_sided;
+  if (decide) FFQ_CUDA_CHECK(cudaMemsetAsync(a.ws_flags, 0, 8, st));
+  if (mode == 3) {
+    switch (x_dtype) {
+      case FFQ_F32: launch_group<float, true>(a, st); break;
+      case FFQ_BF16: launch_group<__nv_bfloat16, true>(a, st); break;
+      default: launch_group<__half, true>(a, st); break;
+    }
+  } else {
+    const unsigned int nvec = a.row_len / ept;
+    switch (x_dtype) {
+      case FFQ_F32: launch_rows_fq<float>(a, nvec, st); break;
+      case FFQ_BF16: launch_rows_fq<__nv_bfloat16>(a, nvec, st); break;
+      default: launch_rows_fq<__half>(a, nvec, st); break;
+    }
+  }
+  FFQ_LAUNCH_CHECK();
+  if (decide) {
+    switch (x_dtype) {
+      case FFQ_F32: launch_sentinel_fixup<float, true>(a, st); break;
+      case FFQ_BF16: launch_sentinel_fixup<__nv_bfloat16, true>(a, st); break;
+      default: launch_sentinel_fixup<__half, true>(a, st); break;
+    }
+    FFQ_LAUNCH_CHECK();
+  }
   return FFQ_OK;
 }
 

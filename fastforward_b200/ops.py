@@ -311,6 +311,44 @@ def parameters_for_range_(
         ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))
 
 
+def calibrate_fake_quantize_(
+    data: torch.Tensor, tile_size, num_bits: float, symmetric: bool, allow_one_sided: bool,
+    scale_out: torch.Tensor, offset_out: Optional[torch.Tensor], quantized_dtype: Optional[torch.dtype] = None,
+    out: Optional[torch.Tensor] = None, run_min: Optional[torch.Tensor] = None, run_max: Optional[torch.Tensor] = None,
+    flags: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Calibrate on ``data`` and snap it to the grid in ONE pass: per-tile min/max (merged into ``run_min`` /
+    ``run_max`` when given) -> ``scale_out`` / ``offset_out`` in place -> ``out = dequantize(quantize(data))``
+    (``out=data`` for in place).  Equals ``tile_minmax`` + ``parameters_for_range_`` + ``fake_quantize_by_tile`` bit for
+    bit.  Raises NotImplementedError for layouts the fused kernels do not cover (calibrate_quantize_mode not 1 or 3)."""
+    x, shape, tile, layout = _prep(data, tile_size)
+    code_dtype = quantized_dtype or x.dtype
+    _bitwidth_guard(code_dtype, num_bits)
+    if x.numel() == 0:
+        raise NotImplementedError("calibrate_fake_quantize_: empty tensor")
+    nt = layout.num_tiles
+    for t, name in ((scale_out, "scale_out"), (offset_out, "offset_out")):
+        if t is not None and (t.dtype != torch.float32 or t.numel() != nt or not t.is_contiguous() or not t.is_cuda):
+            raise RuntimeError(f"{name} must be a contiguous CUDA float32 tensor with {nt} elements")
+    if (run_min is None) != (run_max is None):
+        raise RuntimeError("run_min and run_max go together")
+    for t, name in ((run_min, "run_min"), (run_max, "run_max")):
+        if t is not None and (t.numel() != nt or not t.is_contiguous() or t.dtype != run_min.dtype or
+                              torch.promote_types(t.dtype, x.dtype) != t.dtype):
+            raise RuntimeError(f"{name} must be a contiguous tensor with {nt} elements whose dtype holds {x.dtype}")
+    if out is None:
+        out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    elif out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous() or out.device != x.device:
+        raise RuntimeError("out must be a contiguous tensor like data")
+    ws = workspace if workspace is not None else C.barrier_workspace(x.device, _CALQ_WS)
+    C.check(C.lib.ffq_calibrate_fakequant(
+        x.data_ptr(), C.dtype_tag(x.dtype), out.data_ptr(), C.ptr(run_min), C.ptr(run_max),
+        C.dtype_tag(run_min.dtype if run_min is not None else None), scale_out.data_ptr(), C.ptr(offset_out), C.ptr(flags),
+        layout.ref, float(num_bits), int(bool(symmetric)), int(bool(allow_one_sided)), C.dtype_tag(code_dtype),
+        ws.data_ptr(), ws.numel(), C.current_stream(x.device)))
+    return out
+
+
 def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor, entries) -> None:
     """``parameters_for_range_`` for many quantizers in ONE launch.  ``min_buf`` / ``max_buf``: contiguous buffers
     holding every quantizer's running range; ``entries``: ``(start, length, num_bits, symmetric, allow_one_sided,

@@ -126,6 +126,52 @@ def calibrate_weight_quantizers(model: torch.nn.Module, discovery=None, rank: Op
     return len(targets)
 
 
+def calibrate_and_fuse_qdq_weights(model: torch.nn.Module, *, stub_quantizers: bool = False, discovery=None,
+                                   rank: Optional[int] = None, world_size: Optional[int] = None) -> int:
+    """``calibrate_weight_quantizers`` followed by ``fuse_qdq_weights`` -- the unit of whole-model weight quantization
+    -- with the weight read ONCE: per target one fused launch (per-tile min/max -> the quantizer's scale/offset ->
+    the weight snapped to its grid in place; ``ffq_calibrate_fakequant``) where the layout allows it (per-channel rows,
+    per-group tiles), the two separate steps otherwise.  Bit-identical to the two-step sequence."""
+    from .. import ops
+
+    discovery = ConventionDiscovery() if discovery is None else discovery
+    targets = list(_all_targets(model, discovery))
+    _check_tied(targets)
+    if world_size is not None and world_size > 1:
+        from ..distributed import shard_units
+
+        targets = [targets[i] for i in shard_units(len(targets), rank, world_size)]
+    for module, attr, quantizer in targets:
+        weight = getattr(module, attr)
+        w = weight.data
+        tile = quantizer.granularity.tile_size(w.shape)
+        fused = type(quantizer) is LinearQuantizer and not list(quantizer.overrides) and w.is_cuda and w.is_contiguous() \
+            and ops.calibrate_quantize_mode(w.shape, tile, w.dtype) in (1, 3)
+        if fused:
+            n = quantizer.granularity.parameter_dimensionality(w.shape)
+            if quantizer.has_uninitialized_params:
+                quantizer._initialize_parameters(n)
+            params = [quantizer.scale] + ([] if quantizer.offset is None else [quantizer.offset])
+            fused = all(p.dtype == torch.float32 and p.device == w.device and p.numel() == n and p.is_contiguous() for p in params)
+        if fused:
+            try:
+                with torch.no_grad():
+                    ops.calibrate_fake_quantize_(w, tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
+                                                 quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
+                                                 quantizer.quantized_dtype, out=w)
+            except NotImplementedError:          # e.g. a code dtype that rounds the codes: keep the exact two-step path
+                fused = False
+        if not fused:
+            lo, hi = ops.tile_minmax(w.detach(), tile)
+            quantizer.quantization_range = (lo, hi)
+            _fuse_target(module, attr, quantizer, stub_quantizer=False)
+        if stub_quantizers:
+            for name, child in list(module.named_children()):
+                if child is quantizer:
+                    setattr(module, name, QuantizerStub(_metadata=quantizer.quant_metadata))
+    return len(targets)
+
+
 def _all_targets(model: torch.nn.Module, discovery) -> Iterator[WeightQuantizerTarget]:
     """Like the discovery, but includes quantizers whose parameters are still uninitialised."""
     tag = getattr(discovery, "_tag", "parameter/weight")

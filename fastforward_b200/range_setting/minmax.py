@@ -169,7 +169,7 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
             self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen,
-            workspace=self._arena.barrier_workspace(data.device) if (mode == 2 and self._arena is not None) else None)
+            workspace=self._arena.barrier_workspace(data.device) if (mode in (2, 3) and self._arena is not None) else None)
         if self._settled_host is not None and not self._settled_seen:
             self._settled_host.copy_(self._settled, non_blocking=True)
         if self._eager:

@@ -186,9 +186,10 @@ FFQ_API int ffq_dynamic_quantize(const void* x, int x_dtype, void* q, int q_dtyp
  * (offset may be NULL only for symmetric && !allow_one_sided; it is filled with 0 on the symmetric
  * two-sided branch); run_dtype must hold x_dtype.
  * Layouts: contiguous tiles of 64..4096 16-byte vectors (per-channel weight rows; rowsum_row_len must
- * equal the tile length) or ONE tile (per-tensor; rowsum_row_len divides numel).  Anything else
+ * equal the tile length), ONE tile (per-tensor; rowsum_row_len divides numel), or contiguous tiles of
+ * 1, 2, 4, ... 32 vectors (per-group weights, e.g. g = 128; no row sums).  Anything else
  * returns FFQ_ERR_UNSUPPORTED; ffq_calibrate_quantize_mode() tells in advance (0 unsupported, 1 rows,
- * 2 per-tensor).  The per-tensor kernel is a cooperative launch with a grid barrier: `workspace`
+ * 2 per-tensor, 3 per-group).  The per-tensor kernel is a cooperative launch with a grid barrier: `workspace`
  * (ffq_calibrate_quantize_workspace_bytes(), 16-byte aligned) must be ZERO before its first use and
  * be used by one stream at a time; bit 1 of *flags reports a barrier time-out (never expected).
  * Rows path, symmetric && allow_one_sided: the global one-sided decision (range.py:100) is taken by a second,
@@ -206,6 +207,22 @@ FFQ_API int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q,
                            void* workspace, size_t workspace_bytes, void* stream);
 FFQ_API int ffq_calibrate_quantize_mode(const ffq_layout_t* layout, int x_dtype);
 FFQ_API size_t ffq_calibrate_quantize_workspace_bytes(void);
+
+/* ---- a7 + a6 + (a1 + a2) fused: calibrate a quantizer on a tensor and snap the tensor to its grid ------------
+ * tile min/max of x [merged into run_min/run_max when given] -> (scale, offset) -> y = dequantize(quantize(x)) under
+ * those parameters, x read once; y may alias x (in place).  This is `quantizer.quantization_range = (tile min, tile
+ * max)` followed by `w.copy_(quantizer(w).dequantize())` -- the unit of work of whole-model weight quantization
+ * (BASELINE config 3) -- in 2s bytes per element instead of 3s and one launch (+ the one-sided fix-up launch for
+ * symmetric && allow_one_sided quantizers, which returns after one load unless a tile is entirely non-negative).
+ * Layouts: modes 1 (rows) and 3 (per-group) of ffq_calibrate_quantize_mode; x, y: f32/f16/bf16 of the same dtype;
+ * scale/offset fp32; code_dtype = the quantizer's quantized_dtype (or the data dtype): integer codes turn -0 into +0.
+ * `workspace`: >= 16 bytes, shared with ffq_calibrate_quantize.  Bit-identical to ffq_minmax + ffq_params_for_range +
+ * ffq_fakequant_fwd.
+ * replaces: quantization/fuse.py:91-121 after range_setting/minmax.py:215-239 + nn/linear_quantizer.py:347-357. */
+FFQ_API int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* run_min, void* run_max, int run_dtype,
+                            float* scale, float* offset, int32_t* flags, const ffq_layout_t* layout, double num_bits,
+                            int symmetric, int allow_one_sided, int code_dtype,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- a12: quantized linear (new kernel behind ff.dispatcher "linear") ---------------------
  * y[m,n] = sx * sw[n] * ( sum_k qx[m,k] qw[n,k] + ox*rowsum_w[n] + ow[n]*rowsum_x[m] + K*ox*ow[n] )

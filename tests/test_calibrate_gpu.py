@@ -198,15 +198,16 @@ def test_matches_unfused_kernels_large():
 
 
 def test_unsupported_layouts_fall_back():
-    assert ops.calibrate_quantize_mode((64, 128), (1, 128), torch.bfloat16) == 0       # rows shorter than 64 vectors
+    assert ops.calibrate_quantize_mode((64, 384), (1, 384), torch.bfloat16) == 0       # 48 vectors: neither a group nor a row
+    assert ops.calibrate_quantize_mode((64, 128), (1, 128), torch.bfloat16) == 3       # per-group tiles
     assert ops.calibrate_quantize_mode((64, 4096), (64, 1), torch.bfloat16) == 0       # strided tiles
     assert ops.calibrate_quantize_mode((64, 4096), (1, 4096), torch.int32) == 0
     assert ops.calibrate_quantize_mode((64, 4096), (1, 4096), torch.bfloat16) == 1
     assert ops.calibrate_quantize_mode((64, 4096), (64, 4096), torch.bfloat16) == 2
-    # the estimator silently takes the separate kernels there: per-group weights, float codes, grad mode
-    q = ff.nn.LinearQuantizer(8, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0),
+    # the estimator silently takes the separate kernels there: odd tile sizes, float codes, grad mode
+    q = ff.nn.LinearQuantizer(8, granularity=ff.PerBlock(block_dims=1, block_sizes=96, per_channel_dims=0),
                               quantized_dtype=torch.int8, device=DEV)
-    x = torch.randn(16, 512, device=DEV)
+    x = torch.randn(16, 576, device=DEV)
     with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax):
         out = q(x)
     assert not hasattr(out, "_ffq_rowsum")
@@ -361,3 +362,117 @@ def test_fused_equals_separate_kernels_on_random_configurations(seed):
         assert torch.equal(q, q2), "codes"
         assert torch.equal(rs, q2.reshape(-1, shape[-1]).int().sum(1).to(torch.int32)), "row sums"
         assert int(f1.item()) == int(f2.item())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-group tiles (mode 3) and the fused calibrate + fake-quantize (weight QDQ) entry point
+# ---------------------------------------------------------------------------------------------------------------
+def _variants(shape, g, variant, dt, steps):
+    xs = []
+    for i in range(steps):
+        x = torch.randn(shape, generator=g) * (0.02 + 0.3 * i)
+        if variant == "positive":
+            x = x.abs() + 1e-3
+        elif variant == "some_positive":
+            x[::2] = x[::2].abs()
+        xs.append(x.to(dt))
+    return xs
+
+
+@pytest.mark.parametrize("shape,group,dtype", [((24, 512), 128, torch.bfloat16), ((7, 1024), 64, torch.bfloat16), ((33, 256), 32, torch.float16),
+                                               ((16, 512), 128, torch.float32), ((40, 96), 8, torch.bfloat16), ((5, 64), 4, torch.float32)])
+@pytest.mark.parametrize("symmetric,one_sided", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("variant", ["mixed", "positive", "some_positive"])
+def test_group_tiles_int8_codes_vs_oracle(shape, group, dtype, symmetric, one_sided, variant):
+    tile = (1, group)
+    assert ops.calibrate_quantize_mode(shape, tile, dtype) == 3
+    g = torch.Generator().manual_seed(sum(shape) + group + symmetric * 4 + one_sided * 2 + len(variant))
+    xs = _variants(shape, g, variant, dtype, 3)
+    outs, flags, _ = _run_fused(xs, tile, 4, symmetric, one_sided, rowsum=False)
+    assert flags == 0
+    mn = mx = None
+    for x, (q, rs, scale, offset, rmn, rmx) in zip(xs, outs):
+        mn, mx, s, o, rq = _oracle_step(mn, mx, x, tile, 4, symmetric, one_sided)
+        assert rs is None
+        assert bits_equal(rmn, mn) and bits_equal(rmx, mx) and bits_equal(scale, s)
+        if offset is not None:
+            assert bits_equal(offset, o if o is not None else torch.zeros_like(s))
+        assert bits_equal(q, rq)
+
+
+FQ_CASES = [((24, 512), (1, 128), torch.bfloat16), ((300, 4096), (1, 128), torch.bfloat16), ((9, 1024), (1, 1024), torch.bfloat16),
+            ((64, 4096), (1, 4096), torch.float32), ((5, 14336), (1, 14336), torch.bfloat16), ((17, 256), (1, 32), torch.float16),
+            ((6, 20480), (1, 20480), torch.bfloat16)]
+
+
+@pytest.mark.parametrize("shape,tile,dtype", FQ_CASES)
+@pytest.mark.parametrize("symmetric,one_sided", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("variant", ["mixed", "positive", "some_positive"])
+@pytest.mark.parametrize("bits,qdtype", [(4, None), (8, torch.int8)])
+def test_calibrate_fake_quantize_vs_oracle(shape, tile, dtype, symmetric, one_sided, variant, bits, qdtype):
+    """min/max -> params -> dequantize(quantize(x)) in one launch, in place, against the oracle's three steps."""
+    g = torch.Generator().manual_seed(sum(shape) + tile[1] + symmetric * 4 + one_sided * 2 + len(variant) + bits)
+    x = _variants(shape, g, variant, dtype, 1)[0]
+    x.view(-1)[3] = -0.0
+    nt = (shape[0] // tile[0]) * (shape[1] // tile[1])
+    mn, mx = R.tile_minmax(x, tile)
+    s, o = R.parameters_for_range(mn, mx, bits, symmetric, one_sided)
+    q = R.quantize_by_tile(x, s, tile, bits, qdtype or x.dtype, o)
+    want = R.dequantize_by_tile(q, s, tile, o, x.dtype)
+    scale = torch.empty(nt, device=DEV)
+    offset = None if (symmetric and not one_sided) else torch.empty(nt, device=DEV)
+    w = x.to(DEV)
+    before = ff._cabi.launch_count()
+    out = ops.calibrate_fake_quantize_(w, tile, bits, symmetric, one_sided, scale, offset, qdtype, out=w)
+    assert ff._cabi.launch_count() - before <= 2 and out.data_ptr() == w.data_ptr()
+    assert bits_equal(scale, s)
+    if offset is not None:
+        assert bits_equal(offset, o if o is not None else torch.zeros_like(s))
+    assert bits_equal(w, want)
+
+
+def test_calibrate_fake_quantize_running_range_and_special_values():
+    g = torch.Generator().manual_seed(4)
+    x1 = torch.randn(12, 1024, generator=g); x2 = torch.randn(12, 1024, generator=g) * 3
+    x2[2, 5] = float("nan"); x2[3, :] = 0.0; x2[4, 7] = 1e30
+    for tile in [(1, 128), (1, 1024)]:
+        nt = 12 * (1024 // tile[1])
+        for sym in (True, False):
+            mn = torch.full((nt,), float("inf"), device=DEV); mx = -mn
+            scale, offset = torch.empty(nt, device=DEV), torch.empty(nt, device=DEV)
+            rmn = rmx = None
+            for x in (x1, x2):
+                out = ops.calibrate_fake_quantize_(x.to(DEV), tile, 8, sym, True, scale, offset, None, run_min=mn, run_max=mx)
+                rmn, rmx = R.running_minmax_step(rmn, rmx, x, tile)
+                s, o = R.parameters_for_range(rmn, rmx, 8, sym, True)
+                want = R.dequantize_by_tile(R.quantize_by_tile(x, s, tile, 8, x.dtype, o), s, tile, o, x.dtype)
+                assert bits_equal(mn, rmn) and bits_equal(mx, rmx) and bits_equal(scale, s)
+                assert bits_equal(offset, o if o is not None else torch.zeros_like(s))
+                assert bits_equal(out, want)
+
+
+def test_calibrate_and_fuse_qdq_weights_equals_two_step():
+    """Whole-model weight quantization (BASELINE config 3): the fused per-weight launch gives the same weights and
+    quantizer parameters as calibrate_weight_quantizers + fuse_qdq_weights, with fewer launches."""
+    from fastforward_b200.quantization.fuse import calibrate_and_fuse_qdq_weights, calibrate_weight_quantizers, fuse_qdq_weights
+
+    def build(gran, bits):
+        torch.manual_seed(1)
+        m = torch.nn.Sequential(torch.nn.Linear(512, 256, bias=False), torch.nn.Linear(256, 384, bias=True)).to(DEV).bfloat16()
+        with torch.no_grad():
+            m[1].weight.abs_()                                   # every tile non-negative: the one-sided branch
+        ff.quantize_model(m)
+        ff.find_quantizers(m, "**/[quantizer:parameter/weight]").initialize(ff.nn.LinearQuantizer, num_bits=bits, granularity=gran())
+        return m.to(DEV)
+
+    for gran, bits in [(lambda: ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0), 4), (lambda: ff.PerChannel(0), 8),
+                       (lambda: ff.PerTensor(), 8)]:
+        a, b = build(gran, bits), build(gran, bits)
+        l0 = ff._cabi.launch_count()
+        calibrate_and_fuse_qdq_weights(a)
+        l1 = ff._cabi.launch_count()
+        calibrate_weight_quantizers(b); fuse_qdq_weights(b)
+        l2 = ff._cabi.launch_count()
+        for (na, pa), (nb, pb) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert na == nb and bits_equal(pa, pb), na
+        assert (l1 - l0) <= (l2 - l1)
