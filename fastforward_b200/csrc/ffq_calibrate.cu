@@ -362,7 +362,7 @@ constexpr float CQ_DEFERRED = -1.0f;    // scale sentinel: a legitimate scale is
 // sub-warp shuffles; four tiles' worth of loads in flight per thread.  FQ: fake-quant output (weight QDQ, may run
 // in place); otherwise int8 codes.  The running range is optional (null: the tile's own min/max is the range).
 // Deferred tiles (symmetric one-sided candidates) get the sentinel scale and are finished by calq_sentinel_fixup.
-template <typename XT, int LANES, bool FQ>
+template <typename XT, typename RT, int LANES, bool FQ>
 __global__ void __launch_bounds__(256) calq_group_kernel(const CalqArgs a) {
   constexpr int EPT = 16 / sizeof(XT);
   constexpr int U = 4;
@@ -394,12 +394,14 @@ __global__ void __launch_bounds__(256) calq_group_kernel(const CalqArgs a) {
     rmn[u] = mn; rmx[u] = mx;
     if (!live) continue;
     const unsigned long long tile = tile0 + u * (256 / LANES);
-    if (a.run_min) {
-      rmn[u] = nan_min(load_as_float(a.run_min, a.run_dt, tile), mn);
-      rmx[u] = nan_max(load_as_float(a.run_max, a.run_dt, tile), mx);
+    if (a.run_min) {              // RT: the running range's dtype (the data dtype or fp32), typed accesses
+      RT* __restrict__ run_mn = static_cast<RT*>(a.run_min);
+      RT* __restrict__ run_mx = static_cast<RT*>(a.run_max);
+      rmn[u] = nan_min(Elem<RT>::to_f(run_mn[tile]), mn);
+      rmx[u] = nan_max(Elem<RT>::to_f(run_mx[tile]), mx);
       if (lead) {
-        store_from_float(a.run_min, a.run_dt, tile, rmn[u]);
-        store_from_float(a.run_max, a.run_dt, tile, rmx[u]);
+        run_mn[tile] = Elem<RT>::from_f(rmn[u]);
+        run_mx[tile] = Elem<RT>::from_f(rmx[u]);
       }
     }
     if (lead && a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
@@ -817,19 +819,26 @@ static cudaError_t launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_
   return cudaSuccess;
 }
 
-template <typename XT, bool FQ>
-static void launch_group(const CalqArgs& a, cudaStream_t st) {
+template <typename XT, typename RT, bool FQ>
+static void launch_group_rt(const CalqArgs& a, cudaStream_t st) {
   constexpr int EPT = 16 / sizeof(XT);
   const unsigned long long nvec = a.numel / EPT;
   const unsigned int grid = (unsigned int)((nvec + 256 * 4 - 1) / (256 * 4));
   switch (a.lanes) {
-    case 1: calq_group_kernel<XT, 1, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 2: calq_group_kernel<XT, 2, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 4: calq_group_kernel<XT, 4, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 8: calq_group_kernel<XT, 8, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 16: calq_group_kernel<XT, 16, FQ><<<grid, 256, 0, st>>>(a); break;
-    default: calq_group_kernel<XT, 32, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 1: calq_group_kernel<XT, RT, 1, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 2: calq_group_kernel<XT, RT, 2, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 4: calq_group_kernel<XT, RT, 4, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 8: calq_group_kernel<XT, RT, 8, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 16: calq_group_kernel<XT, RT, 16, FQ><<<grid, 256, 0, st>>>(a); break;
+    default: calq_group_kernel<XT, RT, 32, FQ><<<grid, 256, 0, st>>>(a); break;
   }
+}
+
+template <typename XT, bool FQ>
+static void launch_group(const CalqArgs& a, cudaStream_t st) {
+  // the running range (when there is one) is stored in the data dtype or in fp32 (torch.min promotes)
+  if (a.run_min != nullptr && a.run_dt == FFQ_F32 && !std::is_same<XT, float>::value) launch_group_rt<XT, float, FQ>(a, st);
+  else launch_group_rt<XT, XT, FQ>(a, st);
 }
 
 template <typename XT>

@@ -50,6 +50,24 @@ for shape, tile, dt, sym in [((7, 512), (1, 512), torch.bfloat16, True), ((5, 10
         for _ in range(2):
             ops.calibrate_quantize_(mn, mx, x, tile, 8, sym, True, s, o, flags, settled, rowsum=True)
         assert int(flags.item()) == 0
+# per-group tiles (int8 codes and fake-quant in place) and long rows with fake-quant output, incl. deferred tiles
+for shape, tile, dt in [((24, 512), (1, 128), torch.bfloat16), ((33, 256), (1, 32), torch.float16), ((5, 64), (1, 4), torch.float32),
+                        ((9, 1024), (1, 1024), torch.bfloat16), ((3, 20480), (1, 20480), torch.bfloat16), ((1001, 128), (1, 8), torch.bfloat16)]:
+    nt = (shape[0] // tile[0]) * (shape[1] // tile[1])
+    for variant in ("mixed", "positive", "some"):
+        x = torch.randn(shape, device=dev)
+        x = x.abs() if variant == "positive" else x
+        if variant == "some":
+            x[::2] = x[::2].abs()
+        x = x.to(dt)
+        s = torch.empty(nt, device=dev); o = torch.empty(nt, device=dev)
+        mn = torch.full((nt,), float("inf"), dtype=dt, device=dev); mx = -mn
+        for sym in (True, False):
+            if ops.calibrate_quantize_mode(shape, tile, dt) == 3:
+                ops.calibrate_quantize_(mn, mx, x, tile, 4, sym, True, s, o)
+            ops.calibrate_fake_quantize_(x.clone(), tile, 4, sym, True, s, o, None, run_min=mn, run_max=mx)
+            y = x.clone()
+            ops.calibrate_fake_quantize_(y, tile, 8, sym, True, s, o, torch.int8, out=y)
 # GPTQ block kernel: full and ragged blocks, few and many rows
 from fastforward_b200.quantization import gptq as G
 for rows, ncols in [(5, 128), (1000, 37), (33, 64)]:
