@@ -182,8 +182,10 @@ __device__ __forceinline__ int block_isum(int v, int* smem) {
 // ------------------------------------------------------------------------------------------
 // rows: one CTA per tile, the tile lives in registers
 // ------------------------------------------------------------------------------------------
-template <typename XT, int VPT>
-__global__ void __launch_bounds__(512) calq_rows_kernel(const CalqArgs a) {
+// FULL: the row is exactly blockDim.x * VPT vectors (the usual case: the host sizes the CTA to the row), so no
+// per-vector bounds predicates are needed.
+template <typename XT, int VPT, bool FULL>
+__global__ void __launch_bounds__(512, 2) calq_rows_kernel(const CalqArgs a) {
   constexpr int EPT = 16 / sizeof(XT);
   __shared__ float s_mn[16], s_mx[16];
   __shared__ int s_i[32];
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(512) calq_rows_kernel(const CalqArgs a) {
 #pragma unroll
   for (int u = 0; u < VPT; ++u) {
     const unsigned int j = threadIdx.x + u * blockDim.x;
-    if (j < nvec) xin[u] = ld_stream<XT, EPT>(x + (size_t)j * EPT);
+    if (FULL || j < nvec) xin[u] = ld_stream<XT, EPT>(x + (size_t)j * EPT);
   }
   // the old running range is requested behind the data so that its latency hides under the stream; every thread
   // reads it before the barrier below, thread 0 overwrites it after the barrier
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(512) calq_rows_kernel(const CalqArgs a) {
 #pragma unroll
   for (int u = 0; u < VPT; ++u) {
     const unsigned int j = threadIdx.x + u * blockDim.x;
-    if (j < nvec) {
+    if (FULL || j < nvec) {
       float vmn, vmx;
       vec_minmax<XT, EPT>(xin[u], vmn, vmx);
       mn = nan_min(mn, vmn);
@@ -242,15 +244,23 @@ __global__ void __launch_bounds__(512) calq_rows_kernel(const CalqArgs a) {
   const bool fast = calq_fast_ok(k, rmn, rmx);
   int8_t* __restrict__ q = a.q + row * a.row_len;
   int sum = 0;
+  // the path is chosen once per row, not once per vector
+  auto run = [&](auto kind) {
 #pragma unroll
-  for (int u = 0; u < VPT; ++u) {
-    const unsigned int j = threadIdx.x + u * blockDim.x;
-    if (j < nvec) {
-      uint32_t packed[EPT / 4];
-      calq_vec_any<XT, EPT>(xin[u], k, o, a, fast, packed, sum);
-      calq_store<EPT>(q + (size_t)j * EPT, packed);
+    for (int u = 0; u < VPT; ++u) {
+      const unsigned int j = threadIdx.x + u * blockDim.x;
+      if (FULL || j < nvec) {
+        uint32_t packed[EPT / 4];
+        if constexpr (decltype(kind)::value == 0) calq_vec_fast<XT, EPT, true>(xin[u], k, o, 0, 0, packed, sum);
+        else if constexpr (decltype(kind)::value == 1) calq_vec_fast<XT, EPT, false>(xin[u], k, o, (int)a.lo, (int)a.hi, packed, sum);
+        else calq_vec<XT, EPT>(xin[u], k, o, a.lo, a.hi, a.sat8 != 0, packed, sum);
+        calq_store<EPT>(q + (size_t)j * EPT, packed);
+      }
     }
-  }
+  };
+  if (fast && a.sat8) run(std::integral_constant<int, 0>{});
+  else if (fast) run(std::integral_constant<int, 1>{});
+  else run(std::integral_constant<int, 2>{});
   if (a.rowsum) {
     sum = block_isum(sum, s_i);
     if (threadIdx.x == 0) a.rowsum[row] = sum;
@@ -810,12 +820,19 @@ static cudaError_t launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_
   if ((force == 4 || force == 8) && nvec >= 256 && (unsigned long long)force * 512 >= nvec) vpt = force;
   const unsigned int threads = ((nvec + vpt - 1) / vpt + 31) / 32 * 32;
   const unsigned int grid = (unsigned int)a.rows;
+  const bool full = threads * (unsigned int)vpt == nvec;
+#define FFQ_ROWS_LAUNCH(V)                                                                    \
+  do {                                                                                        \
+    if (full) calq_rows_kernel<XT, V, true><<<grid, threads, 0, st>>>(a);                     \
+    else calq_rows_kernel<XT, V, false><<<grid, threads, 0, st>>>(a);                         \
+  } while (0)
   switch (vpt) {
-    case 1: calq_rows_kernel<XT, 1><<<grid, threads, 0, st>>>(a); break;
-    case 2: calq_rows_kernel<XT, 2><<<grid, threads, 0, st>>>(a); break;
-    case 4: calq_rows_kernel<XT, 4><<<grid, threads, 0, st>>>(a); break;
-    default: calq_rows_kernel<XT, 8><<<grid, threads, 0, st>>>(a); break;
+    case 1: FFQ_ROWS_LAUNCH(1); break;
+    case 2: FFQ_ROWS_LAUNCH(2); break;
+    case 4: FFQ_ROWS_LAUNCH(4); break;
+    default: FFQ_ROWS_LAUNCH(8); break;
   }
+#undef FFQ_ROWS_LAUNCH
   return cudaSuccess;
 }
 
