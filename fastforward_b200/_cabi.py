@@ -17,7 +17,7 @@ import torch  # imported first on purpose: it loads libcudart.so.12, which the l
 from .exceptions import QuantizationError  # noqa: F401  (re-exported for callers)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libffq_b200.so")
+LIB_PATH = os.environ.get("FFQ_LIB_PATH") or os.path.join(_HERE, "lib", "libffq_b200.so")   # override: A/B of two builds
 
 FFQ_MAX_RANK = 8
 
