@@ -164,7 +164,7 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             # a plain host read of the pinned mirror: no sync; a stale 0 only costs one more fix-up launch
             self._settled_seen = bool(self._settled_host[0] != 0)
         tile = quantizer.granularity.tile_size(data.shape)
-        want_rowsum = data.dim() >= 2 and (mode == 2 or self.min.numel() * data.shape[-1] == data.numel())
+        want_rowsum = data.dim() >= 2 and (mode == 2 or (mode == 1 and self.min.numel() * data.shape[-1] == data.numel()))
         codes, rowsum = ops.calibrate_quantize_(
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,

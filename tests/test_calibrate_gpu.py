@@ -476,3 +476,14 @@ def test_calibrate_and_fuse_qdq_weights_equals_two_step():
         for (na, pa), (nb, pb) in zip(a.state_dict().items(), b.state_dict().items()):
             assert na == nb and bits_equal(pa, pb), na
         assert (l1 - l0) <= (l2 - l1)
+
+
+def test_estimator_group_tiles_one_group_per_row():
+    """A per-group quantizer whose group spans the whole (short) row takes the group kernel, which has no row sums."""
+    q = ff.nn.LinearQuantizer(4, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0),
+                              quantized_dtype=torch.int8, device=DEV)
+    x = torch.randn(256, 128, device=DEV).bfloat16()
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax):
+        out = q(x)
+    mn, mx, s, o, rq = _oracle_step(None, None, x.cpu(), (1, 128), 4, True, True)
+    assert bits_equal(out.raw_data, rq) and bits_equal(q.scale.detach(), s) and not hasattr(out, "_ffq_rowsum")
