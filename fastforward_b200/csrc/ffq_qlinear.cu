@@ -51,6 +51,7 @@ struct GemmArgs {
   const int32_t* rowsum_w;                      // per output column: sum_k qw[n,k]
   const void* bias; int bias_dt;                // per output column, optional
   const int32_t* rowsum_x;                      // per output row; used with ow
+  int bn;                                       // pair kernel: output columns per tile (256, or 224 when that evens out the waves)
 };
 
 // Per-column epilogue parameters of one tile, derived where they are consumed (no separate launch, no scratch):
@@ -235,7 +236,9 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t cta = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   constexpr int TM = 2 * BM;                  // 256 rows per pair tile
-  const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + BN - 1) / BN;
+  const int bn = g.bn;                       // columns per tile; the smem / TMEM layout keeps its 256-column pitch
+  const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + bn - 1) / bn;
+  const uint32_t stage_tx = 2u * (uint32_t)(A_STAGE + (bn / 2) * BK);
   const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (g.K + BK - 1) / BK;
 
@@ -265,9 +268,9 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * HALF_STAGE;
-          if (cta == 0) mbar_expect_tx(&full_bar[stage], 2 * HALF_STAGE);
+          if (cta == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
-          tma_load_2d_pair(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * BN + (int)cta * (BN / 2));
+          tma_load_2d_pair(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * bn + (int)cta * (bn / 2));
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
@@ -275,8 +278,8 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
     if (cta == 0 && lane == 0) {
-      // D=S32, A=B=signed int8, K-major, N=256, M=256 (128 rows in each CTA)
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      // D=S32, A=B=signed int8, K-major, N=bn, M=256 (128 rows in each CTA)
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
@@ -312,7 +315,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      stage_col_params(g, tn * BN, BN, ep_tid, 128, col_params, col_ints);
+      stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
@@ -321,16 +324,16 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < bn; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int32_t t = (int32_t)acc[j] + col_ints[2 * BN + c0 + j] + col_ints[3 * BN + c0 + j] * rx;
-          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[BN + c0 + j]);
+          const int32_t t = (int32_t)acc[j] + col_ints[2 * bn + c0 + j] + col_ints[3 * bn + c0 + j] * rx;
+          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[bn + c0 + j]);
         }
-        const int n0 = tn * BN + c0;
+        const int n0 = tn * bn + c0;
         if (row < g.M && n0 < g.N) {
           const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
           store_chunk<OutT>(y + (size_t)row * g.N + n0, v, ncols);
@@ -454,10 +457,22 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   });
   if (attr_err != cudaSuccess) { set_error("qlinear_w8a8: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
   if (use_pair) {
-    CUtensorMap map_b2;     // B box = this CTA's 128-row half
-    if ((rc = make_map(&map_b2, qw, N, K, BN / 2)) != FFQ_OK) return rc;
+    // columns per pair tile: 256, or 224 when that removes a nearly empty last wave (e.g. N = 14336 at M = 2048:
+    // 448 tiles on 74 pairs = 6.05 waves -> 512 tiles = 6.92 waves of 0.94x the per-tile cost; operand delivery,
+    // A 128 rows + B bn/2 rows per CTA and k-block, is what a tile costs)
+    const long long pairs = sm_count() / 2;
+    const long long tiles_m2 = (M + 2 * BM - 1) / (2 * BM);
+    auto cost = [&](int bn) {
+      const long long t = tiles_m2 * ((N + bn - 1) / bn);
+      return (double)((t + pairs - 1) / pairs) * (128.0 + bn / 2.0);
+    };
+    static const bool force_256 = getenv("FFQ_GEMM_BN256") != nullptr;
+    g.bn = (!force_256 && N % 32 == 0 && cost(224) < 0.97 * cost(256)) ? 224 : BN;
+    CUtensorMap map_b2;     // B box = this CTA's half of the tile's columns
+    if ((rc = make_map(&map_b2, qw, N, K, g.bn / 2)) != FFQ_OK) return rc;
     const int max_pairs = sm_count() / 2;
-    const int grid2 = 2 * (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
+    const long long pair_tiles_bn = tiles_m2 * ((N + g.bn - 1) / g.bn);
+    const int grid2 = 2 * (int)(pair_tiles_bn < max_pairs ? pair_tiles_bn : max_pairs);
     switch (y_dtype) {
       case FFQ_F32: w8a8_gemm2_kernel<float><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
       case FFQ_BF16: w8a8_gemm2_kernel<__nv_bfloat16><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;

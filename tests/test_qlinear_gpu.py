@@ -67,7 +67,9 @@ def _run_case(m, k, n, dt, w_sym, bias, seed=0):
 
 
 @pytest.mark.parametrize("m,k,n", [(128, 128, 256), (256, 512, 512), (300, 1024, 700), (17, 96, 40), (2048, 4096, 1024),
-                                   (129, 4096 + 16, 257)])
+                                   (129, 4096 + 16, 257),
+                                   # 224-column pair tiles (chosen when they even out the waves), incl. a ragged last tile
+                                   (2048, 256, 14336), (2048, 128, 14336 - 96)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16] if torch.cuda.is_available() else [])
 @pytest.mark.parametrize("w_sym,bias", [(True, False), (False, True)])
 def test_w8a8_linear(m, k, n, dt, w_sym, bias):
