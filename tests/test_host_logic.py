@@ -256,3 +256,54 @@ def test_disable_quantization_restores_flags_and_overrides():
     assert torch.allclose(y, torch.nn.functional.linear(x, model[0].weight, model[0].bias))
     assert ff.get_strict_quantization() is True
     assert list(model[0].weight_quantizer.overrides) == []
+
+
+# ---- host-only pieces of the fused calibration / GPTQ paths (no compute calls) -----------------
+def test_calibrate_quantize_mode_classification():
+    """Which fused kernel a layout gets is decided on the host from the collapsed tile plan (csrc/ffq_calibrate.cu:
+    calq_mode): 1 = a row per CTA, 2 = whole tensor (grid barrier), 3 = sub-warp groups, 0 = the separate kernels."""
+    from fastforward_b200 import ops
+    bf, f32 = torch.bfloat16, torch.float32
+    assert ops.calibrate_quantize_mode((4096, 4096), (1, 4096), bf) == 1           # per-channel weight
+    assert ops.calibrate_quantize_mode((4096, 14336), (1, 14336), bf) == 1
+    assert ops.calibrate_quantize_mode((2, 3, 4096), (1, 1, 4096), bf) == 1        # leading dims collapse into rows
+    assert ops.calibrate_quantize_mode((1, 2048, 4096), "data_shape", bf) == 2     # per-tensor activation
+    assert ops.calibrate_quantize_mode((14336, 4096), (1, 128), bf) == 3           # g = 128: 16 vectors
+    assert ops.calibrate_quantize_mode((14336, 4096), (1, 128), f32) == 3          # 32 vectors
+    assert ops.calibrate_quantize_mode((64, 256), (1, 256), f32) == 1              # 64 vectors: a row again
+    assert ops.calibrate_quantize_mode((64, 96), (1, 96), bf) == 0                 # 12 vectors: not a power of two
+    assert ops.calibrate_quantize_mode((64, 4096), (64, 1), bf) == 0               # per-channel on the last dim: strided
+    assert ops.calibrate_quantize_mode((64, 4096), (8, 128), bf) == 0              # 2-D tiles
+    assert ops.calibrate_quantize_mode((8, 40000 * 8), (1, 40000 * 8), bf) == 0    # rows longer than 4096 vectors
+    assert ops.calibrate_quantize_mode((64, 4096), (1, 4096), torch.int32) == 0
+    assert ops.calibrate_quantize_mode((0, 4096), (1, 4096), bf) == 0
+    assert ops.calibrate_quantize_mode((8, 100), (1, 100), bf) == 0                # tile not a multiple of the vector width
+
+
+def test_params_for_ranges_encode_words():
+    words = (ctypes.c_int64 * 3)()
+    import struct
+    for bits, sym, one_sided in [(8, True, True), (4, False, True), (2, True, False), (16, False, False)]:
+        _cabi.lib.ffq_params_for_ranges_encode(float(bits), int(sym), int(one_sided), words)
+        lo = -2.0 ** (bits - 1)
+        f = struct.unpack("<4f", struct.pack("<2q", words[0], words[1]))
+        assert f == (abs(lo), abs(-lo - 1), -lo, 2.0 ** bits - 1)
+        assert words[2] == (1 if sym else 0) | (2 if one_sided else 0)
+
+
+def test_gptq_argument_checks_need_no_gpu():
+    from fastforward_b200.quantization import gptq as Gq
+    layer = ff.nn.QuantizedLinear(64, 8, bias=False)
+    with pytest.raises(ValueError, match="LinearQuantizer"):            # stub weight quantizer (gptq.py:47-49)
+        Gq.gptq(layer, [])
+    layer.weight_quantizer = ff.nn.LinearQuantizer(4, granularity=G.PerBlock(block_dims=1, block_sizes=16, per_channel_dims=0,
+                                                                            strict_blocks=False))
+    with pytest.raises(ValueError, match="strict_blocks"):             # gptq.py:59-61
+        Gq.gptq(layer, [])
+    layer.weight_quantizer = ff.nn.LinearQuantizer(4, granularity=G.PerChannel(0))
+    with pytest.raises(NotImplementedError, match="block_size"):
+        Gq.gptq(layer, [], block_size=129)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):          # a CPU layer never reaches a kernel
+        Gq.gptq(layer, [])
+    with pytest.raises(TypeError, match="Unsupported granularity"):     # gptq.py:219-221
+        Gq._check_granularity(G.PerChannel(2))
