@@ -88,11 +88,16 @@ __device__ __forceinline__ void bwd_elem_exact(float x, float g, const BwdTile& 
 // The quotient comes from the shared reciprocal; the vector is redone exactly when the scale or any
 // quotient leaves the box [2^-50, 2^60] in which that quotient is proven to equal __fdiv_rn (this
 // includes vectors containing exact zeros -- rare in dense weights/activations).
+// Returns true when NO element of the vector clips: then dx equals g bit for bit (the caller stores the raw
+// gradient vector, no select / re-pack) and only the q - pre residuals feed dscale.  Calibrated ranges clip few
+// elements, so this is the common case; a vector with a clipped element redoes its sums with the selections
+// from the quotients kept in registers.
 template <int RM, int EPT>
-__device__ __forceinline__ void bwd_vector(const float (&x)[EPT], const float (&g)[EPT], float (&dx)[EPT],
+__device__ __forceinline__ bool bwd_vector(const float (&x)[EPT], const float (&g)[EPT], float (&dx)[EPT],
                                            const BwdTile& t, const BParams& p, float& sum_sc, float& sum_off) {
   const float s = t.k.s, r = t.k.r;
-  float sc = 0.f, off = 0.f, amax = 0.f, amin = INFINITY;
+  float sc = 0.f, amax = 0.f, amin = INFINITY, qmin = INFINITY, qmax = -INFINITY;
+  float qv[EPT], rv[EPT];
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
     const float q0 = __fmul_rn(x[i], r);
@@ -102,23 +107,42 @@ __device__ __forceinline__ void bwd_vector(const float (&x)[EPT], const float (&
     amin = fminf(amin, fabsf(quo));
     const float pre = rndc<RM>(__fsub_rn(rndc<RM>(quo), t.o));
     const float q = rintf(pre);
-    const bool below = q < p.lo, above = q > p.hi, clip = below || above;
-    dx[i] = clip ? 0.f : g[i];
-    if (p.has_offset) off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
-    const float v = clip ? (below ? t.bound_lo : t.bound_hi) : rndc<RM>(__fsub_rn(q, pre));
-    sc += rndc<RM>(__fmul_rn(v, g[i]));
+    qv[i] = q;
+    rv[i] = rndc<RM>(__fsub_rn(q, pre));
+    qmin = fminf(qmin, q);                       // NaN-ignoring: a NaN code does not clip (q < lo, q > hi are false)
+    qmax = fmaxf(qmax, q);
+    sc += rndc<RM>(__fmul_rn(rv[i], g[i]));
   }
   if (!(t.k.ok && amax <= 0x1p60f && amin >= 0x1p-50f)) {
-    sc = 0.f; off = 0.f;
+    sc = 0.f;
+    float off = 0.f;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
       float dsc, doff;
       bwd_elem_exact<RM>(x[i], g[i], t, p, dx[i], dsc, doff);
       sc += dsc; off += doff;
     }
+    sum_sc += sc;
+    sum_off += off;
+    return false;
+  }
+  if (qmin >= p.lo && qmax <= p.hi) {            // nothing clips: dx == g, doffset terms are all zero
+    sum_sc += sc;
+    return true;
+  }
+  sc = 0.f;
+  float off = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const bool below = qv[i] < p.lo, above = qv[i] > p.hi, clip = below || above;
+    dx[i] = clip ? 0.f : g[i];
+    if (p.has_offset) off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
+    const float v = clip ? (below ? t.bound_lo : t.bound_hi) : rv[i];
+    sc += rndc<RM>(__fmul_rn(v, g[i]));
   }
   sum_sc += sc;
   sum_off += off;
+  return false;
 }
 
 template <typename T, int N>
@@ -214,10 +238,13 @@ __global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_group_kernel(const BwdA
       unpack<T, EPT>(xv[u], xf);
       unpack<T, EPT>(gv[u], gf);
       const BwdTile bt = make_bwd_tile<RM>(s, o, a.bp);
-      bwd_vector<RM, EPT>(xf, gf, df, bt, a.bp, sum_sc, sum_off);
-      Vec<T, EPT> d;
-      pack<T, EPT>(df, d);
-      st_vec<T, EPT>(dx + v * EPT, d);
+      if (bwd_vector<RM, EPT>(xf, gf, df, bt, a.bp, sum_sc, sum_off)) {
+        st_vec<T, EPT>(dx + v * EPT, gv[u]);               // no element clipped: dx is the gradient itself
+      } else {
+        Vec<T, EPT> d;
+        pack<T, EPT>(df, d);
+        st_vec<T, EPT>(dx + v * EPT, d);
+      }
     }
     sum_sc = group_sum<LANES>(sum_sc);
     if (a.bp.has_offset) sum_off = group_sum<LANES>(sum_off);
@@ -254,11 +281,15 @@ __device__ __forceinline__ void bwd_stream(const T* __restrict__ x, const T* __r
         float xf[EPT], gf[EPT], df[EPT];
         unpack<T, EPT>(xv[u], xf);
         unpack<T, EPT>(gv[u], gf);
-        bwd_vector<RM, EPT>(xf, gf, df, bt, bp, sum_sc, sum_off);
-        Vec<T, EPT> d;
-        pack<T, EPT>(df, d);
-        if constexpr (EPT == 1) dx[i] = d.v[0];
-        else st_vec<T, EPT>(dx + i, d);
+        if (bwd_vector<RM, EPT>(xf, gf, df, bt, bp, sum_sc, sum_off)) {   // no element clipped: dx is the gradient itself
+          if constexpr (EPT == 1) dx[i] = gv[u].v[0];
+          else st_vec<T, EPT>(dx + i, gv[u]);
+        } else {
+          Vec<T, EPT> d;
+          pack<T, EPT>(df, d);
+          if constexpr (EPT == 1) dx[i] = d.v[0];
+          else st_vec<T, EPT>(dx + i, d);
+        }
       }
     }
   }
