@@ -90,59 +90,65 @@ __device__ __forceinline__ void bwd_elem_exact(float x, float g, const BwdTile& 
 // includes vectors containing exact zeros -- rare in dense weights/activations).
 // Returns true when NO element of the vector clips: then dx equals g bit for bit (the caller stores the raw
 // gradient vector, no select / re-pack) and only the q - pre residuals feed dscale.  Calibrated ranges clip few
-// elements, so this is the common case; a vector with a clipped element redoes its sums with the selections
-// from the quotients kept in registers.
+// elements, so this is the common case; a sub-vector with a clipped element redoes its sums with the selections
+// from the quotients kept in registers.  The vector is processed in sub-vectors of at most 4 elements (fewer live
+// registers for 16-bit data); the sums run sequentially over the elements in every path, so the association --
+// and with it the result -- does not depend on which path a sub-vector took.
 template <int RM, int EPT>
 __device__ __forceinline__ bool bwd_vector(const float (&x)[EPT], const float (&g)[EPT], float (&dx)[EPT],
                                            const BwdTile& t, const BParams& p, float& sum_sc, float& sum_off) {
+  constexpr int SUB = EPT < 4 ? EPT : 4;
   const float s = t.k.s, r = t.k.r;
-  float sc = 0.f, amax = 0.f, amin = INFINITY, qmin = INFINITY, qmax = -INFINITY;
-  float qv[EPT], rv[EPT];
+  float sc = 0.f, off = 0.f;
+  bool clean = true;
 #pragma unroll
-  for (int i = 0; i < EPT; ++i) {
-    const float q0 = __fmul_rn(x[i], r);
-    const float e = __fmaf_rn(-s, q0, x[i]);
-    const float quo = __fmaf_rn(r, e, q0);
-    amax = nan_max(amax, fabsf(quo));
-    amin = fminf(amin, fabsf(quo));
-    const float pre = rndc<RM>(__fsub_rn(rndc<RM>(quo), t.o));
-    const float q = rintf(pre);
-    qv[i] = q;
-    rv[i] = rndc<RM>(__fsub_rn(q, pre));
-    qmin = fminf(qmin, q);                       // NaN-ignoring: a NaN code does not clip (q < lo, q > hi are false)
-    qmax = fmaxf(qmax, q);
-    sc += rndc<RM>(__fmul_rn(rv[i], g[i]));
-  }
-  if (!(t.k.ok && amax <= 0x1p60f && amin >= 0x1p-50f)) {
-    sc = 0.f;
-    float off = 0.f;
+  for (int h = 0; h < EPT; h += SUB) {
+    const float sc0 = sc;
+    float amax = 0.f, amin = INFINITY, qmin = INFINITY, qmax = -INFINITY;
+    float qv[SUB], rv[SUB];
 #pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      float dsc, doff;
-      bwd_elem_exact<RM>(x[i], g[i], t, p, dx[i], dsc, doff);
-      sc += dsc; off += doff;
+    for (int j = 0; j < SUB; ++j) {
+      const int i = h + j;
+      const float q0 = __fmul_rn(x[i], r);
+      const float e = __fmaf_rn(-s, q0, x[i]);
+      const float quo = __fmaf_rn(r, e, q0);
+      amax = nan_max(amax, fabsf(quo));
+      amin = fminf(amin, fabsf(quo));
+      const float pre = rndc<RM>(__fsub_rn(rndc<RM>(quo), t.o));
+      const float q = rintf(pre);
+      qv[j] = q;
+      rv[j] = rndc<RM>(__fsub_rn(q, pre));
+      qmin = fminf(qmin, q);                     // NaN-ignoring: a NaN code does not clip (q < lo, q > hi are false)
+      qmax = fmaxf(qmax, q);
+      sc += rndc<RM>(__fmul_rn(rv[j], g[i]));
+      dx[i] = g[i];
     }
-    sum_sc += sc;
-    sum_off += off;
-    return false;
-  }
-  if (qmin >= p.lo && qmax <= p.hi) {            // nothing clips: dx == g, doffset terms are all zero
-    sum_sc += sc;
-    return true;
-  }
-  sc = 0.f;
-  float off = 0.f;
+    if (!(t.k.ok && amax <= 0x1p60f && amin >= 0x1p-50f)) {     // outside the proven box: plain IEEE division
+      sc = sc0;
+      clean = false;
 #pragma unroll
-  for (int i = 0; i < EPT; ++i) {
-    const bool below = qv[i] < p.lo, above = qv[i] > p.hi, clip = below || above;
-    dx[i] = clip ? 0.f : g[i];
-    if (p.has_offset) off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
-    const float v = clip ? (below ? t.bound_lo : t.bound_hi) : rv[i];
-    sc += rndc<RM>(__fmul_rn(v, g[i]));
+      for (int j = 0; j < SUB; ++j) {
+        float dsc, doff;
+        bwd_elem_exact<RM>(x[h + j], g[h + j], t, p, dx[h + j], dsc, doff);
+        sc += dsc; off += doff;
+      }
+    } else if (!(qmin >= p.lo && qmax <= p.hi)) {               // something clips: redo the sums with the selections
+      sc = sc0;
+      clean = false;
+#pragma unroll
+      for (int j = 0; j < SUB; ++j) {
+        const int i = h + j;
+        const bool below = qv[j] < p.lo, above = qv[j] > p.hi, clip = below || above;
+        dx[i] = clip ? 0.f : g[i];
+        if (p.has_offset) off += clip ? rndc<RM>(__fmul_rn(s, g[i])) : 0.f;
+        const float v = clip ? (below ? t.bound_lo : t.bound_hi) : rv[j];
+        sc += rndc<RM>(__fmul_rn(v, g[i]));
+      }
+    }
   }
   sum_sc += sc;
   sum_off += off;
-  return false;
+  return clean;
 }
 
 template <typename T, int N>
@@ -298,7 +304,7 @@ __device__ __forceinline__ void bwd_stream(const T* __restrict__ x, const T* __r
 // --- medium tiles: one warp per tile ---------------------------------------------------------
 // fp32 data fits 64 registers without spills (4 CTAs per SM: cfg1 55 -> 50 us); the 16-bit variants would spill
 template <typename T, int EPT, int RM>
-__global__ void __launch_bounds__(RD_THREADS, (sizeof(T) >= 4 ? 4 : 3)) bwd_row_warp_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(RD_THREADS, 4) bwd_row_warp_kernel(const BwdArgs a) {
   const unsigned long long tile = (unsigned long long)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
   if (tile >= a.num_tiles) return;
   const unsigned int lane = threadIdx.x & 31;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(RD_THREADS, (sizeof(T) >= 4 ? 4 : 3)) bwd_row_
 
 // --- large / few tiles: one CTA per tile segment ---------------------------------------------
 template <typename T, int EPT, int RM>
-__global__ void __launch_bounds__(RD_THREADS, (sizeof(T) >= 4 ? 4 : 3)) bwd_row_cta_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(RD_THREADS, 4) bwd_row_cta_kernel(const BwdArgs a) {
   __shared__ float smem[32];
   const unsigned long long tile = blockIdx.x / a.S;
   const unsigned int seg = blockIdx.x % a.S;
