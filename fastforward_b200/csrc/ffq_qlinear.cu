@@ -88,7 +88,9 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int bn = g.bn;                       // columns per tile (256 or 128); the smem / TMEM layout keeps its 256-column pitch
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + bn - 1) / bn;
+  const uint32_t stage_tx = (uint32_t)(A_STAGE + bn * BK);
   const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = (g.K + BK - 1) / BK;
 
@@ -119,9 +121,9 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BK, tm * BM);
-          tma_load_2d(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * BN);
+          tma_load_2d(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * bn);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -129,8 +131,8 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      // instruction descriptor: D=S32, A=B=signed int8, both K-major, N=256, M=128
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // instruction descriptor: D=S32, A=B=signed int8, both K-major, N=bn, M=128
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -168,7 +170,7 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t use = (uint32_t)(it >> 1);
       // stage this tile's column parameters in shared memory (named barrier over the 4 epilogue warps)
       asm volatile("bar.sync 1, 128;" ::: "memory");         // previous tile's readers are done
-      stage_col_params(g, tn * BN, BN, ep_tid, 128, col_params, col_ints);
+      stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row = tm * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
@@ -177,16 +179,16 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < bn; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int32_t t = (int32_t)acc[j] + col_ints[2 * BN + c0 + j] + col_ints[3 * BN + c0 + j] * rx;
-          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[BN + c0 + j]);
+          const int32_t t = (int32_t)acc[j] + col_ints[2 * bn + c0 + j] + col_ints[3 * bn + c0 + j] * rx;
+          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[bn + c0 + j]);
         }
-        const int n0 = tn * BN + c0;
+        const int n0 = tn * bn + c0;
         if (row < g.M && n0 < g.N) {
           const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
           store_chunk<OutT>(y + (size_t)row * g.N + n0, v, ncols);
@@ -425,16 +427,14 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   if (ow != nullptr && rowsum_x == nullptr) { set_error("qlinear_w8a8: rowsum_x is required when the weight has an offset"); return FFQ_ERR_INVALID; }
   (void)workspace; (void)workspace_bytes;      // kept in the ABI; the column parameters are derived inside the kernel
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a;
   int rc;
   if ((rc = make_map(&map_a, qx, M, K, BM)) != FFQ_OK) return rc;
-  if ((rc = make_map(&map_b, qw, N, K, BN)) != FFQ_OK) return rc;
   GemmArgs g{};
   g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.y_dt = y_dtype;
   g.sx = sx; g.ox = ox; g.sw = sw; g.ow = ow; g.rowsum_w = rowsum_w; g.bias = bias; g.bias_dt = bias_dtype;
   g.rowsum_x = rowsum_x;
   const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const long long pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   // the pair kernel needs M > 128 to have work for both CTAs; FFQ_GEMM_1CTA=1 forces the single-CTA kernel
   static const bool force_1cta = getenv("FFQ_GEMM_1CTA") != nullptr;
@@ -481,10 +481,26 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
     FFQ_LAUNCH_CHECK();
     return FFQ_OK;
   }
+  // single-CTA kernel: 128 x 256 tiles, or 128 x 128 when the wider ones would leave SMs idle (e.g. the k/v
+  // projections, N = 1024 at M = 2048: 64 tiles -> 128 tiles on 148 SMs at two thirds of the per-tile operand traffic)
+  {
+    const long long sms = sm_count();
+    const long long tm1 = (M + BM - 1) / BM;
+    auto cost1 = [&](int bn) {
+      const long long t = tm1 * ((N + bn - 1) / bn);
+      return (double)((t + sms - 1) / sms) * (128.0 + bn);
+    };
+    static const bool force_256 = getenv("FFQ_GEMM_BN256") != nullptr;
+    g.bn = (!force_256 && N % 32 == 0 && cost1(128) < 0.97 * cost1(BN)) ? 128 : BN;
+  }
+  CUtensorMap map_b1;
+  if ((rc = make_map(&map_b1, qw, N, K, g.bn)) != FFQ_OK) return rc;
+  const long long tiles1 = ((M + BM - 1) / BM) * ((N + g.bn - 1) / g.bn);
+  const int grid1 = (int)(tiles1 < sm_count() ? tiles1 : sm_count());
   switch (y_dtype) {
-    case FFQ_F32: w8a8_gemm_kernel<float><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
-    case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
-    default: w8a8_gemm_kernel<__half><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b, g); break;
+    case FFQ_F32: w8a8_gemm_kernel<float><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, g); break;
+    case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, g); break;
+    default: w8a8_gemm_kernel<__half><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, g); break;
   }
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
