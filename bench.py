@@ -34,7 +34,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference+plugin"],
+                    help="ours: this repository.  reference: the unmodified reference (oracle/_ref) on the host cores.  "
+                         "reference+plugin: the unmodified reference's host code on the GPU with plugin.install() underneath")
     ap.add_argument("--layers", type=int, default=None, help="decoder layers to instantiate (default: all 32)")
     ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--shape", default="8b", choices=["8b", "70b", "tiny"])
@@ -42,9 +44,13 @@ def parse_args():
     ap.add_argument("--cpu-sample-layers", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
-    ap.add_argument("--with-compiled-baseline", action="store_true",
-                    help="also time torch.compile of the reference's op sequence for cfg1 on the GPU (context; ~1 min of compilation)")
-    ap.add_argument("--workload", default="calib", choices=["calib", "w4a16-calib", "wq4"],
+    ap.add_argument("--skip-compiled-baseline", action="store_true",
+                    help="skip the reference's compiled_quant_funcs timing of cfg1 (saves ~1 min of inductor compilation)")
+    ap.add_argument("--skip-drop-in", action="store_true", help="skip the reference+plugin measurements of the default line")
+    ap.add_argument("--memoize-parameters", action="store_true",
+                    help="headline with the estimator's default memoisation of unchanged weights ON (default: OFF, so that every "
+                         "timed step re-quantizes every weight exactly as the reference's step does)")
+    ap.add_argument("--workload", default="calib", choices=["calib", "w4a16-calib", "wq4", "cfg5"],
                     help="calib: configs[1] (default, W8A8 8B-shape).  w4a16-calib: configs[4] recipe (W4 g=128 / A16) on "
                          "--shape.  wq4: configs[2], W4 g=128 weight fake-quant of all linears sharded by layer")
     return ap.parse_args()
@@ -219,10 +225,20 @@ def _time_graph(fn, calls_per_replay, reps=5):
     return e0.elapsed_time(e1) * 1e-3 / (reps * calls_per_replay)
 
 
-def measure_extras(ff, dev, hbm_peak, int8_peak):
+def measure_int8_library_peak(dev):
+    """Sustained int8 tensor throughput of the library GEMM (cuBLASLt through torch._int_mm) at 8192^3: the measured
+    stand-in for an int8 peak, which MEASURED_PEAKS.json does not carry.  Context for `frac`, never on the product path."""
+    n = 8192
+    a = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=dev)
+    b = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=dev)
+    t = _time_cuda(lambda: torch._int_mm(a, b.t()), iters=30, warm=5)
+    return 2.0 * n ** 3 / t / 1e12
+
+
+def measure_extras(ff, dev, hbm_peak, int8_peak, int8_lib_peak):
     """fake-quant fwd+bwd GB/s (configs[0]/cfg1 shape and a weight-sized bf16 tensor), W8A8 linear TOPS
     (configs[3]) and W4 g=128 weight QDQ GB/s (configs[2], one Llama-3-8B gate_proj).  Inputs exceed L2
-    or are cycled so that no iteration re-reads L2-resident data."""
+    or are cycled so that no iteration re-reads L2-resident data.  Runs on EVERY rank (replicas)."""
     import ctypes
     from fastforward_b200 import _cabi as C, ops
     out = {}
@@ -287,15 +303,28 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
 
     def gemm():
         C.check(C.lib.ffq_qlinear_w8a8(qx.data_ptr(), qw.data_ptr(), y.data_ptr(), 2, M, N, K, sx.data_ptr(), ox.data_ptr(), sw.data_ptr(),
-                                       None, rs.data_ptr(), None, None, 255, None, 0, st))
+                                       None, rs.data_ptr(), None, None, 255, None, st))
     t = _time_cuda(gemm)
     t_lib = _time_cuda(lambda: torch._int_mm(qx, qw.t()))
+    # ... with the output quantizer fused into the epilogue (int8 codes + their row sums instead of the bf16 tensor)
+    codes = torch.empty(M, N, dtype=torch.int8, device=dev)
+    rs_out = torch.zeros(M, dtype=torch.int32, device=dev)
+    oq_s = torch.tensor([0.05], device=dev); oq_o = torch.tensor([-2.0], device=dev)
+    rq = C.Requant(oq_s.data_ptr(), oq_o.data_ptr(), 8.0, codes.data_ptr(), rs_out.data_ptr())
+
+    def gemm_requant():
+        C.check(C.lib.ffq_qlinear_w8a8(qx.data_ptr(), qw.data_ptr(), None, 2, M, N, K, sx.data_ptr(), ox.data_ptr(), sw.data_ptr(),
+                                       None, rs.data_ptr(), None, None, 255, ctypes.byref(rq), st))
+    t_rq = _time_cuda(gemm_requant)
     out["w8a8_linear_8192x14336x4096"] = {"us": round(t * 1e6, 1), "TOPS": round(2 * M * N * K / t / 1e12, 1),
                                           "frac_of_int8_peak": round(2 * M * N * K / t / 1e12 / int8_peak, 3),
-                                          "context_cublaslt_int_mm_TOPS": round(2 * M * N * K / t_lib / 1e12, 1)}
-    del qx, qw, y
+                                          "frac_of_library_int8_sustained": round(2 * M * N * K / t / 1e12 / int8_lib_peak, 3),
+                                          "context_cublaslt_int_mm_TOPS": round(2 * M * N * K / t_lib / 1e12, 1),
+                                          "fused_output_requant_us": round(t_rq * 1e6, 1),
+                                          "fused_output_requant_TOPS": round(2 * M * N * K / t_rq / 1e12, 1)}
+    del qx, qw, y, codes
     # W4A16 linear (configs[4] recipe at the configs[3] shape): bf16 activations x 4-bit g=128 codes
-    for M in (256, 2048):     # the dispatcher takes the fused kernel up to 512 rows (nn/qlinear.py: W4A16_MAX_ROWS)
+    for M in (256, 2048):
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         qw = torch.randint(-8, 8, (N, K), dtype=torch.int8, device=dev)
         sw4 = torch.rand(N * (K // 128), device=dev) * 0.01 + 1e-3
@@ -316,7 +345,7 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
         out[f"w4a16_linear_{M}x{N}x{K}_g128"] = {
             "us": round(t * 1e6, 1), "TFLOPS": round(2 * M * N * K / t / 1e12, 1),
             "frac_of_bf16_peak": round(2 * M * N * K / t / 1e12 / (int8_peak / 2), 3),
-            "fallback_dequant_plus_cublas_us": round(t_fb * 1e6, 1), "context_cublas_bf16_gemm_only_us": round(t_mm * 1e6, 1)}
+            "context_dequant_plus_cublas_us": round(t_fb * 1e6, 1), "context_cublas_bf16_gemm_only_us": round(t_mm * 1e6, 1)}
         del x, qw, y, wd
     # W4 g=128 weight QDQ of one 14336x4096 bf16 weight (configs[2] unit of work): min/max + params + fused QDQ in place
     w = [torch.randn(14336, 4096, device=dev, dtype=torch.bfloat16) * 0.02 for _ in range(3)]
@@ -324,17 +353,6 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
     nt = w[0].numel() // 128
     scale = torch.empty(nt, device=dev); offset = torch.empty(nt, device=dev)
     it = [0]
-
-    def qdq():
-        i = it[0] % 3; it[0] += 1
-        mn, mx = ops.tile_minmax(w[i], tile)
-        ops.parameters_for_range_(mn, mx, 4, True, True, scale, offset)
-        ops.fake_quantize_by_tile(w[i], scale, tile, 4.0, None, offset)
-    t = _time_graph(qdq, calls_per_replay=6)
-    by = 3 * w[0].numel() * 2    # read (min/max) + read + write
-    out["w4_g128_weight_qdq_14336x4096_bf16"] = {"us": round(t * 1e6, 1), "GBps": round(by / t / 1e9, 1),
-                                                  "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3),
-                                                  "what": "three launches: min/max, params, fused QDQ (3s bytes/element)"}
 
     def qdq_fused():        # calibrate + snap in ONE launch (ffq_calibrate_fakequant), 2s bytes/element
         i = it[0] % 3; it[0] += 1
@@ -344,62 +362,151 @@ def measure_extras(ff, dev, hbm_peak, int8_peak):
     out["w4_g128_weight_qdq_fused_14336x4096_bf16"] = {"us": round(t * 1e6, 1), "GBps": round(by / t / 1e9, 1),
                                                         "frac_of_measured_hbm": round(by / t / 1e9 / hbm_peak, 3),
                                                         "what": "one launch (+ the early-exit fix-up): read once, write once"}
-    return out
-
-
-def measure_reference_eager_cuda(args, sh, dev):
-    """Context baseline (part of the baseline leg, not of the product): the reference's own aten op sequence --
-    oracle/ref_ops.py is that sequence op for op -- executed on CUDA tensors, i.e. what the unmodified reference
-    does on this GPU without the B200 backend ('the real beat-this bars')."""
-    import bench_workloads as bw
-    from oracle import ref_ops as R
-    from oracle import workload as ow
-
-    out = {}
-    torch.manual_seed(0)
-    x = torch.randn(4096, 4096, device=dev); g = torch.randn(4096, 4096, device=dev)
-    tile = (1, 4096)
-    mn, mx = R.tile_minmax(x, tile)
-    scale, offset = R.parameters_for_range(mn, mx, 8, True, True)
-    t = _time_cuda(lambda: R.fake_quant_fwd_bwd(x, g, scale, offset, tile, 8), iters=10, warm=2)
-    out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_us"] = round(t * 1e6, 1)
-    if args.with_compiled_baseline:
-        # the reference's `compiled_quant_funcs` route: the same op sequence through torch.compile (inductor)
-        try:
-            # (a) forward and backward compiled separately, as autograd runs them (x is read by both: 20 B/element)
-            c_fwd = torch.compile(lambda a: R.dequantize_by_tile(R.quantize_by_tile(a, scale, tile, 8, a.dtype, offset), scale, tile, offset, a.dtype))
-            c_bwd = torch.compile(lambda a, b: R.quantize_by_tile_backward(a, b, scale, tile, 8, offset))
-
-            def sep():
-                c_fwd(x)
-                c_bwd(x, g)
-            t = _time_cuda(sep, iters=10, warm=3)
-            out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_torch_compile_us"] = round(t * 1e6, 1)
-            # (b) both in ONE compiled graph: inductor reads x once (16 B/element) -- not something autograd can do,
-            # the gradient does not exist yet when the forward runs
-            compiled = torch.compile(lambda a, b: R.fake_quant_fwd_bwd(a, b, scale, offset, tile, 8))
-            t = _time_cuda(lambda: compiled(x, g), iters=10, warm=3)
-            out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_torch_compile_single_graph_us"] = round(t * 1e6, 1)
-        except Exception as e:  # noqa: BLE001  (a baseline that cannot be built is reported, not fatal)
-            out["cfg1_4096x4096_fp32_fake_quant_fwd_bwd_torch_compile_us"] = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
-    del x, g
-    layers = 2
-    model = bw.DecoderStack(sh, layers=layers, dtype=torch.bfloat16, device=dev)
-    bw.init_weights_(model, seed=0)
-    ow.oracle_calibration_model(model)
-    tok = torch.randint(0, sh.vocab, (1, args.seq), device=dev)
-    with torch.no_grad():
-        t = _time_cuda(lambda: model(tok), iters=5, warm=2)
-    out["calibration_tokens_per_s"] = round(args.seq / (t * sh.layers / layers), 1)
-    out["calibration_sample"] = f"{layers} of {sh.layers} decoder layers at seq {args.seq}, scaled; eager aten ops + float fallback GEMM, host syncs as in the reference"
-    del model
+    del w
     torch.cuda.empty_cache()
     return out
 
 
 # ---------------------------------------------------------------------------------------------
+# configs[2] and configs[4] as measurements that run on every rank of `bench.py --gpus N`
+# ---------------------------------------------------------------------------------------------
+def _dist_reduce(vals, op, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=op)
+    return t.tolist()
+
+
+def measure_cfg3(ff, sh, dev, rank, world, hbm_peak, steps=5, warmup=2):
+    """configs[2]: W4 per-group (g=128) weight fake-quant of every decoder linear of the 8B-shape model, sharded by
+    layer (layer i -> rank i mod N), no data-path collective: strong scaling.  A step = calibrate each owned weight
+    quantizer on its weight and snap the weight in place (one fused launch per weight, 2s bytes per element)."""
+    import torch.distributed as dist
+
+    import bench_workloads as bw
+    from fastforward_b200 import _cabi
+    from fastforward_b200.quantization.fuse import calibrate_and_fuse_qdq_weights
+
+    mine = list(range(rank, sh.layers, world))
+    model = torch.nn.ModuleList(bw.DecoderLayer(sh, torch.bfloat16, dev) for _ in mine)   # only this rank's layers
+    bw.init_weights_(model, seed=rank)
+    ff.quantize_model(model, extra_conversion=ff.surrogate_quantized_modules(model))
+    ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
+        ff.nn.LinearQuantizer, num_bits=4, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+    n_weights = sum(m.weight.numel() for m in model.modules() if isinstance(m, torch.nn.Linear))
+
+    def step():
+        calibrate_and_fuse_qdq_weights(model)
+    for _ in range(warmup):
+        step()
+    l0 = _cabi.launch_count()
+    step()
+    launches = _cabi.launch_count() - l0
+    torch.cuda.synchronize()
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        step()
+    cg.replay()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        cg.replay()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = t0.elapsed_time(t1) * 1e-3 / steps
+    dt_max = _dist_reduce([dt], dist.ReduceOp.MAX, dev, world)[0]
+    n_all = _dist_reduce([float(n_weights)], dist.ReduceOp.SUM, dev, world)[0]
+    del cg, model
+    torch.cuda.empty_cache()
+    by = 2 * 2 * n_all
+    return {"what": f"{sh.name}: {sh.layers} layers x 7 linears = {n_all / 1e9:.2f} G weights, LinearQuantizer(4, PerBlock g=128), "
+                    "calibrate_and_fuse_qdq_weights (one fused launch per weight, in place, 2s bytes/element); layer i -> rank i mod N; "
+                    "CUDA-graph replay; time = max over ranks",
+            "n_gpus": world, "scaling": "strong", "ms_whole_model": round(dt_max * 1e3, 3),
+            "aggregate_GBps": round(by / dt_max / 1e9, 1), "per_gpu_GBps": round(by / dt_max / 1e9 / world, 1),
+            "frac_of_measured_hbm_per_gpu": round(by / dt_max / 1e9 / world / hbm_peak, 3), "launches_per_step_per_rank": int(launches)}
+
+
+def measure_cfg5(ff, dev, rank, world, steps=2, layers=None, seq=SEQ):
+    """configs[4]: Llama-3-70B-shape W4 (g=128, int8 container) / A16 (per-tensor asymmetric, fp32 codes) data-parallel
+    calibration.  The 80 layers are STREAMED (random-init one layer, calibrate it on this rank's batches inside its own
+    estimate_ranges block with the NCCL MIN/MAX range exchange at block exit, free it): 137 GB of bf16 weights never have
+    to be resident.  Timed: every layer's estimate_ranges block (CUDA events, summed; weight initialisation excluded);
+    tokens/s = N x steps x seq / max-over-ranks time."""
+    import torch.distributed as dist
+
+    import bench_workloads as bw
+    from fastforward_b200 import _cabi
+    from fastforward_b200.nn import qlinear
+
+    sh = bw.LLAMA3_70B
+    n_layers = layers or sh.layers
+    qlinear.install()
+    g = torch.Generator().manual_seed(4321 + rank)
+    hidden = [(torch.randn(1, seq, sh.hidden, generator=g) * 0.5).to(dev, torch.bfloat16) for _ in range(steps)]
+    total_ms, exit_ms = 0.0, 0.0
+    calls0 = qlinear.stats().get("calls_w4a16", 0)
+    l0 = _cabi.launch_count()
+    for li in range(n_layers):
+        layer = bw.DecoderLayer(sh, torch.bfloat16, dev)
+        bw.init_weights_(layer, seed=1000 + li)
+        ff.quantize_model(layer, extra_conversion=ff.surrogate_quantized_modules(layer))
+        ff.set_strict_quantization(False)
+        ff.find_quantizers(layer, "**/[quantizer:parameter/weight]").initialize(
+            ff.nn.LinearQuantizer, num_bits=4, quantized_dtype=torch.int8,
+            granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+        ff.find_quantizers(layer, "**/[quantizer:activation/input]").initialize(
+            ff.nn.LinearQuantizer, num_bits=16, symmetric=False, granularity=ff.PerTensor(), quantized_dtype=torch.float32)
+        est = ff.range_setting.running_minmax(sync_ranges=world > 1, memoize_parameters=False)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        with torch.no_grad(), ff.estimate_ranges(layer, est):
+            for b in range(steps):
+                hidden[b] = layer(hidden[b])
+            e1.record()
+        e2.record()
+        torch.cuda.synchronize()
+        total_ms += e0.elapsed_time(e2)
+        exit_ms += e1.elapsed_time(e2)
+        del layer, est
+    w4_calls = qlinear.stats().get("calls_w4a16", 0) - calls0
+    launches = _cabi.launch_count() - l0
+    torch.cuda.empty_cache()
+    t_max, exit_max = _dist_reduce([total_ms, exit_ms], dist.ReduceOp.MAX, dev, world)
+    finite = bool(torch.isfinite(hidden[-1].float()).all())
+    return {"what": f"{sh.name}, {n_layers} of {sh.layers} layers streamed, W4 g=128 (int8 container) + A16 per-tensor asymmetric "
+                    f"LinearQuantizers, estimate_ranges(running_minmax) per layer, {steps} batch(es) [1,{seq}] per GPU, eager (no CUDA graph), "
+                    "weights re-quantized every step, NCCL MIN/MAX of the activation ranges at every block exit",
+            "n_gpus": world, "scaling": "weak", "tokens_per_s": round(world * steps * seq / (t_max * 1e-3 * sh.layers / n_layers), 1),
+            "ms_per_step_all_layers": round(t_max / steps, 2), "block_exit_ms_total": round(exit_max, 2),
+            "w4a16_kernel_calls": int(w4_calls), "linears_x_steps": 7 * n_layers * steps, "ffq_launches": int(launches),
+            "outputs_finite": finite}
+
+
+# ---------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------
+METRIC_8B = "calib tokens/s (Llama-3-8B-shape W8 per-channel / A8 per-tensor RunningMinMax calibration, seq 2048)"
+
+
+def workload_config(sh, layers, seq, world):
+    """The `config` object both arms print (the reference arm describes its sampling in `cpu_baseline.sample`)."""
+    return {"workload": f"{sh.name} decoder stack ({layers} layers, 7 quantized linears each), W8 PerChannel(0) symmetric + "
+                        f"A8 PerTensor asymmetric LinearQuantizers (int8 codes), estimate_ranges(running_minmax), "
+                        f"batch [1,{seq}] per GPU per step, random-init normal(0,0.02), no lm_head",
+            "parallelism": f"dp{world} calibration, one MIN/MAX all-reduce of ranges at block exit",
+            "l2": "per-step working set (>= 14 GB of weights re-quantized every step) exceeds the 126 MB L2"}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -423,9 +530,10 @@ def run_ours(args):
     bw.init_weights_(model, seed=0)
     if args.workload == "w4a16-calib":
         # W4 per-group (g=128) symmetric weights in an int8 container, A16 per-tensor asymmetric (fp32 codes:
-        # bf16 cannot hold 16 bits, _quantizer_impl.py:44-75); the linear takes the dequantize fallback
+        # bf16 cannot hold 16 bits, _quantizer_impl.py:44-75); the linear is the W4A16 tcgen05 kernel
         extra = ff.surrogate_quantized_modules(model)
         ff.quantize_model(model, extra_conversion=extra)
+        ff.set_strict_quantization(False)
         ff.find_quantizers(model, "**/layers/**/[quantizer:parameter/weight]").initialize(
             ff.nn.LinearQuantizer, num_bits=4, quantized_dtype=torch.int8,
             granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
@@ -444,15 +552,19 @@ def run_ours(args):
     dev_tokens = [t.to(dev) for t in host_tokens]
     static_tokens = torch.empty_like(dev_tokens[0])
 
-    estimator = ff.range_setting.running_minmax(sync_ranges=world > 1)
+    def make_estimator(memoize):
+        return ff.range_setting.running_minmax(sync_ranges=world > 1, memoize_parameters=memoize)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    def region(steps, tokens_src, e2e, graph):
+    def region(steps, tokens_src, e2e, graph, memoize=False, dedupe=True):
         """Enter estimate_ranges, warm up, time `steps` steps + block exit.  Returns seconds (device)."""
         out_host = torch.empty(max(steps, 1), dtype=torch.float32).pin_memory()    # one pinned slot per step
+        estimator = make_estimator(memoize)
+        estimator.dedupe = dedupe
+        estimator._state.dedupe = dedupe
         with torch.no_grad(), ff.estimate_ranges(model, estimator):
             for i in range(args.warmup):
                 static_tokens.copy_(dev_tokens[i])
@@ -467,8 +579,9 @@ def run_ours(args):
                     metric = y.float().abs().mean().reshape(1) if e2e else None
             if world > 1:   # NCCL sets up its MIN/MAX channels lazily: do that outside the timed region
                 for op in (dist.ReduceOp.MIN, dist.ReduceOp.MAX):
-                    dist.all_reduce(torch.zeros(1 << 21, dtype=torch.bfloat16, device=dev), op=op)
+                    dist.all_reduce(torch.zeros(1 << 14, dtype=torch.bfloat16, device=dev), op=op)
                 dist.all_reduce(torch.zeros(1, dtype=torch.int32, device=dev), op=dist.ReduceOp.MAX)
+                dist.all_reduce(torch.zeros(2, 8, dtype=torch.int64, device=dev), op=dist.ReduceOp.MAX)
             barrier(); torch.cuda.synchronize()
             t0, t1, tmid = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             wall0 = time.perf_counter()
@@ -485,14 +598,18 @@ def run_ours(args):
                     # inputs, all of them complete before the region's closing synchronize
                     out_host[i:i + 1].copy_(metric, non_blocking=True)
             tmid.record()
-        # leaving the block: +-inf check (one sync) and, for N>1, the MIN/MAX all-reduce of all ranges
+            wall_exit0 = time.perf_counter()
+        # leaving the block: +-inf check (one sync) and, for N>1, the MIN/MAX all-reduce of the activation ranges
         t1.record()
-        torch.cuda.synchronize(); barrier()
+        torch.cuda.synchronize()
+        region.exit_wall_ms = (time.perf_counter() - wall_exit0) * 1e3
+        barrier()
         if e2e and not bool(torch.isfinite(out_host[:steps]).all()):
             raise RuntimeError("bench: a step's result read back from the device is not finite")
         wall = time.perf_counter() - wall0
         dt = t0.elapsed_time(t1) * 1e-3
         region.exit_ms = tmid.elapsed_time(t1)
+        region.stats = estimator.last_stats
         return max(dt, 0.0), wall
 
     def reset_quantizers():
@@ -500,27 +617,39 @@ def run_ours(args):
             q.reset_parameters()
 
     use_graph = not args.no_graph
+    memo = bool(args.memoize_parameters)
     # ---- timed regions: (1) inputs resident in HBM, (2) end to end (pinned host tokens in, scalar out every step).
     # Each samples nvidia-smi clocks during its own steps.
-    def timed(e2e):
+    def timed(e2e, **kw):
         sampler = ClockSampler(local_rank)
         sampler.start()
-        d, w = region(args.steps, host_tokens if e2e else dev_tokens, e2e=e2e, graph=use_graph)
+        d, w = region(args.steps, host_tokens if e2e else dev_tokens, e2e=e2e, graph=use_graph, memoize=memo, **kw)
         return d, w, region.exit_ms, sampler.stop()
 
     launches0 = _cabi.launch_count()
     dt, wall, exit_ms, clk = timed(False)
-    launches_eager_part = _cabi.launch_count() - launches0
+    exit_wall_ms = region.exit_wall_ms
+    est_stats = region.stats
     reset_quantizers()
     dt_e2e, _, _, clk_e2e = timed(True)
+    # ---- the same steps under other schedules (context, each its own estimate_ranges block) -----------------
+    ablation = {}
+    short = max(3, min(args.steps, 5))
+    for name, kw in (("eager_no_cuda_graph", dict(graph=False, memoize=memo)),
+                     ("memoize_parameters_on" if not memo else "memoize_parameters_off", dict(graph=use_graph, memoize=not memo)),
+                     ("no_dedupe_no_memoize", dict(graph=use_graph, memoize=False, dedupe=False))):
+        reset_quantizers()
+        d, _ = region(short, dev_tokens, e2e=False, **kw)
+        d = allmax_value(d, dev, world)
+        ablation[name] = {"tokens_per_s": round(world * short * seq / d, 1), "ms_per_step": round(1e3 * d / short, 3), "steps": short}
     # ---- instrumented eager pass for the roofline of the dominant kernel ------------------------
     reset_quantizers()
     lc0 = _cabi.launch_count()
-    region(1, dev_tokens, e2e=False, graph=False)
+    region(1, dev_tokens, e2e=False, graph=False, memoize=memo)
     launches_per_step = (_cabi.launch_count() - lc0) / (1 + args.warmup)
     reset_quantizers()
     census = KernelCensus(ff)
-    with torch.no_grad(), ff.estimate_ranges(model, ff.range_setting.running_minmax()):
+    with torch.no_grad(), ff.estimate_ranges(model, make_estimator(memo)):
         static_tokens.copy_(dev_tokens[0])
         model(static_tokens)                      # first forward of a block materialises the lazy parameters
         census.install()
@@ -529,32 +658,49 @@ def run_ours(args):
     per_op = census.replay()
     qlin = qlinear.stats()
 
-    def allmax(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    dt, dt_e2e = allmax(dt), allmax(dt_e2e)
+    dt, dt_e2e = allmax_value(dt, dev, world), allmax_value(dt_e2e, dev, world)
+    exit_ms = allmax_value(exit_ms, dev, world)
     tokens = world * args.steps * seq
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+    int8_peak = 2.0 * bf16_peak      # kind::i8 issues at twice the kind::f16 rate on sm_100
+
+    # ---- pieces measured on EVERY rank (replicas / shards) and aggregated ------------------------------------
+    extras = cfg3 = cfg5 = None
+    int8_lib_peak = None
+    if not args.skip_extras:
+        del census
+        torch.cuda.empty_cache()
+        int8_lib_peak = measure_int8_library_peak(dev)
+        extras = measure_extras(ff, dev, hbm_peak, int8_peak, int8_lib_peak)
+        if world > 1:      # configs[3] sharded over M: every rank runs its own 8192-token shard; aggregate = sum
+            ent = extras["w8a8_linear_8192x14336x4096"]
+            tot = _dist_reduce([ent["TOPS"]], dist.ReduceOp.SUM, dev, world)[0]
+            mn = _dist_reduce([-ent["TOPS"]], dist.ReduceOp.MAX, dev, world)[0]
+            ent.update(aggregate_TOPS_all_ranks=round(tot, 1), min_rank_TOPS=round(-mn, 1), ranks=world,
+                       sharding="rows of X (8192 tokens per rank), W replicated, no collective")
+        if args.shape == "8b" and args.workload == "calib":
+            cfg3 = measure_cfg3(ff, sh, dev, rank, world, hbm_peak)
+            cfg5 = measure_cfg5(ff, dev, rank, world)
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
-        int8_peak = 2.0 * bf16_peak      # kind::i8 issues at twice the kind::f16 rate on sm_100
         dominant = max(per_op.items(), key=lambda kv: kv[1]["total_ms"]) if per_op else (None, None)
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of one
-        # decoder layer (profiles/r01s3_ncu_full_layer.md) -- a profiler figure, never measured inside this run
-        try:
-            ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        except OSError:
-            ncu_traffic = {}
+        # decoder layer -- a profiler figure, never measured inside this run
+        ncu_traffic = {}
+        for fn in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                break
+            except OSError:
+                continue
 
         def traffic_of(kind):
             key = "w8a8_gemm2_kernel" if kind.startswith("w8a8") else None
@@ -567,36 +713,36 @@ def run_ours(args):
                 roofline = dict(bound="tensor", kernel=dominant[0], achieved=round(d["rate"] / 1e12, 1), peak=int8_peak,
                                 unit="TOP/s", frac=round(d["rate"] / 1e12 / int8_peak, 4), traffic=traffic_of(dominant[0]),
                                 traffic_unit="DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the "
-                                             "7 linears of a layer; profiles/r01s3_ncu_full_layer.md); int8 operands + bf16 output "
-                                             "are 67.7 MB per launch algorithmic, the rest is served by L2",
+                                             "7 linears of a layer); int8 operands + bf16 output are 67.7 MB per launch algorithmic, "
+                                             "the rest is served by L2",
                                 peak_source="2 x MEASURED_PEAKS.json bf16_tflops (burst): int8 MMA issues at twice the bf16 rate",
+                                frac_of_library_int8_sustained=(round(d["rate"] / 1e12 / int8_lib_peak, 4) if int8_lib_peak else None),
                                 algorithmic="2*M*N*K ops per launch, M=2048 (the step's 224 linears)")
             else:
                 roofline = dict(bound="hbm", kernel=dominant[0], achieved=round(d["rate"] / 1e9, 1), peak=hbm_peak, unit="GB/s",
                                 frac=round(d["rate"] / 1e9 / hbm_peak, 4), traffic=None, peak_source=peak_src)
             roofline.update(avg_launch_us=d["avg_us"], launches_per_step=d["launches"], kernel_ms_per_step=d["total_ms"],
                             method="all launches of this kind in one step replayed back to back from a CUDA graph, CUDA events on the launching stream")
-        extras = None
-        if not args.skip_extras:
-            torch.cuda.empty_cache()
-            extras = measure_extras(ff, dev, hbm_peak, int8_peak)
-        cpu_baseline = None
-        ref_eager_cuda = None
+        cpu_baseline = drop_in = cfg1_ref = None
         if not args.skip_cpu_baseline:
-            cpu_baseline = run_reference_sample(args, sh, sample_layers=args.cpu_sample_layers, steps=3, warmup=1)
-            ref_eager_cuda = measure_reference_eager_cuda(args, sh, dev)
+            import bench_reference as br
+            cpu_baseline = br.cpu_calibration(sh, seq, layers, args.cpu_sample_layers, steps=3, warmup=1)
+            if br.reference_available() and args.shape == "8b":
+                cfg1_ref = br.cfg1_fake_quant(dev, compiled=not args.skip_compiled_baseline)
+                if not args.skip_drop_in:
+                    del model
+                    torch.cuda.empty_cache()
+                    drop_in = br.gpu_calibration(sh, seq, layers, dev)
+        config = workload_config(sh, layers, seq, world)
+        schedule = {"cuda_graph": use_graph, "dedupe_shared_inputs": True, "memoize_parameters": memo,
+                    "note": "how THIS arm runs the config's steps; every timed step re-quantizes every weight unless "
+                            "memoize_parameters is true"}
         line = {
-            "metric": "calib tokens/s (Llama-3-8B-shape W8 per-channel / A8 per-tensor RunningMinMax calibration, seq 2048)"
-            if args.shape == "8b" else f"calib tokens/s ({sh.name})",
+            "metric": METRIC_8B if args.shape == "8b" else f"calib tokens/s ({sh.name})",
             "value": round(tokens / dt, 1), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 data / fp32 quantizer arithmetic / int8 codes", "data": "synthetic",
-            "config": {"workload": f"{sh.name} decoder stack ({layers} layers, 7 quantized linears each), W8 PerChannel(0) symmetric + "
-                                   f"A8 PerTensor asymmetric LinearQuantizers (int8 codes), estimate_ranges(running_minmax), "
-                                   f"batch [1,{seq}] per GPU per step, random-init normal(0,0.02), no lm_head",
-                       "parallelism": f"dp{world} calibration, one MIN/MAX all-reduce of ranges at block exit",
-                       "cuda_graph": use_graph,
-                       "l2": "per-step working set (>= 14 GB of weights re-quantized every step) exceeds the 126 MB L2"},
+            "config": config, "schedule": schedule,
             "e2e": {"value": round(tokens / dt_e2e, 1), "unit": "tokens/s", "h2d_bytes_per_step": seq * 8,
                     "d2h_bytes_per_step": 4, "clocks": clk_e2e},
             "gpu_launches": int(round(launches_per_step * args.steps)),
@@ -605,62 +751,82 @@ def run_ours(args):
             "kernels": {k: dict(launches=v["launches"], ms_per_step=v["total_ms"], avg_us=v["avg_us"],
                                 rate=(f"{v['rate'] / 1e12:.0f} TOP/s" if k.startswith("w8a8") else f"{v['rate'] / 1e9:.0f} G(B|elem)/s"))
                         for k, v in per_op.items()},
-            "qlinear": qlin, "extras": extras, "reference_eager_cuda": ref_eager_cuda,
-            "peaks": {"hbm_GBps": hbm_peak, "int8_TOPS": int8_peak, "note": "hbm and bf16 from MEASURED_PEAKS.json; int8 = 2 x measured bf16 burst"},
-            "wall_s_timed_region": round(wall, 3), "block_exit_ms": round(exit_ms, 2),
+            "estimator": est_stats, "ablation": ablation,
+            "qlinear": qlin, "extras": extras, "cfg3_wq4": cfg3, "cfg5_70b_w4a16": cfg5,
+            "cfg1_reference": cfg1_ref, "drop_in": drop_in,
+            "peaks": {"hbm_GBps": hbm_peak, "int8_TOPS": int8_peak, "int8_library_sustained_TOPS": (round(int8_lib_peak, 1) if int8_lib_peak else None),
+                      "note": "hbm and bf16 from MEASURED_PEAKS.json; int8 = 2 x measured bf16 burst; int8_library_sustained = "
+                              "torch._int_mm (cuBLASLt) 8192^3 measured in this run"},
+            "wall_s_timed_region": round(wall, 3), "block_exit_ms": round(exit_ms, 2), "block_exit_wall_ms": round(exit_wall_ms, 2),
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
+def allmax_value(v, dev, world):
+    if world == 1:
+        return v
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the same workload on the host cores
+# reference arms: the unmodified reference (oracle/_ref) through its own public API
 # ---------------------------------------------------------------------------------------------
-def run_reference_sample(args, sh, sample_layers, steps, warmup):
-    import bench_workloads as bw
-    from oracle import workload as ow
-
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    seq = args.seq
-    model = bw.DecoderStack(sh, layers=sample_layers, dtype=torch.bfloat16, device="cpu")
-    bw.init_weights_(model, seed=0)
-    ow.oracle_calibration_model(model)
-    g = torch.Generator().manual_seed(1234)
-    toks = [torch.randint(0, sh.vocab, (1, seq), generator=g) for _ in range(warmup + steps)]
-    with torch.no_grad():
-        for i in range(warmup):
-            model(toks[i])
-        t0 = time.perf_counter()
-        for i in range(steps):
-            model(toks[warmup + i])
-        dt = time.perf_counter() - t0
-    full_layers = args.layers or sh.layers
-    tok_s = steps * seq / (dt * full_layers / sample_layers)
-    return dict(value=round(tok_s, 2), unit="tokens/s", cores=cores, kind="port",
-                sample=f"{sample_layers} of {full_layers} decoder layers at seq {seq}, {steps} step(s), bf16, "
-                       f"torch CPU eager ops in the reference's order (oracle/workload.py); tokens/s scaled by "
-                       f"{sample_layers}/{full_layers}", seconds=round(dt, 2))
-
-
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU eager path on the host cores.  K timed steps are really run; a step
+    is one calibration forward of a bounded sample of the workload (`--cpu-sample-layers` of the decoder layers, same
+    per-layer shapes), `ms_per_step` is that step's measured time and tokens/s is scaled to the full depth."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import bench_reference as br
+
     sh = shape_of(args.shape)
-    cb = run_reference_sample(args, sh, sample_layers=args.cpu_sample_layers, steps=max(1, min(args.steps, 3)),
-                              warmup=min(args.warmup, 1))
+    layers = args.layers or sh.layers
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cb = br.cpu_calibration(sh, args.seq, layers, args.cpu_sample_layers, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference",
-        "metric": "calib tokens/s (Llama-3-8B-shape W8 per-channel / A8 per-tensor RunningMinMax calibration, seq 2048)"
-        if args.shape == "8b" else f"calib tokens/s ({sh.name})",
-        "value": cb["value"], "unit": "tokens/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * args.seq / cb["value"], 1),
+        "metric": METRIC_8B if args.shape == "8b" else f"calib tokens/s ({sh.name})",
+        "value": cb["value"], "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_sample_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (CPU eager)", "data": "synthetic",
-        "config": {"workload": f"{sh.name} decoder stack, same quantizers and batches as the GPU arm; CPU sample: {cb['sample']}"},
+        "config": workload_config(sh, layers, args.seq, world),
+        "sampling": {"layers_per_step": args.cpu_sample_layers, "of_layers": layers,
+                     "note": "ms_per_step is the measured time of one sampled step; value = seq / (ms_per_step x of_layers / layers_per_step)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_reference_plugin(args):
+    """`--impl reference+plugin`: the drop-in measured -- the unmodified reference's host code on cuda:0, alone and with
+    this repository's kernels registered through plugin.install().  Eager, no CUDA graph (the reference's estimator
+    synchronises the host twice per quantizer per forward)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import bench_reference as br
+
+    sh = shape_of(args.shape)
+    layers = args.layers or sh.layers
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    res = br.gpu_calibration(sh, args.seq, layers, dev, steps=args.steps, warmup=args.warmup)
+    best = res["reference_plus_plugin_estimators"]
+    line = {
+        "impl": "reference+plugin",
+        "metric": METRIC_8B if args.shape == "8b" else f"calib tokens/s ({sh.name})",
+        "value": best["tokens_per_s"], "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 data / fp32 quantizer arithmetic / int8 codes", "data": "synthetic",
+        "config": workload_config(sh, layers, args.seq, 1), "drop_in": res,
     }
     print(json.dumps(line))
 
@@ -760,6 +926,8 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference+plugin":
+        run_reference_plugin(a)
     elif a.workload == "wq4":
         run_wq4(a)
     else:

@@ -154,6 +154,7 @@ def quantize_for_w8a8(ff, model: torch.nn.Module, w_bits: int = 8, a_bits: int =
 
     extra = ff.surrogate_quantized_modules(model)
     ff.quantize_model(model, extra_conversion=extra)
+    ff.set_strict_quantization(False)      # as the quick-start does (quick_start_quantize_llms.nb.py:145): stubs stay stubs
     qdt = torch.int8 if int8_codes else None
     ff.find_quantizers(model, "**/layers/**/[quantizer:parameter/weight]").initialize(
         ff.nn.LinearQuantizer, num_bits=w_bits, granularity=w_granularity or ff.PerChannel(0), quantized_dtype=qdt)

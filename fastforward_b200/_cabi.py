@@ -60,6 +60,21 @@ class Layout(ctypes.Structure):
     ]
 
 
+class Requant(ctypes.Structure):
+    """ffq_requant_t: the output quantizer fused into the W8A8 epilogue"""
+
+    _fields_ = [
+        ("scale", ctypes.c_void_p),
+        ("offset", ctypes.c_void_p),
+        ("num_bits", ctypes.c_double),
+        ("codes", ctypes.c_void_p),
+        ("rowsum", ctypes.c_void_p),
+    ]
+
+
+ABI_VERSION = 2
+
+
 @functools.lru_cache(maxsize=4096)
 def make_layout(shape: tuple, tile: tuple) -> Layout:
     if len(shape) != len(tile):
@@ -111,8 +126,7 @@ def _load() -> ctypes.CDLL:
         "ffq_minmax": (i32, [vp, i32, vp, vp, vp, vp, i32, vp, lp, vp, sz, vp]),
         "ffq_params_for_range": (i32, [vp, vp, i32, i64, dbl, i32, i32, i32, vp, i32, vp, i32, vp, sz, vp]),
         "ffq_dynamic_quantize": (i32, [vp, i32, vp, i32, vp, vp, lp, dbl, i32, i32, vp, sz, vp]),
-        "ffq_qlinear_w8a8": (i32, [vp, vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, vp, sz, vp]),
-        "ffq_qlinear_workspace_bytes": (sz, [i64]),
+        "ffq_qlinear_w8a8": (i32, [vp, vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, i32, ctypes.POINTER(Requant), vp]),
         "ffq_rowsum_i8": (i32, [vp, vp, i64, i64, vp]),
         "ffq_fakequant_fwd_bwd_host": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, lp, dbl, i32]),
         "ffq_selftest_shared_div": (i32, [ctypes.c_uint64, ctypes.c_uint32, vp, vp]),
@@ -131,8 +145,9 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.ffq_abi_version() != 1:
-        raise ImportError(f"fastforward_b200: ABI version mismatch ({lib.ffq_abi_version()} != 1)")
+    if lib.ffq_abi_version() != ABI_VERSION:
+        raise ImportError(f"fastforward_b200: ABI version mismatch ({lib.ffq_abi_version()} != {ABI_VERSION}); rebuild "
+                          "the library (make -C fastforward_b200/csrc)")
     return lib
 
 
@@ -140,7 +155,7 @@ lib = _load()
 EXPORTED = (
     "ffq_abi_version ffq_last_error ffq_launch_count ffq_workspace_bytes ffq_num_tiles ffq_quantize "
     "ffq_dequantize ffq_fakequant_fwd ffq_quantize_bwd ffq_minmax ffq_params_for_range "
-    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_qlinear_workspace_bytes ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16 "
+    "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16 "
     "ffq_calibrate_quantize ffq_calibrate_quantize_mode ffq_calibrate_quantize_workspace_bytes ffq_gptq_block "
     "ffq_params_for_ranges_batched ffq_params_for_ranges_encode ffq_calibrate_fakequant"
 ).split()
@@ -179,6 +194,30 @@ def current_stream(device: torch.device) -> int:
     if _raw_stream is not None:
         return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_of(device: torch.device):
+    """Context manager that makes ``device`` current for the C-ABI calls inside it -- the library launches on the
+    stream it is given but reads per-device state (SM count, opt-in shared-memory attributes, occupancy) from the
+    current device.  Free when the device is already current (the usual one-process-per-GPU case)."""
+    idx = device.index
+    if idx is None or _get_device is None or idx == _get_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:

@@ -25,9 +25,8 @@
 
 #include <cstdlib>
 
-#include <map>
-#include <mutex>
-#include <tuple>
+#include <atomic>
+#include <cmath>
 
 #include "ffq_common.cuh"
 #include "ffq_umma.cuh"
@@ -41,34 +40,116 @@ constexpr int A_STAGE = BM * BK, B_STAGE = BN * BK;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;   // 48 KB
 constexpr int GEMM_THREADS = 192;                // 6 warps
 constexpr int TMEM_COLS = 512;                   // 2 accumulators x 256 columns
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 4 * BN * 4 + 256 + 1024;   // + column params + barriers + align
+constexpr int COL_BYTES = 5 * BN * 4;            // per-column epilogue parameters (COL_SLOTS x BN words)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + COL_BYTES + 256 + 1024;   // + column params + barriers + align
 
 struct GemmArgs {
   int M, N, K;
-  void* y; int y_dt;
+  void* y; int y_dt;                            // may be null when only the requantized codes are wanted
   const float* sx; const float* ox;             // activation scale / offset (one element each; ox may be null)
   const float* sw; const float* ow;             // per output column (ow may be null)
   const int32_t* rowsum_w;                      // per output column: sum_k qw[n,k]
   const void* bias; int bias_dt;                // per output column, optional
   const int32_t* rowsum_x;                      // per output row; used with ow
-  int bn;                                       // pair kernel: output columns per tile (256, or 224 when that evens out the waves)
+  int bn;                                       // output columns per tile (256; 224 / 128 when that evens out the waves)
+  // fused output quantizer (ffq_requant_t): per-tensor, int8 codes of the output rounded to y_dt
+  const float* rq_scale; const float* rq_offset; float rq_lo, rq_hi; int8_t* rq_codes; int32_t* rq_rowsum;
 };
+
+constexpr int COL_SLOTS = 5;                     // alpha, bias, int constant, weight offset, float constant
 
 // Per-column epilogue parameters of one tile, derived where they are consumed (no separate launch, no scratch):
 //   alpha[n] = sx*sw[n];  bias[n] as float;  cnst[n] = ox*rowsum_w[n] + K*ox*ow[n];  own[n] = ow[n]
-// with ox, ow rounded to integers exactly as dequantize_by_tile rounds them.
-__device__ __forceinline__ void stage_col_params(const GemmArgs& g, int n0, int bn, int tid, int nthreads,
+// with ox, ow rounded to integers exactly as dequantize_by_tile rounds them.  The int32 form of the constant and of
+// own*rowsum_x is exact; when a column's terms could leave int32 (offsets far from zero relative to the range's
+// width) the function returns true and the tile's epilogue adds the same terms in float, as the reference's
+// dequantize-then-float path does.
+__device__ __forceinline__ bool stage_col_params(const GemmArgs& g, int n0, int bn, int tid, int nthreads,
                                                  float* col_params, int32_t* col_ints) {
   const float sx = g.sx[0];
-  const int o_x = g.ox ? __float2int_rn(rintf(g.ox[0])) : 0;
+  const float oxf = g.ox ? rintf(g.ox[0]) : 0.f;
+  const long long o_x = (long long)oxf;
+  bool wide = !(fabsf(oxf) < 1.0e9f);
   for (int c = tid; c < bn; c += nthreads) {
     const int n = n0 + c;
     const bool in = n < g.N;
-    const int o_w = (in && g.ow) ? __float2int_rn(rintf(g.ow[n])) : 0;
+    const float owf = (in && g.ow) ? rintf(g.ow[n]) : 0.f;
+    const long long o_w = (long long)owf;
+    const long long c64 = in ? o_x * (long long)g.rowsum_w[n] + (long long)g.K * o_x * o_w : 0;
+    // |acc| <= K * 2^14, |own * rowsum_x| <= |o_w| * K * 2^7
+    const long long bound = (c64 < 0 ? -c64 : c64) + (o_w < 0 ? -o_w : o_w) * (long long)g.K * 128 + (long long)g.K * 16384;
+    wide = wide || !(fabsf(owf) < 1.0e9f) || bound >= 0x7fffffffll;
     col_params[c] = in ? sx * g.sw[n] : 0.f;
     col_params[bn + c] = (in && g.bias) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
-    col_ints[2 * bn + c] = in ? o_x * g.rowsum_w[n] + g.K * o_x * o_w : 0;
-    col_ints[3 * bn + c] = o_w;
+    col_ints[2 * bn + c] = (int32_t)c64;
+    col_ints[3 * bn + c] = (int32_t)o_w;
+    col_params[4 * bn + c] = in ? (oxf * (float)g.rowsum_w[n] + (float)g.K * oxf * owf) : 0.f;
+  }
+  return wide;
+}
+
+// barrier over the 4 epilogue warps that also ORs a predicate (the tile's "wide constants" decision)
+__device__ __forceinline__ bool epilogue_bar_or(bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %1, 0;\n\t"
+      "barrier.cta.red.or.pred q, 1, 128, p;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
+
+// One 32-column chunk of one accumulator row: offset corrections, dequantisation, optional requantisation, stores.
+template <typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&acc)[32], const float* col_params,
+                                               const int32_t* col_ints, int bn, int c0, bool wide, int32_t rx, int row,
+                                               int n0, float rq_s, float rq_o, int& rq_sum) {
+  float v[32];
+  if (!wide) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int32_t t = (int32_t)acc[j] + col_ints[2 * bn + c0 + j] + col_ints[3 * bn + c0 + j] * rx;
+      v[j] = fmaf(col_params[c0 + j], (float)t, col_params[bn + c0 + j]);
+    }
+  } else {
+    const float rxf = (float)rx;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = (float)(int32_t)acc[j] + col_params[4 * bn + c0 + j] + (float)col_ints[3 * bn + c0 + j] * rxf;
+      v[j] = fmaf(col_params[c0 + j], t, col_params[bn + c0 + j]);
+    }
+  }
+  if (row >= g.M || n0 >= g.N) return;
+  const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
+  if (g.y) store_chunk<OutT>(static_cast<OutT*>(g.y) + (size_t)row * g.N + n0, v, ncols);
+  if (g.rq_codes) {
+    // output_quantizer(y): y is first rounded to the output dtype (what the quantizer would read back), then
+    // quantize_by_tile's arithmetic in the promoted dtype of (y, fp32 scale) = fp32
+    uint32_t packed[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = 4 * w + b;
+        const float yr = Elem<OutT>::to_f(Elem<OutT>::from_f(v[j]));
+        float t = __fsub_rn(__fdiv_rn(yr, rq_s), rq_o);
+        t = nan_clamp(rintf(t), g.rq_lo, g.rq_hi);
+        const int c = __float2int_rz(t);
+        word |= ((uint32_t)c & 0xffu) << (8 * b);
+        if (j < ncols) rq_sum += c;
+      }
+      packed[w] = word;
+    }
+    int8_t* dst = g.rq_codes + (size_t)row * g.N + n0;
+    if (ncols == 32 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      *reinterpret_cast<uint4*>(dst + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols) dst[j] = (int8_t)((packed[j >> 2] >> (8 * (j & 3))) & 0xffu);
+    }
   }
 }
 
@@ -78,9 +159,9 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* col_params = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [4][BN]
+  float* col_params = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [COL_SLOTS][bn]
   int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * BN * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + COL_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;   // [2]
@@ -162,7 +243,8 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===== epilogue (warps 2..5): TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int ep_tid = threadIdx.x - 64;                     // 0..127
-    OutT* __restrict__ y = static_cast<OutT*>(g.y);
+    const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
+    const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile % tiles_m, tn = tile / tiles_m;
@@ -170,10 +252,10 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t use = (uint32_t)(it >> 1);
       // stage this tile's column parameters in shared memory (named barrier over the 4 epilogue warps)
       asm volatile("bar.sync 1, 128;" ::: "memory");         // previous tile's readers are done
-      stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool wide = epilogue_bar_or(stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints));
       const int row = tm * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
+      int rq_sum = 0;
 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
@@ -182,18 +264,9 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int c0 = 0; c0 < bn; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int32_t t = (int32_t)acc[j] + col_ints[2 * bn + c0 + j] + col_ints[3 * bn + c0 + j] * rx;
-          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[bn + c0 + j]);
-        }
-        const int n0 = tn * bn + c0;
-        if (row < g.M && n0 < g.N) {
-          const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
-          store_chunk<OutT>(y + (size_t)row * g.N + n0, v, ncols);
-        }
+        epilogue_chunk<OutT>(g, acc, col_params, col_ints, bn, c0, wide, rx, row, tn * bn + c0, rq_s, rq_o, rq_sum);
       }
+      if (g.rq_rowsum && row < g.M) atomicAdd(&g.rq_rowsum[row], rq_sum);     // integer: exact, order independent
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);          // 4 arrivals (one per epilogue warp) free the accumulator
@@ -208,44 +281,53 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ================================================================================================
-// 2-CTA variant: a CTA pair (cluster 2x1x1, two SMs of one TPC) owns a 256x256 output tile.
-// Each CTA stages its own 128 rows of A and its own 128-row half of B (32 KB per k-block instead of
-// 48 KB: the operand traffic per MMA drops by a third, which is what bounds the 1-CTA kernel), the
-// leader CTA issues tcgen05.mma.cta_group::2 (M=256) reading both CTAs' shared memory, and each
-// CTA's TMEM holds its 128 accumulator rows.  TMA completions of both CTAs land on the leader's
-// "full" barrier (cta_group::2 loads), tcgen05.commit multicasts "slot free" / "tile ready" to both
-// CTAs, and the peer's epilogue warps release the accumulator on the leader's barrier.
+// CTA-pair variant, in clusters of P pairs.  A CTA pair (two SMs of one TPC) owns a 256 x bn output tile: each
+// CTA stages its own 128 rows of A and its own half of the tile's B rows (32 KB per k-block instead of 48 KB:
+// operand delivery from L2 is what bounds the kernel), the pair's leader issues tcgen05.mma.cta_group::2 (M = 256)
+// reading both CTAs' shared memory, and each CTA's TMEM holds its 128 accumulator rows.
+// With P > 1 the P pairs of a cluster work on P consecutive M tiles of the SAME B panel, and each B half is
+// fetched from L2 once per cluster: CTA (pair p, rank r) loads slice p of "B half r" and TMA-multicasts it to the
+// rank-r CTA of every pair, so a CTA receives 16 KB of A + 16/P KB of B per k-block from L2 (P = 1: 32 KB,
+// P = 2: 24 KB, P = 4: 20 KB) while its shared memory still fills with the whole 32 KB.
+// Barriers: TMA completions of a pair (its own A loads and every B slice multicast into it) land on the pair
+// leader's "full" barrier; a stage is refilled only after ALL P pairs have consumed it, because every pair writes
+// into every other pair's stage (tcgen05.commit multicast to the whole cluster, "empty" barriers count P);
+// "tile ready" goes to the pair only, and the pair's 8 epilogue warps release the accumulator on the leader.
 // ================================================================================================
 constexpr int STAGES2 = 6;
 constexpr int HALF_STAGE = A_STAGE + BM * BK;      // A 128x128B + B half 128x128B = 32 KB
-constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + 4 * BN * 4 + 256 + 1024;
-template <typename OutT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + COL_BYTES + 256 + 1024;
+template <typename OutT, int P>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE);       // [4][BN]
+  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE);       // [COL_SLOTS][bn]
   int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + 4 * BN * 4);
-  uint64_t* full_bar = bars;                  // [STAGES2]  (the leader's copy is the one in use)
-  uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  (each CTA waits on its own copy)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + COL_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES2]  (the pair leader's copy is the one in use)
+  uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  (each CTA waits on its own copy; P arrivals)
   uint64_t* tmem_full = bars + 2 * STAGES2;   // [2]        (each CTA waits on its own copy)
-  uint64_t* tmem_empty = bars + 2 * STAGES2 + 2;   // [2]   (leader's copy, 8 arrivals)
+  uint64_t* tmem_empty = bars + 2 * STAGES2 + 2;   // [2]   (pair leader's copy, 8 arrivals)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
 
+  constexpr int CSIZE = 2 * P;                // CTAs per cluster
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t cta = crank & 1u;            // rank inside the pair
+  const int p = (int)(crank >> 1);            // pair inside the cluster
+  const int cluster = blockIdx.x / CSIZE, num_clusters = gridDim.x / CSIZE;
   constexpr int TM = 2 * BM;                  // 256 rows per pair tile
-  const int bn = g.bn;                       // columns per tile; the smem / TMEM layout keeps its 256-column pitch
+  const int bn = g.bn;                        // columns per tile; the smem / TMEM layout keeps its 256-column pitch
   const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + bn - 1) / bn;
+  const int groups_m = (tiles_m + P - 1) / P; // P consecutive M tiles share one B panel
   const uint32_t stage_tx = 2u * (uint32_t)(A_STAGE + (bn / 2) * BK);
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = groups_m * tiles_n;   // cluster tiles
   const int k_blocks = (g.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -255,43 +337,53 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc_fence_before();
-  cluster_sync_all();                         // barriers of BOTH CTAs are initialised before any remote use
+  cluster_sync_all();                         // barriers of ALL CTAs are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (both CTAs; completions count on the leader's full barrier) =====
+    // ===== TMA producer (every CTA; completions count on the pair leaders' full barriers) =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      const int slice = (bn / 2) / P;         // B rows this CTA fetches for all rank-`cta` CTAs of the cluster
+      uint16_t mc_mask = 0;
+#pragma unroll
+      for (int q = 0; q < P; ++q) mc_mask |= (uint16_t)(1u << (2 * q + (int)cta));
       int stage = 0; uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
+      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+        const int tm = (tile % groups_m) * P + p, tn = tile / groups_m;     // tm >= tiles_m: zero-filled rows
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * HALF_STAGE;
           if (cta == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
-          tma_load_2d_pair(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * bn + (int)cta * (bn / 2));
+          if constexpr (P == 1) {
+            tma_load_2d_pair(sa + A_STAGE, &map_b, &full_bar[stage], kb * BK, tn * bn + (int)cta * (bn / 2));
+          } else {
+            tma_load_2d_pair_mc(sa + A_STAGE + p * slice * BK, &map_b, &full_bar[stage], kb * BK,
+                                tn * bn + (int)cta * (bn / 2) + p * slice, mc_mask);
+          }
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA only) =====
+    // ===== MMA issuer (pair leaders only) =====
     if (cta == 0 && lane == 0) {
       // D=S32, A=B=signed int8, K-major, N=bn, M=256 (128 rows in each CTA)
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint16_t all_mask = (uint16_t)((1u << CSIZE) - 1u), pair_mask = (uint16_t)(3u << (2 * p));
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      for (int tile = cluster; tile < num_tiles; tile += num_clusters, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        mbar_wait_bounded(&tmem_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_bounded(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * HALF_STAGE);
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_STAGE);
@@ -300,47 +392,39 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             umma_i8_pair(tmem_d, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), idesc,
                          (kb | k) ? 1u : 0u);
           }
-          umma_commit_pair(&empty_bar[stage]);               // both CTAs' producers may refill the slot
-          if (kb == k_blocks - 1) umma_commit_pair(&tmem_full[buf]);
+          umma_commit_mc(&empty_bar[stage], all_mask);       // every producer of the cluster may refill the slot
+          if (kb == k_blocks - 1) umma_commit_mc(&tmem_full[buf], pair_mask);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ===== epilogue (warps 2..5 of both CTAs): this CTA's 128 rows =====
+    // ===== epilogue (warps 2..5 of every CTA): this CTA's 128 rows =====
     const int quad = warp & 3;
     const int ep_tid = threadIdx.x - 64;
-    OutT* __restrict__ y = static_cast<OutT*>(g.y);
+    const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
+    const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
     int it = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int tm = tile % tiles_m, tn = tile / tiles_m;
+    for (int tile = cluster; tile < num_tiles; tile += num_clusters, ++it) {
+      const int tm = (tile % groups_m) * P + p, tn = tile / groups_m;
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const bool wide = epilogue_bar_or(stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints));
       const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
+      int rq_sum = 0;
 
-      mbar_wait(&tmem_full[buf], use & 1);
+      mbar_wait_bounded(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < bn; c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int32_t t = (int32_t)acc[j] + col_ints[2 * bn + c0 + j] + col_ints[3 * bn + c0 + j] * rx;
-          v[j] = fmaf(col_params[c0 + j], (float)t, col_params[bn + c0 + j]);
-        }
-        const int n0 = tn * bn + c0;
-        if (row < g.M && n0 < g.N) {
-          const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
-          store_chunk<OutT>(y + (size_t)row * g.N + n0, v, ncols);
-        }
+        epilogue_chunk<OutT>(g, acc, col_params, col_ints, bn, c0, wide, rx, row, tn * bn + c0, rq_s, rq_o, rq_sum);
       }
+      if (g.rq_rowsum && row < g.M) atomicAdd(&g.rq_rowsum[row], rq_sum);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);   // 8 arrivals (4 warps x 2 CTAs) free the accumulator
@@ -348,7 +432,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 
   tc_fence_before();
-  cluster_sync_all();                         // nobody leaves while the peer may still touch its smem / barriers
+  cluster_sync_all();                         // nobody leaves while a peer may still touch its smem / barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
@@ -401,8 +485,6 @@ using namespace ffq;
 
 extern "C" {
 
-size_t ffq_qlinear_workspace_bytes(int64_t N) { (void)N; return 0; }
-
 int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream) {
   if (R <= 0) return FFQ_OK;
   rowsum_i8_kernel<<<(unsigned int)((R + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, rowsum, R, K);
@@ -410,10 +492,67 @@ int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* 
   return FFQ_OK;
 }
 
+}  // extern "C"
+
+// cluster launch of the pair kernel: P pairs (2P CTAs) per cluster
+template <typename OutT, int P>
+static int launch_pairs(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, long long cluster_tiles,
+                        cudaStream_t st) {
+  static std::atomic<uint64_t> attr_done{0};
+  static int max_clusters[64] = {0};
+  auto kern = w8a8_gemm2_kernel<OutT, P>;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  const cudaError_t e = once_per_device(attr_done, [&]() -> cudaError_t {
+    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
+    if (r != cudaSuccess) return r;
+    if (P > 4) { r = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (r != cudaSuccess) return r; }
+    cfg.gridDim = dim3(2 * P * (sm_count() / (2 * P)));
+    int n = 0;
+    r = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);      // GPCs with an SM count that 2P does not divide fit fewer
+    if (r != cudaSuccess) return r;
+    max_clusters[dev] = n > 0 ? n : 1;
+    return cudaSuccess;
+  });
+  if (e != cudaSuccess) { set_error("qlinear_w8a8: cannot configure the %d-CTA cluster kernel: %s", 2 * P, cudaGetErrorString(e)); return FFQ_ERR_CUDA; }
+  const long long clusters = cluster_tiles < max_clusters[dev] ? cluster_tiles : max_clusters[dev];
+  cfg.gridDim = dim3((unsigned)(2 * P * clusters));
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, g);
+  count_launch();
+  if (le != cudaSuccess) { cudaGetLastError(); set_error("qlinear_w8a8: cluster launch failed: %s", cudaGetErrorString(le)); return FFQ_ERR_CUDA; }
+  return FFQ_OK;
+}
+
+template <int P>
+static int launch_pairs_dt(int y_dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, long long t, cudaStream_t st) {
+  switch (y_dtype) {
+    case FFQ_F32: return launch_pairs<float, P>(a, b, g, t, st);
+    case FFQ_BF16: return launch_pairs<__nv_bfloat16, P>(a, b, g, t, st);
+    default: return launch_pairs<__half, P>(a, b, g, t, st);
+  }
+}
+
+// pairs per cluster for the pair kernel: FFQ_GEMM_CLUSTER = 2 | 4 | 8 CTAs overrides the shape heuristic
+static int env_cluster_pairs() {
+  static const int v = [] {
+    const char* e = getenv("FFQ_GEMM_CLUSTER");
+    const int c = e ? atoi(e) : 0;
+    return (c == 2 || c == 4 || c == 8) ? c / 2 : 0;
+  }();
+  return v;
+}
+
+extern "C" {
+
 int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
                      const float* sx, const float* ox, const float* sw, const float* ow, const int32_t* rowsum_w,
-                     const int32_t* rowsum_x, const void* bias, int bias_dtype, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+                     const int32_t* rowsum_x, const void* bias, int bias_dtype, const ffq_requant_t* requant,
+                     void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (M <= 0 || N <= 0) return FFQ_OK;
   if (K <= 0 || K % 16 != 0) { set_error("qlinear_w8a8: K must be a positive multiple of 16 (got %lld)", (long long)K); return FFQ_ERR_UNSUPPORTED; }
@@ -425,7 +564,7 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   }
   if (M > 0x7fffffffll || N > 0x7fffffffll || K > 0x7fffffffll) { set_error("qlinear_w8a8: dimension too large"); return FFQ_ERR_UNSUPPORTED; }
   if (ow != nullptr && rowsum_x == nullptr) { set_error("qlinear_w8a8: rowsum_x is required when the weight has an offset"); return FFQ_ERR_INVALID; }
-  (void)workspace; (void)workspace_bytes;      // kept in the ABI; the column parameters are derived inside the kernel
+  if (y == nullptr && (requant == nullptr || requant->codes == nullptr)) { set_error("qlinear_w8a8: no output requested"); return FFQ_ERR_INVALID; }
 
   CUtensorMap map_a;
   int rc;
@@ -434,6 +573,12 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.y_dt = y_dtype;
   g.sx = sx; g.ox = ox; g.sw = sw; g.ow = ow; g.rowsum_w = rowsum_w; g.bias = bias; g.bias_dt = bias_dtype;
   g.rowsum_x = rowsum_x;
+  if (requant != nullptr && requant->codes != nullptr) {
+    if (requant->scale == nullptr) { set_error("qlinear_w8a8: requant needs a scale"); return FFQ_ERR_INVALID; }
+    if (!(requant->num_bits >= 1 && requant->num_bits <= 8)) { set_error("qlinear_w8a8: requant codes are int8: num_bits must be in [1, 8]"); return FFQ_ERR_BITWIDTH; }
+    g.rq_scale = requant->scale; g.rq_offset = requant->offset; g.rq_codes = requant->codes; g.rq_rowsum = requant->rowsum;
+    g.rq_lo = -(float)exp2(requant->num_bits - 1.0); g.rq_hi = (float)exp2(requant->num_bits - 1.0) - 1.f;
+  }
   const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const long long pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   // the pair kernel needs M > 128 to have work for both CTAs; FFQ_GEMM_1CTA=1 forces the single-CTA kernel
@@ -443,44 +588,39 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   // kernel finishes the same work in half-size tiles, all at once
   const bool underfilled = pair_tiles < sm_count() / 2 && tiles <= sm_count();
   const bool use_pair = !force_1cta && M > BM && !underfilled;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    cudaError_t e1 = cudaFuncSetAttribute(w8a8_gemm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(w8a8_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaError_t e3 = cudaFuncSetAttribute(w8a8_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    attr_err = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
-    cudaError_t f1 = cudaFuncSetAttribute(w8a8_gemm2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-    cudaError_t f2 = cudaFuncSetAttribute(w8a8_gemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-    cudaError_t f3 = cudaFuncSetAttribute(w8a8_gemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES);
-    if (attr_err == cudaSuccess) attr_err = f1 != cudaSuccess ? f1 : (f2 != cudaSuccess ? f2 : f3);
-  });
-  if (attr_err != cudaSuccess) { set_error("qlinear_w8a8: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
   if (use_pair) {
     // columns per pair tile: 256, or 224 when that removes a nearly empty last wave (e.g. N = 14336 at M = 2048:
     // 448 tiles on 74 pairs = 6.05 waves -> 512 tiles = 6.92 waves of 0.94x the per-tile cost; operand delivery,
     // A 128 rows + B bn/2 rows per CTA and k-block, is what a tile costs)
     const long long pairs = sm_count() / 2;
     const long long tiles_m2 = (M + 2 * BM - 1) / (2 * BM);
+    // pairs per cluster (B multicast): only when the M tiles fill the cluster
+    int P = env_cluster_pairs();
+    if (P == 0) P = 1;
+    while (P > 1 && tiles_m2 % P != 0) P >>= 1;
     auto cost = [&](int bn) {
       const long long t = tiles_m2 * ((N + bn - 1) / bn);
-      return (double)((t + pairs - 1) / pairs) * (128.0 + bn / 2.0);
+      return (double)((t + pairs - 1) / pairs) * (128.0 + bn / 2.0 / P);
     };
     static const bool force_256 = getenv("FFQ_GEMM_BN256") != nullptr;
-    g.bn = (!force_256 && N % 32 == 0 && cost(224) < 0.97 * cost(256)) ? 224 : BN;
-    CUtensorMap map_b2;     // B box = this CTA's half of the tile's columns
-    if ((rc = make_map(&map_b2, qw, N, K, g.bn / 2)) != FFQ_OK) return rc;
-    const int max_pairs = sm_count() / 2;
-    const long long pair_tiles_bn = tiles_m2 * ((N + g.bn - 1) / g.bn);
-    const int grid2 = 2 * (int)(pair_tiles_bn < max_pairs ? pair_tiles_bn : max_pairs);
-    switch (y_dtype) {
-      case FFQ_F32: w8a8_gemm2_kernel<float><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
-      case FFQ_BF16: w8a8_gemm2_kernel<__nv_bfloat16><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
-      default: w8a8_gemm2_kernel<__half><<<grid2, GEMM_THREADS, SMEM2_BYTES, st>>>(map_a, map_b2, g); break;
+    g.bn = (!force_256 && P <= 2 && N % 32 == 0 && cost(224) < 0.97 * cost(256)) ? 224 : BN;
+    CUtensorMap map_b2;     // B box = the slice of the tile's columns this CTA fetches
+    if ((rc = make_map(&map_b2, qw, N, K, g.bn / 2 / P)) != FFQ_OK) return rc;
+    const long long cluster_tiles = (tiles_m2 / P) * ((N + g.bn - 1) / g.bn);
+    switch (P) {
+      case 4: return launch_pairs_dt<4>(y_dtype, map_a, map_b2, g, cluster_tiles, st);
+      case 2: return launch_pairs_dt<2>(y_dtype, map_a, map_b2, g, cluster_tiles, st);
+      default: return launch_pairs_dt<1>(y_dtype, map_a, map_b2, g, cluster_tiles, st);
     }
-    FFQ_LAUNCH_CHECK();
-    return FFQ_OK;
   }
+  static std::atomic<uint64_t> attr_done{0};
+  const cudaError_t attr_err = once_per_device(attr_done, []() -> cudaError_t {
+    cudaError_t e1 = cudaFuncSetAttribute(w8a8_gemm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e2 = cudaFuncSetAttribute(w8a8_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e3 = cudaFuncSetAttribute(w8a8_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    return e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+  });
+  if (attr_err != cudaSuccess) { set_error("qlinear_w8a8: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
   // single-CTA kernel: 128 x 256 tiles, or 128 x 128 when the wider ones would leave SMs idle (e.g. the k/v
   // projections, N = 1024 at M = 2048: 64 tiles -> 128 tiles on 148 SMs at two thirds of the per-tile operand traffic)
   {

@@ -32,6 +32,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Same wait, but a barrier that does not complete within ~2 s of SM clocks traps instead of hanging the GPU: a
+// protocol bug in a multi-CTA pipeline then surfaces as a launch failure the host can report.
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, polls = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    if ((++polls & 0x3ffu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
@@ -86,6 +104,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
           "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1) : "memory");
 }
+// cta_group::2 load whose box lands at the same shared-memory offset of every CTA in `mask` (cluster ranks), the bytes
+// being credited to the full barrier of each destination CTA's pair leader
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::
+          "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & PEER_MASK), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+// commit of the pair's MMAs arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                   "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
                    "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -116,7 +146,9 @@ __device__ __forceinline__ void store_chunk(OutT* dst, const float (&v)[32], int
       st_vec<OutT, PER>(dst + j, o);
     }
   } else {
-    for (int j = 0; j < ncols; ++j) dst[j] = Elem<OutT>::from_f(v[j]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)        // static indices: v stays in registers
+      if (j < ncols) dst[j] = Elem<OutT>::from_f(v[j]);
   }
 }
 

@@ -37,6 +37,21 @@ def can_support_bitwidth(dtype: torch.dtype, num_bits: float) -> bool:
     return avail + 2 >= num_bits
 
 
+def _on_device(fn):
+    """Run the op with its first tensor argument's device current (see _cabi.device_of): tensors on a GPU other than
+    the current one work, as they do in the reference (device_map-sharded models)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(first, *args, **kwargs):
+        guard = C.device_of(first.device) if isinstance(first, torch.Tensor) and first.is_cuda else C._NO_GUARD
+        if guard is C._NO_GUARD:
+            return fn(first, *args, **kwargs)
+        with guard:
+            return fn(first, *args, **kwargs)
+    return wrapped
+
+
 def _bitwidth_guard(dtype: torch.dtype, num_bits: float) -> None:
     if not can_support_bitwidth(dtype, num_bits):
         raise RuntimeError(f"Provided dtype ({dtype}) is not enough to store {num_bits} bits quantized values.")
@@ -85,6 +100,7 @@ def _prep(data: torch.Tensor, tile_size, what: str = "data"):
 
 
 # ------------------------------------------------------------------------------------------
+@_on_device
 def quantize_by_tile(
     data: torch.Tensor,
     scale: torch.Tensor,
@@ -113,6 +129,7 @@ def quantize_by_tile(
     return q
 
 
+@_on_device
 def dequantize_by_tile(
     data: torch.Tensor,
     scale: torch.Tensor,
@@ -138,6 +155,7 @@ def dequantize_by_tile(
     return y
 
 
+@_on_device
 def fake_quantize_by_tile(
     data: torch.Tensor,
     scale: torch.Tensor,
@@ -168,6 +186,7 @@ def fake_quantize_by_tile(
     return (y, codes) if return_codes else y
 
 
+@_on_device
 def quantize_by_tile_backward(
     data: torch.Tensor,
     output_grad: torch.Tensor,
@@ -214,6 +233,7 @@ def quantize_by_tile_backward(
     return [dx, dscale, doffset]
 
 
+@_on_device
 def quantize_dynamic_by_tile(
     data: torch.Tensor,
     tile_size,
@@ -254,6 +274,7 @@ def _minmax_call(x, layout, tile_min, tile_max, run_min, run_max, flags):
         C.ptr(flags), layout.ref, C.ptr(ws), ws_bytes, C.current_stream(x.device)))
 
 
+@_on_device
 def tile_minmax(data: torch.Tensor, tile_size) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per-tile ``(min, max)`` in the data dtype: ``torch.min/max(tiles_to_rows(data), -1).values``."""
     x, shape, tile, layout = _prep(data, tile_size)
@@ -266,6 +287,7 @@ def tile_minmax(data: torch.Tensor, tile_size) -> Tuple[torch.Tensor, torch.Tens
     return mn, mx
 
 
+@_on_device
 def running_minmax_update_(
     run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size,
     flags: Optional[torch.Tensor] = None,
@@ -285,6 +307,7 @@ def running_minmax_update_(
     _minmax_call(x, layout, None, None, run_min, run_max, flags)
 
 
+@_on_device
 def parameters_for_range_(
     min_range: torch.Tensor, max_range: torch.Tensor, num_bits: float, symmetric: bool, allow_one_sided: bool,
     scale_out: torch.Tensor, offset_out: Optional[torch.Tensor], round_offset: bool = False,
@@ -311,6 +334,7 @@ def parameters_for_range_(
         ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))
 
 
+@_on_device
 def calibrate_fake_quantize_(
     data: torch.Tensor, tile_size, num_bits: float, symmetric: bool, allow_one_sided: bool,
     scale_out: torch.Tensor, offset_out: Optional[torch.Tensor], quantized_dtype: Optional[torch.dtype] = None,
@@ -349,6 +373,7 @@ def calibrate_fake_quantize_(
     return out
 
 
+@_on_device
 def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor, entries) -> None:
     """``parameters_for_range_`` for many quantizers in ONE launch.  ``min_buf`` / ``max_buf``: contiguous buffers
     holding every quantizer's running range; ``entries``: ``(start, length, num_bits, symmetric, allow_one_sided,
@@ -398,6 +423,7 @@ def calibrate_quantize_mode(shape: Sequence[int], tile_size, dtype: torch.dtype)
 _CALQ_WS = int(C.lib.ffq_calibrate_quantize_workspace_bytes())
 
 
+@_on_device
 def calibrate_quantize_(
     run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size, num_bits: float,
     symmetric: bool, allow_one_sided: bool, scale_out: torch.Tensor, offset_out: Optional[torch.Tensor],
@@ -444,6 +470,7 @@ def calibrate_quantize_(
 # ------------------------------------------------------------------------------------------
 # fused MSE grid search (range_setting/min_error.py:206-216)
 # ------------------------------------------------------------------------------------------
+@_on_device
 def grid_mse(
     data: torch.Tensor, cand_scale: torch.Tensor, cand_offset: Optional[torch.Tensor], tile_size, num_bits: float,
     quantized_dtype: Optional[torch.dtype] = None,

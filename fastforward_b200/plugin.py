@@ -51,78 +51,53 @@ def _cuda_dynamic(data, tile_size, num_bits, symmetric, allow_one_sided, output_
 def install(fastforward_module: Optional[Any] = None, *, register_linear: bool = True,
             patch_estimators: bool = False) -> dict:
     """Register the B200 kernels with ``fastforward`` (imported if not given).  Idempotent."""
-    if _installed:
-        return _installed
     if fastforward_module is None:
         import fastforward as fastforward_module  # type: ignore[no-redef]
     ff = fastforward_module
-    impl = ff.quantization._quantizer_impl
-    table = {
-        "quantize_by_tile": (impl.quantize_by_tile_impl, _cuda_quantize),
-        "dequantize_by_tile": (impl.dequantize_by_tile_impl, _cuda_dequantize),
-        "quantize_by_tile_backward": (impl.quant_dequant_by_tile_grad_impl, _cuda_backward),
-        "quantize_dynamic_by_tile": (impl.quantize_dynamic_by_tile_impl, _cuda_dynamic),
-    }
-    for name, (op_def, kernel) in table.items():
-        op_def.register_kernel("cuda")(kernel)       # torch.library.custom_op -> CustomOpDef
-        _installed[name] = kernel
-    if register_linear:
+    if "quantize_by_tile" not in _installed:
+        impl = ff.quantization._quantizer_impl
+        table = {
+            "quantize_by_tile": (impl.quantize_by_tile_impl, _cuda_quantize),
+            "dequantize_by_tile": (impl.dequantize_by_tile_impl, _cuda_dequantize),
+            "quantize_by_tile_backward": (impl.quant_dequant_by_tile_grad_impl, _cuda_backward),
+            "quantize_dynamic_by_tile": (impl.quantize_dynamic_by_tile_impl, _cuda_dynamic),
+        }
+        for name, (op_def, kernel) in table.items():
+            op_def.register_kernel("cuda")(kernel)       # torch.library.custom_op -> CustomOpDef
+            _installed[name] = kernel
+    if register_linear and "linear" not in _installed:
         _installed["linear"] = _register_linear(ff)
     if patch_estimators:
-        from .range_setting import minmax as ours
-
-        ff.range_setting.running_minmax = ours.RunningMinMaxRangeEstimator
-        ff.range_setting.minmax.running_minmax = ours.RunningMinMaxRangeEstimator
-        _installed["running_minmax"] = ours.RunningMinMaxRangeEstimator
+        install_estimators(ff)
     return _installed
 
 
+def install_estimators(ff) -> None:
+    """Seam 3: ``ff.range_setting.running_minmax`` becomes the sync-free estimator (same name, same arguments).  It
+    recognises the reference's own ``LinearQuantizer`` and override chain, so the fused calibration step (one kernel
+    per quantizer per forward, no host sync) runs under the unmodified ``ff.estimate_ranges``."""
+    from .range_setting import minmax as ours
+
+    if "running_minmax" in _installed:
+        return
+    _installed["running_minmax_original"] = (ff.range_setting.running_minmax, ff.range_setting.minmax.running_minmax)
+    ff.range_setting.running_minmax = ours.RunningMinMaxRangeEstimator
+    ff.range_setting.minmax.running_minmax = ours.RunningMinMaxRangeEstimator
+    _installed["running_minmax"] = ours.RunningMinMaxRangeEstimator
+
+
+def uninstall_estimators(ff) -> None:
+    orig = _installed.pop("running_minmax_original", None)
+    _installed.pop("running_minmax", None)
+    if orig is not None:
+        ff.range_setting.running_minmax, ff.range_setting.minmax.running_minmax = orig
+
+
 def _register_linear(ff):
-    """The reference's QuantizedTensor / params classes differ from ours only by identity, so the
-    predicate and kernel are rebuilt against the reference's types."""
-    from . import _cabi as C
+    """The reference's QuantizedTensor / params classes differ from ours only by identity, so the predicates and
+    kernels of nn/qlinear.py are rebuilt against the reference's types and registered with ITS dispatcher:
+    W8A8 and W4A16 ``linear``, int8 ``matmul`` / ``mm`` / ``bmm`` (dispatcher.py:233-265)."""
+    from .nn import qlinear
 
-    QT = ff.QuantizedTensor
-    gran = ff.quantization.granularity
-
-    def accepts(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None) -> bool:
-        if not (isinstance(input, QT) and isinstance(weight, QT)) or isinstance(bias, QT):
-            return False
-        px, pw = input.quant_args(), weight.quant_args()
-        ok = (input.is_cuda and input.raw_data.dtype == torch.int8 and weight.raw_data.dtype == torch.int8
-              and weight.dim() == 2 and gran.is_per_tensor(px.granularity) and gran.is_per_channel(pw.granularity)
-              and tuple(pw.granularity.channel_dims) == (0,) and weight.shape[1] % 16 == 0
-              and getattr(px, "num_bits", 99) <= 8 and getattr(pw, "num_bits", 99) <= 8)
-        if not ok:
-            return False
-        tensors = [px.scale, pw.scale] + [o for o in (px.offset, pw.offset) if o is not None]
-        return all(isinstance(t, torch.Tensor) and t.dtype == torch.float32 for t in tensors)
-
-    def kernel(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None):
-        px, pw = input.quant_args(), weight.quant_args()
-        qx = input.raw_data
-        k = qx.shape[-1]
-        qx2, qw = qx.reshape(-1, k).contiguous(), weight.raw_data.contiguous()
-        m, n = qx2.shape[0], qw.shape[0]
-        out_dtype = px.dequantize_dtype or torch.float32
-        y = torch.empty((m, n), dtype=out_dtype, device=qx.device)
-        stream = C.current_stream(qx.device)
-        rs_w = torch.empty(n, dtype=torch.int32, device=qx.device)
-        C.check(C.lib.ffq_rowsum_i8(qw.data_ptr(), rs_w.data_ptr(), n, k, stream))
-        rs_x = None
-        if pw.offset is not None:
-            rs_x = torch.empty(m, dtype=torch.int32, device=qx.device)
-            C.check(C.lib.ffq_rowsum_i8(qx2.data_ptr(), rs_x.data_ptr(), m, k, stream))
-        sx, sw = px.scale.detach().reshape(-1), pw.scale.detach().reshape(-1).contiguous()
-        ox = None if px.offset is None else px.offset.detach().reshape(-1)
-        ow = None if pw.offset is None else pw.offset.detach().reshape(-1).contiguous()
-        b = None if bias is None else bias.detach().contiguous()
-        ws = torch.empty(4 * n, dtype=torch.float32, device=qx.device)
-        C.check(C.lib.ffq_qlinear_w8a8(
-            qx2.data_ptr(), qw.data_ptr(), y.data_ptr(), C.dtype_tag(out_dtype), m, n, k, sx.data_ptr(), C.ptr(ox),
-            sw.data_ptr(), C.ptr(ow), rs_w.data_ptr(), C.ptr(rs_x), C.ptr(b),
-            C.dtype_tag(b.dtype if b is not None else None), ws.data_ptr(), ws.numel() * 4, stream))
-        y = y.reshape(*qx.shape[:-1], n)
-        return output_quantizer(y) if output_quantizer is not None else y
-
-    return ff.dispatcher.register("linear", ff.dispatcher.Predicate(accepts), kernel)
+    kernels = qlinear.build(qlinear.reference_host(ff))
+    return qlinear.register_all(kernels, ff.dispatcher.register, ff.dispatcher.Predicate)

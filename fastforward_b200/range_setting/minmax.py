@@ -11,54 +11,127 @@ What changed for B200 -- behaviour is the same, the schedule is not:
   * ``process_group`` (or an initialised default group with ``sync_ranges=True``) all-reduces the
     running ranges with MIN/MAX at the end of the block: data-parallel calibration;
   * when the step is followed by the quantizer's own int8 quantization (the usual W8A8 calibration
-    forward) and the layout is a per-channel row or a whole tensor, estimate_step + range setter +
-    quantize (+ the code row sums the W8A8 linear needs) are ONE kernel reading the tensor once
-    (``ops.calibrate_quantize_``; pass ``fused=False`` to the estimator to keep the separate kernels).
-"""
+    forward) and the layout is a per-channel row, a whole tensor or a per-group tile, estimate_step +
+    range setter + quantize (+ the code row sums the W8A8 linear needs) are ONE kernel reading the tensor
+    once (``ops.calibrate_quantize_``; pass ``fused=False`` to the estimator to keep the separate kernels);
+  * quantizers that are handed the SAME tensor object with the same configuration (the q/k/v and the
+    gate/up input quantizers of a decoder layer) share one launch and one set of codes (``dedupe``);
+  * a quantizer whose input is an unchanged ``nn.Parameter`` (same storage, same version counter) since
+    its previous step returns its previous codes: the running range cannot move, so parameters and
+    codes are bit-identical (``memoize_parameters``).
+
+The estimator recognises the unmodified reference's ``LinearQuantizer`` and override chain as well as this
+package's, so ``plugin.install(patch_estimators=True)`` puts all of this under ``fastforward.estimate_ranges``."""
 
 from __future__ import annotations
 
 import logging
-from typing import Iterator, Optional, Sequence
+import sys
+import types
+import weakref
+from typing import Iterator, List, Optional, Sequence
 
 import torch
 
-from .. import flags as _flags
 from .. import ops
-from ..forward_override import _Chain
-from ..nn.quantized_module import named_quantizers
 from ..nn.quantizer import Quantizer
 from .common import RangeEstimator, RangeSettable, SimpleEstimatorStep
 
 logger = logging.getLogger(__name__)
+
+_OWN_ROOT = __name__.partition(".")[0]
 
 
 def _param_count(quantizer, data: torch.Tensor) -> int:
     return quantizer.granularity.parameter_dimensionality(data.shape)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# host-package adapters: this package's classes, or an installed unmodified ``fastforward``
+# ---------------------------------------------------------------------------------------------------------------
+_HOSTS: dict = {}
+
+
+def _host_of(quantizer):
+    """Classes of the package a quantizer belongs to (QuantizedTensor, QuantizationContext, export flag)."""
+    root = type(quantizer).__module__.partition(".")[0]
+    host = _HOSTS.get(root)
+    if host is None:
+        mod = sys.modules[root]
+        fn_mod = sys.modules[f"{root}.quantization.function"]
+        lq_mod = sys.modules.get(f"{root}.nn.linear_quantizer")
+        host = types.SimpleNamespace(
+            QuantizedTensor=mod.QuantizedTensor, QuantizationContext=fn_mod.QuantizationContext,
+            get_export_mode=mod.get_export_mode, LinearQuantizer=getattr(lq_mod, "LinearQuantizer", None))
+        _HOSTS[root] = host
+    return host
+
+
+def _is_quantizer(module) -> bool:
+    if isinstance(module, Quantizer):
+        return True
+    return isinstance(module, torch.nn.Module) and all(
+        callable(getattr(module, name, None)) for name in ("register_override", "is_stub", "quantize"))
+
+
+def _next_is_own_quantize(callback, quantizer) -> bool:
+    """True when calling ``callback`` would run ``quantizer.quantize`` and nothing else (no other override in
+    between): this package's ``_Chain`` or the reference's ``_WrappedOverriddenFn`` (forward_override.py:76-96)."""
+    pending = getattr(callback, "_pending", None)
+    fn = getattr(callback, "_fn", None)
+    if pending is None:
+        pending = getattr(callback, "override_stack", None)
+        fn = getattr(callback, "overridden_fn", None)
+    if pending is None or pending:
+        return False
+    return getattr(fn, "__self__", None) is quantizer and getattr(fn, "__func__", None) is type(quantizer).quantize
+
+
+def _set_range_direct(quantizer, lo: torch.Tensor, hi: torch.Tensor) -> bool:
+    """``quantizer.quantization_range = (lo, hi)`` for a LinearQuantizer of either host with ONE sync-free kernel
+    writing scale/offset in place (nn/linear_quantizer.py:327-357).  False: the caller uses the property setter."""
+    host = _host_of(quantizer)
+    if host.LinearQuantizer is None or type(quantizer) is not host.LinearQuantizer or not lo.is_cuda:
+        return False
+    if quantizer.has_uninitialized_params:
+        quantizer._initialize_parameters(lo.numel())
+    scale, offset = quantizer.scale, quantizer.offset
+    n = lo.numel()
+    for p in (scale, offset):
+        if p is not None and (p.dtype != torch.float32 or p.device != lo.device or p.numel() != n or not p.is_contiguous()):
+            return False
+    with torch.no_grad():
+        ops.parameters_for_range_(lo, hi, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
+                                  scale.data, None if offset is None else offset.data)
+    return True
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-block state shared by all steps of one estimate_ranges block
+# ---------------------------------------------------------------------------------------------------------------
 class _RangeArena:
-    """Running ranges of ALL quantizers of one estimate_ranges block live in a few flat buffers
-    (one min and one max buffer per dtype/device), so the data-parallel exchange at the end of the
-    block is two collectives on contiguous memory -- no packing of hundreds of tiny tensors -- and
-    one flag word serves every quantizer."""
+    """Running ranges of many quantizers live in a few flat buffers (one min and one max buffer per dtype/device), so
+    the data-parallel exchange at the end of the block is two collectives on contiguous memory -- no packing of
+    hundreds of tiny tensors -- and one flag word serves every quantizer."""
 
     CHUNK = 1 << 21
 
-    def __init__(self) -> None:
+    def __init__(self, chunk: Optional[int] = None) -> None:
+        self.chunk = chunk or self.CHUNK
         self.chunks: dict = {}     # (device, dtype) -> list of [min_buf, max_buf, used]
         self.flags: dict = {}      # device -> int32[1]
         self.barriers: dict = {}   # device -> zeroed scratch of the fused per-tensor kernel's grid barrier
 
     def take(self, n: int, like: torch.Tensor):
+        """(min view, max view, (chunk index, offset)) of a fresh slot of n elements."""
         key = (like.device, like.dtype)
         chunks = self.chunks.setdefault(key, [])
         if not chunks or chunks[-1][2] + n > chunks[-1][0].numel():
-            size = max(self.CHUNK, n)
+            size = max(self.chunk, n)
             chunks.append([like.new_full((size,), float("inf")), like.new_full((size,), float("-inf")), 0])
         mn, mx, used = chunks[-1]
         chunks[-1][2] = used + n
-        return mn[used:used + n], mx[used:used + n]
+        return mn[used:used + n], mx[used:used + n], (len(chunks) - 1, used)
 
     def flag(self, device: torch.device) -> torch.Tensor:
         if device not in self.flags:
@@ -79,25 +152,79 @@ class _RangeArena:
                     yield mn[:used], mx[:used]
 
 
+class _BlockState:
+    """What the steps of one block share: the arenas (activations apart from parameters: only the former differ
+    between data-parallel ranks), the most recent fused outputs by input tensor (dedupe) and the counters."""
+
+    def __init__(self, dedupe: bool, memoize: bool) -> None:
+        self.act = _RangeArena(chunk=1 << 14)
+        self.param = _RangeArena()
+        self.recent: dict = {}        # (data_ptr, shape, dtype) -> _Recent
+        self.aliases: List["RunningMinMaxEstimator"] = []
+        self.dedupe, self.memoize = dedupe, memoize
+        self.stats = {"fused": 0, "deduped": 0, "memoized": 0, "separate": 0}
+
+    def flag(self, device):
+        return self.param.flag(device)        # one flag word per device for the whole block
+
+    def all_flags(self):
+        return list(self.param.flags.values())
+
+
+class _Recent:
+    __slots__ = ("ref", "version", "step", "codes", "rowsum")
+
+    def __init__(self, data, step, codes, rowsum) -> None:
+        self.ref, self.version, self.step, self.codes, self.rowsum = weakref.ref(data), data._version, step, codes, rowsum
+
+
+def _same_config(a, b) -> bool:
+    return (type(a) is type(b) and a.num_bits == b.num_bits and a.symmetric == b.symmetric
+            and a.allow_one_sided == b.allow_one_sided and a.quantized_dtype == b.quantized_dtype
+            and repr(a.granularity) == repr(b.granularity))
+
+
 class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
     def __init__(self, quantizer, disable_quantization: bool = False, eager_checks: bool = False,
-                 arena: Optional[_RangeArena] = None, fused: bool = True) -> None:
+                 arena: Optional[_RangeArena] = None, fused: bool = True, state: Optional[_BlockState] = None) -> None:
         super().__init__(disable_quantization=disable_quantization)
-        self._arena = arena
+        self._state = state
+        self._arena = arena               # explicit arena (tests); otherwise chosen from the state by the data's kind
         self._fused = fused
+        self._quantizer_ref = weakref.ref(quantizer)
         self._settled = None          # device int32[1]: set by the kernel once every running min is negative
         self._settled_host = None     # pinned mirror, refreshed asynchronously: lets later steps skip the fix-up launch
         self._settled_seen = False
+        self._nsteps = 0
+        self._alias_of: Optional["RunningMinMaxEstimator"] = None
+        self._memo = None             # (weakref(data), version, output) of the previous fused step on a Parameter
+        self._slot = None             # (arena, chunk index, offset, n) of the running range when it lives in an arena
+        self._param_data = False      # the data this quantizer sees is an nn.Parameter (identical on every DP rank)
         lo, hi = quantizer.quantization_range       # continues from an existing range (minmax.py:198-200)
+        self._fresh = lo is None and hi is None
         self.register_buffer("min", None if lo is None else lo.detach().clone())
         self.register_buffer("max", None if hi is None else hi.detach().clone())
         self.register_buffer("flags", None)
         self._eager = eager_checks
 
+    # ---- running range storage ---------------------------------------------------------------------------
+    def _arena_for(self, data) -> Optional[_RangeArena]:
+        if self._arena is not None:
+            return self._arena
+        if self._state is None:
+            return None
+        return self._state.param if self._param_data else self._state.act
+
     def initialize_parameters(self, quantizer, data: torch.Tensor) -> None:
+        if self.min is not None and self.max is not None and self.flags is not None and \
+                self.min.dtype == data.dtype and self.min.device == data.device:
+            return                                  # steady state: nothing to do
+        self._param_data = isinstance(data, torch.nn.Parameter)
         n = _param_count(quantizer, data)
-        if self.min is None and self.max is None and self._arena is not None:
-            self.min, self.max = self._arena.take(n, data)
+        arena = self._arena_for(data)
+        if self.min is None and self.max is None and arena is not None:
+            self.min, self.max, (ci, off) = arena.take(n, data)
+            self._slot = (arena, ci, off, n)
         if self.min is None:
             self.min = data.new_full((n,), float("inf"))
         if self.max is None:
@@ -106,12 +233,19 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             # torch.min(self.min, data_min) in the reference promotes; keep the running range in the
             # promoted dtype so that nothing is lost
             dt = torch.promote_types(self.min.dtype, data.dtype)
-            self.min, self.max = self.min.to(device=data.device, dtype=dt), self.max.to(device=data.device, dtype=dt)
+            if dt != self.min.dtype or self.min.device != data.device:
+                self.min, self.max = self.min.to(device=data.device, dtype=dt), self.max.to(device=data.device, dtype=dt)
+                self._slot = None
         if self.flags is None:
-            self.flags = self._arena.flag(data.device) if self._arena is not None else \
-                torch.zeros(1, dtype=torch.int32, device=data.device)
+            if self._state is not None:
+                self.flags = self._state.flag(data.device)
+            elif self._arena is not None:
+                self.flags = self._arena.flag(data.device)
+            else:
+                self.flags = torch.zeros(1, dtype=torch.int32, device=data.device)
 
     def estimate_step(self, quantizer, data: torch.Tensor) -> None:
+        self._unalias()
         self.initialize_parameters(quantizer, data)
         with torch.no_grad():
             tile = quantizer.granularity.tile_size(data.shape)
@@ -120,7 +254,11 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             ops.running_minmax_update_(self.min, self.max, data.detach(), tile, self.flags)
             if self._eager:
                 self.check_finite()
-        quantizer.quantization_range = (self.min, self.max)
+        self._nsteps += 1
+        if self._state is not None:
+            self._state.stats["separate"] += 1
+        if not _set_range_direct(quantizer, self.min, self.max):
+            quantizer.quantization_range = (self.min, self.max)
 
     def check_finite(self) -> None:
         if self.flags is not None:
@@ -128,31 +266,91 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
 
     # ---- fused step: min/max + running update + range->params + int8 quantize in one kernel ----
     def _fused_mode(self, quantizer, callback, data) -> int:
-        from ..nn.linear_quantizer import LinearQuantizer
-        from ..quantized_tensor import QuantizedTensor
-
-        if not self._fused or self._disable_quantization or type(quantizer) is not LinearQuantizer:
+        if not self._fused or self._disable_quantization:
+            return 0
+        host = _host_of(quantizer)
+        if host.LinearQuantizer is None or type(quantizer) is not host.LinearQuantizer:
             return 0
         if quantizer.quantized_dtype != torch.int8 or quantizer.num_bits > 8 or torch.is_grad_enabled():
             return 0
-        if not isinstance(data, torch.Tensor) or isinstance(data, QuantizedTensor) or not data.is_cuda:
+        if not isinstance(data, torch.Tensor) or isinstance(data, host.QuantizedTensor) or not data.is_cuda:
             return 0
-        if _flags.get_export_mode():
+        if host.get_export_mode():
             return 0
         # the quantizer's own quantize must be what runs next (no other overrides in between)
-        if not isinstance(callback, _Chain) or callback._pending or \
-                getattr(callback._fn, "__func__", None) is not LinearQuantizer.quantize:
+        if not _next_is_own_quantize(callback, quantizer):
             return 0
         for p in (quantizer.scale, quantizer.offset):
             if p is not None and (p.dtype != torch.float32 or p.device != data.device):
                 return 0
         return ops.calibrate_quantize_mode(data.shape, quantizer.granularity.tile_size(data.shape), data.dtype)
 
-    def _fused_step(self, quantizer, data: torch.Tensor, mode: int):
-        from ..quantization.affine.function import AffineQuantizationFunction
-        from ..quantization.function import QuantizationContext
-        from ..quantized_tensor import QuantizedTensor
+    def _wrap(self, quantizer, codes, rowsum, data_dtype):
+        host = _host_of(quantizer)
+        params = quantizer.quantization_parameters()
+        params = params.with_changes(dequantize_dtype=params.dequantize_dtype or data_dtype)
+        out = host.QuantizedTensor(codes, host.QuantizationContext(quantizer.quantization_function, params))
+        if rowsum is not None:
+            out._ffq_rowsum = rowsum          # consumed by nn/qlinear.py instead of a separate row-sum pass
+        return out
 
+    def _become_alias(self, quantizer, master: "RunningMinMaxEstimator") -> None:
+        """Share the master's running range and (for the length of the block) its parameter storage: both quantizers
+        have seen exactly the same tensors, so everything derived from them is equal by construction."""
+        mq = master._quantizer_ref()
+        n = master.min.numel()
+        if quantizer.has_uninitialized_params:
+            quantizer._initialize_parameters(n)
+        self.min, self.max, self.flags = master.min, master.max, master.flags
+        self._slot, self._param_data = None, master._param_data
+        with torch.no_grad():
+            quantizer.scale.data = mq.scale.data
+            if quantizer.offset is not None:
+                quantizer.offset.data = mq.offset.data
+        self._alias_of = master
+        self._state.aliases.append(self)
+
+    def _unalias(self) -> None:
+        """Give an aliased quantizer its own copies back (values unchanged)."""
+        if self._alias_of is None:
+            return
+        q = self._quantizer_ref()
+        self._alias_of = None
+        self.min, self.max = self.min.clone(), self.max.clone()
+        if q is not None:
+            with torch.no_grad():
+                q.scale.data = q.scale.data.clone()
+                if q.offset is not None:
+                    q.offset.data = q.offset.data.clone()
+
+    def _fused_step(self, quantizer, data: torch.Tensor, mode: int):
+        st = self._state
+        # (1) an unchanged parameter since this quantizer's previous step: same range, same parameters, same codes
+        if self._memo is not None:
+            ref, version, out = self._memo
+            if ref() is data and data._version == version:
+                self._nsteps += 1
+                st.stats["memoized"] += 1
+                return out
+            self._memo = None
+        # (2) another quantizer of the same configuration has just processed this very tensor
+        key = None
+        if st is not None and st.dedupe:
+            key = (data.data_ptr(), data.shape, data.dtype)
+            ent = st.recent.get(key)
+            if ent is not None and ent.step is not self and ent.ref() is data and ent.version == data._version:
+                master = ent.step
+                hit = self._alias_of is master and master._nsteps == self._nsteps + 1
+                if not hit and self._alias_of is None and self._nsteps == 0 and master._nsteps == 1 and self._fresh \
+                        and master._fresh and master._alias_of is None and self.min is None \
+                        and _same_config(quantizer, master._quantizer_ref()):
+                    self._become_alias(quantizer, master)
+                    hit = True
+                if hit:
+                    self._nsteps += 1
+                    st.stats["deduped"] += 1
+                    return self._wrap(quantizer, ent.codes, ent.rowsum, data.dtype)
+        self._unalias()
         self.initialize_parameters(quantizer, data)
         if quantizer.has_uninitialized_params:
             quantizer._initialize_parameters(self.min.numel())
@@ -164,28 +362,39 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             # a plain host read of the pinned mirror: no sync; a stale 0 only costs one more fix-up launch
             self._settled_seen = bool(self._settled_host[0] != 0)
         tile = quantizer.granularity.tile_size(data.shape)
-        want_rowsum = data.dim() >= 2 and (mode == 2 or (mode == 1 and self.min.numel() * data.shape[-1] == data.numel()))
+        # row sums ride along when the rows are whole 16-byte vectors (the kernels' vector width); other shapes get
+        # them from ffq_rowsum_i8 inside the linear
+        vec = 16 // data.element_size()
+        want_rowsum = data.dim() >= 2 and data.shape[-1] % vec == 0 and \
+            (mode == 2 or (mode == 1 and self.min.numel() * data.shape[-1] == data.numel()))
+        ws = None
+        if mode in (2, 3):
+            arena = self._arena_for(data)
+            ws = arena.barrier_workspace(data.device) if arena is not None else None
         codes, rowsum = ops.calibrate_quantize_(
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
             self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen,
-            workspace=self._arena.barrier_workspace(data.device) if (mode in (2, 3) and self._arena is not None) else None)
+            workspace=ws)
         if self._settled_host is not None and not self._settled_seen:
             self._settled_host.copy_(self._settled, non_blocking=True)
         if self._eager:
             self.check_finite()
-        params = quantizer.quantization_parameters()
-        params = params.with_changes(dequantize_dtype=params.dequantize_dtype or data.dtype)
-        out = QuantizedTensor(codes, QuantizationContext(AffineQuantizationFunction, params))
-        if rowsum is not None:
-            out._ffq_rowsum = rowsum          # consumed by nn/qlinear.py instead of a separate row-sum pass
+        self._nsteps += 1
+        out = self._wrap(quantizer, codes, rowsum, data.dtype)
+        if st is not None:
+            st.stats["fused"] += 1
+            if key is not None:
+                st.recent[key] = _Recent(data, self, codes, rowsum)
+            if st.memoize and isinstance(data, torch.nn.Parameter):
+                self._memo = (weakref.ref(data), data._version, out)
         return out
 
     def forward(self, quantizer, callback, args: tuple, kwargs: dict):
         data = args[0] if args else kwargs.get("data", next(iter(kwargs.values()), None))
         mode = self._fused_mode(quantizer, callback, data)
-        if mode and self.min is not None and (self.min.device != data.device or
-                                              torch.promote_types(self.min.dtype, data.dtype) != self.min.dtype):
+        if mode and self.min is not None and self._alias_of is None and \
+                (self.min.device != data.device or torch.promote_types(self.min.dtype, data.dtype) != self.min.dtype):
             mode = 0     # a continued range on another device / in a narrower dtype: the plain path converts it
         if not mode:
             return super().forward(quantizer, callback, args, kwargs)
@@ -249,9 +458,11 @@ class _MinMaxRangeEstimatorBase(RangeEstimator):
         metadata.remove()
 
     def split_module(self, module: torch.nn.Module) -> Iterator[Quantizer]:
-        quantizers = [("", module)] if isinstance(module, Quantizer) and not module.is_stub() else []
-        quantizers += [(n, q) for n, q in named_quantizers(module, recurse=True) if q is not module]
-        for _, quantizer in quantizers:
+        seen = set()
+        for _, quantizer in module.named_modules(remove_duplicate=True):
+            if not _is_quantizer(quantizer) or quantizer.is_stub() or id(quantizer) in seen:
+                continue
+            seen.add(id(quantizer))
             if isinstance(quantizer, RangeSettable) or not self.skip_unsupported_quantizers:
                 yield quantizer
             else:
@@ -260,72 +471,181 @@ class _MinMaxRangeEstimatorBase(RangeEstimator):
 
 
 class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
+    """``ff.estimate_ranges(model, running_minmax)``.  Keyword extras (all default to the reference's behaviour where
+    they change anything observable):
+
+    eager_checks        raise ``NotImplementedError("Infinite")`` at the offending step (one host sync per step)
+                        instead of when the block ends
+    sync_ranges /       data-parallel calibration: all-reduce (MIN/MAX) the running ranges of the quantizers whose
+    process_group       input is NOT an ``nn.Parameter`` when the block ends (parameters are rank-identical replicas;
+                        ``sync_parameters=True`` reduces them too)
+    fused               one kernel per quantizer per forward where the layout allows (default True)
+    dedupe              identically configured quantizers fed the same tensor object share one launch (default True)
+    memoize_parameters  an unchanged ``nn.Parameter`` is not re-quantized on later steps (default True)
+    """
+
     def __init__(self, disable_quantization: bool = False, skip_unsupported_quantizers: bool = False, *,
-                 eager_checks: bool = False, sync_ranges: bool = False, process_group=None, fused: bool = True) -> None:
+                 eager_checks: bool = False, sync_ranges: bool = False, process_group=None, fused: bool = True,
+                 dedupe: bool = True, memoize_parameters: bool = True, sync_parameters: bool = False) -> None:
         self.disable_quantization = disable_quantization
         self.skip_unsupported_quantizers = skip_unsupported_quantizers
         self.eager_checks = eager_checks
         self.sync_ranges = sync_ranges or process_group is not None
         self.process_group = process_group
         self.fused = fused
+        self.dedupe, self.memoize_parameters, self.sync_parameters = dedupe, memoize_parameters, sync_parameters
         self._steps: list = []
-        self._arena = _RangeArena()
+        self._state = _BlockState(dedupe, memoize_parameters)
+        self.last_stats: dict = {}
+        self.last_exit: dict = {}
 
     def prepare(self, module):
         self._check(module)
         step = RunningMinMaxEstimator(module, disable_quantization=self.disable_quantization,
-                                      eager_checks=self.eager_checks, arena=self._arena, fused=self.fused)
+                                      eager_checks=self.eager_checks, fused=self.fused, state=self._state)
         self._steps.append((module, step))
         return module.register_override(step)
 
+    def cleanup(self, module, metadata) -> None:
+        # under the reference's own estimate_ranges nobody calls finalize(): the first cleanup of a block that ended
+        # without an exception does
+        if self._steps:
+            if sys.exc_info()[0] is None:
+                self.finalize(())
+            else:                                # the block failed: drop its half-finished state
+                for s in self._state.aliases:
+                    s._unalias()
+                self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters)
+        super().cleanup(module, metadata)
+
+    # ---- block exit -------------------------------------------------------------------------------------
     def finalize(self, prepared: Sequence[tuple]) -> None:
         del prepared
-        steps = [(q, s) for q, s in self._steps if s.min is not None]
-        flags = list({id(s.flags): s.flags for _, s in steps if s.flags is not None}.values())
-        if self.sync_ranges:
-            from ..distributed import all_reduce_minmax_buffers, all_reduce_ranges
-
-            arena_ids = {id(mn.untyped_storage()) for mn, _ in self._arena.buffers()}
-            loose = [(s.min, s.max) for _, s in steps if id(s.min.untyped_storage()) not in arena_ids]
-            all_reduce_minmax_buffers(list(self._arena.buffers()), flags, group=self.process_group)
-            all_reduce_ranges(loose, None, group=self.process_group)
-            self._reset_parameters_from_ranges(steps)
+        steps, state = self._steps, self._state
+        self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters)
+        try:
+            if self.sync_ranges:
+                self._sync(steps, state)
+        finally:
+            for s in state.aliases:             # aliased quantizers get their own parameter storage back
+                s._unalias()
+            state.recent.clear()
+        self.last_stats = dict(state.stats)
         # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks
+        flags = state.all_flags() + [s.flags for _, s in steps if s.flags is not None and s._state is None]
         if flags and not self.eager_checks:
             value = 0
-            for v in torch.stack([f.reshape(()) for f in flags]).tolist():
+            for v in torch.stack([f.reshape(()) for f in {id(f): f for f in flags}.values()]).tolist():
                 value |= int(v)
             _raise_for_flags(value)
-        self._steps = []
-        self._arena = _RangeArena()
 
+    def _sync(self, steps, state) -> None:
+        """Merge the running ranges across the data-parallel ranks and re-derive (scale, offset) from them.
+        Slots of the activation arena are handed out in the order quantizers first see data, which control flow that
+        depends on the data (experts without tokens on one shard) can make rank dependent: the ranks first agree on
+        the slot layout (one small MAX all-reduce of a signature vector); identical layouts all-reduce the arena in
+        place (one MIN + one MAX collective per dtype), anything else is packed per quantizer in ``prepare`` order
+        with neutral fill for quantizers a rank did not see."""
+        import torch.distributed as dist
 
-    def _reset_parameters_from_ranges(self, steps) -> None:
+        from ..distributed import _active, all_reduce_minmax_buffers
+
+        group = self.process_group
+        if not _active(group):
+            return
+        todo = [(i, q, s) for i, (q, s) in enumerate(steps)
+                if s._alias_of is None and (self.sync_parameters or not s._param_data)]
+        device = None
+        for _, _, s in todo:
+            if s.min is not None:
+                device = s.min.device
+                break
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() and \
+                dist.get_backend(group) == "nccl" else torch.device("cpu")
+        # signature: slot position inside the activation arena, -1 = not seen here, -2 = seen but outside the arena
+        sig = []
+        for _, _, s in todo:
+            if s.min is None:
+                sig.append(-1)
+            elif s._slot is not None and s.min.numel() == s._slot[3] and (s._slot[0] is state.act or s._slot[0] is state.param):
+                sig.append((int(s._slot[0] is state.param) << 60) | (s._slot[1] << 40) | s._slot[2])
+            else:
+                sig.append(-2)
+        sig_t = torch.tensor([sig, [-v for v in sig]], dtype=torch.int64, device=device)
+        dist.all_reduce(sig_t, op=dist.ReduceOp.MAX, group=group)
+        same = bool(torch.equal(sig_t[0], -sig_t[1])) and -2 not in sig
+        flags = state.all_flags()
+        if same:
+            all_reduce_minmax_buffers(list(state.act.buffers()), flags, group=group)
+            if self.sync_parameters:
+                all_reduce_minmax_buffers(list(state.param.buffers()), None, group=group)
+        else:
+            self._sync_packed(todo, device, group)
+            all_reduce_minmax_buffers([], flags, group=group)
+        self._reset_parameters_from_ranges([(q, s) for _, q, s in todo if s.min is not None], state)
+
+    def _sync_packed(self, todo, device, group) -> None:
+        import torch.distributed as dist
+
+        sizes = torch.tensor([0 if s.min is None else s.min.numel() for _, _, s in todo], dtype=torch.int64, device=device)
+        lo_sz = torch.where(sizes > 0, sizes, torch.full_like(sizes, torch.iinfo(torch.int64).max))
+        hi_sz = sizes.clone()
+        dist.all_reduce(hi_sz, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(lo_sz, op=dist.ReduceOp.MIN, group=group)
+        hi, lo = hi_sz.tolist(), lo_sz.tolist()
+        for (i, q, s), a, b in zip(todo, hi, lo):
+            if a > 0 and b != a:
+                raise RuntimeError(f"estimate_ranges: quantizer #{i} ({type(q).__name__}) has {b} range entries on one rank "
+                                   f"and {a} on another; data-parallel calibration needs identical granularities")
+        total = sum(hi)
+        if total == 0:
+            return
+        packed_min = torch.full((total,), float("inf"), dtype=torch.float32, device=device)
+        packed_max = torch.full((total,), float("-inf"), dtype=torch.float32, device=device)
+        pos = 0
+        for (_, _, s), n in zip(todo, hi):
+            if s.min is not None:
+                packed_min[pos:pos + n] = s.min.reshape(-1).float()
+                packed_max[pos:pos + n] = s.max.reshape(-1).float()
+            pos += n
+        dist.all_reduce(packed_min, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(packed_max, op=dist.ReduceOp.MAX, group=group)
+        pos = 0
+        for (_, q, s), n in zip(todo, hi):
+            if n and s.min is not None:
+                s.min.copy_(packed_min[pos:pos + n].to(s.min.dtype))
+                s.max.copy_(packed_max[pos:pos + n].to(s.max.dtype))
+            elif n:
+                # this rank never ran the quantizer: it adopts the range the other ranks measured
+                s.min, s.max = packed_min[pos:pos + n].clone(), packed_max[pos:pos + n].clone()
+                if torch.isfinite(s.min).all() and not _set_range_direct(q, s.min, s.max):
+                    q.quantization_range = (s.min, s.max)
+                s.min = None            # already applied
+            pos += n
+
+    def _reset_parameters_from_ranges(self, steps, state) -> None:
         """After the ranges were merged across ranks: every quantizer's (scale, offset) from its merged range.  The
         quantizers whose running range lives in an arena chunk and whose parameters are materialised fp32 tensors of
         the right size are done with ONE launch per chunk; the rest go through the ``quantization_range`` setter."""
-        from ..nn.linear_quantizer import LinearQuantizer
-
-        chunks = {}
-        for chunk_list in self._arena.chunks.values():
-            for mn, mx, used in chunk_list:
-                if used:
-                    chunks[mn.untyped_storage().data_ptr()] = (mn, mx, [])
+        per_chunk: dict = {}
         for quantizer, step in steps:
-            entry = chunks.get(step.min.untyped_storage().data_ptr())
-            n = step.min.numel()
-            ok = entry is not None and type(quantizer) is LinearQuantizer and not quantizer.has_uninitialized_params \
-                and step.min.is_contiguous() and step.max.storage_offset() == step.min.storage_offset() \
-                and quantizer.scale.dtype == torch.float32 and quantizer.scale.numel() == n \
-                and quantizer.scale.device == step.min.device and quantizer.scale.is_contiguous() \
-                and (quantizer.offset is None or (quantizer.offset.dtype == torch.float32 and quantizer.offset.numel() == n
-                                                  and quantizer.offset.is_contiguous()))
-            if not ok:
-                quantizer.quantization_range = (step.min, step.max)
+            slot = step._slot
+            entry = None
+            if slot is not None and not quantizer.has_uninitialized_params:
+                scale, offset = quantizer.scale, quantizer.offset
+                n = slot[3]
+                if scale.dtype == torch.float32 and scale.numel() == n and scale.is_contiguous() and \
+                        (offset is None or (offset.dtype == torch.float32 and offset.numel() == n and offset.is_contiguous())):
+                    entry = (slot[2], n, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
+                             scale.data, None if offset is None else offset.data)
+            if entry is None:
+                if not _set_range_direct(quantizer, step.min, step.max):
+                    quantizer.quantization_range = (step.min, step.max)
                 continue
-            entry[2].append((step.min.storage_offset(), n, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
-                             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data))
-        for mn, mx, entries in chunks.values():
+            per_chunk.setdefault((id(slot[0]), slot[1], step.min.device, step.min.dtype), (slot, []))[1].append(entry)
+        for (_, ci, dev, dt), (slot, entries) in per_chunk.items():
+            mn, mx, used = slot[0].chunks[(dev, dt)][ci]
             ops.parameters_for_ranges_batched_(mn, mx, entries)
 
 

@@ -40,7 +40,7 @@ extern "C" {
 #define FFQ_API
 #endif
 
-#define FFQ_ABI_VERSION 1
+#define FFQ_ABI_VERSION 2
 #define FFQ_MAX_RANK 8
 
 typedef enum {
@@ -232,17 +232,30 @@ FFQ_API int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* r
  * dequantisation fused into the epilogue.  y_dtype in {F32, BF16, F16}.
  * rowsum_w: int32[N] precomputed with ffq_rowsum_i8 (weights are static); rowsum_x may be NULL
  * when ow is NULL.  K must be a multiple of 16 (TMA row pitch); M and N are arbitrary.
- * replaces: _gen/fallback.py:77-112 (dequantize x2 + torch.nn.functional.linear), selected via
- *           dispatcher.py:268-283. */
+ * The offset corrections are added in int32 (exact) whenever they fit; for offsets so far from zero that
+ * K*ox*ow or ox*rowsum_w could leave int32 they are added in float, like the reference's float path.
+ * `requant` (may be NULL): the linear's output quantizer fused into the epilogue -- see ffq_requant_t.
+ * replaces: _gen/fallback.py:77-112 (dequantize x2 + torch.nn.functional.linear [+ output_quantizer,
+ *           fallback.py:109-110]), selected via dispatcher.py:268-283. */
+/* Static per-tensor output quantizer applied in the GEMM epilogue:
+ *   codes[m,n] = int8(clamp(rint(cast_y_dtype(y[m,n]) / scale - rint(offset)), -2^(b-1), 2^(b-1)-1))
+ * i.e. quantize_by_tile (_quantizer_impl.py:144-169) of the output tensor the fallback would have written, without
+ * that tensor making a round trip through HBM.  scale/offset: device fp32[1] (offset may be NULL); num_bits <= 8;
+ * codes: int8 [M,N]; rowsum (may be NULL): int32[M], ZERO-initialised by the caller, receives the row sums of the
+ * codes (what the next W8A8 linear needs).  `y` of ffq_qlinear_w8a8 may be NULL when only the codes are wanted. */
+typedef struct {
+  const float* scale;
+  const float* offset;
+  double num_bits;
+  int8_t* codes;
+  int32_t* rowsum;
+} ffq_requant_t;
 FFQ_API int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype,
                      int64_t M, int64_t N, int64_t K,
                      const float* sx, const float* ox, const float* sw, const float* ow,
                      const int32_t* rowsum_w, const int32_t* rowsum_x,
                      const void* bias, int bias_dtype,
-                     void* workspace, size_t workspace_bytes, void* stream);
-/* scratch for ffq_qlinear_w8a8: none since the column parameters are derived inside the kernel (returns 0;
- * `workspace` may be NULL) -- kept for ABI stability */
-FFQ_API size_t ffq_qlinear_workspace_bytes(int64_t N);
+                     const ffq_requant_t* requant, void* stream);
 
 /* rowsum[r] = sum_k q[r,k]  (int8 [R,K] -> int32[R]) */
 FFQ_API int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream);

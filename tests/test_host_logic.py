@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} is declared in include/ffq_b200.h but not exported"
     assert sorted(_cabi.EXPORTED) == declared
-    assert lib.ffq_abi_version() == 1
+    assert lib.ffq_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_layout_planning_through_the_abi():
