@@ -37,6 +37,7 @@ from .quantization.granularity import PerTile as PerTile
 from .quantized_tensor import QuantizedTensor as QuantizedTensor
 from .range_setting import estimate_ranges as estimate_ranges
 from .quantization import fuse as _fuse  # noqa: E402  (after nn: it needs LinearQuantizer)
+from .quantization import view_ops as _view_ops  # noqa: E402,F401  (registers the per-tensor view ops with the dispatcher)
 from .quantization.fuse import fuse_qdq_weights as fuse_qdq_weights
 
 __version__ = "0.1.0"

@@ -539,12 +539,9 @@ static int launch_pairs_dt(int y_dtype, const CUtensorMap& a, const CUtensorMap&
 
 // pairs per cluster for the pair kernel: FFQ_GEMM_CLUSTER = 2 | 4 | 8 CTAs overrides the shape heuristic
 static int env_cluster_pairs() {
-  static const int v = [] {
-    const char* e = getenv("FFQ_GEMM_CLUSTER");
-    const int c = e ? atoi(e) : 0;
-    return (c == 2 || c == 4 || c == 8) ? c / 2 : 0;
-  }();
-  return v;
+  const char* e = getenv("FFQ_GEMM_CLUSTER");       // read per call: tests and A/B runs switch it inside one process
+  const int c = e ? atoi(e) : 0;
+  return (c == 2 || c == 4 || c == 8) ? c / 2 : 0;
 }
 
 extern "C" {

@@ -57,12 +57,17 @@ def _host_of(quantizer):
     root = type(quantizer).__module__.partition(".")[0]
     host = _HOSTS.get(root)
     if host is None:
-        mod = sys.modules[root]
-        fn_mod = sys.modules[f"{root}.quantization.function"]
+        mod = sys.modules.get(root)
+        fn_mod = sys.modules.get(f"{root}.quantization.function")
         lq_mod = sys.modules.get(f"{root}.nn.linear_quantizer")
-        host = types.SimpleNamespace(
-            QuantizedTensor=mod.QuantizedTensor, QuantizationContext=fn_mod.QuantizationContext,
-            get_export_mode=mod.get_export_mode, LinearQuantizer=getattr(lq_mod, "LinearQuantizer", None))
+        if mod is None or fn_mod is None or not hasattr(mod, "QuantizedTensor"):
+            # a quantizer from neither host package (a user's own RangeSettable): separate kernels + its own setter
+            host = types.SimpleNamespace(QuantizedTensor=(), QuantizationContext=None, get_export_mode=lambda: False,
+                                         LinearQuantizer=None)
+        else:
+            host = types.SimpleNamespace(
+                QuantizedTensor=mod.QuantizedTensor, QuantizationContext=fn_mod.QuantizationContext,
+                get_export_mode=mod.get_export_mode, LinearQuantizer=getattr(lq_mod, "LinearQuantizer", None))
         _HOSTS[root] = host
     return host
 

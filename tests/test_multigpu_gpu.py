@@ -42,14 +42,17 @@ def _ranges(ff, model):
     return out
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, fused=False):
     import torch.distributed as dist
 
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
     ff, model = _build(dev)
-    est = ff.range_setting.running_minmax(disable_quantization=True, sync_ranges=True)
+    if fused:
+        from fastforward_b200.nn import qlinear
+        qlinear.install()
+    est = ff.range_setting.running_minmax(disable_quantization=not fused, sync_ranges=True)
     with torch.no_grad(), ff.strict_quantization(False), ff.estimate_ranges(model, est):
         for b in _batches()[rank::world]:
             model(b.to(dev))
@@ -84,3 +87,35 @@ def test_dp_calibration_matches_single_gpu():
             gs, go = got[rank][name]
             assert torch.equal(gs, s), f"rank {rank} {name}: scale differs"
             assert (o is None and go is None) or torch.equal(go, o), f"rank {rank} {name}: offset differs"
+
+
+@pytest.mark.skipif(NGPU < 2, reason="needs 2 GPUs")
+def test_dp_fused_calibration_ranks_agree():
+    """The production schedule (fused steps, dedupe, memoisation, W8A8 linears, activations-only exchange): after the
+    block every rank holds the same parameters, and the weight parameters equal a single-GPU calibration."""
+    import torch.multiprocessing as mp
+
+    ff, model = _build(torch.device("cuda", 0))
+    from fastforward_b200.nn import qlinear
+    qlinear.install()
+    with torch.no_grad(), ff.estimate_ranges(model, ff.range_setting.running_minmax()):
+        for b in _batches()[0::2]:
+            model(b.to("cuda:0"))
+    single = _ranges(ff, model)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[0].keys() == got[1].keys() == single.keys()
+    for name in got[0]:
+        assert torch.equal(got[0][name][0], got[1][name][0]), f"{name}: scale differs between ranks"
+        if got[0][name][1] is not None:
+            assert torch.equal(got[0][name][1], got[1][name][1]), f"{name}: offset differs between ranks"
+        if name.endswith("weight_quantizer"):
+            assert torch.equal(got[0][name][0], single[name][0]), f"{name}: weight scale differs from single GPU"
