@@ -394,6 +394,7 @@ def measure_cfg3(ff, sh, dev, rank, world, hbm_peak, steps=5, warmup=2):
     ff.quantize_model(model, extra_conversion=ff.surrogate_quantized_modules(model))
     ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
         ff.nn.LinearQuantizer, num_bits=4, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+    model.to(dev)                    # the quantizers were created on the CPU
     n_weights = sum(m.weight.numel() for m in model.modules() if isinstance(m, torch.nn.Linear))
 
     def step():
@@ -463,6 +464,7 @@ def measure_cfg5(ff, dev, rank, world, steps=2, layers=None, seq=SEQ):
             granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
         ff.find_quantizers(layer, "**/[quantizer:activation/input]").initialize(
             ff.nn.LinearQuantizer, num_bits=16, symmetric=False, granularity=ff.PerTensor(), quantized_dtype=torch.float32)
+        layer.to(dev)
         est = ff.range_setting.running_minmax(sync_ranges=world > 1, memoize_parameters=False)
         if world > 1:
             dist.barrier()

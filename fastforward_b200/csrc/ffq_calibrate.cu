@@ -45,6 +45,7 @@ struct CalqArgs {
   unsigned long long numel;
   float int_min_abs, int_max_abs, neg_int_min, steps, lo, hi;
   int symmetric, allow_one_sided, sat8;
+  int rcp_div;                          // scalar divisions of parameters_for_range as aten's CUDA kernel does them
   // tensor kernel
   float* part;                          // [2 * gridDim.x]
   unsigned int* bar;                    // [0] arrivals (wraps to 0), [1] generation; zero before first use
@@ -64,14 +65,14 @@ constexpr int CQ_U = 4;               // 16-byte loads in flight per lane
 // parameters_for_range for one tile (affine/range.py:89-122), fp32; `one_sided` is the global decision
 __device__ __forceinline__ void calq_params(const CalqArgs& a, float mn, float mx, bool one_sided, float& sc, float& off) {
   if (a.symmetric && !one_sided) {
-    const float neg = __fdiv_rn(fabsf(mn), a.int_min_abs);
-    const float pos = __fdiv_rn(fabsf(mx), a.int_max_abs);
+    const float neg = scalar_div(fabsf(mn), a.int_min_abs, a.rcp_div != 0);
+    const float pos = scalar_div(fabsf(mx), a.int_max_abs, a.rcp_div != 0);
     sc = nan_max(neg, pos);
     off = 0.f;
     return;
   }
   if (a.symmetric) mn = 0.f;
-  sc = __fdiv_rn(__fsub_rn(mx, mn), a.steps);
+  sc = scalar_div(__fsub_rn(mx, mn), a.steps, a.rcp_div != 0);
   const float eps = 1.1920928955078125e-07f;
   sc = (sc != sc) ? sc : fmaxf(sc, eps);
   off = __fadd_rn(__fdiv_rn(mn, sc), a.neg_int_min);
@@ -917,6 +918,8 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
                            float* scale, float* offset, int32_t* rowsum, int64_t rowsum_row_len, int32_t* flags,
                            int32_t* settled, int run_fixup, const ffq_layout_t* layout, double num_bits, int symmetric,
                            int allow_one_sided, void* workspace, size_t workspace_bytes, void* stream) {
+  const int rcp_div = (allow_one_sided & FFQ_FLAG_SCALAR_DIV_RECIPROCAL) ? 1 : 0;
+  allow_one_sided &= FFQ_FLAG_ALLOW_ONE_SIDED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan plan;
   int rc = make_plan(layout, &plan);
@@ -945,7 +948,7 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
   a.neg_int_min = (float)(-lo);
   a.steps = (float)(pow(2.0, num_bits) - 1.0);
   a.lo = (float)lo; a.hi = (float)(-lo - 1.0);
-  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided;
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided; a.rcp_div = rcp_div;
   a.sat8 = (a.lo == -128.f && a.hi == 127.f) ? 1 : 0;
   const int ept = 16 / dt_size(x_dtype);
   if (mode == 3) {
@@ -1044,6 +1047,8 @@ int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* run_min, 
                             float* scale, float* offset, int32_t* flags, const ffq_layout_t* layout, double num_bits,
                             int symmetric, int allow_one_sided, int code_dtype, void* workspace, size_t workspace_bytes,
                             void* stream) {
+  const int rcp_div = (allow_one_sided & FFQ_FLAG_SCALAR_DIV_RECIPROCAL) ? 1 : 0;
+  allow_one_sided &= FFQ_FLAG_ALLOW_ONE_SIDED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Plan plan;
   int rc = make_plan(layout, &plan);
@@ -1083,7 +1088,7 @@ int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* run_min, 
   a.neg_int_min = (float)(-lo);
   a.steps = (float)(pow(2.0, num_bits) - 1.0);
   a.lo = (float)lo; a.hi = (float)(-lo - 1.0);
-  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided;
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided; a.rcp_div = rcp_div;
   a.sat8 = 0;
   a.code_is_int = float_codes ? 0 : 1;
   const int ept = 16 / dt_size(x_dtype);

@@ -502,6 +502,9 @@ static int run_elementwise(int op, EwArgs& a, const ffq_layout_t* layout, double
       rm = a.qp.m_div;
   }
   if (rm >= 0 && (param_rm(a.s_dt) != rm || (a.offset && param_rm(a.o_dt) != rm))) rm = -1;
+  // dequantize into an integer dtype (codes of integer data: dequantize_dtype = the data dtype, affine/function.py:137):
+  // the generic kernel casts like aten does, (q + o) * s truncated toward zero
+  if (op == OP_DEQUANT && !is_float_dt(a.out_dt)) rm = -1;
 
   const int in_sz = dt_size(a.in_dt), out_sz = dt_size(a.out_dt), code_sz = a.codes ? dt_size(a.codes_dt) : 0;
   const int p_sz = dt_size(a.s_dt);
@@ -617,7 +620,6 @@ int ffq_dequantize(const void* q, int q_dtype, void* y, int y_dtype, const void*
   if ((rc = check_dt(q_dtype, "dequantize: codes")) || (rc = check_dt(y_dtype, "dequantize: output")) ||
       (rc = check_dt(scale_dtype, "dequantize: scale")))
     return rc;
-  if (!is_float_dt(y_dtype)) { set_error("dequantize: output dtype must be floating point"); return FFQ_ERR_UNSUPPORTED; }
   if (offset == nullptr) offset_dtype = FFQ_NONE;
   else if ((rc = check_dt(offset_dtype, "dequantize: offset"))) return rc;
   EwArgs a{};

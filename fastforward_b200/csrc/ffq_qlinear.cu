@@ -54,6 +54,10 @@ struct GemmArgs {
   int bn;                                       // output columns per tile (256; 224 / 128 when that evens out the waves)
   // fused output quantizer (ffq_requant_t): per-tensor, int8 codes of the output rounded to y_dt
   const float* rq_scale; const float* rq_offset; float rq_lo, rq_hi; int8_t* rq_codes; int32_t* rq_rowsum;
+  // test hook (ffq_debug_gemm_profile): per CTA 8 x u64 of SM clocks -- [0] producer waiting for a free stage, [1] producer
+  // total, [2] MMA issuer waiting for operands, [3] MMA issuer waiting for a free accumulator, [4] MMA issuer total,
+  // [5] epilogue waiting for a finished tile, [6] epilogue total
+  unsigned long long* prof;
 };
 
 constexpr int COL_SLOTS = 5;                     // alpha, bias, int constant, weight offset, float constant
@@ -351,10 +355,15 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
       for (int q = 0; q < P; ++q) mc_mask |= (uint16_t)(1u << (2 * q + (int)cta));
       int stage = 0; uint32_t phase = 0;
+      const bool prof = g.prof != nullptr;
+      long long t_wait = 0;
+      const long long t_begin = prof ? clock64() : 0;
       for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
         const int tm = (tile % groups_m) * P + p, tn = tile / groups_m;     // tm >= tiles_m: zero-filled rows
         for (int kb = 0; kb < k_blocks; ++kb) {
+          const long long w0 = prof ? clock64() : 0;
           mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+          if (prof) t_wait += clock64() - w0;
           uint8_t* sa = stage_base + stage * HALF_STAGE;
           if (cta == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
@@ -367,6 +376,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
+      if (prof) { g.prof[blockIdx.x * 8 + 0] = (unsigned long long)t_wait; g.prof[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (pair leaders only) =====
@@ -376,14 +386,21 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint16_t all_mask = (uint16_t)((1u << CSIZE) - 1u), pair_mask = (uint16_t)(3u << (2 * p));
       int stage = 0; uint32_t phase = 0;
       int it = 0;
+      const bool prof = g.prof != nullptr;
+      long long t_full = 0, t_acc = 0;
+      const long long t_begin = prof ? clock64() : 0;
       for (int tile = cluster; tile < num_tiles; tile += num_clusters, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
+        long long w0 = prof ? clock64() : 0;
         mbar_wait_bounded(&tmem_empty[buf], (use & 1) ^ 1);
+        if (prof) t_acc += clock64() - w0;
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
+          w0 = prof ? clock64() : 0;
           mbar_wait_bounded(&full_bar[stage], phase);
+          if (prof) t_full += clock64() - w0;
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * HALF_STAGE);
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_STAGE);
@@ -397,6 +414,10 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
+      if (prof) {
+        g.prof[blockIdx.x * 8 + 2] = (unsigned long long)t_full; g.prof[blockIdx.x * 8 + 3] = (unsigned long long)t_acc;
+        g.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_begin);
+      }
     }
   } else {
     // ===== epilogue (warps 2..5 of every CTA): this CTA's 128 rows =====
@@ -405,6 +426,9 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
     const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
     int it = 0;
+    const bool prof = g.prof != nullptr && ep_tid == 0;
+    long long t_tile = 0;
+    const long long t_begin = prof ? clock64() : 0;
     for (int tile = cluster; tile < num_tiles; tile += num_clusters, ++it) {
       const int tm = (tile % groups_m) * P + p, tn = tile / groups_m;
       const int buf = it & 1;
@@ -415,7 +439,9 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
       int rq_sum = 0;
 
+      const long long w0 = prof ? clock64() : 0;
       mbar_wait_bounded(&tmem_full[buf], use & 1);
+      if (prof) t_tile += clock64() - w0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
@@ -429,6 +455,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);   // 8 arrivals (4 warps x 2 CTAs) free the accumulator
     }
+    if (prof) { g.prof[blockIdx.x * 8 + 5] = (unsigned long long)t_tile; g.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
   }
 
   tc_fence_before();
@@ -483,6 +510,8 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K,
 
 using namespace ffq;
 
+static unsigned long long* g_gemm_prof = nullptr;     // test hook, see ffq_debug_gemm_profile
+
 extern "C" {
 
 int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* stream) {
@@ -491,6 +520,8 @@ int ffq_rowsum_i8(const int8_t* q, int32_t* rowsum, int64_t R, int64_t K, void* 
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
 }
+
+void ffq_debug_gemm_profile(unsigned long long* counters_dev) { g_gemm_prof = counters_dev; }
 
 }  // extern "C"
 
@@ -570,6 +601,7 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.y_dt = y_dtype;
   g.sx = sx; g.ox = ox; g.sw = sw; g.ow = ow; g.rowsum_w = rowsum_w; g.bias = bias; g.bias_dt = bias_dtype;
   g.rowsum_x = rowsum_x;
+  g.prof = g_gemm_prof;
   if (requant != nullptr && requant->codes != nullptr) {
     if (requant->scale == nullptr) { set_error("qlinear_w8a8: requant needs a scale"); return FFQ_ERR_INVALID; }
     if (!(requant->num_bits >= 1 && requant->num_bits <= 8)) { set_error("qlinear_w8a8: requant codes are int8: num_bits must be in [1, 8]"); return FFQ_ERR_BITWIDTH; }

@@ -682,7 +682,7 @@ struct PrArgs {
   const void* mn; const void* mx; int r_dt;
   unsigned long long n;
   float int_min_abs, int_max_abs, neg_int_min, steps;
-  int symmetric, allow_one_sided, round_offset;
+  int symmetric, allow_one_sided, round_offset, rcp;
   void* scale; int s_dt; void* offset; int o_dt;
   float* part; unsigned int nparts;
 };
@@ -715,14 +715,14 @@ __global__ void __launch_bounds__(RD_THREADS) pr_apply_kernel(const PrArgs a) {
   float mn = load_as_float(a.mn, a.r_dt, i);
   const float mx = load_as_float(a.mx, a.r_dt, i);
   if (a.symmetric && !one_sided) {
-    const float neg = __fdiv_rn(fabsf(mn), a.int_min_abs);
-    const float pos = __fdiv_rn(fabsf(mx), a.int_max_abs);
+    const float neg = scalar_div(fabsf(mn), a.int_min_abs, a.rcp != 0);
+    const float pos = scalar_div(fabsf(mx), a.int_max_abs, a.rcp != 0);
     store_from_float(a.scale, a.s_dt, i, nan_max(neg, pos));
     if (a.offset) store_from_float(a.offset, a.o_dt, i, 0.f);
     return;
   }
   if (a.symmetric) mn = 0.f;
-  float sc = __fdiv_rn(__fsub_rn(mx, mn), a.steps);
+  float sc = scalar_div(__fsub_rn(mx, mn), a.steps, a.rcp != 0);
   const float eps = 1.1920928955078125e-07f;
   sc = (sc != sc) ? sc : fmaxf(sc, eps);
   float off = __fadd_rn(__fdiv_rn(mn, sc), a.neg_int_min);   // min/scale - int_min
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(RD_THREADS) pr_batched_kernel(const void* mn_b
   float* offset = reinterpret_cast<float*>(d[3]);
   const float int_min_abs = __int_as_float((int)(d[4] & 0xffffffffll)), int_max_abs = __int_as_float((int)(d[4] >> 32));
   const float neg_int_min = __int_as_float((int)(d[5] & 0xffffffffll)), steps = __int_as_float((int)(d[5] >> 32));
-  const bool symmetric = (d[6] & 1) != 0, allow_one_sided = (d[6] & 2) != 0;
+  const bool symmetric = (d[6] & 1) != 0, allow_one_sided = (d[6] & 2) != 0, rcp = (d[6] & 4) != 0;
   bool one_sided = false;
   if (symmetric && allow_one_sided) {
     float mn = INFINITY, dummy = 0.f;
@@ -759,12 +759,12 @@ __global__ void __launch_bounds__(RD_THREADS) pr_batched_kernel(const void* mn_b
     float mn = load_as_float(mn_base, r_dt, start + i);
     const float mx = load_as_float(mx_base, r_dt, start + i);
     if (symmetric && !one_sided) {
-      scale[i] = nan_max(__fdiv_rn(fabsf(mn), int_min_abs), __fdiv_rn(fabsf(mx), int_max_abs));
+      scale[i] = nan_max(scalar_div(fabsf(mn), int_min_abs, rcp), scalar_div(fabsf(mx), int_max_abs, rcp));
       if (offset) offset[i] = 0.f;
       continue;
     }
     if (symmetric) mn = 0.f;
-    float sc = __fdiv_rn(__fsub_rn(mx, mn), steps);
+    float sc = scalar_div(__fsub_rn(mx, mn), steps, rcp);
     const float eps = 1.1920928955078125e-07f;
     sc = (sc != sc) ? sc : fmaxf(sc, eps);
     scale[i] = sc;
@@ -950,7 +950,9 @@ int ffq_params_for_range(const void* min_range, const void* max_range, int range
   a.int_max_abs = (float)fabs(-lo - 1.0);
   a.neg_int_min = (float)(-lo);
   a.steps = (float)(pow(2.0, num_bits) - 1.0);
-  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided; a.round_offset = round_offset;
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided & FFQ_FLAG_ALLOW_ONE_SIDED; a.round_offset = round_offset;
+  a.rcp = (allow_one_sided & FFQ_FLAG_SCALAR_DIV_RECIPROCAL) ? 1 : 0;
+  allow_one_sided &= FFQ_FLAG_ALLOW_ONE_SIDED;
   a.scale = scale_out; a.s_dt = scale_dtype; a.offset = offset_out; a.o_dt = offset_out ? offset_dtype : FFQ_NONE;
   a.part = static_cast<float*>(workspace);
   a.nparts = 0;
@@ -1007,7 +1009,8 @@ void ffq_params_for_ranges_encode(double num_bits, int symmetric, int allow_one_
   memcpy(u, f, sizeof(u));
   words[0] = (int64_t)(((uint64_t)u[1] << 32) | u[0]);
   words[1] = (int64_t)(((uint64_t)u[3] << 32) | u[2]);
-  words[2] = (symmetric ? 1 : 0) | (allow_one_sided ? 2 : 0);
+  words[2] = (symmetric ? 1 : 0) | ((allow_one_sided & FFQ_FLAG_ALLOW_ONE_SIDED) ? 2 : 0) |
+             ((allow_one_sided & FFQ_FLAG_SCALAR_DIV_RECIPROCAL) ? 4 : 0);
 }
 
 int ffq_params_for_ranges_batched(const void* min_base, const void* max_base, int range_dtype, const int64_t* desc_dev,

@@ -52,6 +52,12 @@ def _on_device(fn):
     return wrapped
 
 
+def _flags(allow_one_sided, reciprocal_scalar_division: bool = False) -> int:
+    """The C ABI's `allow_one_sided` word: bit 0 the flag itself, bit 1 FFQ_FLAG_SCALAR_DIV_RECIPROCAL (the scalar
+    divisions of parameters_for_range done as aten's CUDA kernel does them: what the reference computes on a GPU)."""
+    return int(bool(allow_one_sided)) | (2 if reciprocal_scalar_division else 0)
+
+
 def _bitwidth_guard(dtype: torch.dtype, num_bits: float) -> None:
     if not can_support_bitwidth(dtype, num_bits):
         raise RuntimeError(f"Provided dtype ({dtype}) is not enough to store {num_bits} bits quantized values.")
@@ -241,6 +247,7 @@ def quantize_dynamic_by_tile(
     symmetric: bool,
     allow_one_sided: bool,
     output_dtype: Optional[torch.dtype],
+    reciprocal_scalar_division: bool = False,
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """``torch.ops.fastforward.quantize_dynamic_by_tile`` (quantization/_quantizer_impl.py:243-285):
     returns ``(codes, scale, rounded_offset)``, scale/offset in float32."""
@@ -258,7 +265,8 @@ def quantize_dynamic_by_tile(
     C.check(C.lib.ffq_dynamic_quantize(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), C.dtype_tag(out_dtype),
         scale.data_ptr(), offset.data_ptr(), layout.ref, float(num_bits),
-        int(bool(symmetric)), int(bool(allow_one_sided)), ws.data_ptr(), ws_bytes, C.current_stream(x.device)))
+        int(bool(symmetric)), _flags(allow_one_sided, reciprocal_scalar_division), ws.data_ptr(), ws_bytes,
+        C.current_stream(x.device)))
     return q, scale, offset
 
 
@@ -311,6 +319,7 @@ def running_minmax_update_(
 def parameters_for_range_(
     min_range: torch.Tensor, max_range: torch.Tensor, num_bits: float, symmetric: bool, allow_one_sided: bool,
     scale_out: torch.Tensor, offset_out: Optional[torch.Tensor], round_offset: bool = False,
+    reciprocal_scalar_division: bool = False,
 ) -> None:
     """Device-side, sync-free ``parameters_for_range`` (quantization/affine/range.py:54-122) writing
     straight into a quantizer's ``scale`` / ``offset`` storage (nn/linear_quantizer.py:347-357)."""
@@ -328,7 +337,7 @@ def parameters_for_range_(
     ws = C.scratch(mn.device, 4096)
     C.check(C.lib.ffq_params_for_range(
         mn.data_ptr(), mx.data_ptr(), C.dtype_tag(mn.dtype), n, float(num_bits),
-        int(bool(symmetric)), int(bool(allow_one_sided)), int(bool(round_offset)),
+        int(bool(symmetric)), _flags(allow_one_sided, reciprocal_scalar_division), int(bool(round_offset)),
         scale_out.data_ptr(), C.dtype_tag(scale_out.dtype),
         C.ptr(offset_out), C.dtype_tag(offset_out.dtype if offset_out is not None else None),
         ws.data_ptr(), ws.numel(), C.current_stream(mn.device)))
@@ -340,6 +349,7 @@ def calibrate_fake_quantize_(
     scale_out: torch.Tensor, offset_out: Optional[torch.Tensor], quantized_dtype: Optional[torch.dtype] = None,
     out: Optional[torch.Tensor] = None, run_min: Optional[torch.Tensor] = None, run_max: Optional[torch.Tensor] = None,
     flags: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+    reciprocal_scalar_division: bool = False,
 ) -> torch.Tensor:
     """Calibrate on ``data`` and snap it to the grid in ONE pass: per-tile min/max (merged into ``run_min`` /
     ``run_max`` when given) -> ``scale_out`` / ``offset_out`` in place -> ``out = dequantize(quantize(data))``
@@ -368,13 +378,14 @@ def calibrate_fake_quantize_(
     C.check(C.lib.ffq_calibrate_fakequant(
         x.data_ptr(), C.dtype_tag(x.dtype), out.data_ptr(), C.ptr(run_min), C.ptr(run_max),
         C.dtype_tag(run_min.dtype if run_min is not None else None), scale_out.data_ptr(), C.ptr(offset_out), C.ptr(flags),
-        layout.ref, float(num_bits), int(bool(symmetric)), int(bool(allow_one_sided)), C.dtype_tag(code_dtype),
+        layout.ref, float(num_bits), int(bool(symmetric)), _flags(allow_one_sided, reciprocal_scalar_division), C.dtype_tag(code_dtype),
         ws.data_ptr(), ws.numel(), C.current_stream(x.device)))
     return out
 
 
 @_on_device
-def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor, entries) -> None:
+def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor, entries,
+                                   reciprocal_scalar_division: bool = False) -> None:
     """``parameters_for_range_`` for many quantizers in ONE launch.  ``min_buf`` / ``max_buf``: contiguous buffers
     holding every quantizer's running range; ``entries``: ``(start, length, num_bits, symmetric, allow_one_sided,
     scale, offset_or_None)`` with fp32 contiguous CUDA ``scale`` / ``offset`` of ``length`` elements."""
@@ -394,7 +405,7 @@ def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor,
             raise RuntimeError("parameters_for_ranges_batched_: range outside the buffers")
         key = (float(num_bits), bool(symmetric), bool(allow_one_sided))
         if key not in enc:
-            C.lib.ffq_params_for_ranges_encode(key[0], int(key[1]), int(key[2]), words)
+            C.lib.ffq_params_for_ranges_encode(key[0], int(key[1]), _flags(key[2], reciprocal_scalar_division), words)
             enc[key] = (int(words[0]), int(words[1]), int(words[2]))
         w = enc[key]
         rows.append((int(start), int(length), scale.data_ptr(), 0 if offset is None else offset.data_ptr(), w[0], w[1], w[2], 0))
@@ -428,7 +439,7 @@ def calibrate_quantize_(
     run_min: torch.Tensor, run_max: torch.Tensor, data: torch.Tensor, tile_size, num_bits: float,
     symmetric: bool, allow_one_sided: bool, scale_out: torch.Tensor, offset_out: Optional[torch.Tensor],
     flags: Optional[torch.Tensor] = None, settled: Optional[torch.Tensor] = None, rowsum: bool = False,
-    run_fixup: bool = True, workspace: Optional[torch.Tensor] = None,
+    run_fixup: bool = True, workspace: Optional[torch.Tensor] = None, reciprocal_scalar_division: bool = False,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """One RunningMinMax calibration step in one pass over ``data``: updates ``run_min``/``run_max`` in place
     (range_setting/minmax.py:229-237), writes the quantizer's ``scale``/``offset`` for the updated range in place
@@ -462,7 +473,7 @@ def calibrate_quantize_(
     C.check(C.lib.ffq_calibrate_quantize(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), run_min.data_ptr(), run_max.data_ptr(), C.dtype_tag(run_min.dtype),
         scale_out.data_ptr(), C.ptr(offset_out), C.ptr(rs), row_len, C.ptr(flags), C.ptr(settled), int(bool(run_fixup)),
-        layout.ref, float(num_bits), int(bool(symmetric)), int(bool(allow_one_sided)),
+        layout.ref, float(num_bits), int(bool(symmetric)), _flags(allow_one_sided, reciprocal_scalar_division),
         ws.data_ptr(), ws.numel(), C.current_stream(x.device)))
     return q, rs
 

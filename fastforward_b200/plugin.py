@@ -45,7 +45,9 @@ def _cuda_backward(data, output_grad, scale, tile_size, num_bits, offset=None) -
 
 
 def _cuda_dynamic(data, tile_size, num_bits, symmetric, allow_one_sided, output_dtype):
-    return ops.quantize_dynamic_by_tile(data, tuple(tile_size), num_bits, symmetric, allow_one_sided, output_dtype)
+    # the reference computes these parameters with aten's CUDA kernels when its tensors live on a GPU: same flavour
+    return ops.quantize_dynamic_by_tile(data, tuple(tile_size), num_bits, symmetric, allow_one_sided, output_dtype,
+                                        reciprocal_scalar_division=True)
 
 
 def install(fastforward_module: Optional[Any] = None, *, register_linear: bool = True,

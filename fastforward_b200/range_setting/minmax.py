@@ -63,11 +63,15 @@ def _host_of(quantizer):
         if mod is None or fn_mod is None or not hasattr(mod, "QuantizedTensor"):
             # a quantizer from neither host package (a user's own RangeSettable): separate kernels + its own setter
             host = types.SimpleNamespace(QuantizedTensor=(), QuantizationContext=None, get_export_mode=lambda: False,
-                                         LinearQuantizer=None)
+                                         LinearQuantizer=None, rcp=False)
         else:
             host = types.SimpleNamespace(
                 QuantizedTensor=mod.QuantizedTensor, QuantizationContext=fn_mod.QuantizationContext,
-                get_export_mode=mod.get_export_mode, LinearQuantizer=getattr(lq_mod, "LinearQuantizer", None))
+                get_export_mode=mod.get_export_mode, LinearQuantizer=getattr(lq_mod, "LinearQuantizer", None),
+                # an unmodified reference computes parameters_for_range with aten's CUDA kernels on a GPU (its scalar
+                # divisions multiply by the reciprocal): its quantizers get that flavour, ours the CPU flavour the
+                # golden vectors pin
+                rcp=root != _OWN_ROOT)
         _HOSTS[root] = host
     return host
 
@@ -107,7 +111,7 @@ def _set_range_direct(quantizer, lo: torch.Tensor, hi: torch.Tensor) -> bool:
             return False
     with torch.no_grad():
         ops.parameters_for_range_(lo, hi, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
-                                  scale.data, None if offset is None else offset.data)
+                                  scale.data, None if offset is None else offset.data, reciprocal_scalar_division=host.rcp)
     return True
 
 
@@ -380,7 +384,7 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
             self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen,
-            workspace=ws)
+            workspace=ws, reciprocal_scalar_division=_host_of(quantizer).rcp)
         if self._settled_host is not None and not self._settled_seen:
             self._settled_host.copy_(self._settled, non_blocking=True)
         if self._eager:
@@ -648,10 +652,11 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
                 if not _set_range_direct(quantizer, step.min, step.max):
                     quantizer.quantization_range = (step.min, step.max)
                 continue
-            per_chunk.setdefault((id(slot[0]), slot[1], step.min.device, step.min.dtype), (slot, []))[1].append(entry)
-        for (_, ci, dev, dt), (slot, entries) in per_chunk.items():
+            per_chunk.setdefault((id(slot[0]), slot[1], step.min.device, step.min.dtype, _host_of(quantizer).rcp),
+                                 (slot, []))[1].append(entry)
+        for (_, ci, dev, dt, rcp), (slot, entries) in per_chunk.items():
             mn, mx, used = slot[0].chunks[(dev, dt)][ci]
-            ops.parameters_for_ranges_batched_(mn, mx, entries)
+            ops.parameters_for_ranges_batched_(mn, mx, entries, reciprocal_scalar_division=rcp)
 
 
 class SmoothedMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):

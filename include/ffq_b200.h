@@ -74,6 +74,16 @@ typedef struct {
   int64_t tile[FFQ_MAX_RANK];
 } ffq_layout_t;
 
+/* Bits of the `allow_one_sided` argument of ffq_params_for_range, ffq_params_for_ranges_encode, ffq_dynamic_quantize,
+ * ffq_calibrate_quantize and ffq_calibrate_fakequant (0 / 1 keep their plain meaning).
+ * FFQ_FLAG_SCALAR_DIV_RECIPROCAL: do the three tensor / Python-scalar divisions of parameters_for_range
+ * (affine/range.py:112-120) as aten's CUDA kernel does them, x * (1.0f / d), instead of the IEEE division of aten's CPU
+ * kernel -- one ulp apart for divisors that are not powers of two.  The plugin sets it, so that a GPU run of the
+ * unmodified reference gets bit-identical parameters with and without this backend; the default (CPU flavour) is what
+ * the reference's golden vectors pin. */
+#define FFQ_FLAG_ALLOW_ONE_SIDED 1
+#define FFQ_FLAG_SCALAR_DIV_RECIPROCAL 2
+
 /* Which scratch requirement ffq_workspace_bytes() reports. */
 typedef enum {
   FFQ_WS_QUANTIZE_BWD = 0,
@@ -323,6 +333,12 @@ FFQ_API int ffq_gptq_block(float* w, int64_t ldw, float* q, int64_t ldq, float* 
  * [3] strict-accepted quotients that differ from __fdiv_rn                   -- must stay 0 */
 FFQ_API int ffq_selftest_shared_div(unsigned long long n, unsigned int seed, unsigned long long* counts_dev,
                                     void* stream);
+
+/* Test hook: while `counters_dev` is non-NULL, the CTA-pair kernel of ffq_qlinear_w8a8 records per CTA eight uint64 of
+ * SM clocks (see GemmArgs::prof in csrc/ffq_qlinear.cu): how long the TMA producer waited for a free stage, the MMA
+ * issuer for operands and for a free accumulator, the epilogue for a finished tile, and each role's total.
+ * counters_dev: uint64[8 * grid] (grid <= 8 * SM count).  NULL switches it off.  Used by tools/prof_gemm_roles.py. */
+FFQ_API void ffq_debug_gemm_profile(unsigned long long* counters_dev);
 
 #ifdef __cplusplus
 }

@@ -209,7 +209,7 @@ def test_w4a16_quantized_16bit_activations_3d_input_and_predicate():
         wq = lin.weight_quantizer(lin.weight)
         assert qlinear._accepts_w4a16(input=x, weight=wq, bias=None)
         assert not qlinear._accepts_w4a16(input=x.float(), weight=wq, bias=None)            # fp32 activations
-        assert not qlinear._accepts_w4a16(input=x.repeat(8, 1, 1), weight=wq, bias=None)    # 800 rows > W4A16_MAX_ROWS
+        assert qlinear._accepts_w4a16(input=x.repeat(8, 1, 1), weight=wq, bias=None)        # 800 rows: no row limit any more
         assert not qlinear._accepts_w4a16(input=x[..., :448], weight=wq, bias=None)         # K mismatch
         odd = ff.nn.LinearQuantizer(4, granularity=ff.PerBlock(block_dims=1, block_sizes=32, per_channel_dims=0),
                                     quantized_dtype=torch.int8).to(DEV)

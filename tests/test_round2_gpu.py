@@ -26,6 +26,7 @@ def _tiny(seed=3):
     model = bw.DecoderStack(bw.TINY, dtype=torch.bfloat16, device=DEV)
     bw.init_weights_(model, seed=seed)
     bw.quantize_for_w8a8(ff, model)
+    model.to(DEV)                   # quantizers are created on the CPU (LinearQuantizer's default device)
     qlinear.install()
     return model
 
@@ -136,7 +137,8 @@ def _gemm(qx, qw, sx, ox, sw, ow, bias=None, out_dtype=torch.bfloat16, requant=N
 
 
 def _ref_f64(qx, qw, sx, ox, sw, ow, bias=None):
-    acc = torch._int_mm(qx, qw.t()).double() if qx.shape[0] > 16 else (qx.double() @ qw.double().t())
+    ok = qx.shape[0] > 16 and qx.shape[1] % 8 == 0 and qw.shape[0] % 8 == 0            # torch._int_mm's shape rules
+    acc = torch._int_mm(qx, qw.t()).double() if ok else (qx.double() @ qw.double().t())
     oxr = 0.0 if ox is None else torch.round(ox.double())
     owr = torch.zeros_like(sw, dtype=torch.float64) if ow is None else torch.round(ow.double())
     k = qx.shape[1]
@@ -342,12 +344,15 @@ def test_w4a16_kernel_steps_aside_for_autograd_and_strict_mode():
         qw = wq(w)
     x = torch.randn(32, 256, device=DEV, dtype=torch.bfloat16)
     k = qlinear.own()
-    assert k.accepts_w4a16(input=x, weight=qw, bias=None, output_quantizer=None, strict_quantization=False)
-    assert not k.accepts_w4a16(input=x, weight=qw, bias=None, output_quantizer=None, strict_quantization=True)
     xg = x.clone().requires_grad_()
-    assert not k.accepts_w4a16(input=xg, weight=qw, bias=None, output_quantizer=None, strict_quantization=False)
     with torch.no_grad():
+        assert k.accepts_w4a16(input=x, weight=qw, bias=None, output_quantizer=None, strict_quantization=False)
+        assert not k.accepts_w4a16(input=x, weight=qw, bias=None, output_quantizer=None, strict_quantization=True)
         assert k.accepts_w4a16(input=xg, weight=qw, bias=None, output_quantizer=None, strict_quantization=False)
+    # with autograd recording and something that requires grad (the input, or the quantizer's scale Parameter) the
+    # kernel steps aside: the fallback's dequantize + F.linear carries the gradients
+    assert not k.accepts_w4a16(input=xg, weight=qw, bias=None, output_quantizer=None, strict_quantization=False)
+    assert not k.accepts_w4a16(input=x, weight=qw, bias=None, output_quantizer=None, strict_quantization=False)
     # gradients flow through the fallback
     qlinear.install()
     from fastforward_b200.nn import functional as F
@@ -364,6 +369,7 @@ def _frozen_model():
     ff.quantize_model(model)
     ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
         ff.nn.LinearQuantizer, num_bits=3, granularity=ff.PerChannel(0))
+    model.to(DEV)
     with torch.no_grad(), ff.estimate_ranges(model, ff.range_setting.running_minmax), ff.strict_quantization(False):
         model(torch.randn(4, 8, 64, device=DEV))
     return model
