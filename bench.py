@@ -729,12 +729,11 @@ def run_ours(args):
         if not args.skip_cpu_baseline:
             import bench_reference as br
             cpu_baseline = br.cpu_calibration(sh, seq, layers, args.cpu_sample_layers, steps=3, warmup=1)
-            if br.reference_available() and args.shape == "8b":
-                cfg1_ref = br.cfg1_fake_quant(dev, compiled=not args.skip_compiled_baseline)
-                if not args.skip_drop_in:
-                    del model
-                    torch.cuda.empty_cache()
-                    drop_in = br.gpu_calibration(sh, seq, layers, dev)
+            if br.reference_available() and args.shape == "8b" and not args.skip_drop_in:
+                del model
+                torch.cuda.empty_cache()
+                cfg1_ref = {}
+                drop_in = br.gpu_calibration(sh, seq, layers, dev, cfg1=cfg1_ref, compiled=not args.skip_compiled_baseline)
         config = workload_config(sh, layers, seq, world)
         schedule = {"cuda_graph": use_graph, "dedupe_shared_inputs": True, "memoize_parameters": memo,
                     "note": "how THIS arm runs the config's steps; every timed step re-quantizes every weight unless "

@@ -41,6 +41,7 @@ def _build_model(ff, sh, layers, device, disable_strict=True):
     model = bw.DecoderStack(sh, layers=layers, dtype=torch.bfloat16, device=device)
     bw.init_weights_(model, seed=0)
     bw.quantize_for_w8a8(ff, model)
+    model.to(device)                 # the quantizers are created on the CPU (LinearQuantizer's default device)
     return model
 
 
@@ -114,8 +115,10 @@ def _time_steps(model, ctx_factory, tokens, steps, warmup):
                 wall_ms_per_step=round(1e3 * wall / steps, 2), steps=steps, warmup=warmup)
 
 
-def gpu_calibration(sh, seq, layers, dev, steps=3, warmup=2, with_plugin=True):
-    """(a) reference alone on CUDA, (b) reference + plugin kernels, (c) + sync-free estimator.  All eager."""
+def gpu_calibration(sh, seq, layers, dev, steps=3, warmup=2, with_plugin=True, cfg1=None, compiled=True):
+    """(a) reference alone on CUDA, (b) reference + plugin kernels, (c) + sync-free estimator.  All eager.
+    `cfg1` (a dict) additionally receives BASELINE configs[0] measured the same three ways: plugin.install() cannot be
+    undone inside a process, so everything "reference alone" runs first."""
     from fastforward_b200 import _cabi
 
     ff = _ref()
@@ -134,11 +137,15 @@ def gpu_calibration(sh, seq, layers, dev, steps=3, warmup=2, with_plugin=True):
     stock = lambda: ff.estimate_ranges(model, ff.range_setting.running_minmax)      # noqa: E731
     if "quantize_by_tile" not in _plugin_state():
         out["reference_alone_eager_cuda"] = _time_steps(model, stock, tokens, steps, warmup)
+        if cfg1 is not None:
+            cfg1.update(cfg1_fake_quant(dev, cpu=True, cuda=True, compiled=compiled, with_plugin=False))
     if with_plugin:
         from fastforward_b200 import plugin
 
         reset()
         plugin.install(ff, patch_estimators=False)
+        if cfg1 is not None:
+            cfg1.update(cfg1_fake_quant(dev, cpu=False, cuda=False, compiled=False, with_plugin=True))
         l0 = _cabi.launch_count()
         out["reference_plus_plugin"] = _time_steps(model, stock, tokens, steps, warmup)
         out["reference_plus_plugin"]["ffq_launches_per_step"] = round((_cabi.launch_count() - l0) / (steps + warmup), 1)

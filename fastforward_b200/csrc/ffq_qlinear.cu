@@ -58,6 +58,7 @@ struct GemmArgs {
   // total, [2] MMA issuer waiting for operands, [3] MMA issuer waiting for a free accumulator, [4] MMA issuer total,
   // [5] epilogue waiting for a finished tile, [6] epilogue total
   unsigned long long* prof;
+  int dbg;                                      // test hook (FFQ_GEMM_DEBUG): 1 skip the epilogue, 2 skip its stores, 4 skip its column parameters
 };
 
 constexpr int COL_SLOTS = 5;                     // alpha, bias, int constant, weight offset, float constant
@@ -70,6 +71,8 @@ constexpr int COL_SLOTS = 5;                     // alpha, bias, int constant, w
 // dequantize-then-float path does.
 __device__ __forceinline__ bool stage_col_params(const GemmArgs& g, int n0, int bn, int tid, int nthreads,
                                                  float* col_params, int32_t* col_ints) {
+  // layout: uint4 per column {alpha, bias, int constant, weight offset} (one 16-byte shared load per column in the
+  // epilogue), followed by the float form of the constant for the wide path at word 4*256 + c
   const float sx = g.sx[0];
   const float oxf = g.ox ? rintf(g.ox[0]) : 0.f;
   const long long o_x = (long long)oxf;
@@ -83,13 +86,22 @@ __device__ __forceinline__ bool stage_col_params(const GemmArgs& g, int n0, int 
     // |acc| <= K * 2^14, |own * rowsum_x| <= |o_w| * K * 2^7
     const long long bound = (c64 < 0 ? -c64 : c64) + (o_w < 0 ? -o_w : o_w) * (long long)g.K * 128 + (long long)g.K * 16384;
     wide = wide || !(fabsf(owf) < 1.0e9f) || bound >= 0x7fffffffll;
-    col_params[c] = in ? sx * g.sw[n] : 0.f;
-    col_params[bn + c] = (in && g.bias) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
-    col_ints[2 * bn + c] = (int32_t)c64;
-    col_ints[3 * bn + c] = (int32_t)o_w;
-    col_params[4 * bn + c] = in ? (oxf * (float)g.rowsum_w[n] + (float)g.K * oxf * owf) : 0.f;
+    float4 v;
+    v.x = in ? sx * g.sw[n] : 0.f;
+    v.y = (in && g.bias) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
+    v.z = __int_as_float((int32_t)c64);
+    v.w = __int_as_float((int32_t)o_w);
+    reinterpret_cast<float4*>(col_params)[c] = v;
+    col_params[4 * BN + c] = in ? (oxf * (float)g.rowsum_w[n] + (float)g.K * oxf * owf) : 0.f;
   }
+  (void)col_ints;
   return wide;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
 }
 
 // barrier over the 4 epilogue warps that also ORs a predicate (the tile's "wide constants" decision)
@@ -109,21 +121,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
                                                const int32_t* col_ints, int bn, int c0, bool wide, int32_t rx, int row,
                                                int n0, float rq_s, float rq_o, int& rq_sum) {
   float v[32];
-  if (!wide) {
+  const uint32_t cp = smem_u32(col_params) + (uint32_t)c0 * 16u;
+  if (g.dbg & 4) {                       // test hook: no per-column parameters (isolates their shared-memory traffic)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (float)(int32_t)acc[j] * 0.001f;
+  } else if (!wide) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const int32_t t = (int32_t)acc[j] + col_ints[2 * bn + c0 + j] + col_ints[3 * bn + c0 + j] * rx;
-      v[j] = fmaf(col_params[c0 + j], (float)t, col_params[bn + c0 + j]);
+      const uint4 p = lds128(cp + (uint32_t)j * 16u);
+      const int32_t t = (int32_t)acc[j] + (int32_t)p.z + (int32_t)p.w * rx;
+      v[j] = fmaf(__uint_as_float(p.x), (float)t, __uint_as_float(p.y));
     }
   } else {
     const float rxf = (float)rx;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float t = (float)(int32_t)acc[j] + col_params[4 * bn + c0 + j] + (float)col_ints[3 * bn + c0 + j] * rxf;
-      v[j] = fmaf(col_params[c0 + j], t, col_params[bn + c0 + j]);
+      const uint4 p = lds128(cp + (uint32_t)j * 16u);
+      const float t = (float)(int32_t)acc[j] + col_params[4 * BN + c0 + j] + (float)(int32_t)p.w * rxf;
+      v[j] = fmaf(__uint_as_float(p.x), t, __uint_as_float(p.y));
     }
   }
-  if (row >= g.M || n0 >= g.N) return;
+  if (row >= g.M || n0 >= g.N || (g.dbg & 2)) return;
   const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
   if (g.y) store_chunk<OutT>(static_cast<OutT*>(g.y) + (size_t)row * g.N + n0, v, ncols);
   if (g.rq_codes) {
@@ -445,7 +463,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < bn; c0 += 32) {
+      for (int c0 = 0; c0 < ((g.dbg & 1) ? 0 : bn); c0 += 32) {
         uint32_t acc[32];
         tmem_ld32(taddr + (uint32_t)c0, acc);
         epilogue_chunk<OutT>(g, acc, col_params, col_ints, bn, c0, wide, rx, row, tn * bn + c0, rq_s, rq_o, rq_sum);
@@ -602,6 +620,7 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   g.sx = sx; g.ox = ox; g.sw = sw; g.ow = ow; g.rowsum_w = rowsum_w; g.bias = bias; g.bias_dt = bias_dtype;
   g.rowsum_x = rowsum_x;
   g.prof = g_gemm_prof;
+  { const char* e = getenv("FFQ_GEMM_DEBUG"); g.dbg = e ? atoi(e) : 0; }
   if (requant != nullptr && requant->codes != nullptr) {
     if (requant->scale == nullptr) { set_error("qlinear_w8a8: requant needs a scale"); return FFQ_ERR_INVALID; }
     if (!(requant->num_bits >= 1 && requant->num_bits <= 8)) { set_error("qlinear_w8a8: requant codes are int8: num_bits must be in [1, 8]"); return FFQ_ERR_BITWIDTH; }

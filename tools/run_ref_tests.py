@@ -34,9 +34,7 @@ HOT = [
     "tests/test_range_setting.py", "tests/test_quantized_tensor.py", "tests/test_dispatcher.py", "tests/test_overrides.py",
 ]
 CUDA_K = "cuda or test_dispatch or test_quantized_tensor_to"
-# default-cuda mode: tests that cannot pass with a CUDA default device for reasons unrelated to this backend
-# (substring of the test id -> why).  Filled from the first run on the B200; see profiles/r02_ref_tests_default_cuda.md.
-KNOWN_DEFAULT_CUDA: dict = {}
+
 
 
 def build_command(mode: str, extra=(), no_plugin: bool = False, estimators: bool = False):
