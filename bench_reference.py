@@ -221,7 +221,7 @@ def cfg1_fake_quant(dev, cpu=True, cuda=True, compiled=True, with_plugin=True):
         out["reference_eager_cuda"] = {"us": round(t * 1e6, 1), "GBps_algorithmic": round(by / t / 1e9, 1)}
         if compiled:
             try:
-                with ff.compiled_quant_funcs(True):
+                with ff.flags.compiled_quant_funcs(True):
                     step = make(dev)
                     t = time_cuda(step, iters=20, warm=4)
                 out["reference_compiled_quant_funcs_cuda"] = {"us": round(t * 1e6, 1), "GBps_algorithmic": round(by / t / 1e9, 1),

@@ -27,6 +27,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstring>
 
 #include "ffq_common.cuh"
 #include "ffq_umma.cuh"
@@ -41,7 +42,8 @@ constexpr int STAGE_BYTES = A_STAGE + B_STAGE;   // 48 KB
 constexpr int GEMM_THREADS = 192;                // 6 warps
 constexpr int TMEM_COLS = 512;                   // 2 accumulators x 256 columns
 constexpr int COL_BYTES = 5 * BN * 4;            // per-column epilogue parameters (COL_SLOTS x BN words)
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + COL_BYTES + 256 + 1024;   // + column params + barriers + align
+constexpr int OUT_STAGE_BYTES = 4 * 32 * 128;    // epilogue staging: one [32 rows x 128 B] box per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + COL_BYTES + 256 + 1024;   // + staging + column params + barriers + align
 
 struct GemmArgs {
   int M, N, K;
@@ -58,6 +60,7 @@ struct GemmArgs {
   // total, [2] MMA issuer waiting for operands, [3] MMA issuer waiting for a free accumulator, [4] MMA issuer total,
   // [5] epilogue waiting for a finished tile, [6] epilogue total
   unsigned long long* prof;
+  int tma_store;                                // the output has a tensor map: staged TMA-store epilogue
   int dbg;                                      // test hook (FFQ_GEMM_DEBUG): 1 skip the epilogue, 2 skip its stores, 4 skip its column parameters
 };
 
@@ -119,7 +122,7 @@ __device__ __forceinline__ bool epilogue_bar_or(bool pred) {
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t (&acc)[32], const float* col_params,
                                                const int32_t* col_ints, int bn, int c0, bool wide, int32_t rx, int row,
-                                               int n0, float rq_s, float rq_o, int& rq_sum) {
+                                               int n0, float rq_s, float rq_o, int& rq_sum, uint8_t* stage) {
   float v[32];
   const uint32_t cp = smem_u32(col_params) + (uint32_t)c0 * 16u;
   if (g.dbg & 4) {                       // test hook: no per-column parameters (isolates their shared-memory traffic)
@@ -141,9 +144,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       v[j] = fmaf(__uint_as_float(p.x), t, __uint_as_float(p.y));
     }
   }
-  if (row >= g.M || n0 >= g.N || (g.dbg & 2)) return;
+  if (g.dbg & 2) return;
+  if (stage != nullptr) {
+    // ---- staged store: this lane's 32 values go into its row of the warp's [32 rows x 128 B] box, 128B-swizzled (16-byte
+    // chunk index XOR row%8: conflict-free writes, undone by the TMA store); one TMA store per full box ----
+    constexpr int PER = 16 / sizeof(OutT);                    // elements per 16-byte chunk
+    constexpr int CHUNKS = 32 / PER;                          // 16-byte chunks this call fills (4 for 16-bit, 8 for fp32)
+    const int lane = threadIdx.x & 31;
+    const int q0 = (sizeof(OutT) == 2) ? ((c0 >> 5) & 1) * 4 : 0;   // 16-bit: two 32-column calls fill one 128-byte row
+    uint8_t* rowp = stage + lane * 128;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      Vec<OutT, PER> o;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) o.v[i] = Elem<OutT>::from_f(v[c * PER + i]);
+      *reinterpret_cast<Vec<OutT, PER>*>(rowp + (((q0 + c) ^ (lane & 7)) << 4)) = o;
+    }
+  } else if (row < g.M && n0 < g.N && g.y) {
+    const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
+    store_chunk<OutT>(static_cast<OutT*>(g.y) + (size_t)row * g.N + n0, v, ncols);
+  }
+  if (row >= g.M || n0 >= g.N) return;
   const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
-  if (g.y) store_chunk<OutT>(static_cast<OutT*>(g.y) + (size_t)row * g.N + n0, v, ncols);
   if (g.rq_codes) {
     // output_quantizer(y): y is first rounded to the output dtype (what the quantizer would read back), then
     // quantize_by_tile's arithmetic in the promoted dtype of (y, fp32 scale) = fp32
@@ -175,15 +197,61 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
   }
 }
 
+
+// TMA store of one [32 rows x 128 B] box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
+               "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// The epilogue of one tile for one warp (32 accumulator rows): TMEM -> registers -> dequantisation -> either direct
+// vector stores (64-byte row segments per lane) or, when the output allows a tensor map (`map_y`), a 128B-swizzled
+// staging box in shared memory drained by TMA stores: whole 128-byte lines reach L2 instead of 16-byte pieces of 32
+// different rows per instruction, and the stores leave the LSU path the operand loads' completions share.
+template <typename OutT>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const CUtensorMap* map_y, uint32_t taddr, int bn, int row,
+                                              int row0_warp, int n_tile0, bool wide, int32_t rx, float* col_params,
+                                              const int32_t* col_ints, uint8_t* stage, float rq_s, float rq_o, bool& pending) {
+  const int lane = threadIdx.x & 31;
+  constexpr int COLS_PER_BOX = 128 / (int)sizeof(OutT);       // 64 (16-bit) or 32 (fp32) columns per staged box
+  int rq_sum = 0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < ((g.dbg & 1) ? 0 : bn); c0 += 32) {
+    uint32_t acc[32];
+    tmem_ld32(taddr + (uint32_t)c0, acc);
+    // a lone trailing 32-column chunk of a 16-bit tile (bn = 224) cannot fill a box: direct stores
+    const bool box_first = (c0 % COLS_PER_BOX) == 0;
+    const bool staged = stage != nullptr && (sizeof(OutT) == 4 || !box_first || c0 + 32 < bn);
+    if (staged && box_first && pending) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has been read
+      __syncwarp();
+      pending = false;
+    }
+    epilogue_chunk<OutT>(g, acc, col_params, col_ints, bn, c0, wide, rx, row, n_tile0 + c0, rq_s, rq_o, rq_sum,
+                         staged ? stage : nullptr);
+    if (staged && ((c0 + 32) % COLS_PER_BOX) == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      const int nb = n_tile0 + c0 + 32 - COLS_PER_BOX;
+      if (lane == 0 && nb < g.N && row0_warp < g.M) tma_store_2d(map_y, stage, nb, row0_warp);
+      pending = true;
+    }
+  }
+  if (g.rq_rowsum && row < g.M) atomicAdd(&g.rq_rowsum[row], rq_sum);     // integer: exact, order independent
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_y, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* col_params = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [COL_SLOTS][bn]
+  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;                                // [4 warps][32 rows][128 B], swizzled
+  float* col_params = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + OUT_STAGE_BYTES);
   int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + COL_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + OUT_STAGE_BYTES + COL_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;   // [2]
@@ -267,6 +335,7 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int ep_tid = threadIdx.x - 64;                     // 0..127
     const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
     const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
+    bool store_pending = false;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile % tiles_m, tn = tile / tiles_m;
@@ -277,22 +346,17 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const bool wide = epilogue_bar_or(stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints));
       const int row = tm * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
-      int rq_sum = 0;
 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < bn; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + (uint32_t)c0, acc);
-        epilogue_chunk<OutT>(g, acc, col_params, col_ints, bn, c0, wide, rx, row, tn * bn + c0, rq_s, rq_o, rq_sum);
-      }
-      if (g.rq_rowsum && row < g.M) atomicAdd(&g.rq_rowsum[row], rq_sum);     // integer: exact, order independent
+      epilogue_tile<OutT>(g, &map_y, taddr, bn, row, tm * BM + quad * 32, tn * bn, wide, rx, col_params, col_ints,
+                          g.tma_store ? out_stage + quad * 4096 : nullptr, rq_s, rq_o, store_pending);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);          // 4 arrivals (one per epilogue warp) free the accumulator
     }
+    if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -318,16 +382,18 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // ================================================================================================
 constexpr int STAGES2 = 6;
 constexpr int HALF_STAGE = A_STAGE + BM * BK;      // A 128x128B + B half 128x128B = 32 KB
-constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + COL_BYTES + 256 + 1024;
+constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + OUT_STAGE_BYTES + COL_BYTES + 256 + 1024;
 template <typename OutT, int P>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_y, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE);       // [COL_SLOTS][bn]
+  uint8_t* out_stage = smem + STAGES2 * HALF_STAGE;                                // [4 warps][32 rows][128 B], swizzled
+  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE + OUT_STAGE_BYTES);
   int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + COL_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + OUT_STAGE_BYTES + COL_BYTES);
   uint64_t* full_bar = bars;                  // [STAGES2]  (the pair leader's copy is the one in use)
   uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  (each CTA waits on its own copy; P arrivals)
   uint64_t* tmem_full = bars + 2 * STAGES2;   // [2]        (each CTA waits on its own copy)
@@ -444,6 +510,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
     const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
     int it = 0;
+    bool store_pending = false;
     const bool prof = g.prof != nullptr && ep_tid == 0;
     long long t_tile = 0;
     const long long t_begin = prof ? clock64() : 0;
@@ -455,24 +522,19 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool wide = epilogue_bar_or(stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints));
       const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
-      int rq_sum = 0;
 
       const long long w0 = prof ? clock64() : 0;
       mbar_wait_bounded(&tmem_full[buf], use & 1);
       if (prof) t_tile += clock64() - w0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < ((g.dbg & 1) ? 0 : bn); c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + (uint32_t)c0, acc);
-        epilogue_chunk<OutT>(g, acc, col_params, col_ints, bn, c0, wide, rx, row, tn * bn + c0, rq_s, rq_o, rq_sum);
-      }
-      if (g.rq_rowsum && row < g.M) atomicAdd(&g.rq_rowsum[row], rq_sum);
+      epilogue_tile<OutT>(g, &map_y, taddr, bn, row, tm * TM + (int)cta * BM + quad * 32, tn * bn, wide, rx, col_params,
+                          col_ints, g.tma_store ? out_stage + quad * 4096 : nullptr, rq_s, rq_o, store_pending);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);   // 8 arrivals (4 warps x 2 CTAs) free the accumulator
     }
+    if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (prof) { g.prof[blockIdx.x * 8 + 5] = (unsigned long long)t_tile; g.prof[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_begin); }
   }
 
@@ -524,6 +586,23 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K,
   return FFQ_OK;
 }
 
+// [M, N] output, boxes of 32 rows x 128 bytes, 128B-swizzled in shared memory
+static int make_out_map(CUtensorMap* map, void* y, int64_t M, int64_t N, int y_dtype) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("qlinear: cuTensorMapEncodeTiled is not available from the driver"); return FFQ_ERR_CUDA; }
+  const int es = y_dtype == FFQ_F32 ? 4 : 2;
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)N * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = y_dtype == FFQ_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (y_dtype == FFQ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+  const CUresult r = enc(map, dt, 2, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("qlinear: cuTensorMapEncodeTiled (output) failed with CUresult %d", (int)r); return FFQ_ERR_CUDA; }
+  return FFQ_OK;
+}
+
 }  // namespace ffq
 
 using namespace ffq;
@@ -545,8 +624,8 @@ void ffq_debug_gemm_profile(unsigned long long* counters_dev) { g_gemm_prof = co
 
 // cluster launch of the pair kernel: P pairs (2P CTAs) per cluster
 template <typename OutT, int P>
-static int launch_pairs(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmArgs& g, long long cluster_tiles,
-                        cudaStream_t st) {
+static int launch_pairs(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_y, const GemmArgs& g,
+                        long long cluster_tiles, cudaStream_t st) {
   static std::atomic<uint64_t> attr_done{0};
   static int max_clusters[64] = {0};
   auto kern = w8a8_gemm2_kernel<OutT, P>;
@@ -571,18 +650,19 @@ static int launch_pairs(const CUtensorMap& map_a, const CUtensorMap& map_b, cons
   if (e != cudaSuccess) { set_error("qlinear_w8a8: cannot configure the %d-CTA cluster kernel: %s", 2 * P, cudaGetErrorString(e)); return FFQ_ERR_CUDA; }
   const long long clusters = cluster_tiles < max_clusters[dev] ? cluster_tiles : max_clusters[dev];
   cfg.gridDim = dim3((unsigned)(2 * P * clusters));
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, g);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, g);
   count_launch();
   if (le != cudaSuccess) { cudaGetLastError(); set_error("qlinear_w8a8: cluster launch failed: %s", cudaGetErrorString(le)); return FFQ_ERR_CUDA; }
   return FFQ_OK;
 }
 
 template <int P>
-static int launch_pairs_dt(int y_dtype, const CUtensorMap& a, const CUtensorMap& b, const GemmArgs& g, long long t, cudaStream_t st) {
+static int launch_pairs_dt(int y_dtype, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& y, const GemmArgs& g,
+                           long long t, cudaStream_t st) {
   switch (y_dtype) {
-    case FFQ_F32: return launch_pairs<float, P>(a, b, g, t, st);
-    case FFQ_BF16: return launch_pairs<__nv_bfloat16, P>(a, b, g, t, st);
-    default: return launch_pairs<__half, P>(a, b, g, t, st);
+    case FFQ_F32: return launch_pairs<float, P>(a, b, y, g, t, st);
+    case FFQ_BF16: return launch_pairs<__nv_bfloat16, P>(a, b, y, g, t, st);
+    default: return launch_pairs<__half, P>(a, b, y, g, t, st);
   }
 }
 
@@ -621,6 +701,15 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   g.rowsum_x = rowsum_x;
   g.prof = g_gemm_prof;
   { const char* e = getenv("FFQ_GEMM_DEBUG"); g.dbg = e ? atoi(e) : 0; }
+  // staged TMA-store epilogue whenever the output can be described by a tensor map (16-byte aligned rows);
+  // FFQ_GEMM_DIRECT_STORE=1 keeps the per-lane vector stores (A/B switch)
+  CUtensorMap map_y;
+  memset(&map_y, 0, sizeof(map_y));
+  const int es_y = y_dtype == FFQ_F32 ? 4 : 2;
+  if (y != nullptr && (N * es_y) % 16 == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0 && getenv("FFQ_GEMM_DIRECT_STORE") == nullptr) {
+    if ((rc = make_out_map(&map_y, y, M, N, y_dtype)) != FFQ_OK) return rc;
+    g.tma_store = 1;
+  }
   if (requant != nullptr && requant->codes != nullptr) {
     if (requant->scale == nullptr) { set_error("qlinear_w8a8: requant needs a scale"); return FFQ_ERR_INVALID; }
     if (!(requant->num_bits >= 1 && requant->num_bits <= 8)) { set_error("qlinear_w8a8: requant codes are int8: num_bits must be in [1, 8]"); return FFQ_ERR_BITWIDTH; }
@@ -656,9 +745,9 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
     if ((rc = make_map(&map_b2, qw, N, K, g.bn / 2 / P)) != FFQ_OK) return rc;
     const long long cluster_tiles = (tiles_m2 / P) * ((N + g.bn - 1) / g.bn);
     switch (P) {
-      case 4: return launch_pairs_dt<4>(y_dtype, map_a, map_b2, g, cluster_tiles, st);
-      case 2: return launch_pairs_dt<2>(y_dtype, map_a, map_b2, g, cluster_tiles, st);
-      default: return launch_pairs_dt<1>(y_dtype, map_a, map_b2, g, cluster_tiles, st);
+      case 4: return launch_pairs_dt<4>(y_dtype, map_a, map_b2, map_y, g, cluster_tiles, st);
+      case 2: return launch_pairs_dt<2>(y_dtype, map_a, map_b2, map_y, g, cluster_tiles, st);
+      default: return launch_pairs_dt<1>(y_dtype, map_a, map_b2, map_y, g, cluster_tiles, st);
     }
   }
   static std::atomic<uint64_t> attr_done{0};
@@ -686,9 +775,9 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   const long long tiles1 = ((M + BM - 1) / BM) * ((N + g.bn - 1) / g.bn);
   const int grid1 = (int)(tiles1 < sm_count() ? tiles1 : sm_count());
   switch (y_dtype) {
-    case FFQ_F32: w8a8_gemm_kernel<float><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, g); break;
-    case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, g); break;
-    default: w8a8_gemm_kernel<__half><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, g); break;
+    case FFQ_F32: w8a8_gemm_kernel<float><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, map_y, g); break;
+    case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, map_y, g); break;
+    default: w8a8_gemm_kernel<__half><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, map_y, g); break;
   }
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;

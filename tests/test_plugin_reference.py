@@ -3,6 +3,8 @@
 itself: the CUDA-key kernels appear next to the reference's CompositeExplicitAutograd implementations, the
 reference's dispatcher receives the linear / matmul kernels, and CPU tensors keep taking the reference's own path.
 With a GPU (``-m gpu``) the reference's own public API runs on our kernels and is compared with its CPU results."""
+import copy
+
 import pytest
 import torch
 
@@ -89,13 +91,16 @@ def test_reference_api_on_b200_kernels_matches_reference_cpu(ref_ff):
             x = torch.randn(shape) * 3
             g = torch.randn(shape)
             res = {}
+            # the parameters are derived once, on the CPU, and copied: the reference's own range setter gives scales one
+            # ulp apart on the two devices (aten's CUDA kernels divide by a scalar as x * (1/d)), which is not under test
+            q_cpu = ff.nn.LinearQuantizer(4, symmetric=symmetric, granularity=gran)
+            tile = gran.tile_size(x.shape)
+            tile = x.shape if isinstance(tile, str) else tile
+            rows = ff.quantization.tiled_tensor.tiles_to_rows(x, tile)
+            q_cpu.quantization_range = (rows.min(1).values * 0.7, rows.max(1).values * 0.7)
             for device in ("cpu", "cuda"):
-                q = ff.nn.LinearQuantizer(4, symmetric=symmetric, granularity=gran).to(device)
+                q = copy.deepcopy(q_cpu).to(device)
                 xd = x.detach().clone().to(device).requires_grad_()
-                tile = gran.tile_size(x.shape)
-                tile = x.shape if isinstance(tile, str) else tile
-                rows = ff.quantization.tiled_tensor.tiles_to_rows(x, tile)
-                q.quantization_range = (rows.min(1).values.to(device) * 0.7, rows.max(1).values.to(device) * 0.7)
                 l0 = _cabi.launch_count()
                 out = q(xd)
                 deq = out.dequantize()

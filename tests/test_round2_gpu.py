@@ -300,9 +300,11 @@ def test_cfg1_full_shape_bit_exact():
 def _qt(x, bits=8, symmetric=False):
     q = ff.nn.LinearQuantizer(bits, symmetric=symmetric, quantized_dtype=torch.int8).to(x.device)
     q.quantization_range = (x.min(), x.max())
-    return q(x)
+    with torch.no_grad():        # inference: with autograd recording, the scale Parameter would route to the fallback
+        return q(x)
 
 
+@torch.no_grad()
 def test_int8_matmul_and_bmm():
     from fastforward_b200.nn import functional as F
 
