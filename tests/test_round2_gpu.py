@@ -332,7 +332,7 @@ def test_int8_matmul_and_bmm():
         y = F.mm(a, b)
     want = a.dequantize().double() @ b.dequantize().double()
     assert y.dtype == torch.float32 and (y.double() - want).abs().max() <= 1e-5 * want.abs().max() + 1e-6
-    with pytest.raises(ff.QuantizationError):
+    with ff.strict_quantization(True), pytest.raises(ff.QuantizationError):
         F.matmul(a, b)                     # strict quantization without an output quantizer: the fallback's error
 
 
