@@ -28,6 +28,8 @@
 //
 // Arithmetic is the same op-by-op sequence as the unfused kernels (ffq_common.cuh), so the results are
 // bit-identical to them and to the reference (tests/test_calibrate_gpu.py).
+#include <cstdlib>
+
 #include "ffq_common.cuh"
 
 namespace ffq {
@@ -484,6 +486,118 @@ __global__ void __launch_bounds__(256) calq_group_kernel(const CalqArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Short tiles of 16-bit data, ONE THREAD PER TILE (g = 64 / 128 elements = 128 / 256 bytes): the tile is read with
+// 32-byte loads (LDG.256: one whole sector per lane per instruction; a warp's eight loads sweep 8 KB of consecutive
+// memory), reduced, parameterised and quantized entirely in the thread's registers -- no shuffles for the extrema, no
+// parameter broadcast, parameters derived once per 128 elements.  That takes the per-element instruction count of the
+// sub-warp kernel above (28: 2 for the shuffle trees, 2 for the parameter broadcast, the rest arithmetic) to ~14, which
+// is what an instruction-issue-bound kernel needs (at 6.4 TB/s a bf16 in/out stream leaves ~22 issue slots per element).
+// ZOFF: symmetric quantizer -- every tile finished here has offset 0 (one-sided candidates are deferred), so the
+// subtraction of the rounded offset disappears (x - 0 == x bit for bit; the +0 of the dequantize step stays: it turns
+// -0 codes into +0 as the reference's addition does).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld256_stream(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+template <typename XT> struct Packed2;
+template <> struct Packed2<__nv_bfloat16> {
+  using T = __nv_bfloat162;
+  static __device__ __forceinline__ T mn(T a, T b) { return __hmin2_nan(a, b); }
+  static __device__ __forceinline__ T mx(T a, T b) { return __hmax2_nan(a, b); }
+};
+template <> struct Packed2<__half> {
+  using T = __half2;
+  static __device__ __forceinline__ T mn(T a, T b) { return __hmin2_nan(a, b); }
+  static __device__ __forceinline__ T mx(T a, T b) { return __hmax2_nan(a, b); }
+};
+
+template <typename XT, typename RT, int NV, bool FQ, bool ZOFF>
+__global__ void __launch_bounds__(256) calq_tile_thread_kernel(const CalqArgs a) {
+  static_assert(sizeof(XT) == 2 && NV % 2 == 0, "16-bit data, whole 32-byte accesses");
+  constexpr int EPT = 8;
+  using P2 = Packed2<XT>;
+  const unsigned long long ntiles = a.numel / (unsigned long long)(NV * EPT);
+  const unsigned long long tile = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+  const bool decide = a.symmetric && a.allow_one_sided;
+  bool neg = false, def = false;
+  if (tile < ntiles) {
+    const XT* __restrict__ x = static_cast<const XT*>(a.x) + tile * (unsigned long long)(NV * EPT);
+    uint4 w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) ld256_stream(x + i * EPT, w[i], w[i + 1]);
+    // extrema in the packed domain (NaN-propagating HMNMX2), one unpack at the end
+    typename P2::T lo2, hi2;
+    {
+      const typename P2::T* h = reinterpret_cast<const typename P2::T*>(&w[0]);
+      lo2 = h[0]; hi2 = h[0];
+#pragma unroll
+      for (int i = 1; i < NV * 4; ++i) { lo2 = P2::mn(lo2, h[i]); hi2 = P2::mx(hi2, h[i]); }
+    }
+    const float mn = nan_min(__low2float(lo2), __high2float(lo2));
+    const float mx = nan_max(__low2float(hi2), __high2float(hi2));
+    float rmn = mn, rmx = mx;
+    if (a.run_min) {
+      RT* __restrict__ run_mn = static_cast<RT*>(a.run_min);
+      RT* __restrict__ run_mx = static_cast<RT*>(a.run_max);
+      rmn = nan_min(Elem<RT>::to_f(run_mn[tile]), mn);
+      rmx = nan_max(Elem<RT>::to_f(run_mx[tile]), mx);
+      run_mn[tile] = Elem<RT>::from_f(rmn);
+      run_mx[tile] = Elem<RT>::from_f(rmx);
+    }
+    if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+    neg = !(rmn >= 0.f);
+    if (decide && rmn >= 0.f) {            // finished by calq_sentinel_fixup_kernel
+      a.scale[tile] = CQ_DEFERRED;
+      def = true;
+    } else {
+      float sc, off;
+      calq_params(a, rmn, rmx, false, sc, off);
+      a.scale[tile] = sc;
+      if (a.offset) a.offset[tile] = off;
+      const SharedRcp k = make_shared_rcp(sc);
+      const bool fast = calq_fast_ok(k, rmn, rmx);
+      const float o = ZOFF ? 0.0f : rintf(off);
+      if constexpr (FQ) {
+        const FqConst fqc{a.lo, a.hi, a.code_is_int != 0};
+        XT* __restrict__ y = static_cast<XT*>(a.y) + tile * (unsigned long long)(NV * EPT);
+#pragma unroll
+        for (int i = 0; i < NV; i += 2) {
+          const Vec<XT, EPT> y0 = calq_vec_fq<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i]), k, o, fqc, fast);
+          const Vec<XT, EPT> y1 = calq_vec_fq<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 1]), k, o, fqc, fast);
+          st256(y + i * EPT, *reinterpret_cast<const uint4*>(&y0), *reinterpret_cast<const uint4*>(&y1));
+        }
+      } else {
+        int8_t* __restrict__ q = a.q + tile * (unsigned long long)(NV * EPT);
+        int sum = 0;
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) {       // four 16-byte vectors -> 32 bytes of codes
+          uint32_t p0[2], p1[2], p2[2], p3[2];
+          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i]), k, o, a, fast, p0, sum);
+          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 1]), k, o, a, fast, p1, sum);
+          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 2]), k, o, a, fast, p2, sum);
+          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 3]), k, o, a, fast, p3, sum);
+          st256(q + i * EPT, make_uint4(p0[0], p0[1], p1[0], p1[1]), make_uint4(p2[0], p2[1], p3[0], p3[1]));
+        }
+      }
+    }
+  }
+  if (decide) {
+    // one word each, written at most once per CTA and only while still unset
+    const int n = __syncthreads_or(neg ? 1 : 0);
+    const int d = __syncthreads_or(def ? 1 : 0);
+    if (threadIdx.x == 0) {
+      if (n && *reinterpret_cast<volatile unsigned int*>(a.ws_flags + 1) == 0) a.ws_flags[1] = 1;
+      if (d && *reinterpret_cast<volatile unsigned int*>(a.ws_flags) == 0) a.ws_flags[0] = 1;
+    }
+  }
+}
+
 // Long rows with fake-quant output: calq_rows_kernel's structure (row in registers), the sentinel protocol for
 // deferred rows, optional running range.
 template <typename XT, int VPT>
@@ -618,11 +732,14 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
-template <typename XT>
-__global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) {
+// T threads per CTA, CV 16-byte vectors per chunk.  (256, 2048): four 32 KB CTAs per SM; (1024, 8192): ONE 128 KB CTA per SM --
+// a quarter of the arrivals at the grid barrier and of the partials every CTA re-reduces, which is what a 16 MB
+// activation tensor (one chunk per CTA either way) spends its time on.
+template <typename XT, int T, int CV>
+__global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 4)) calq_tensor_kernel(const CalqArgs a) {
   constexpr int EPT = 16 / sizeof(XT);
-  constexpr int VPW = CQ_CHUNK_VECS / (CQ_T / 32);       // vectors of a chunk owned by one warp (contiguous)
-  extern __shared__ uint4 s_chunk[];                      // CQ_CHUNK_VECS vectors
+  constexpr int VPW = CV / (T / 32);       // vectors of a chunk owned by one warp (contiguous)
+  extern __shared__ uint4 s_chunk[];                      // CV vectors
   __shared__ float s_f[64];
   __shared__ float s_par[4];
   const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -636,13 +753,13 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
     old_mx = load_as_float(a.run_max, a.run_dt, 0);
   }
   if (a.rowsum)
-    for (unsigned long long r = (unsigned long long)blockIdx.x * CQ_T + threadIdx.x; r < a.rows; r += (unsigned long long)G * CQ_T)
+    for (unsigned long long r = (unsigned long long)blockIdx.x * T + threadIdx.x; r < a.rows; r += (unsigned long long)G * T)
       a.rowsum[r] = 0;
 
   // ---- phase 1: extrema of this CTA's chunks; the first chunk stays in shared memory ----
   float mn = INFINITY, mx = -INFINITY;
   for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
-    const unsigned long long v0 = (unsigned long long)c * CQ_CHUNK_VECS + warp * VPW + lane;
+    const unsigned long long v0 = (unsigned long long)c * CV + warp * VPW + lane;
     const bool keep = c == blockIdx.x;
 #pragma unroll
     for (int ub = 0; ub < VPW / 32; ub += CQ_U) {
@@ -720,7 +837,7 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
   const bool simple_rows = a.rowsum != nullptr && (a.row_len % (VPW * EPT)) == 0;
   // ---- phase 3: quantize; a warp owns VPW contiguous vectors, so its codes fall in few rows ----
   for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
-    const unsigned long long w0 = (unsigned long long)c * CQ_CHUNK_VECS + warp * VPW;   // warp's first vector
+    const unsigned long long w0 = (unsigned long long)c * CV + warp * VPW;   // warp's first vector
     const bool keep = c == blockIdx.x;
     unsigned long long row0 = 0;
     unsigned int rem0 = 0;
@@ -783,24 +900,30 @@ __global__ void __launch_bounds__(CQ_T, 4) calq_tensor_kernel(const CalqArgs a) 
   }
 }
 
-static int g_tensor_occ[3] = {-1, -1, -1};   // CTAs per SM of calq_tensor_kernel<bf16 | f16 | float>
+constexpr int CQ_FAT_T = 1024, CQ_FAT_CHUNK_VECS = 8192;     // one 128 KB CTA per SM
 
-template <typename XT>
-static int tensor_grid_cap(int slot) {
-  if (g_tensor_occ[slot] < 0) {
+template <typename XT, int T, int CV>
+static int tensor_grid_cap() {
+  static std::atomic<uint64_t> done{0};
+  static int occ_dev[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  once_per_device(done, [&]() -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(calq_tensor_kernel<XT, T, CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV * 16);
+    if (e != cudaSuccess) return e;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, calq_tensor_kernel<XT>, CQ_T, CQ_CHUNK_VECS * 16) != cudaSuccess)
-      occ = 1;
-    g_tensor_occ[slot] = occ < 1 ? 1 : occ;
-  }
-  return g_tensor_occ[slot] * sm_count();
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, calq_tensor_kernel<XT, T, CV>, T, CV * 16) != cudaSuccess) occ = 1;
+    occ_dev[dev] = occ < 1 ? 1 : occ;
+    return cudaSuccess;
+  });
+  return (occ_dev[dev] < 1 ? 1 : occ_dev[dev]) * sm_count();
 }
 
-template <typename XT>
+template <typename XT, int T, int CV>
 static cudaError_t launch_tensor(const CalqArgs& a, unsigned int grid, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CQ_T);
-  cfg.dynamicSmemBytes = CQ_CHUNK_VECS * 16; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = CV * 16; cfg.stream = st;
   // cooperative: the driver guarantees that the whole grid is co-resident (the barrier cannot starve behind
   // another kernel).  FFQ_CALQ_COOP=0 launches it as an ordinary kernel (same grid, sized to the occupancy).
   static const bool coop = []() { const char* e = getenv("FFQ_CALQ_COOP"); return !(e && e[0] == '0'); }();
@@ -808,7 +931,31 @@ static cudaError_t launch_tensor(const CalqArgs& a, unsigned int grid, cudaStrea
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = coop ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, calq_tensor_kernel<XT>, a);
+  return cudaLaunchKernelEx(&cfg, calq_tensor_kernel<XT, T, CV>, a);
+}
+
+// chunks, grid and launch of the per-tensor kernel in one of its two shapes
+template <typename XT, int T, int CV>
+static int run_tensor(CalqArgs& a, unsigned long long nvec, cudaStream_t st) {
+  const unsigned long long nchunks = (nvec + CV - 1) / CV;
+  if (nchunks >= (1ull << 31)) { set_error("calibrate_quantize: tensor too large"); return FFQ_ERR_UNSUPPORTED; }
+  a.nchunks = (unsigned int)nchunks;
+  int cap = tensor_grid_cap<XT, T, CV>();
+  if (cap > 4096) cap = 4096;              // partial extrema of at most 4096 CTAs fit the workspace
+  const unsigned int grid = (unsigned int)(nchunks < (unsigned long long)cap ? nchunks : (unsigned long long)cap);
+  const cudaError_t e = launch_tensor<XT, T, CV>(a, grid, st);
+  count_launch();
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("calibrate_quantize: per-tensor kernel launch failed: %s", cudaGetErrorString(e)); return FFQ_ERR_CUDA; }
+  return FFQ_OK;
+}
+
+template <typename XT>
+static int run_tensor_any(CalqArgs& a, unsigned long long nvec, cudaStream_t st) {
+  // the fat shape from ~2 MB per SM-wave on; FFQ_CALQ_TENSOR_FAT=0 keeps the four-small-CTAs shape (A/B switch)
+  static const bool no_fat = []() { const char* e = getenv("FFQ_CALQ_TENSOR_FAT"); return e && e[0] == '0'; }();
+  if (!no_fat && nvec >= (unsigned long long)CQ_FAT_CHUNK_VECS * 32)
+    return run_tensor<XT, CQ_FAT_T, CQ_FAT_CHUNK_VECS>(a, nvec, st);
+  return run_tensor<XT, CQ_T, CQ_CHUNK_VECS>(a, nvec, st);
 }
 
 template <typename XT>
@@ -841,6 +988,25 @@ template <typename XT, typename RT, bool FQ>
 static void launch_group_rt(const CalqArgs& a, cudaStream_t st) {
   constexpr int EPT = 16 / sizeof(XT);
   const unsigned long long nvec = a.numel / EPT;
+  if constexpr (sizeof(XT) == 2) {
+    // 16-bit tiles of 128 / 256 bytes whose data (and output) sit on 32-byte boundaries: one thread per tile
+    static const bool off = getenv("FFQ_CALQ_GROUP_SUBWARP") != nullptr;      // A/B switch: keep the sub-warp kernel
+    const void* out = FQ ? a.y : static_cast<const void*>(a.q);
+    const bool al = (reinterpret_cast<uintptr_t>(a.x) & 31u) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0;
+    if (!off && al && (a.lanes == 8 || a.lanes == 16)) {
+      const unsigned long long ntiles = nvec / a.lanes;
+      const unsigned int grid = (unsigned int)((ntiles + 255) / 256);
+      const bool z = a.symmetric != 0;
+#define FFQ_TT(NV)                                                                                              \
+      do {                                                                                                        \
+        if (z) calq_tile_thread_kernel<XT, RT, NV, FQ, true><<<grid, 256, 0, st>>>(a);                            \
+        else calq_tile_thread_kernel<XT, RT, NV, FQ, false><<<grid, 256, 0, st>>>(a);                             \
+      } while (0)
+      if (a.lanes == 8) FFQ_TT(8); else FFQ_TT(16);
+#undef FFQ_TT
+      return;
+    }
+  }
   const unsigned int grid = (unsigned int)((nvec + 256 * 4 - 1) / (256 * 4));
   switch (a.lanes) {
     case 1: calq_group_kernel<XT, RT, 1, FQ><<<grid, 256, 0, st>>>(a); break;
@@ -1023,24 +1189,11 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
   a.bar = static_cast<unsigned int*>(workspace);
   a.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
   const unsigned long long nvec = a.numel / ept;
-  const unsigned long long nchunks = (nvec + CQ_CHUNK_VECS - 1) / CQ_CHUNK_VECS;
-  if (nchunks >= (1ull << 31)) { set_error("calibrate_quantize: tensor too large"); return FFQ_ERR_UNSUPPORTED; }
-  a.nchunks = (unsigned int)nchunks;
-  int cap = (x_dtype == FFQ_F32) ? tensor_grid_cap<float>(2) : (x_dtype == FFQ_BF16 ? tensor_grid_cap<__nv_bfloat16>(0) : tensor_grid_cap<__half>(1));
-  if (cap > 4096) cap = 4096;
-  const unsigned int grid = (unsigned int)(nchunks < (unsigned long long)cap ? nchunks : (unsigned long long)cap);
-  cudaError_t e;
   switch (x_dtype) {
-    case FFQ_F32: e = launch_tensor<float>(a, grid, st); break;
-    case FFQ_BF16: e = launch_tensor<__nv_bfloat16>(a, grid, st); break;
-    default: e = launch_tensor<__half>(a, grid, st); break;
+    case FFQ_F32: return run_tensor_any<float>(a, nvec, st);
+    case FFQ_BF16: return run_tensor_any<__nv_bfloat16>(a, nvec, st);
+    default: return run_tensor_any<__half>(a, nvec, st);
   }
-  if (e != cudaSuccess) {
-    set_error("calibrate_quantize: cooperative launch failed: %s", cudaGetErrorString(e));
-    return FFQ_ERR_CUDA;
-  }
-  FFQ_LAUNCH_CHECK();
-  return FFQ_OK;
 }
 
 int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* run_min, void* run_max, int run_dtype,

@@ -5,7 +5,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, ".."); sys.path.insert(0, ".")
 from fastforward_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda")
