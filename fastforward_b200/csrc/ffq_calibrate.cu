@@ -518,12 +518,11 @@ template <> struct Packed2<__half> {
 };
 
 template <typename XT, typename RT, int NV, bool FQ, bool ZOFF>
-__global__ void __launch_bounds__(256) calq_tile_thread_kernel(const CalqArgs a) {
+__device__ __forceinline__ void calq_tile_thread_body(const CalqArgs& a, unsigned long long tile) {
   static_assert(sizeof(XT) == 2 && NV % 2 == 0, "16-bit data, whole 32-byte accesses");
   constexpr int EPT = 8;
   using P2 = Packed2<XT>;
   const unsigned long long ntiles = a.numel / (unsigned long long)(NV * EPT);
-  const unsigned long long tile = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
   const bool decide = a.symmetric && a.allow_one_sided;
   bool neg = false, def = false;
   if (tile < ntiles) {
@@ -596,6 +595,36 @@ __global__ void __launch_bounds__(256) calq_tile_thread_kernel(const CalqArgs a)
       if (d && *reinterpret_cast<volatile unsigned int*>(a.ws_flags) == 0) a.ws_flags[0] = 1;
     }
   }
+}
+
+template <typename XT, typename RT, int NV, bool FQ, bool ZOFF>
+__global__ void __launch_bounds__(256) calq_tile_thread_kernel(const CalqArgs a) {
+  calq_tile_thread_body<XT, RT, NV, FQ, ZOFF>(a, (unsigned long long)blockIdx.x * 256ull + threadIdx.x);
+}
+
+// ---- many tensors in ONE launch (whole-model weight fake-quant: quantization/fuse.py over every linear) -----------
+// items[t] = {x, y, scale, offset, numel}; block_start[t] = first CTA of tensor t (prefix sums of ceil(tiles_t / 256),
+// n + 1 entries); flags_base + 2t = the tensor's {deferred, negative} words.  Every CTA belongs to one tensor.
+struct FqItem { const void* x; void* y; float* scale; float* offset; long long numel; };
+
+__device__ __forceinline__ int find_item(const unsigned int* __restrict__ block_start, int n, unsigned int block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(block_start + mid) <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <typename XT, int NV, bool ZOFF>
+__global__ void __launch_bounds__(256) calq_tile_thread_batched_kernel(CalqArgs a, const FqItem* __restrict__ items,
+                                                                       const unsigned int* __restrict__ block_start, int n,
+                                                                       unsigned int* flags_base) {
+  const int t = find_item(block_start, n, blockIdx.x);
+  const FqItem it = items[t];
+  a.x = it.x; a.y = it.y; a.scale = it.scale; a.offset = it.offset; a.numel = (unsigned long long)it.numel;
+  a.ws_flags = flags_base + 2 * t;
+  calq_tile_thread_body<XT, XT, NV, true, ZOFF>(a, (unsigned long long)(blockIdx.x - __ldg(block_start + t)) * 256ull + threadIdx.x);
 }
 
 // Long rows with fake-quant output: calq_rows_kernel's structure (row in registers), the sentinel protocol for
@@ -672,13 +701,11 @@ __global__ void __launch_bounds__(512) calq_rows_fq_kernel(const CalqArgs a) {
 // calq_rows_fq_kernel and returns after one load unless something was deferred (weights whose tiles are all
 // non-negative are the only case).  The global decision: one-sided unless some tile min was negative or NaN.
 template <typename XT, bool FQ>
-__global__ void __launch_bounds__(256) calq_sentinel_fixup_kernel(const CalqArgs a) {
+__device__ __forceinline__ void calq_sentinel_fixup_body(const CalqArgs& a, unsigned long long warp0, unsigned long long nwarps) {
   constexpr int EPT = 16 / sizeof(XT);
   if (*reinterpret_cast<volatile unsigned int*>(a.ws_flags) == 0) return;
   const bool one_sided = *reinterpret_cast<volatile unsigned int*>(a.ws_flags + 1) == 0;
   const unsigned int lane = threadIdx.x & 31;
-  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   const unsigned int tvec = a.row_len / EPT;
   const FqConst fqc{a.lo, a.hi, a.code_is_int != 0};
   for (unsigned long long tile = warp0; tile < a.rows; tile += nwarps) {
@@ -721,6 +748,25 @@ __global__ void __launch_bounds__(256) calq_sentinel_fixup_kernel(const CalqArgs
       if (a.offset) a.offset[tile] = off;
     }
   }
+}
+
+template <typename XT, bool FQ>
+__global__ void __launch_bounds__(256) calq_sentinel_fixup_kernel(const CalqArgs a) {
+  calq_sentinel_fixup_body<XT, FQ>(a, ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
+                                   ((unsigned long long)gridDim.x * blockDim.x) >> 5);
+}
+
+constexpr int FQ_FIXUP_BLOCKS = 8;      // CTAs per tensor of the batched fix-up (they return at once unless a tile was deferred)
+template <typename XT>
+__global__ void __launch_bounds__(256) calq_sentinel_fixup_batched_kernel(CalqArgs a, const FqItem* __restrict__ items,
+                                                                          unsigned int* flags_base) {
+  const int t = blockIdx.x / FQ_FIXUP_BLOCKS;
+  const FqItem it = items[t];
+  a.x = it.x; a.y = it.y; a.scale = it.scale; a.offset = it.offset; a.numel = (unsigned long long)it.numel;
+  a.rows = (unsigned long long)it.numel / a.row_len;
+  a.ws_flags = flags_base + 2 * t;
+  calq_sentinel_fixup_body<XT, true>(a, (unsigned long long)(blockIdx.x % FQ_FIXUP_BLOCKS) * 8 + (threadIdx.x >> 5),
+                                     (unsigned long long)FQ_FIXUP_BLOCKS * 8);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1272,6 +1318,64 @@ int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* run_min, 
       case FFQ_BF16: launch_sentinel_fixup<__nv_bfloat16, true>(a, st); break;
       default: launch_sentinel_fixup<__half, true>(a, st); break;
     }
+    FFQ_LAUNCH_CHECK();
+  }
+  return FFQ_OK;
+}
+
+int ffq_calibrate_fakequant_batched(const ffq_fq_item_t* items_dev, const uint32_t* block_start_dev, int64_t num_items,
+                                    int64_t total_blocks, int x_dtype, int64_t tile_len, double num_bits, int symmetric,
+                                    int allow_one_sided, int code_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  static_assert(sizeof(ffq_fq_item_t) == sizeof(FqItem), "descriptor layout");
+  const int rcp_div = (allow_one_sided & FFQ_FLAG_SCALAR_DIV_RECIPROCAL) ? 1 : 0;
+  allow_one_sided &= FFQ_FLAG_ALLOW_ONE_SIDED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (num_items <= 0 || total_blocks <= 0) return FFQ_OK;
+  if (!(x_dtype == FFQ_BF16 || x_dtype == FFQ_F16) || !(tile_len == 64 || tile_len == 128)) {
+    set_error("calibrate_fakequant_batched: 16-bit data in tiles of 64 or 128 elements only");
+    return FFQ_ERR_UNSUPPORTED;
+  }
+  if (items_dev == nullptr || block_start_dev == nullptr || num_items > 0x7fffffffll / (2 * FQ_FIXUP_BLOCKS) || total_blocks > 0x7fffffffll) {
+    set_error("calibrate_fakequant_batched: bad descriptor table");
+    return FFQ_ERR_INVALID;
+  }
+  const bool float_codes = code_dtype == FFQ_F32 || code_dtype == FFQ_F16 || code_dtype == FFQ_BF16;
+  if (!float_codes && !is_int_dt(code_dtype)) { set_error("calibrate_fakequant_batched: bad code dtype"); return FFQ_ERR_INVALID; }
+  const int mant = code_dtype == FFQ_F32 ? 23 : (code_dtype == FFQ_F16 ? 10 : 7);
+  if (float_codes && mant + 1 < num_bits) { set_error("calibrate_fakequant_batched: %s codes round %g-bit values", dt_name(code_dtype), num_bits); return FFQ_ERR_UNSUPPORTED; }
+  if (!float_codes && num_bits > dt_size(code_dtype) * 8) { set_error("calibrate_fakequant_batched: code dtype too narrow"); return FFQ_ERR_UNSUPPORTED; }
+  const size_t need = (size_t)num_items * 8;
+  if (workspace == nullptr || workspace_bytes < need) { set_error("calibrate_fakequant_batched: workspace of %zu bytes required", need); return FFQ_ERR_WORKSPACE; }
+  CalqArgs a{};
+  const double lo = -pow(2.0, num_bits - 1.0);
+  a.int_min_abs = (float)fabs(lo);
+  a.int_max_abs = (float)fabs(-lo - 1.0);
+  a.neg_int_min = (float)(-lo);
+  a.steps = (float)(pow(2.0, num_bits) - 1.0);
+  a.lo = (float)lo; a.hi = (float)(-lo - 1.0);
+  a.symmetric = symmetric; a.allow_one_sided = allow_one_sided; a.rcp_div = rcp_div;
+  a.code_is_int = float_codes ? 0 : 1;
+  a.row_len = (unsigned int)tile_len;
+  a.lanes = (unsigned int)(tile_len / 8);
+  unsigned int* flags_base = static_cast<unsigned int*>(workspace);
+  const bool decide = symmetric && allow_one_sided;
+  if (decide) FFQ_CUDA_CHECK(cudaMemsetAsync(flags_base, 0, need, st));
+  const FqItem* items = reinterpret_cast<const FqItem*>(items_dev);
+  const unsigned int grid = (unsigned int)total_blocks;
+  const int n = (int)num_items;
+#define FFQ_TTB(XT, NV)                                                                                                 \
+  do {                                                                                                                \
+    if (symmetric) calq_tile_thread_batched_kernel<XT, NV, true><<<grid, 256, 0, st>>>(a, items, block_start_dev, n, flags_base);   \
+    else calq_tile_thread_batched_kernel<XT, NV, false><<<grid, 256, 0, st>>>(a, items, block_start_dev, n, flags_base);            \
+  } while (0)
+  if (x_dtype == FFQ_BF16) { if (tile_len == 64) FFQ_TTB(__nv_bfloat16, 8); else FFQ_TTB(__nv_bfloat16, 16); }
+  else { if (tile_len == 64) FFQ_TTB(__half, 8); else FFQ_TTB(__half, 16); }
+#undef FFQ_TTB
+  FFQ_LAUNCH_CHECK();
+  if (decide) {
+    const unsigned int fgrid = (unsigned int)(num_items * FQ_FIXUP_BLOCKS);
+    if (x_dtype == FFQ_BF16) calq_sentinel_fixup_batched_kernel<__nv_bfloat16><<<fgrid, 256, 0, st>>>(a, items, flags_base);
+    else calq_sentinel_fixup_batched_kernel<__half><<<fgrid, 256, 0, st>>>(a, items, flags_base);
     FFQ_LAUNCH_CHECK();
   }
   return FFQ_OK;

@@ -383,6 +383,45 @@ def calibrate_fake_quantize_(
     return out
 
 
+class FakeQuantBatch:
+    """Device-side descriptor table of ``calibrate_fake_quantize_batched_``: built once for a set of (tensor, scale,
+    offset) triples and reusable for as long as their storages stay where they are (the call itself is then free of
+    host-to-device copies, so it can be captured in a CUDA graph)."""
+
+    def __init__(self, tensors, scales, offsets, tile_len: int) -> None:
+        dev = tensors[0].device
+        rows, starts, blocks = [], [0], 0
+        for w, s, o in zip(tensors, scales, offsets):
+            nt = w.numel() // tile_len
+            if w.device != dev or w.dtype != tensors[0].dtype or not w.is_contiguous() or w.numel() % tile_len or \
+                    w.data_ptr() % 32 or s.dtype != torch.float32 or s.numel() != nt or not s.is_contiguous() or \
+                    (o is not None and (o.dtype != torch.float32 or o.numel() != nt or not o.is_contiguous())):
+                raise NotImplementedError("calibrate_fake_quantize_batched_: tensor outside the batched kernel's layout")
+            rows.append((w.data_ptr(), w.data_ptr(), s.data_ptr(), 0 if o is None else o.data_ptr(), w.numel()))
+            blocks += (nt + 255) // 256
+            starts.append(blocks)
+        self.key = tuple(r[:4] for r in rows)
+        self.items = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.block_start = torch.tensor(starts, dtype=torch.int64).to(torch.int32).to(dev)      # read as uint32
+        self.workspace = torch.zeros(8 * len(rows), dtype=torch.uint8, device=dev)
+        self.n, self.blocks, self.dtype, self.device, self.tile_len = len(rows), blocks, tensors[0].dtype, dev, tile_len
+
+
+def calibrate_fake_quantize_batched_(batch: FakeQuantBatch, num_bits: float, symmetric: bool, allow_one_sided: bool,
+                                     quantized_dtype: Optional[torch.dtype] = None,
+                                     reciprocal_scalar_division: bool = False) -> None:
+    """``calibrate_fake_quantize_(w, out=w)`` for every tensor of ``batch`` in ONE launch (+ one fix-up launch):
+    per-tile min/max -> scale/offset in place -> the tensor snapped to its grid in place.  16-bit tensors, tiles of 64
+    or 128 contiguous elements, one quantizer configuration for all of them."""
+    code_dtype = quantized_dtype or batch.dtype
+    _bitwidth_guard(code_dtype, num_bits)
+    with C.device_of(batch.device):
+        C.check(C.lib.ffq_calibrate_fakequant_batched(
+            batch.items.data_ptr(), batch.block_start.data_ptr(), batch.n, batch.blocks, C.dtype_tag(batch.dtype),
+            batch.tile_len, float(num_bits), int(bool(symmetric)), _flags(allow_one_sided, reciprocal_scalar_division),
+            C.dtype_tag(code_dtype), batch.workspace.data_ptr(), batch.workspace.numel(), C.current_stream(batch.device)))
+
+
 @_on_device
 def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor, entries,
                                    reciprocal_scalar_division: bool = False) -> None:

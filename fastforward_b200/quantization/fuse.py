@@ -11,6 +11,7 @@ whole-model W4 g=128 weight quantization sharded by layer across GPUs, no collec
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Iterator, List, Optional, Tuple
 
 import torch
@@ -126,12 +127,18 @@ def calibrate_weight_quantizers(model: torch.nn.Module, discovery=None, rank: Op
     return len(targets)
 
 
+# model -> {configuration: FakeQuantBatch} of its last whole-model call, reused while the storages stay where they are
+_BATCH_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
 def calibrate_and_fuse_qdq_weights(model: torch.nn.Module, *, stub_quantizers: bool = False, discovery=None,
-                                   rank: Optional[int] = None, world_size: Optional[int] = None) -> int:
+                                   rank: Optional[int] = None, world_size: Optional[int] = None, batched: bool = True) -> int:
     """``calibrate_weight_quantizers`` followed by ``fuse_qdq_weights`` -- the unit of whole-model weight quantization
-    -- with the weight read ONCE: per target one fused launch (per-tile min/max -> the quantizer's scale/offset ->
-    the weight snapped to its grid in place; ``ffq_calibrate_fakequant``) where the layout allows it (per-channel rows,
-    per-group tiles), the two separate steps otherwise.  Bit-identical to the two-step sequence."""
+    -- with the weight read ONCE: per-tile min/max -> the quantizer's scale/offset -> the weight snapped to its grid in
+    place (``ffq_calibrate_fakequant``) where the layout allows it (per-channel rows, per-group tiles), the two
+    separate steps otherwise.  Per-group weights of one dtype and one quantizer configuration (the usual W4 g=128
+    recipe over every linear of a model) go through ONE launch for all of them (``ffq_calibrate_fakequant_batched``;
+    ``batched=False`` keeps one launch per weight).  Bit-identical to the two-step sequence."""
     from .. import ops
 
     discovery = ConventionDiscovery() if discovery is None else discovery
@@ -141,7 +148,54 @@ def calibrate_and_fuse_qdq_weights(model: torch.nn.Module, *, stub_quantizers: b
         from ..distributed import shard_units
 
         targets = [targets[i] for i in shard_units(len(targets), rank, world_size)]
-    for module, attr, quantizer in targets:
+    # ---- per-group 16-bit weights that share a configuration: one launch for all of them ------------------------
+    done = set()
+    if batched:
+        groups: dict = {}
+        seen_weights = set()
+        for idx, (module, attr, quantizer) in enumerate(targets):
+            w = getattr(module, attr).data
+            if type(quantizer) is not LinearQuantizer or list(quantizer.overrides) or not w.is_cuda or not w.is_contiguous() \
+                    or w.dtype not in (torch.bfloat16, torch.float16) or w.dim() != 2 or id(getattr(module, attr)) in seen_weights:
+                continue
+            tile = quantizer.granularity.tile_size(w.shape)
+            if isinstance(tile, str) or tuple(tile[:-1]) != (1,) * (w.dim() - 1) or tile[-1] not in (64, 128) or w.data_ptr() % 32:
+                continue
+            n = quantizer.granularity.parameter_dimensionality(w.shape)
+            if quantizer.has_uninitialized_params:
+                quantizer._initialize_parameters(n)
+            params = [quantizer.scale] + ([] if quantizer.offset is None else [quantizer.offset])
+            if not all(p.dtype == torch.float32 and p.device == w.device and p.numel() == n and p.is_contiguous() for p in params):
+                continue
+            seen_weights.add(id(getattr(module, attr)))
+            key = (w.device, w.dtype, tile[-1], quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
+                   quantizer.quantized_dtype)
+            groups.setdefault(key, []).append(idx)
+        cache = _BATCH_CACHE.setdefault(model, {})
+        for key, idxs in groups.items():
+            if len(idxs) < 2:
+                continue
+            ws = [getattr(targets[i][0], targets[i][1]).data for i in idxs]
+            ss = [targets[i][2].scale.data for i in idxs]
+            os_ = [None if targets[i][2].offset is None else targets[i][2].offset.data for i in idxs]
+            sig = tuple((w.data_ptr(), s.data_ptr(), 0 if o is None else o.data_ptr()) for w, s, o in zip(ws, ss, os_))
+            batch = cache.get(key)
+            if batch is None or batch.sig != sig:
+                try:
+                    batch = ops.FakeQuantBatch(ws, ss, os_, key[2])
+                except NotImplementedError:
+                    continue
+                batch.sig = sig
+                cache[key] = batch
+            try:
+                with torch.no_grad():
+                    ops.calibrate_fake_quantize_batched_(batch, key[3], key[4], key[5], key[6])
+            except NotImplementedError:      # e.g. a code dtype that rounds the codes: the per-tensor path decides
+                continue
+            done.update(idxs)
+    for idx, (module, attr, quantizer) in enumerate(targets):
+        if idx in done:
+            continue
         weight = getattr(module, attr)
         w = weight.data
         tile = quantizer.granularity.tile_size(w.shape)
@@ -165,7 +219,8 @@ def calibrate_and_fuse_qdq_weights(model: torch.nn.Module, *, stub_quantizers: b
             lo, hi = ops.tile_minmax(w.detach(), tile)
             quantizer.quantization_range = (lo, hi)
             _fuse_target(module, attr, quantizer, stub_quantizer=False)
-        if stub_quantizers:
+    if stub_quantizers:
+        for module, attr, quantizer in targets:
             for name, child in list(module.named_children()):
                 if child is quantizer:
                     setattr(module, name, QuantizerStub(_metadata=quantizer.quant_metadata))

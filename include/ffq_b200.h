@@ -234,6 +234,25 @@ FFQ_API int ffq_calibrate_fakequant(const void* x, int x_dtype, void* y, void* r
                             int symmetric, int allow_one_sided, int code_dtype,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same for MANY tensors in one launch (+ one fix-up launch): whole-model weight fake-quant, the loop of
+ * quantization/fuse.py:199-241 over every quantized linear, without one launch (and one launch tail) per weight.
+ * items_dev: device array of descriptors; block_start_dev: device uint32[num_items + 1], prefix sums of
+ * ceil(num_tiles_i / 256) (CTAs per tensor), total_blocks = block_start[num_items].  All tensors: dtype x_dtype
+ * (bf16 / f16), 32-byte aligned, contiguous tiles of tile_len (64 or 128) elements, one quantizer configuration;
+ * y may alias x.  workspace: >= 8 * num_items bytes (zeroed by the call).  Per tensor bit-identical to
+ * ffq_calibrate_fakequant without a running range.  Anything else returns FFQ_ERR_UNSUPPORTED (use the per-tensor call). */
+typedef struct {
+  const void* x;
+  void* y;
+  float* scale;   /* fp32 [numel / tile_len] */
+  float* offset;  /* fp32 [numel / tile_len] or NULL */
+  int64_t numel;
+} ffq_fq_item_t;
+FFQ_API int ffq_calibrate_fakequant_batched(const ffq_fq_item_t* items_dev, const uint32_t* block_start_dev,
+                                    int64_t num_items, int64_t total_blocks, int x_dtype, int64_t tile_len,
+                                    double num_bits, int symmetric, int allow_one_sided, int code_dtype,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a12: quantized linear (new kernel behind ff.dispatcher "linear") ---------------------
  * y[m,n] = sx * sw[n] * ( sum_k qx[m,k] qw[n,k] + ox*rowsum_w[n] + ow[n]*rowsum_x[m] + K*ox*ow[n] )
  *          + bias[n]

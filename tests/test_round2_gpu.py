@@ -418,3 +418,78 @@ def test_ops_work_on_a_non_current_device():
     assert torch.cuda.current_device() == 0
     mn, mx = ops.tile_minmax(x, (1, 256))
     assert torch.equal(mn.cpu(), x.cpu().min(1).values) and torch.cuda.current_device() == 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# per-group calibration: one-thread-per-tile kernel, batched whole-model launch
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("g", [64, 128])
+@pytest.mark.parametrize("bits,symmetric,allow,qdtype", [(4, True, True, None), (4, False, True, torch.int8), (3, True, False, None),
+                                                         (8, True, True, torch.int8)])
+def test_group_fake_quant_thread_per_tile_matches_oracle(dtype, g, bits, symmetric, allow, qdtype):
+    """calibrate + snap of per-group tiles (the one-thread-per-tile kernel) against the oracle's three steps, incl.
+    all-positive tiles next to mixed ones (the deferred one-sided decision), NaN and inf, and the int8-code variant."""
+    torch.manual_seed(11)
+    w = (torch.randn(96, 1024) * 0.05).to(dtype)
+    w[3, :256] = w[3, :256].abs()              # tiles that are entirely non-negative
+    w[7, 130] = float("nan")
+    w[9, 700] = float("inf")
+    tile = (1, g)
+    mn, mx = R.tile_minmax(w, tile)
+    s, o = R.parameters_for_range(mn.float(), mx.float(), bits, symmetric, allow)
+    cd = qdtype or dtype
+    want = R.dequantize_by_tile(R.quantize_by_tile(w, s, tile, bits, cd, o), s, tile, o, dtype)
+    wd = w.to(DEV)
+    nt = w.numel() // g
+    scale = torch.empty(nt, device=DEV)
+    offset = None if (symmetric and not allow) else torch.empty(nt, device=DEV)
+    out = ops.calibrate_fake_quantize_(wd, tile, bits, symmetric, allow, scale, offset, qdtype)
+    from conftest import bits_equal
+    assert bits_equal(scale.cpu(), s)
+    if o is not None:
+        assert bits_equal(offset.cpu(), o)
+    elif offset is not None:
+        assert torch.equal(offset.cpu(), torch.zeros(nt))
+    assert bits_equal(out.cpu(), want)
+    if bits <= 8:
+        run_mn = torch.full((nt,), float("inf"), dtype=dtype, device=DEV); run_mx = -run_mn
+        sc2 = torch.empty(nt, device=DEV); of2 = torch.empty(nt, device=DEV)
+        codes, _ = ops.calibrate_quantize_(run_mn, run_mx, wd, tile, bits, symmetric, True, sc2, of2)
+        s2, o2 = R.parameters_for_range(mn.float(), mx.float(), bits, symmetric, True)
+        assert bits_equal(sc2.cpu(), s2) and torch.equal(codes.cpu(), R.quantize_by_tile(w, s2, tile, bits, torch.int8, o2))
+        assert bits_equal(run_mn.cpu(), mn) and bits_equal(run_mx.cpu(), mx)
+
+
+def test_whole_model_batched_fake_quant_equals_per_weight():
+    import bench_workloads as bw
+    from fastforward_b200.quantization.fuse import calibrate_and_fuse_qdq_weights
+
+    def build():
+        model = torch.nn.ModuleList(bw.DecoderLayer(bw.TINY, torch.bfloat16, DEV) for _ in range(2))
+        bw.init_weights_(model, seed=5)
+        with torch.no_grad():
+            model[0].mlp.up_proj.weight.abs_()             # an all-positive weight: the global one-sided decision
+        ff.quantize_model(model, extra_conversion=ff.surrogate_quantized_modules(model))
+        ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(
+            ff.nn.LinearQuantizer, num_bits=4, granularity=ff.PerBlock(block_dims=1, block_sizes=128, per_channel_dims=0))
+        return model.to(DEV)
+
+    a, b = build(), build()
+    l0 = C.launch_count()
+    assert calibrate_and_fuse_qdq_weights(a) == 14
+    batched_launches = C.launch_count() - l0
+    l0 = C.launch_count()
+    calibrate_and_fuse_qdq_weights(b, batched=False)
+    assert batched_launches == 2 and C.launch_count() - l0 == 28
+    for (na, pa), (nb, pb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert na == nb and torch.equal(pa, pb), na
+    # second call: the cached descriptor table is reused (CUDA-graph capturable) and the result is idempotent
+    before = {k: v.clone() for k, v in a.state_dict().items()}
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        calibrate_and_fuse_qdq_weights(a)
+    g.replay(); torch.cuda.synchronize()
+    for k, v in a.state_dict().items():
+        if "scale" not in k and "offset" not in k:
+            assert torch.equal(v, before[k]), k
