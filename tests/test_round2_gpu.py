@@ -484,12 +484,12 @@ def test_whole_model_batched_fake_quant_equals_per_weight():
     assert batched_launches == 2 and C.launch_count() - l0 == 28
     for (na, pa), (nb, pb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert na == nb and torch.equal(pa, pb), na
-    # second call: the cached descriptor table is reused (CUDA-graph capturable) and the result is idempotent
-    before = {k: v.clone() for k, v in a.state_dict().items()}
+    # second call: the cached descriptor table is reused, so the call is free of host-to-device copies and can be
+    # captured in a CUDA graph; replaying it equals calling the per-weight path on the same (already snapped) weights
+    calibrate_and_fuse_qdq_weights(b, batched=False)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         calibrate_and_fuse_qdq_weights(a)
     g.replay(); torch.cuda.synchronize()
-    for k, v in a.state_dict().items():
-        if "scale" not in k and "offset" not in k:
-            assert torch.equal(v, before[k]), k
+    for (na, pa), (nb, pb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(pa, pb), na
