@@ -26,8 +26,8 @@
 // weight element per M-tile, about half of the issue capacity left beside the MMAs.
 #include <cuda.h>
 
+#include <atomic>
 #include <cstdlib>
-#include <mutex>
 
 #include "ffq_common.cuh"
 #include "ffq_umma.cuh"
@@ -38,7 +38,11 @@ namespace w4 {
 constexpr int BM = 128, BN = 256, BK = 64;        // BK in 16-bit elements: one 128B swizzle atom
 constexpr int TM = 2 * BM;
 constexpr int UMMA_K = 16;
-constexpr int SA = 6, SB = 3, SR = 8;             // ring depths: A operand / dequantized B / raw codes
+constexpr int SB = 3, SR = 8;                     // ring depths: dequantized B / raw codes
+// MT = M tiles (of 256 rows) per pair tile.  MT = 2: ONE dequantized B stage feeds the MMAs of two 256-row tiles (two
+// 128 x 256 fp32 accumulators per CTA = all 512 TMEM columns), so the dequantisation -- what bounds the kernel, see the
+// header -- is done once per 512 activation rows; the price is an epilogue that no longer overlaps the next tile's MMAs.
+template <int MT> struct RingA { static constexpr int depth = MT == 1 ? 6 : 3; };   // A ring: stages of MT x 16 KB
 constexpr int A_BYTES = BM * BK * 2;              // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;        // 16 KB: this CTA's half of B, as 16-bit floats
 constexpr int RAW_BYTES = (BN / 2) * BK;          // 8 KB: the same half as int8 codes
@@ -47,7 +51,7 @@ constexpr int DQ_WARPS = 8;
 constexpr int WARP_TMA_A = 0, WARP_MMA = 1, WARP_TMA_RAW = 2, WARP_EPI0 = 4, WARP_DQ0 = 8;
 constexpr int THREADS = (WARP_DQ0 + DQ_WARPS) * 32;   // 512 (warp 3 idles)
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = SA * A_BYTES + SB * B_BYTES + SR * RAW_BYTES + BN * 4 + 512 + 1024;
+constexpr int SMEM_BYTES = 6 * A_BYTES + SB * B_BYTES + SR * RAW_BYTES + BN * 4 + 512 + 1024;     // same for MT = 1 and 2
 
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0;
@@ -101,13 +105,16 @@ __device__ __forceinline__ void dequant4_fast(uint32_t w, float c_fast, float s,
   f[3] = __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7443)), c_fast), s);
 }
 
-template <typename T>
+template <typename T, int MT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_raw, const Args g) {
+  constexpr int SA = RingA<MT>::depth;
+  constexpr int A_STAGE = MT * A_BYTES;
+  constexpr int TMQ = MT * TM;                                // rows of a pair tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_base = smem;                                   // [SA][128 rows x 128 B]   A operand, TMA, 128B swizzle
-  uint8_t* b_base = a_base + SA * A_BYTES;                  // [SB][128 rows x 128 B]   this CTA's half of B, written by the dequantizers
+  uint8_t* b_base = a_base + SA * A_STAGE;                  // [SB][128 rows x 128 B]   this CTA's half of B, written by the dequantizers
   uint8_t* r_base = b_base + SB * B_BYTES;                  // [SR][128 rows x 64 B]    raw int8 codes, TMA, unswizzled
   float* col_bias = reinterpret_cast<float*>(r_base + SR * RAW_BYTES);      // [BN]
   uint64_t* bars = reinterpret_cast<uint64_t*>(col_bias + BN);
@@ -124,7 +131,7 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int tiles_m = (g.M + TM - 1) / TM, tiles_n = (g.N + BN - 1) / BN;
+  const int tiles_m = (g.M + TMQ - 1) / TMQ, tiles_n = (g.N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int k_blocks = g.K / BK;
 
@@ -154,8 +161,11 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int tm = tile % tiles_m;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&a_empty[stage], phase ^ 1);
-          if (cta == 0) mbar_expect_tx(&a_full[stage], 2 * A_BYTES);
-          tma_load_2d_pair(a_base + stage * A_BYTES, &map_a, &a_full[stage], kb * BK, tm * TM + (int)cta * BM);
+          if (cta == 0) mbar_expect_tx(&a_full[stage], 2 * A_STAGE);
+#pragma unroll
+          for (int h = 0; h < MT; ++h)
+            tma_load_2d_pair(a_base + stage * A_STAGE + h * A_BYTES, &map_a, &a_full[stage], kb * BK,
+                             tm * TMQ + h * TM + (int)cta * BM);
           if (++stage == SA) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,8 +194,9 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
+        // MT = 1: two accumulators alternate between tiles; MT = 2: both belong to this tile (one per 256-row half)
+        const int buf = MT == 1 ? (it & 1) : 0;
+        const uint32_t use = MT == 1 ? (uint32_t)(it >> 1) : (uint32_t)it;
         mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
@@ -193,12 +204,15 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mbar_wait(&a_full[sa], pa);
           mbar_wait(&b_full[sb], pb);
           tc_fence_after();
-          const uint64_t da = make_smem_desc(smem_u32(a_base + sa * A_BYTES));
           const uint64_t db = make_smem_desc(smem_u32(b_base + sb * B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // +16 elements = +32 bytes inside the swizzle atom == +2 in the (>>4) start-address field
-            umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          for (int h = 0; h < MT; ++h) {
+            const uint64_t da = make_smem_desc(smem_u32(a_base + sa * A_STAGE + h * A_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // +16 elements = +32 bytes inside the swizzle atom == +2 in the (>>4) start-address field
+              umma_f16_pair(tmem_d + (uint32_t)(h * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+            }
           }
           umma_commit_pair(&a_empty[sa]);
           umma_commit_pair(&b_empty[sb]);
@@ -216,30 +230,33 @@ w4a16_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int tm = tile % tiles_m, tn = tile / tiles_m;
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
+      const int buf = MT == 1 ? (it & 1) : 0;
+      const uint32_t use = MT == 1 ? (uint32_t)(it >> 1) : (uint32_t)it;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = ep_tid; c < BN; c += 128) {
         const int n = tn * BN + c;
         col_bias[c] = (g.bias && n < g.N) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
 
       mbar_wait_backoff(&tmem_full[buf], use & 1);           // a whole k-loop away: do not burn issue slots
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + (uint32_t)c0, acc);
-        float v[32];
+      for (int h = 0; h < MT; ++h) {
+        const int row = tm * TMQ + h * TM + (int)cta * BM + quad * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((MT == 1 ? buf : h) * BN);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + (uint32_t)c0, acc);
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(acc[j]), col_bias[c0 + j]);
-        const int n0 = tn * BN + c0;
-        if (row < g.M && n0 < g.N) {
-          const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
-          store_chunk<T>(y + (size_t)row * g.N + n0, v, ncols);
+          for (int j = 0; j < 32; ++j) v[j] = __fadd_rn(__uint_as_float(acc[j]), col_bias[c0 + j]);
+          const int n0 = tn * BN + c0;
+          if (row < g.M && n0 < g.N) {
+            const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
+            store_chunk<T>(y + (size_t)row * g.N + n0, v, ncols);
+          }
         }
       }
       tc_fence_before();
@@ -387,19 +404,29 @@ extern "C" int ffq_qlinear_w4a16(const void* x, int x_dtype, const int8_t* qw, v
   w4::Args g{};
   g.M = (int)M; g.N = (int)N; g.K = (int)K; g.y = y; g.sw = sw; g.ow = ow; g.group = (int)group; g.groups = (int)(K / group); g.kb_per_group = (int)(group / w4::BK);
   g.bias = bias; g.bias_dt = bias_dtype;
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    cudaError_t e1 = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
-    cudaError_t e2 = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
-    attr_err = e1 != cudaSuccess ? e1 : e2;
+  static std::atomic<uint64_t> attr_done{0};
+  const cudaError_t attr_err = once_per_device(attr_done, []() -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__nv_bfloat16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__nv_bfloat16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(w4::w4a16_gemm2_kernel<__half, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, w4::SMEM_BYTES);
+    return e;
   });
   if (attr_err != cudaSuccess) { set_error("qlinear_w4a16: cannot reserve %d bytes of shared memory: %s", w4::SMEM_BYTES, cudaGetErrorString(attr_err)); return FFQ_ERR_CUDA; }
-  const long long pair_tiles = ((M + w4::TM - 1) / w4::TM) * ((N + w4::BN - 1) / w4::BN);
+  // two 256-row tiles per dequantized weight stage from 257 activation rows on (FFQ_W4A16_MT=1|2 overrides: A/B switch)
+  int mt = M > w4::TM ? 2 : 1;
+  { const char* e = getenv("FFQ_W4A16_MT"); if (e && (e[0] == '1' || e[0] == '2')) mt = e[0] - '0'; }
+  const long long tmq = (long long)mt * w4::TM;
+  const long long pair_tiles = ((M + tmq - 1) / tmq) * ((N + w4::BN - 1) / w4::BN);
   const int max_pairs = sm_count() / 2;
   const int grid = 2 * (int)(pair_tiles < max_pairs ? pair_tiles : max_pairs);
-  if (x_dtype == FFQ_BF16) w4::w4a16_gemm2_kernel<__nv_bfloat16><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
-  else w4::w4a16_gemm2_kernel<__half><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+  if (x_dtype == FFQ_BF16) {
+    if (mt == 2) w4::w4a16_gemm2_kernel<__nv_bfloat16, 2><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+    else w4::w4a16_gemm2_kernel<__nv_bfloat16, 1><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+  } else {
+    if (mt == 2) w4::w4a16_gemm2_kernel<__half, 2><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+    else w4::w4a16_gemm2_kernel<__half, 1><<<grid, w4::THREADS, w4::SMEM_BYTES, st>>>(map_a, map_raw, g);
+  }
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
 }

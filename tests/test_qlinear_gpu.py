@@ -176,7 +176,9 @@ def test_w4a16_one_hot_activations_give_the_dequantized_weight_bit_exact(k, n, g
 
 
 @pytest.mark.parametrize("m,k,n,gran", [(256, 512, 512, "g128"), (300, 1024, 700, "g64"), (17, 128, 40, "pc"),
-                                        (2048, 4096, 1024, "g128"), (129, 4096 + 64, 257, "pc"), (64, 256, 256, "pt")])
+                                        (2048, 4096, 1024, "g128"), (129, 4096 + 64, 257, "pc"), (64, 256, 256, "pt"),
+                                        # two 256-row tiles per dequantized weight stage (M > 256), ragged in M and N
+                                        (513, 256, 512, "g128"), (1000, 512, 300, "g64"), (257, 128, 264, "pc")])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16] if torch.cuda.is_available() else [])
 @pytest.mark.parametrize("w_sym,bias", [(True, False), (False, True)])
 def test_w4a16_linear(m, k, n, gran, dt, w_sym, bias):

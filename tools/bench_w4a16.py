@@ -3,7 +3,7 @@ import sys
 
 import torch
 
-sys.path.insert(0, ".")
+sys.path.insert(0, ".."); sys.path.insert(0, ".")
 from fastforward_b200 import _cabi as C, ops  # noqa: E402
 
 dev = torch.device("cuda")
