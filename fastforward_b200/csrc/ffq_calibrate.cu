@@ -345,7 +345,8 @@ __device__ __forceinline__ Vec<XT, EPT> calq_vec_fq_impl(const Vec<XT, EPT>& xin
       t = __fsub_rn(__fdiv_rn(x, k.s), o);
     }
     float q = nan_clamp(rintf(t), c.lo, c.hi);
-    if constexpr (INT_ZERO) q = __fadd_rn(q, 0.0f);
+    // integer code dtype: the cast to it turns -0 into +0 and NaN into 0 (what aten's float -> int conversion gives)
+    if constexpr (INT_ZERO) q = (q == q) ? __fadd_rn(q, 0.0f) : 0.0f;
     y[i] = __fmul_rn(__fadd_rn(q, o), k.s);
   }
   Vec<XT, EPT> out;
