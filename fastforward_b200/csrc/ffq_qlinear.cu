@@ -167,6 +167,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
   if (row >= g.M || n0 >= g.N) return;
   const int ncols = (g.N - n0) < 32 ? (g.N - n0) : 32;
   if (g.rq_codes) {
+    const SharedRcp rq_k = make_shared_rcp(rq_s);
     // output_quantizer(y): y is first rounded to the output dtype (what the quantizer would read back), then
     // quantize_by_tile's arithmetic in the promoted dtype of (y, fp32 scale) = fp32
     uint32_t packed[8];
@@ -177,7 +178,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, const uint32_t
       for (int b = 0; b < 4; ++b) {
         const int j = 4 * w + b;
         const float yr = Elem<OutT>::to_f(Elem<OutT>::from_f(v[j]));
-        float t = __fsub_rn(__fdiv_rn(yr, rq_s), rq_o);
+        // exact y / s with the reciprocal shared by the whole tensor (ffq_common.cuh: shared_div); outside its guard
+        // (never for sane scales) the IEEE division itself
+        bool ok = rq_k.ok;
+        float quo = shared_div<false>(yr, rq_k, ok);
+        if (!ok) quo = __fdiv_rn(yr, rq_s);
+        float t = __fsub_rn(quo, rq_o);
         t = nan_clamp(rintf(t), g.rq_lo, g.rq_hi);
         const int c = __float2int_rz(t);
         word |= ((uint32_t)c & 0xffu) << (8 * b);
