@@ -254,13 +254,15 @@ def test_shared_reciprocal_division_is_ieee_exact():
     assert acc > (1 << 28) and acc_strict > (1 << 28), counts.tolist()   # the guard accepts the bulk
 
 
-def test_host_buffer_entry_point():
-    """ffq_fakequant_fwd_bwd_host: the end-to-end C-ABI call with HOST buffers (H2D, two kernels, D2H)."""
+@pytest.mark.parametrize("rows", [512, 4104])
+def test_host_buffer_entry_point(rows):
+    """ffq_fakequant_fwd_bwd_host: the end-to-end C-ABI call with HOST buffers (H2D, two kernels, D2H).  4104 rows
+    (16 MB) take the pipelined path: eight groups of whole tiles, the last one ragged, copies overlapping the kernels."""
     import ctypes
     from fastforward_b200 import _cabi as C
 
     torch.manual_seed(11)
-    shape, tile = (512, 1024), (1, 1024)
+    shape, tile = (rows, 1024), (1, 1024)
     x, g = torch.randn(shape), torch.randn(shape)
     scale = (x.abs().amax(1) * 0.6 / 128).contiguous()
     offset = (torch.randn(shape[0]) * 3).contiguous()
