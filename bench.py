@@ -561,7 +561,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
-    def region(steps, tokens_src, e2e, graph, memoize=False, dedupe=True):
+    def region(steps, tokens_src, e2e, graph, memoize=False, dedupe=True, align_ranks_before_exit=False):
         """Enter estimate_ranges, warm up, time `steps` steps + block exit.  Returns seconds (device)."""
         out_host = torch.empty(max(steps, 1), dtype=torch.float32).pin_memory()    # one pinned slot per step
         estimator = make_estimator(memoize)
@@ -599,6 +599,8 @@ def run_ours(args):
                     # D2H read of the step's result into that step's pinned slot; asynchronous like the H2D copy of the
                     # inputs, all of them complete before the region's closing synchronize
                     out_host[i:i + 1].copy_(metric, non_blocking=True)
+            if align_ranks_before_exit:      # diagnostic regions only: take the ranks' skew out of the exit time
+                torch.cuda.synchronize(); barrier()
             tmid.record()
             wall_exit0 = time.perf_counter()
         # leaving the block: +-inf check (one sync) and, for N>1, the MIN/MAX all-reduce of the activation ranges
@@ -644,6 +646,11 @@ def run_ours(args):
         d, _ = region(short, dev_tokens, e2e=False, **kw)
         d = allmax_value(d, dev, world)
         ablation[name] = {"tokens_per_s": round(world * short * seq / d, 1), "ms_per_step": round(1e3 * d / short, 3), "steps": short}
+    # the block exit alone (ranks aligned first: inside the timed regions the exit also absorbs the ranks' skew)
+    reset_quantizers()
+    region(2, dev_tokens, e2e=False, graph=use_graph, memoize=memo, align_ranks_before_exit=True)
+    exit_aligned_ms = allmax_value(region.exit_ms, dev, world)
+    exit_aligned_wall_ms = allmax_value(region.exit_wall_ms, dev, world)
     # ---- instrumented eager pass for the roofline of the dominant kernel ------------------------
     reset_quantizers()
     lc0 = _cabi.launch_count()
@@ -758,7 +765,10 @@ def run_ours(args):
             "peaks": {"hbm_GBps": hbm_peak, "int8_TOPS": int8_peak, "int8_library_sustained_TOPS": (round(int8_lib_peak, 1) if int8_lib_peak else None),
                       "note": "hbm and bf16 from MEASURED_PEAKS.json; int8 = 2 x measured bf16 burst; int8_library_sustained = "
                               "torch._int_mm (cuBLASLt) 8192^3 measured in this run"},
-            "wall_s_timed_region": round(wall, 3), "block_exit_ms": round(exit_ms, 2), "block_exit_wall_ms": round(exit_wall_ms, 2),
+            "wall_s_timed_region": round(wall, 3), "block_exit_ms": round(exit_ms, 2),
+            "block_exit_alone": {"device_ms": round(exit_aligned_ms, 2), "host_wall_ms": round(exit_aligned_wall_ms, 2),
+                                 "note": "ranks aligned by a barrier first; block_exit_ms (inside the timed region) also contains "
+                                         "the skew between ranks that the exit's collectives absorb"},
         }
         print(json.dumps(line))
     if world > 1:

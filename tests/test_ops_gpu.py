@@ -276,5 +276,6 @@ def test_host_buffer_entry_point(rows):
     assert bits_equal(y, R.dequantize_by_tile(q, scale, tile, offset, x.dtype))
     rdx, rdsc, rdof = R.quantize_by_tile_backward_f64(x, g, scale, tile, 8, offset)
     assert bits_equal(dx, rdx)
-    torch.testing.assert_close(dsc.double(), rdsc, rtol=1e-5, atol=1e-4)
-    torch.testing.assert_close(dof.double(), rdof, rtol=1e-5, atol=1e-4)
+    # per-tile sums of 1024 fp32 terms against the fp64 oracle (contract: 4 eps sum|terms|; |terms| <= ~4 here)
+    torch.testing.assert_close(dsc.double(), rdsc, rtol=1e-4, atol=5e-4)
+    torch.testing.assert_close(dof.double(), rdof, rtol=1e-4, atol=5e-4)
