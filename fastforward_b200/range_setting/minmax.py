@@ -416,6 +416,35 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         return f"min={self.min}, max={self.max}"
 
 
+def _unalias_all(steps) -> None:
+    """``_unalias`` for many estimators at once: every aliased range / parameter tensor gets its own copy with ONE
+    multi-tensor launch per dtype (x * 1 is exact, keeps the sign of zero and NaN) instead of four clones per quantizer."""
+    todo = []          # (owner object, attribute, source tensor)
+    for s in steps:
+        if s._alias_of is None:
+            continue
+        s._alias_of = None
+        todo.append((s, "min", s.min))
+        todo.append((s, "max", s.max))
+        q = s._quantizer_ref()
+        if q is not None:
+            todo.append((q.scale, "data", q.scale.data))
+            if q.offset is not None:
+                todo.append((q.offset, "data", q.offset.data))
+    groups: dict = {}
+    for ent in todo:
+        groups.setdefault((ent[2].device, ent[2].dtype), []).append(ent)
+    with torch.no_grad():
+        for ents in groups.values():
+            srcs = [e[2] for e in ents]
+            if srcs[0].is_floating_point() and len(srcs) > 1:
+                copies = torch._foreach_mul(srcs, 1)
+            else:
+                copies = [t.clone() for t in srcs]
+            for (owner, attr, _), c in zip(ents, copies):
+                setattr(owner, attr, c)
+
+
 def _raise_for_flags(value: int) -> None:
     if value & 2:
         raise RuntimeError("fastforward_b200: the grid barrier of the fused calibration kernel timed out "
@@ -530,38 +559,54 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
     # ---- block exit -------------------------------------------------------------------------------------
     def finalize(self, prepared: Sequence[tuple]) -> None:
         del prepared
+        import time
+
         steps, state = self._steps, self._state
         self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters)
+        t0 = time.perf_counter()
+        flags_value = None
         try:
             if self.sync_ranges:
-                self._sync(steps, state)
+                flags_value = self._sync(steps, state)
         finally:
-            for s in state.aliases:             # aliased quantizers get their own parameter storage back
-                s._unalias()
+            t1 = time.perf_counter()
+            _unalias_all(state.aliases)         # aliased quantizers get their own parameter storage back
             state.recent.clear()
+        t2 = time.perf_counter()
         self.last_stats = dict(state.stats)
-        # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks
-        flags = state.all_flags() + [s.flags for _, s in steps if s.flags is not None and s._state is None]
+        # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks.  A data-parallel exit has
+        # already read the (rank-merged) flags of the block's arenas together with the slot signature.
+        flags = [s.flags for _, s in steps if s.flags is not None and s._state is None]
+        if flags_value is None:
+            flags = state.all_flags() + flags
+        value = flags_value or 0
         if flags and not self.eager_checks:
-            value = 0
             for v in torch.stack([f.reshape(()) for f in {id(f): f for f in flags}.values()]).tolist():
                 value |= int(v)
+        t3 = time.perf_counter()
+        self.last_exit = {"sync_ms": (t1 - t0) * 1e3, "unalias_ms": (t2 - t1) * 1e3, "flags_ms": (t3 - t2) * 1e3,
+                          "aliased": len(state.aliases), **getattr(self, "_exit_detail", {})}
+        if not self.eager_checks or flags_value is not None:
             _raise_for_flags(value)
 
-    def _sync(self, steps, state) -> None:
+    def _sync(self, steps, state) -> Optional[int]:
         """Merge the running ranges across the data-parallel ranks and re-derive (scale, offset) from them.
         Slots of the activation arena are handed out in the order quantizers first see data, which control flow that
         depends on the data (experts without tokens on one shard) can make rank dependent: the ranks first agree on
-        the slot layout (one small MAX all-reduce of a signature vector); identical layouts all-reduce the arena in
-        place (one MIN + one MAX collective per dtype), anything else is packed per quantizer in ``prepare`` order
-        with neutral fill for quantizers a rank did not see."""
+        the slot layout (one small MAX all-reduce of a signature vector, which also carries the block's +-inf flags so
+        that the exit has ONE host sync); identical layouts all-reduce the arena in place (one MIN + one MAX
+        collective per dtype, asynchronous), anything else is packed per quantizer in ``prepare`` order with neutral
+        fill for quantizers a rank did not see.  Returns the flags merged over the ranks (None: nothing exchanged)."""
+        import time
+
         import torch.distributed as dist
 
         from ..distributed import _active, all_reduce_minmax_buffers
 
         group = self.process_group
         if not _active(group):
-            return
+            return None
+        t0 = time.perf_counter()
         todo = [(i, q, s) for i, (q, s) in enumerate(steps)
                 if s._alias_of is None and (self.sync_parameters or not s._param_data)]
         device = None
@@ -581,18 +626,35 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
                 sig.append((int(s._slot[0] is state.param) << 60) | (s._slot[1] << 40) | s._slot[2])
             else:
                 sig.append(-2)
-        sig_t = torch.tensor([sig, [-v for v in sig]], dtype=torch.int64, device=device)
-        dist.all_reduce(sig_t, op=dist.ReduceOp.MAX, group=group)
-        same = bool(torch.equal(sig_t[0], -sig_t[1])) and -2 not in sig
-        flags = state.all_flags()
+        n = len(sig)
+        # [sig | -sig | flag bit 0 | flag bit 1]: MAX over the ranks gives max(sig), -min(sig) and the OR of each flag bit
+        msg = torch.tensor(sig + [-v for v in sig] + [0, 0], dtype=torch.int64).to(device, non_blocking=True)
+        flags = [f for f in state.all_flags() if f.device == device]
+        for f in flags:
+            f64 = f.reshape(()).to(torch.int64)
+            msg[2 * n] |= f64 & 1
+            msg[2 * n + 1] |= (f64 >> 1) & 1
+        dist.all_reduce(msg, op=dist.ReduceOp.MAX, group=group)
+        got = msg.tolist()                       # the exit's one host sync
+        t1 = time.perf_counter()
+        same = all(a == -b for a, b in zip(got[:n], got[n:2 * n])) and -2 not in sig
+        flags_value = int(got[2 * n]) | (int(got[2 * n + 1]) << 1)
+        other_flags = [f for f in state.all_flags() if f.device != device]     # a block spanning devices: the old way
         if same:
-            all_reduce_minmax_buffers(list(state.act.buffers()), flags, group=group)
+            all_reduce_minmax_buffers(list(state.act.buffers()), other_flags, group=group)
             if self.sync_parameters:
                 all_reduce_minmax_buffers(list(state.param.buffers()), None, group=group)
         else:
             self._sync_packed(todo, device, group)
-            all_reduce_minmax_buffers([], flags, group=group)
+            all_reduce_minmax_buffers([], other_flags, group=group)
+        for f in other_flags:
+            flags_value |= int(f.item())
+        t2 = time.perf_counter()
         self._reset_parameters_from_ranges([(q, s) for _, q, s in todo if s.min is not None], state)
+        t3 = time.perf_counter()
+        self._exit_detail = {"signature_ms": (t1 - t0) * 1e3, "allreduce_issue_ms": (t2 - t1) * 1e3,
+                             "params_ms": (t3 - t2) * 1e3, "exchanged_quantizers": n, "same_layout": same}
+        return flags_value
 
     def _sync_packed(self, todo, device, group) -> None:
         import torch.distributed as dist

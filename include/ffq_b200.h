@@ -353,10 +353,11 @@ FFQ_API int ffq_gptq_block(float* w, int64_t ldw, float* q, int64_t ldq, float* 
 FFQ_API int ffq_selftest_shared_div(unsigned long long n, unsigned int seed, unsigned long long* counts_dev,
                                     void* stream);
 
-/* Test hook: while `counters_dev` is non-NULL, the CTA-pair kernel of ffq_qlinear_w8a8 records per CTA eight uint64 of
+/* Test hook: while `counters_dev` is non-NULL, the CTA-pair kernel of ffq_qlinear_w8a8 records per CTA sixteen uint64 of
  * SM clocks (see GemmArgs::prof in csrc/ffq_qlinear.cu): how long the TMA producer waited for a free stage, the MMA
- * issuer for operands and for a free accumulator, the epilogue for a finished tile, and each role's total.
- * counters_dev: uint64[8 * grid] (grid <= 8 * SM count).  NULL switches it off.  Used by tools/prof_gemm_roles.py. */
+ * issuer for operands and for a free accumulator, the epilogue for a finished tile, each role's total, and the
+ * epilogue's phases (column parameters, tcgen05.ld, staging box, arithmetic, store issue).
+ * counters_dev: uint64[16 * grid] (grid <= 8 * SM count).  NULL switches it off.  Used by tools/prof_gemm_roles.py. */
 FFQ_API void ffq_debug_gemm_profile(unsigned long long* counters_dev);
 
 #ifdef __cplusplus

@@ -14,8 +14,12 @@ import torch  # noqa: E402
 from fastforward_b200 import _cabi as C  # noqa: E402
 
 
-def run(M, N, K, cluster=None):
+def run(M, N, K, cluster=None, kernel=None):
     dev = torch.device("cuda")
+    if kernel:
+        os.environ["FFQ_GEMM_KERNEL"] = kernel
+    else:
+        os.environ.pop("FFQ_GEMM_KERNEL", None)
     if cluster:
         os.environ["FFQ_GEMM_CLUSTER"] = str(cluster)
     else:
@@ -33,18 +37,18 @@ def run(M, N, K, cluster=None):
                                        sw.data_ptr(), None, rs.data_ptr(), None, None, 255, None, st))
     for _ in range(3):
         gemm()
-    prof = torch.zeros(8 * 8 * 148, dtype=torch.int64, device=dev)
+    prof = torch.zeros(16 * 8 * 148, dtype=torch.int64, device=dev)
     C.lib.ffq_debug_gemm_profile(prof.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); gemm(); e1.record()
     torch.cuda.synchronize()
     C.lib.ffq_debug_gemm_profile(None)
     us = e0.elapsed_time(e1) * 1e3
-    p = prof.view(-1, 8).double().cpu()
+    p = prof.view(-1, 16).double().cpu()
     live = p[p[:, 1] > 0]
     leaders = live[live[:, 4] > 0]
     out = {
-        "shape": f"{M}x{N}x{K}", "cluster_ctas": cluster or 2, "us": round(us, 1), "TOPS": round(2 * M * N * K / us / 1e6, 1),
+        "shape": f"{M}x{N}x{K}", "kernel": kernel or "default", "cluster_ctas": cluster or 2, "us": round(us, 1), "TOPS": round(2 * M * N * K / us / 1e6, 1),
         "ctas": int(live.shape[0]),
         "kernel_clocks_median": float(live[:, 1].median()),
         "clock_MHz_implied": round(float(live[:, 1].median()) / us, 1),
@@ -53,6 +57,18 @@ def run(M, N, K, cluster=None):
         "mma_blocked_on_accumulator": round(float((leaders[:, 3] / leaders[:, 4]).mean()), 3),
         "epilogue_blocked_on_tile": round(float((live[:, 5] / live[:, 6].clamp_min(1)).mean()), 3),
     }
+    ep = live[live[:, 12] > 0]
+    if ep.shape[0]:
+        tiles = ep[:, 12]
+        out["epilogue_clocks_per_tile"] = {
+            "total_busy": round(float(((ep[:, 6] - ep[:, 5]) / tiles).mean())),
+            "column_parameters_and_barriers": round(float((ep[:, 7] / tiles).mean())),
+            "tcgen05_ld": round(float((ep[:, 8] / tiles).mean())),
+            "wait_staging_box_free": round(float((ep[:, 9] / tiles).mean())),
+            "arithmetic_and_staging": round(float((ep[:, 10] / tiles).mean())),
+            "fence_and_store_issue": round(float((ep[:, 11] / tiles).mean())),
+            "tiles_per_cta": round(float(tiles.mean()), 1),
+        }
     return out
 
 
@@ -61,5 +77,5 @@ if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     shapes = [tuple(int(v) for v in args[:3])] if len(args) >= 3 else [(8192, 14336, 4096), (2048, 4096, 4096), (2048, 14336, 4096)]
     for shp in shapes:
-        for c in (None, 4):
-            print(json.dumps(run(*shp, cluster=c)), flush=True)
+        for kern in ("pair", "wide"):
+            print(json.dumps(run(*shp, kernel=kern)), flush=True)
