@@ -54,7 +54,6 @@ struct GemmArgs {
   const void* bias; int bias_dt;                // per output column, optional
   const int32_t* rowsum_x;                      // per output row; used with ow
   int bn;                                       // output columns per tile (256; 224 / 128 when that evens out the waves)
-  int bn1;                                      // wide kernel: bn = tokens of half 0, bn1 = tokens of half 1 (0: one half)
   // fused output quantizer (ffq_requant_t): per-tensor, int8 codes of the output rounded to y_dt
   const float* rq_scale; const float* rq_offset; float rq_lo, rq_hi; int8_t* rq_codes; int32_t* rq_rowsum;
   // test hook (ffq_debug_gemm_profile): per CTA PROF_SLOTS x u64 of SM clocks -- [0] producer waiting for a free stage, [1] producer
@@ -62,8 +61,6 @@ struct GemmArgs {
   // [5] epilogue waiting for a finished tile, [6] epilogue total
   unsigned long long* prof;
   int tma_store;                                // the output has a tensor map: staged TMA-store epilogue
-  int l2pf;                                     // k-blocks the producers prefetch into L2 ahead of their tile loads (0: off)
-  int group;                                    // wide kernel: k-blocks issued into one half before the other half catches up
   int dbg;                                      // test hook (FFQ_GEMM_DEBUG): 1 skip the epilogue, 2 skip its stores, 4 skip its column parameters
 };
 
@@ -467,10 +464,6 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
           if (prof) t_wait += clock64() - w0;
           uint8_t* sa = stage_base + stage * HALF_STAGE;
-          if (g.l2pf > 0 && kb + g.l2pf < k_blocks) {
-            tma_prefetch_l2_2d(&map_a, (kb + g.l2pf) * BK, tm * TM + (int)cta * BM);
-            if (P == 1) tma_prefetch_l2_2d(&map_b, (kb + g.l2pf) * BK, tn * bn + (int)cta * (bn / 2));
-          }
           if (cta == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d_pair(sa, &map_a, &full_bar[stage], kb * BK, tm * TM + (int)cta * BM);
           if constexpr (P == 1) {
@@ -576,315 +569,6 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
-
-// ================================================================================================
-// Swapped, wide variant: D^T = W * X^T.  The 256 accumulator rows of a CTA pair (TMEM lanes, 128 per CTA) are 256
-// OUTPUT COLUMNS n (weight rows), the TMEM columns are tokens m.  Two consequences:
-//  * an epilogue thread owns one output column: alpha[n], bias[n] and the offset constant live in registers for the
-//    whole tile (the row-per-thread epilogue above fetches four words per ELEMENT from shared memory and is bound by
-//    the LSU pipe, which the MMA's operand reads share); the 32 lanes of a warp write 32 consecutive outputs of one
-//    token row -- whole 64/128-byte segments straight from registers, no staging;
-//  * a tile is 256 n x (bm0 + bm1 <= 512) tokens: all 512 TMEM columns hold ONE tile as two halves S0 | S1 that
-//    share the tile's weight k-blocks.  Per k-block a CTA receives 16 KB of W + (bm0 + bm1)/2 x 128 B of X for
-//    128 x (bm0 + bm1) x 128 MACs: 48 B/clk at the full MMA rate instead of the 64 B/clk of a 256 x 256 tile.  The
-//    kernel is bound by L2 -> SM delivery (ncu: lts2xbar at its cap, tensor pipe 66 % with 256 x 256 tiles), so
-//    bytes per MAC is what buys speed.
-// There is no second accumulator to hide the epilogue behind, so the halves run SKEWED: S1 trails S0 by W3_SKEW
-// k-blocks.  At a tile boundary S0 finishes first and is drained while S1's last k-blocks are issued; the next
-// tile's S0 then runs ahead alone while S1 is drained.  W k-blocks live in their own ring (held until S1 has used
-// them), the X half k-blocks of both halves travel through one FIFO ring in exactly the order the MMAs consume them.
-// Barriers: fullB[b] (on the pair leader) counts the bytes of B entry b and, for an S0 entry, of the W k-block that
-// is loaded with it; emptyA / emptyB are released by tcgen05.commit multicast to both CTAs; tmem_full[h] /
-// tmem_empty[h] hand half h between the MMA issuer and the 8 epilogue warps of the pair.
-// ================================================================================================
-constexpr int W3_ENTRY = 128 * BK;               // one ring entry: 128 rows x 128 B = 16 KB
-constexpr int W3_NA = 6, W3_NB = 8;              // ring depths: W k-blocks / X half k-blocks
-constexpr int W3_GROUP = 4;                      // k-blocks issued into S0 before S1 catches up (<= W3_NA - 2)
-constexpr int SMEM3_BYTES = (W3_NA + W3_NB) * W3_ENTRY + 512 + 1024;
-
-// One chunk of W (32 or 16) tokens of this thread's output column n.
-template <typename OutT, int W>
-__device__ __forceinline__ void epilogue3_chunk(const GemmArgs& g, const uint32_t (&acc)[32], int m0c, int n, bool n_ok,
-                                                float alpha, float bias, int32_t ci, float cf, int32_t own, bool wide,
-                                                float rq_s, float rq_o, const SharedRcp& rq_k) {
-  const int lane = threadIdx.x & 31;
-  const bool full = m0c + W <= g.M;
-  float v[W];
-  if (g.ow == nullptr) {
-    if (!wide) {
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = fmaf(alpha, (float)((int32_t)acc[j] + ci), bias);
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j) v[j] = fmaf(alpha, (float)(int32_t)acc[j] + cf, bias);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-      const int32_t rx = (m0c + j < g.M) ? __ldg(g.rowsum_x + m0c + j) : 0;
-      if (!wide) v[j] = fmaf(alpha, (float)((int32_t)acc[j] + ci + own * rx), bias);
-      else v[j] = fmaf(alpha, (float)(int32_t)acc[j] + cf + (float)own * (float)rx, bias);
-    }
-  }
-  if (g.dbg & 2) return;
-  if (g.y != nullptr && n_ok) {
-    OutT* yp = static_cast<OutT*>(g.y) + (size_t)m0c * g.N + n;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < W; ++j) yp[(size_t)j * g.N] = Elem<OutT>::from_f(v[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j)
-        if (m0c + j < g.M) yp[(size_t)j * g.N] = Elem<OutT>::from_f(v[j]);
-    }
-  }
-  if (g.rq_codes != nullptr) {
-    // output_quantizer(y): y rounded to the output dtype first, then quantize_by_tile's fp32 arithmetic
-    int8_t* cp = g.rq_codes + (size_t)m0c * g.N + n;
-    int mine = 0;
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-      const float yr = Elem<OutT>::to_f(Elem<OutT>::from_f(v[j]));
-      bool ok = rq_k.ok;
-      float quo = shared_div<false>(yr, rq_k, ok);
-      if (!ok) quo = __fdiv_rn(yr, rq_s);
-      float t = __fsub_rn(quo, rq_o);
-      t = nan_clamp(rintf(t), g.rq_lo, g.rq_hi);
-      const int c = __float2int_rz(t);
-      const bool live = n_ok && (m0c + j < g.M);
-      if (live) cp[(size_t)j * g.N] = (int8_t)c;
-      if (g.rq_rowsum != nullptr) {
-        const int s = __reduce_add_sync(0xffffffffu, live ? c : 0);     // over the warp's 32 output columns
-        if (lane == j) mine = s;
-      }
-    }
-    if (g.rq_rowsum != nullptr && lane < W && m0c + lane < g.M) atomicAdd(&g.rq_rowsum[m0c + lane], mine);
-  }
-}
-
-template <typename OutT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-w8a8_gemm3_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x0,
-                  const __grid_constant__ CUtensorMap map_x1, const GemmArgs g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring_a = smem;                                   // [W3_NA][16 KB]: this CTA's 128 weight rows of a k-block
-  uint8_t* ring_b = smem + W3_NA * W3_ENTRY;                // [W3_NB][16 KB]: this CTA's half of a token half's k-block
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (W3_NA + W3_NB) * W3_ENTRY);
-  uint64_t* full_b = bars;                                  // [W3_NB]  (pair leader's copy)
-  uint64_t* empty_b = bars + W3_NB;                         // [W3_NB]  (own copy)
-  uint64_t* empty_a = bars + 2 * W3_NB;                     // [W3_NA]  (own copy)
-  uint64_t* tmem_full = bars + 2 * W3_NB + W3_NA;           // [2]      (own copy)
-  uint64_t* tmem_empty = bars + 2 * W3_NB + W3_NA + 2;      // [2]      (pair leader's copy, 8 arrivals)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * W3_NB + W3_NA + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta = cluster_ctarank() & 1u;
-  const int cluster = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const int bm0 = g.bn, bm1 = g.bn1, tw = bm0 + bm1;        // tokens per half / per tile
-  const int halves = bm1 > 0 ? 2 : 1;
-  const int group = g.group;                                 // k-blocks issued into one half before switching to the other (1..W3_NA - 2)
-  const int tiles_n = (g.N + 255) / 256, tiles_m = (g.M + tw - 1) / tw;
-  const int num_tiles = tiles_n * tiles_m;
-  const int k_blocks = (g.K + BK - 1) / BK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < W3_NB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < W3_NA; ++s) mbar_init(&empty_a[s], 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                 "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs; bytes are credited to the pair leader's full barriers) =====
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x0) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x1) : "memory");
-      int ia = 0, ib = 0; uint32_t pa = 0, pb = 0;
-      const bool prof = g.prof != nullptr;
-      long long t_wait = 0;
-      const long long t_begin = prof ? clock64() : 0;
-      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
-        const int n_row = tn * 256 + (int)cta * 128;
-        const int m_row0 = tm * tw + (int)cta * (bm0 / 2), m_row1 = tm * tw + bm0 + (int)cta * (bm1 / 2);
-        for (int g0 = 0; g0 < k_blocks; g0 += group) {
-          const int ge = g0 + group < k_blocks ? g0 + group : k_blocks;
-          for (int i = g0; i < ge; ++i) {
-            const long long w0 = prof ? clock64() : 0;
-            mbar_wait_bounded(&empty_a[ia], pa ^ 1);
-            mbar_wait_bounded(&empty_b[ib], pb ^ 1);
-            if (prof) t_wait += clock64() - w0;
-            if (g.l2pf > 0 && i + g.l2pf < k_blocks) {
-              tma_prefetch_l2_2d(&map_w, (i + g.l2pf) * BK, n_row);
-              tma_prefetch_l2_2d(&map_x0, (i + g.l2pf) * BK, m_row0);
-              if (halves == 2) tma_prefetch_l2_2d(&map_x1, (i + g.l2pf) * BK, m_row1);
-            }
-            if (cta == 0) mbar_expect_tx(&full_b[ib], 2u * (uint32_t)(W3_ENTRY + (bm0 / 2) * BK));
-            tma_load_2d_pair(ring_a + ia * W3_ENTRY, &map_w, &full_b[ib], i * BK, n_row);
-            tma_load_2d_pair(ring_b + ib * W3_ENTRY, &map_x0, &full_b[ib], i * BK, m_row0);
-            if (++ia == W3_NA) { ia = 0; pa ^= 1; }
-            if (++ib == W3_NB) { ib = 0; pb ^= 1; }
-          }
-          if (halves == 2) {
-            for (int j = g0; j < ge; ++j) {
-              const long long w0 = prof ? clock64() : 0;
-              mbar_wait_bounded(&empty_b[ib], pb ^ 1);
-              if (prof) t_wait += clock64() - w0;
-              if (cta == 0) mbar_expect_tx(&full_b[ib], 2u * (uint32_t)((bm1 / 2) * BK));
-              tma_load_2d_pair(ring_b + ib * W3_ENTRY, &map_x1, &full_b[ib], j * BK, m_row1);
-              if (++ib == W3_NB) { ib = 0; pb ^= 1; }
-            }
-          }
-        }
-      }
-      if (prof) { g.prof[blockIdx.x * PROF_SLOTS + 0] = (unsigned long long)t_wait; g.prof[blockIdx.x * PROF_SLOTS + 1] = (unsigned long long)(clock64() - t_begin); }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (pair leader) =====
-    if (cta == 0 && lane == 0) {
-      // D = S32, A = B = signed int8, K-major, M = 256 (128 weight rows in each CTA), N = tokens of the half
-      const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 4) << 24);
-      const uint32_t idesc0 = idesc_base | ((uint32_t)(bm0 >> 3) << 17), idesc1 = idesc_base | ((uint32_t)(bm1 >> 3) << 17);
-      int ia0 = 0, ia1 = 0, ib = 0; uint32_t pb = 0;          // W ring positions of S0 / S1, X ring position
-      int it = 0;
-      const bool prof = g.prof != nullptr;
-      long long t_full = 0, t_acc = 0;
-      const long long t_begin = prof ? clock64() : 0;
-      for (int tile = cluster; tile < num_tiles; tile += num_clusters, ++it) {
-        for (int g0 = 0; g0 < k_blocks; g0 += group) {
-          const int ge = g0 + group < k_blocks ? g0 + group : k_blocks;
-          for (int i = g0; i < ge; ++i) {
-            long long w0 = prof ? clock64() : 0;
-            // one half per tile: the two TMEM halves are two accumulators used by alternate tiles (double buffering)
-            const int buf0 = halves == 1 ? (it & 1) : 0;
-            const uint32_t use0 = halves == 1 ? (uint32_t)(it >> 1) : (uint32_t)it;
-            if (i == 0) { mbar_wait_bounded(&tmem_empty[buf0], (use0 & 1u) ^ 1u); if (prof) { const long long w1 = clock64(); t_acc += w1 - w0; w0 = w1; } }
-            mbar_wait_bounded(&full_b[ib], pb);
-            if (prof) t_full += clock64() - w0;
-            tc_fence_after();
-            const uint64_t da = make_smem_desc(smem_u32(ring_a + ia0 * W3_ENTRY)), db = make_smem_desc(smem_u32(ring_b + ib * W3_ENTRY));
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_i8_pair(tmem_base + (uint32_t)(buf0 * 256), da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), idesc0, (i | k) ? 1u : 0u);
-            umma_commit_mc(&empty_b[ib], 3);
-            if (halves == 1) umma_commit_mc(&empty_a[ia0], 3);
-            if (i == k_blocks - 1) umma_commit_mc(&tmem_full[buf0], 3);
-            if (++ia0 == W3_NA) ia0 = 0;
-            if (++ib == W3_NB) { ib = 0; pb ^= 1; }
-          }
-          if (halves == 2) {
-            for (int j = g0; j < ge; ++j) {
-              long long w0 = prof ? clock64() : 0;
-              if (j == 0) { mbar_wait_bounded(&tmem_empty[1], (uint32_t)(it & 1) ^ 1u); if (prof) { const long long w1 = clock64(); t_acc += w1 - w0; w0 = w1; } }
-              mbar_wait_bounded(&full_b[ib], pb);
-              if (prof) t_full += clock64() - w0;
-              tc_fence_after();
-              const uint64_t da = make_smem_desc(smem_u32(ring_a + ia1 * W3_ENTRY)), db = make_smem_desc(smem_u32(ring_b + ib * W3_ENTRY));
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_i8_pair(tmem_base + 256u, da + (uint64_t)(k * (UMMA_K >> 4)), db + (uint64_t)(k * (UMMA_K >> 4)), idesc1, (j | k) ? 1u : 0u);
-              umma_commit_mc(&empty_b[ib], 3);
-              umma_commit_mc(&empty_a[ia1], 3);
-              if (j == k_blocks - 1) umma_commit_mc(&tmem_full[1], 3);
-              if (++ia1 == W3_NA) ia1 = 0;
-              if (++ib == W3_NB) { ib = 0; pb ^= 1; }
-            }
-          }
-        }
-      }
-      if (prof) {
-        g.prof[blockIdx.x * PROF_SLOTS + 2] = (unsigned long long)t_full; g.prof[blockIdx.x * PROF_SLOTS + 3] = (unsigned long long)t_acc;
-        g.prof[blockIdx.x * PROF_SLOTS + 4] = (unsigned long long)(clock64() - t_begin);
-      }
-    }
-  } else {
-    // ===== epilogue (warps 2..5 of both CTAs): thread = one output column n, chunks of 32 tokens =====
-    const int quad = warp & 3;
-    const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
-    const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
-    const SharedRcp rq_k = make_shared_rcp(rq_s);
-    const float sx = g.sx[0];
-    const float oxf = g.ox ? rintf(g.ox[0]) : 0.f;
-    const long long o_x = (long long)oxf;
-    const bool prof = g.prof != nullptr && threadIdx.x == 64;
-    long long t_tile = 0, t_cols = 0, t_ld = 0, t_math = 0;
-    const long long t_begin = prof ? clock64() : 0;
-    int it = 0;
-    for (int tile = cluster; tile < num_tiles; tile += num_clusters, ++it) {
-      const int tm = tile % tiles_m, tn = tile / tiles_m;
-      const int n = tn * 256 + (int)cta * 128 + quad * 32 + lane;
-      const bool n_ok = n < g.N;
-      // this column's epilogue parameters (see stage_col_params): registers for the whole tile
-      const long long c0t = prof ? clock64() : 0;
-      const float owf = (n_ok && g.ow) ? rintf(g.ow[n]) : 0.f;
-      const long long o_w = (long long)owf;
-      const long long rsw = n_ok ? (long long)g.rowsum_w[n] : 0;
-      const long long c64 = o_x * rsw + (long long)g.K * o_x * o_w;
-      const long long bound = (c64 < 0 ? -c64 : c64) + (o_w < 0 ? -o_w : o_w) * (long long)g.K * 128 + (long long)g.K * 16384;
-      const bool wide = !(fabsf(oxf) < 1.0e9f) || !(fabsf(owf) < 1.0e9f) || bound >= 0x7fffffffll;
-      const float alpha = n_ok ? sx * g.sw[n] : 0.f;
-      const float bias = (n_ok && g.bias) ? load_as_float(g.bias, g.bias_dt, n) : 0.f;
-      const int32_t ci = (int32_t)c64, own = (int32_t)o_w;
-      const float cf = oxf * (float)rsw + (float)g.K * oxf * owf;
-      if (prof) t_cols += clock64() - c0t;
-      for (int hh = 0; hh < halves; ++hh) {
-        const int bm = hh ? bm1 : bm0;
-        const int m_half = tm * tw + hh * bm0;
-        const int h = halves == 1 ? (it & 1) : hh;                       // TMEM half holding this accumulator
-        const uint32_t use = halves == 1 ? (uint32_t)(it >> 1) : (uint32_t)it;
-        const long long w0 = prof ? clock64() : 0;
-        mbar_wait_bounded(&tmem_full[h], use & 1u);
-        if (prof) t_tile += clock64() - w0;
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(h * 256);
-        if (!(g.dbg & 1)) {
-#pragma unroll 1
-          for (int c0 = 0; c0 < bm; c0 += 32) {
-            uint32_t acc[32];
-            long long q0 = prof ? clock64() : 0;
-            if (m_half + c0 >= g.M) break;                       // nothing of this tile below here is inside the output
-            if (c0 + 32 <= bm) {
-              tmem_ld32(taddr + (uint32_t)c0, acc);
-              if (prof) { const long long q1 = clock64(); t_ld += q1 - q0; q0 = q1; }
-              epilogue3_chunk<OutT, 32>(g, acc, m_half + c0, n, n_ok, alpha, bias, ci, cf, own, wide, rq_s, rq_o, rq_k);
-            } else {
-              tmem_ld16(taddr + (uint32_t)c0, acc);
-              if (prof) { const long long q1 = clock64(); t_ld += q1 - q0; q0 = q1; }
-              epilogue3_chunk<OutT, 16>(g, acc, m_half + c0, n, n_ok, alpha, bias, ci, cf, own, wide, rq_s, rq_o, rq_k);
-            }
-            if (prof) t_math += clock64() - q0;
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(&tmem_empty[h]);     // 8 arrivals (4 warps x 2 CTAs) free the half
-      }
-    }
-    if (prof) {
-      unsigned long long* o = g.prof + (size_t)blockIdx.x * PROF_SLOTS;
-      o[5] = (unsigned long long)t_tile; o[6] = (unsigned long long)(clock64() - t_begin); o[7] = (unsigned long long)t_cols;
-      o[8] = (unsigned long long)t_ld; o[9] = 0; o[10] = (unsigned long long)t_math; o[11] = 0;
-      o[12] = (unsigned long long)(it * halves);
-    }
-  }
-
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
-  }
-}
 
 // ---- small helper kernels ------------------------------------------------------------------------
 // rowsum[r] = sum_k q[r,k]   (one warp per row, 16-byte loads, dp4a against ones)
@@ -1015,53 +699,6 @@ static int env_cluster_pairs() {
 }
 
 
-// ---- wide kernel: tile width selection + launch ------------------------------------------------------
-// Tokens per tile (two equal halves, each a multiple of 16 and <= 256).  Cost of a k-block for one CTA: the larger of
-// the MMA time (128 x tw x 128 MACs at 8192 MACs/clk) and the L2 -> SM delivery of its operands (16 KB of W +
-// tw/2 x 128 B of X at ~47 B/clk/SM, what ffq_debug_gemm_profile / ncu show the chip sustains); a tile adds the
-// exposed part of its two drains; waves of tiles over the CTA pairs.
-static void choose_wide_tile(long long M, long long N, long long K, int* bm0, int* bm1) {
-  const char* e = getenv("FFQ_GEMM_WIDE_TW");
-  const int forced = e ? atoi(e) : 0;
-  if (M <= 256 && forced == 0) { *bm0 = (int)((M + 15) / 16 * 16); *bm1 = 0; return; }
-  { const char* eh = getenv("FFQ_GEMM_WIDE_HALVES");        // 1: independent, double-buffered tiles of `forced` (<= 256) tokens
-    if (eh && atoi(eh) == 1) { *bm0 = forced > 0 && forced <= 256 ? forced / 16 * 16 : 256; *bm1 = 0; return; } }
-  const long long pairs = sm_count() / 2, tiles_n = (N + 255) / 256, k_blocks = (K + BK - 1) / BK;
-  double best = 1e300;
-  int best_tw = 512;
-  for (int tw = 512; tw >= 64; tw -= 32) {
-    if (forced && tw != forced) continue;
-    const long long tiles = ((M + tw - 1) / tw) * tiles_n;
-    const long long waves = (tiles + pairs - 1) / pairs;
-    const double mma = 2.0 * tw, l2 = 2.72 * (128.0 + tw / 2.0);
-    const double cost = (double)waves * ((double)k_blocks * (mma > l2 ? mma : l2) + 1500.0);
-    if (cost < best * 0.999) { best = cost; best_tw = tw; }
-  }
-  *bm0 = *bm1 = best_tw / 2;
-}
-
-template <typename OutT>
-static int launch_wide(const CUtensorMap& map_w, const CUtensorMap& map_x0, const CUtensorMap& map_x1, const GemmArgs& g,
-                       long long tiles, cudaStream_t st) {
-  static std::atomic<uint64_t> attr_done{0};
-  auto kern = w8a8_gemm3_kernel<OutT>;
-  const cudaError_t e = once_per_device(attr_done, [&]() -> cudaError_t {
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES);
-  });
-  if (e != cudaSuccess) { set_error("qlinear_w8a8: cannot configure the wide kernel: %s", cudaGetErrorString(e)); return FFQ_ERR_CUDA; }
-  cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  const long long pairs = sm_count() / 2;
-  cfg.gridDim = dim3((unsigned)(2 * (tiles < pairs ? tiles : pairs)));
-  cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM3_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, map_w, map_x0, map_x1, g);
-  count_launch();
-  if (le != cudaSuccess) { cudaGetLastError(); set_error("qlinear_w8a8: wide kernel launch failed: %s", cudaGetErrorString(le)); return FFQ_ERR_CUDA; }
-  return FFQ_OK;
-}
-
 extern "C" {
 
 int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, int64_t M, int64_t N, int64_t K,
@@ -1090,8 +727,6 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   g.rowsum_x = rowsum_x;
   g.prof = g_gemm_prof;
   { const char* e = getenv("FFQ_GEMM_DEBUG"); g.dbg = e ? atoi(e) : 0; }
-  { const char* e = getenv("FFQ_GEMM_L2PF"); g.l2pf = e ? atoi(e) : 0; }
-  { const char* e = getenv("FFQ_GEMM_WIDE_GROUP"); g.group = e ? atoi(e) : W3_GROUP; if (g.group < 1) g.group = 1; if (g.group > W3_NA - 2) g.group = W3_NA - 2; }
   // staged TMA-store epilogue whenever the output can be described by a tensor map (16-byte aligned rows);
   // FFQ_GEMM_DIRECT_STORE=1 keeps the per-lane vector stores (A/B switch)
   CUtensorMap map_y;
@@ -1106,29 +741,6 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
     if (!(requant->num_bits >= 1 && requant->num_bits <= 8)) { set_error("qlinear_w8a8: requant codes are int8: num_bits must be in [1, 8]"); return FFQ_ERR_BITWIDTH; }
     g.rq_scale = requant->scale; g.rq_offset = requant->offset; g.rq_codes = requant->codes; g.rq_rowsum = requant->rowsum;
     g.rq_lo = -(float)exp2(requant->num_bits - 1.0); g.rq_hi = (float)exp2(requant->num_bits - 1.0) - 1.f;
-  }
-  // ---- kernel choice.  FFQ_GEMM_KERNEL = wide | pair | single forces one (A/B runs, tests); default: the wide
-  // swapped kernel whenever its 256-column x <=512-token tiles give every CTA pair work, the older kernels otherwise
-  {
-    const char* ek = getenv("FFQ_GEMM_KERNEL");
-    const bool force_wide = ek && !strcmp(ek, "wide");
-    const bool force_other = ek && (!strcmp(ek, "pair") || !strcmp(ek, "single"));
-    int bm0 = 0, bm1 = 0;
-    choose_wide_tile(M, N, K, &bm0, &bm1);
-    const long long wtiles = ((N + 255) / 256) * ((M + bm0 + bm1 - 1) / (bm0 + bm1));
-    const bool auto_wide = !force_other && getenv("FFQ_GEMM_1CTA") == nullptr && wtiles * 2 >= sm_count() / 2 && N >= 128;
-    if (force_wide || auto_wide) {
-      CUtensorMap map_w, map_x0, map_x1;
-      if ((rc = make_map(&map_w, qw, N, K, 128)) != FFQ_OK) return rc;
-      if ((rc = make_map(&map_x0, qx, M, K, bm0 / 2)) != FFQ_OK) return rc;
-      if ((rc = make_map(&map_x1, qx, M, K, bm1 > 0 ? bm1 / 2 : bm0 / 2)) != FFQ_OK) return rc;
-      g.bn = bm0; g.bn1 = bm1;
-      switch (y_dtype) {
-        case FFQ_F32: return launch_wide<float>(map_w, map_x0, map_x1, g, wtiles, st);
-        case FFQ_BF16: return launch_wide<__nv_bfloat16>(map_w, map_x0, map_x1, g, wtiles, st);
-        default: return launch_wide<__half>(map_w, map_x0, map_x1, g, wtiles, st);
-      }
-    }
   }
   const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const long long pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);

@@ -36,8 +36,6 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--clusters", default="")
     ap.add_argument("--shapes", default="", help="comma list of MxNxK (default: the built-in list)")
-    ap.add_argument("--kernels", default="pair,wide", help="FFQ_GEMM_KERNEL values to time next to the default choice")
-    ap.add_argument("--wide-tw", default="", help="comma list of FFQ_GEMM_WIDE_TW values to time with the wide kernel")
     a = ap.parse_args()
     dev = torch.device("cuda")
     res = {}
@@ -62,25 +60,7 @@ def main():
             i = it[0] % nbuf; it[0] += 1
             torch._int_mm(qx[i], qw[i].t())
         ent = {}
-        for kname in [k for k in a.kernels.split(",") if k]:
-            os.environ["FFQ_GEMM_KERNEL"] = kname
-            try:
-                t = time_fn(gemm)
-                ent[kname] = {"us": round(t * 1e6, 1), "TOPS": round(2 * M * N * K / t / 1e12, 1)}
-            except Exception as e:  # noqa: BLE001
-                ent[kname] = f"error: {e}"
-                torch.cuda.synchronize()
-        for tw in [v for v in a.wide_tw.split(",") if v]:
-            os.environ["FFQ_GEMM_KERNEL"] = "wide"; os.environ["FFQ_GEMM_WIDE_TW"] = tw
-            try:
-                t = time_fn(gemm)
-                ent[f"wide_tw{tw}"] = {"us": round(t * 1e6, 1), "TOPS": round(2 * M * N * K / t / 1e12, 1)}
-            except Exception as e:  # noqa: BLE001
-                ent[f"wide_tw{tw}"] = f"error: {e}"
-                torch.cuda.synchronize()
-        os.environ.pop("FFQ_GEMM_KERNEL", None); os.environ.pop("FFQ_GEMM_WIDE_TW", None)
         for c in [c for c in a.clusters.split(",") if c]:
-            os.environ["FFQ_GEMM_KERNEL"] = "pair"
             os.environ["FFQ_GEMM_CLUSTER"] = c
             try:
                 t = time_fn(gemm)
@@ -88,7 +68,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 ent[f"cluster{c}"] = f"error: {e}"
                 torch.cuda.synchronize()
-        os.environ.pop("FFQ_GEMM_CLUSTER", None); os.environ.pop("FFQ_GEMM_KERNEL", None)
+        os.environ.pop("FFQ_GEMM_CLUSTER", None)
         t = time_fn(gemm)
         ent["default"] = {"us": round(t * 1e6, 1), "TOPS": round(2 * M * N * K / t / 1e12, 1)}
         t = time_fn(lib)

@@ -14,12 +14,8 @@ import torch  # noqa: E402
 from fastforward_b200 import _cabi as C  # noqa: E402
 
 
-def run(M, N, K, cluster=None, kernel=None):
+def run(M, N, K, cluster=None):
     dev = torch.device("cuda")
-    if kernel:
-        os.environ["FFQ_GEMM_KERNEL"] = kernel
-    else:
-        os.environ.pop("FFQ_GEMM_KERNEL", None)
     if cluster:
         os.environ["FFQ_GEMM_CLUSTER"] = str(cluster)
     else:
@@ -48,7 +44,7 @@ def run(M, N, K, cluster=None, kernel=None):
     live = p[p[:, 1] > 0]
     leaders = live[live[:, 4] > 0]
     out = {
-        "shape": f"{M}x{N}x{K}", "kernel": kernel or "default", "cluster_ctas": cluster or 2, "us": round(us, 1), "TOPS": round(2 * M * N * K / us / 1e6, 1),
+        "shape": f"{M}x{N}x{K}", "cluster_ctas": cluster or 2, "us": round(us, 1), "TOPS": round(2 * M * N * K / us / 1e6, 1),
         "ctas": int(live.shape[0]),
         "kernel_clocks_median": float(live[:, 1].median()),
         "clock_MHz_implied": round(float(live[:, 1].median()) / us, 1),
@@ -77,5 +73,4 @@ if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     shapes = [tuple(int(v) for v in args[:3])] if len(args) >= 3 else [(8192, 14336, 4096), (2048, 4096, 4096), (2048, 14336, 4096)]
     for shp in shapes:
-        for kern in ("pair", "wide"):
-            print(json.dumps(run(*shp, kernel=kern)), flush=True)
+        print(json.dumps(run(*shp)), flush=True)
