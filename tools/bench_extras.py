@@ -9,6 +9,6 @@ peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.absp
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 hbm = float(peaks.get("hbm_gbs", 6453.7))
-out = bench.measure_extras(ff, dev, hbm, 3321.8)
+out = bench.measure_extras(ff, dev, hbm, 3321.8, bench.measure_int8_library_peak(dev))
 for k, v in out.items():
     print(k, json.dumps(v))
