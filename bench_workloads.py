@@ -57,21 +57,24 @@ _ROPE_CACHE: dict = {}
 
 
 def rope_tables(s: int, d: int, device, dtype, theta: float = 500000.0):
+    """(cos, sin_signed), each [S, 1, D] in the half-split layout; sin_signed = (-sin | +sin) so that
+    rotate_half(x) * sin == roll(x, D/2) * sin_signed bit for bit (a sign flip commutes with rounding)."""
     key = (s, d, str(device), dtype)
     if key not in _ROPE_CACHE:
         pos = torch.arange(s, device=device, dtype=torch.float32)
         inv = 1.0 / (theta ** (torch.arange(0, d, 2, device=device, dtype=torch.float32) / d))
         ang = torch.cat((pos[:, None] * inv[None, :],) * 2, dim=-1)          # [S, D], half-split layout
-        _ROPE_CACHE[key] = (ang.cos().to(dtype), ang.sin().to(dtype))
+        cos, sin = ang.cos().to(dtype), ang.sin().to(dtype)
+        sin_signed = torch.cat((-sin[:, : d // 2], sin[:, d // 2:]), dim=-1)
+        _ROPE_CACHE[key] = (cos[:, None, :].contiguous(), sin_signed[:, None, :].contiguous())
     return _ROPE_CACHE[key]
 
 
 def rope(x: torch.Tensor) -> torch.Tensor:
-    # x: [B, H, S, D]; rotate-half formulation with tables computed once per (S, D)
-    cos, sin = rope_tables(x.shape[-2], x.shape[-1], x.device, x.dtype)
-    half = x.shape[-1] // 2
-    rot = torch.cat((-x[..., half:], x[..., :half]), dim=-1)
-    return x * cos + rot * sin
+    """x: [B, S, H, D] (as the projection wrote it).  The rotate-half formulation of the reference's model code,
+    q*cos + rotate_half(q)*sin, with the rotation done by one roll instead of neg + two slices + cat."""
+    cos, sin_signed = rope_tables(x.shape[1], x.shape[-1], x.device, x.dtype)
+    return x * cos + torch.roll(x, x.shape[-1] // 2, dims=-1) * sin_signed
 
 
 class Attention(torch.nn.Module):
@@ -87,10 +90,9 @@ class Attention(torch.nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         b, s, _ = x.shape
         sh = self.sh
-        q = self.q_proj(x).view(b, s, sh.q_heads, sh.head_dim).transpose(1, 2)
-        k = self.k_proj(x).view(b, s, sh.kv_heads, sh.head_dim).transpose(1, 2)
+        q = rope(self.q_proj(x).view(b, s, sh.q_heads, sh.head_dim)).transpose(1, 2)
+        k = rope(self.k_proj(x).view(b, s, sh.kv_heads, sh.head_dim)).transpose(1, 2)
         v = self.v_proj(x).view(b, s, sh.kv_heads, sh.head_dim).transpose(1, 2)
-        q, k = rope(q), rope(k)
         o = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=True)
         return self.o_proj(o.transpose(1, 2).reshape(b, s, sh.q_heads * sh.head_dim))
 

@@ -50,7 +50,8 @@ struct CalqArgs {
   int rcp_div;                          // scalar divisions of parameters_for_range as aten's CUDA kernel does them
   // tensor kernel
   float* part;                          // [2 * gridDim.x]
-  unsigned int* bar;                    // [0] arrivals (wraps to 0), [1] generation; zero before first use
+  unsigned int* bar;                    // [0] root arrivals (wraps to 0), [1] generation; zero before first use
+  unsigned int* bar_groups;             // first-level arrival counters, one per 32 bytes (wrap to 0)
   unsigned int nchunks;
   FastDiv rdiv;                         // division by row_len (tensor kernel row sums)
   // fake-quant output mode (calq_group_kernel / calq_rows_fq_kernel): y = dequantize(quantize(x)), may alias x
@@ -58,11 +59,13 @@ struct CalqArgs {
   int code_is_int;                      // integer code dtype between quantize and dequantize: -0 becomes +0
   unsigned int* ws_flags;               // [0] some tile was deferred, [1] some (running) tile min is negative/NaN
   unsigned int lanes;                   // group kernel: 16-byte vectors per tile
+  int prof;                             // test hook (FFQ_CALQ_PROF=1): the tensor kernel leaves %globaltimer stamps in the workspace
 };
 
 constexpr int CQ_CHUNK_VECS = 2048;     // tensor kernel: 32 KB of input per CTA chunk
 constexpr int CQ_T = 256;
 constexpr int CQ_U = 4;               // 16-byte loads in flight per lane
+constexpr unsigned int CQ_BAR_GROUPS = 16;   // first-level groups of the tensor kernel's grid barrier
 
 // parameters_for_range for one tile (affine/range.py:89-122), fp32; `one_sided` is the global decision
 __device__ __forceinline__ void calq_params(const CalqArgs& a, float mn, float mx, bool one_sided, float& sc, float& off) {
@@ -779,6 +782,12 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // T threads per CTA, CV 16-byte vectors per chunk.  (256, 2048): four 32 KB CTAs per SM; (1024, 8192): ONE 128 KB CTA per SM --
 // a quarter of the arrivals at the grid barrier and of the partials every CTA re-reduces, which is what a 16 MB
 // activation tensor (one chunk per CTA either way) spends its time on.
@@ -794,6 +803,14 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 4)) calq_tensor_kernel(con
   const unsigned long long nvec = a.numel / EPT;
   const XT* __restrict__ x = static_cast<const XT*>(a.x);
 
+  // test hook: thread 0 of every CTA stamps the nanosecond timer at start / extrema done / barrier passed / parameters
+  // known / end, 8 u64 per CTA behind the partial extrema (tools/prof_calq_phases.py); grids of <= 448 CTAs only
+  unsigned long long* stamps = (a.prof && G <= 448 && threadIdx.x == 0)
+                                   ? reinterpret_cast<unsigned long long*>(a.part + 1024) + (size_t)blockIdx.x * 8 : nullptr;
+  auto stamp = [&](int i) {
+    if (stamps) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); stamps[i] = t; }
+  };
+  stamp(0);
   float old_mn = 0.f, old_mx = 0.f;
   if (threadIdx.x == 0) {
     old_mn = load_as_float(a.run_min, a.run_dt, 0);
@@ -830,27 +847,43 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 4)) calq_tensor_kernel(con
     }
   }
   block_minmax(mn, mx, s_f);
+  stamp(1);
   // ---- grid barrier (all CTAs are co-resident: cooperative launch, grid <= occupancy).  Sense-reversing:
   // bar[0] counts arrivals and wraps to 0 with the last one, which then bumps the generation bar[1]; nothing to
   // reset between launches, any grid size ----
   if (threadIdx.x == 0) {
     a.part[blockIdx.x] = mn;
     a.part[G + blockIdx.x] = mx;
-    const unsigned int gen0 = ld_acquire_u32(&a.bar[1]);
+    // the generation is polled with RELAXED loads (an acquire load per poll drags a gpu-scope fence through every
+    // iteration: the barrier took 4.9 us of a 12.8 us launch that way); one fence after the loop orders the reads of
+    // the partials behind the last arrival's release
+    const unsigned int gen0 = ld_relaxed_u32(&a.bar[1]);
+    // two-level arrival: ~150 atomics on ONE address serialise in its L2 slice (~27 clocks each: the last arrival
+    // waited 3-4 us); CTAs first meet in CQ_BAR_GROUPS groups on separate words, the last of a group arrives at the root
+    const unsigned int ngroups = G < CQ_BAR_GROUPS ? G : CQ_BAR_GROUPS;
+    const unsigned int grp = blockIdx.x % ngroups;
+    const unsigned int members = G / ngroups + (grp < G % ngroups ? 1u : 0u);
     unsigned int old;
-    asm volatile("atom.inc.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.bar), "r"(G - 1) : "memory");
-    if (old == G - 1) {
+    asm volatile("atom.inc.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.bar_groups + grp * 8), "r"(members - 1) : "memory");
+    bool last = false;
+    if (old == members - 1) {
+      asm volatile("atom.inc.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.bar), "r"(ngroups - 1) : "memory");
+      last = old == ngroups - 1;
+    }
+    if (last) {
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar + 1) : "memory");
     } else {
       unsigned int spins = 0;
-      while (ld_acquire_u32(&a.bar[1]) == gen0) {
-        if (++spins > (1u << 22)) {           // ~1 s: never hang the GPU; the host raises on bit 1
+      while (ld_relaxed_u32(&a.bar[1]) == gen0) {
+        if (++spins > (1u << 21)) {           // ~1 s of L2 round trips: never hang the GPU; the host raises on bit 1
           if (a.flags) atomicOr(a.flags, 2);
           break;
         }
       }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
   }
+  stamp(2);
   __syncthreads();
   // ---- phase 2: warp 0 of every CTA reduces the partials to the same (min, max) and derives the parameters ----
   if (warp == 0) {
@@ -877,6 +910,7 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 4)) calq_tensor_kernel(con
     }
   }
   __syncthreads();
+  stamp(3);
   const float s = s_par[0], o = rintf(s_par[1]);
   const SharedRcp k = make_shared_rcp(s);
   const bool fast = calq_fast_ok(k, s_par[2], s_par[3]);
@@ -945,6 +979,8 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 4)) calq_tensor_kernel(con
       if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
     }
   }
+  __syncthreads();
+  stamp(4);
 }
 
 constexpr int CQ_FAT_T = 1024, CQ_FAT_CHUNK_VECS = 8192;     // one 128 KB CTA per SM
@@ -1123,8 +1159,8 @@ int ffq_calibrate_quantize_mode(const ffq_layout_t* layout, int x_dtype) {
 }
 
 size_t ffq_calibrate_quantize_workspace_bytes(void) {
-  // [bar0, bar1, pad x2 | partial mins and maxes of up to 148 * 16 CTAs]
-  return 16 + (size_t)2 * 4096 * sizeof(float);
+  // [bar0, bar1, pad x2 | partial mins and maxes of up to 4096 CTAs | first-level barrier counters, 32 B apart]
+  return 16 + (size_t)2 * 4096 * sizeof(float) + (size_t)CQ_BAR_GROUPS * 32;
 }
 
 int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min, void* run_max, int run_dtype,
@@ -1233,8 +1269,10 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
     a.rows = 0; a.row_len = (unsigned int)ept;
   }
   a.rdiv = make_fast_div(a.row_len);
+  { static const bool prof = []() { const char* e = getenv("FFQ_CALQ_PROF"); return e && e[0] == '1'; }(); a.prof = prof ? 1 : 0; }
   a.bar = static_cast<unsigned int*>(workspace);
   a.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
+  a.bar_groups = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 16 + (size_t)2 * 4096 * sizeof(float));
   const unsigned long long nvec = a.numel / ept;
   switch (x_dtype) {
     case FFQ_F32: return run_tensor_any<float>(a, nvec, st);

@@ -442,7 +442,10 @@ def _unalias_all(steps) -> None:
             else:
                 copies = [t.clone() for t in srcs]
             for (owner, attr, _), c in zip(ents, copies):
-                setattr(owner, attr, c)
+                if attr == "data":
+                    owner.data = c
+                else:
+                    owner._buffers[attr] = c          # a registered buffer: skip Module.__setattr__'s bookkeeping
 
 
 def _raise_for_flags(value: int) -> None:

@@ -154,7 +154,8 @@ def test_quantized_linear_fallback_matches_reference(i):
     tol = dict(rtol=1e-4, atol=1e-4) if dt is torch.float32 else dict(rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(y.cpu(), c["y"], **tol)
     with pytest.raises(ff.QuantizationError):           # strict mode: an output quantizer stub returns a plain tensor
-        with ff.dispatcher.register("linear", None, ff.nn.functional.fallback.linear):
+        # (set explicitly: the flag is process-wide and other test modules switch it off)
+        with ff.strict_quantization(True), ff.dispatcher.register("linear", None, ff.nn.functional.fallback.linear):
             ff.nn.functional.linear(x, lin.weight, None, output_quantizer=None)
 
 
