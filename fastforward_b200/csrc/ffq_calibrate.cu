@@ -521,6 +521,36 @@ template <> struct Packed2<__half> {
   static __device__ __forceinline__ T mx(T a, T b) { return __hmax2_nan(a, b); }
 };
 
+// The whole tile through ONE variant of the per-element code.  The variant (exact-division fast path or not, integer
+// codes or not, saturating 8-bit pack or not) is chosen once per thread OUTSIDE the unrolled loops: with the choice
+// inside, the variants of all 16 vectors interleave in one 10 000-instruction body of which a warp executes 1 800
+// scattered over 160 KB, and a third of its stall samples are instruction-cache misses (`no_instruction`, ncu).
+template <typename XT, int NV, bool FAST, bool IZ>
+__device__ __forceinline__ void tt_fq_all(const uint4 (&w)[NV], XT* __restrict__ y, const SharedRcp& k, float o, const FqConst& fqc) {
+#pragma unroll
+  for (int i = 0; i < NV; i += 2) {
+    const Vec<XT, 8> y0 = calq_vec_fq_impl<XT, 8, FAST, IZ>(*reinterpret_cast<const Vec<XT, 8>*>(&w[i]), k, o, fqc);
+    const Vec<XT, 8> y1 = calq_vec_fq_impl<XT, 8, FAST, IZ>(*reinterpret_cast<const Vec<XT, 8>*>(&w[i + 1]), k, o, fqc);
+    st256(y + i * 8, *reinterpret_cast<const uint4*>(&y0), *reinterpret_cast<const uint4*>(&y1));
+  }
+}
+template <typename XT, int NV, int MODE>     // 0: fast + saturating 8-bit pack, 1: fast, 2: guarded division
+__device__ __forceinline__ void tt_codes_all(const uint4 (&w)[NV], int8_t* __restrict__ q, const SharedRcp& k, float o, const CalqArgs& a) {
+  int sum = 0;
+#pragma unroll
+  for (int i = 0; i < NV; i += 4) {       // four 16-byte vectors -> 32 bytes of codes
+    uint32_t p[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Vec<XT, 8>& xv = *reinterpret_cast<const Vec<XT, 8>*>(&w[i + j]);
+      if constexpr (MODE == 0) calq_vec_fast<XT, 8, true>(xv, k, o, 0, 0, p[j], sum);
+      else if constexpr (MODE == 1) calq_vec_fast<XT, 8, false>(xv, k, o, (int)a.lo, (int)a.hi, p[j], sum);
+      else calq_vec<XT, 8>(xv, k, o, a.lo, a.hi, a.sat8 != 0, p[j], sum);
+    }
+    st256(q + i * 8, make_uint4(p[0][0], p[0][1], p[1][0], p[1][1]), make_uint4(p[2][0], p[2][1], p[3][0], p[3][1]));
+  }
+}
+
 template <typename XT, typename RT, int NV, bool FQ, bool ZOFF>
 __device__ __forceinline__ void calq_tile_thread_body(const CalqArgs& a, unsigned long long tile) {
   static_assert(sizeof(XT) == 2 && NV % 2 == 0, "16-bit data, whole 32-byte accesses");
@@ -537,10 +567,13 @@ __device__ __forceinline__ void calq_tile_thread_body(const CalqArgs& a, unsigne
     // extrema in the packed domain (NaN-propagating HMNMX2), one unpack at the end
     typename P2::T lo2, hi2;
     {
+      // four independent chains (min / max are exact: any association gives the same bits)
       const typename P2::T* h = reinterpret_cast<const typename P2::T*>(&w[0]);
-      lo2 = h[0]; hi2 = h[0];
+      typename P2::T l4[4] = {h[0], h[1], h[2], h[3]}, h4[4] = {h[0], h[1], h[2], h[3]};
 #pragma unroll
-      for (int i = 1; i < NV * 4; ++i) { lo2 = P2::mn(lo2, h[i]); hi2 = P2::mx(hi2, h[i]); }
+      for (int i = 4; i < NV * 4; ++i) { l4[i & 3] = P2::mn(l4[i & 3], h[i]); h4[i & 3] = P2::mx(h4[i & 3], h[i]); }
+      lo2 = P2::mn(P2::mn(l4[0], l4[1]), P2::mn(l4[2], l4[3]));
+      hi2 = P2::mx(P2::mx(h4[0], h4[1]), P2::mx(h4[2], h4[3]));
     }
     const float mn = nan_min(__low2float(lo2), __high2float(lo2));
     const float mx = nan_max(__low2float(hi2), __high2float(hi2));
@@ -569,24 +602,18 @@ __device__ __forceinline__ void calq_tile_thread_body(const CalqArgs& a, unsigne
       if constexpr (FQ) {
         const FqConst fqc{a.lo, a.hi, a.code_is_int != 0};
         XT* __restrict__ y = static_cast<XT*>(a.y) + tile * (unsigned long long)(NV * EPT);
-#pragma unroll
-        for (int i = 0; i < NV; i += 2) {
-          const Vec<XT, EPT> y0 = calq_vec_fq<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i]), k, o, fqc, fast);
-          const Vec<XT, EPT> y1 = calq_vec_fq<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 1]), k, o, fqc, fast);
-          st256(y + i * EPT, *reinterpret_cast<const uint4*>(&y0), *reinterpret_cast<const uint4*>(&y1));
+        if (fast) {
+          if (fqc.int_zero) tt_fq_all<XT, NV, true, true>(w, y, k, o, fqc);
+          else tt_fq_all<XT, NV, true, false>(w, y, k, o, fqc);
+        } else {
+          if (fqc.int_zero) tt_fq_all<XT, NV, false, true>(w, y, k, o, fqc);
+          else tt_fq_all<XT, NV, false, false>(w, y, k, o, fqc);
         }
       } else {
         int8_t* __restrict__ q = a.q + tile * (unsigned long long)(NV * EPT);
-        int sum = 0;
-#pragma unroll
-        for (int i = 0; i < NV; i += 4) {       // four 16-byte vectors -> 32 bytes of codes
-          uint32_t p0[2], p1[2], p2[2], p3[2];
-          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i]), k, o, a, fast, p0, sum);
-          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 1]), k, o, a, fast, p1, sum);
-          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 2]), k, o, a, fast, p2, sum);
-          calq_vec_any<XT, EPT>(*reinterpret_cast<const Vec<XT, EPT>*>(&w[i + 3]), k, o, a, fast, p3, sum);
-          st256(q + i * EPT, make_uint4(p0[0], p0[1], p1[0], p1[1]), make_uint4(p2[0], p2[1], p3[0], p3[1]));
-        }
+        if (fast && a.sat8) tt_codes_all<XT, NV, 0>(w, q, k, o, a);
+        else if (fast) tt_codes_all<XT, NV, 1>(w, q, k, o, a);
+        else tt_codes_all<XT, NV, 2>(w, q, k, o, a);
       }
     }
   }
@@ -782,6 +809,81 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   return v;
 }
 
+// Phase 3 of calq_tensor_kernel for one (MODE, ROWS) variant.  MODE 0: fast exact division + saturating 8-bit pack,
+// 1: fast, 2: guarded division.  ROWS 0: no row sums, 1: a warp's span lies in one row (one atomic per chunk),
+// 2: rows straddle warp spans (one atomic per (warp, row), sums carried while the whole warp stays in one row).
+template <typename XT, int T, int CV, int MODE, int ROWS>
+__device__ __forceinline__ void calq_tensor_pass3(const CalqArgs& a, const uint4* s_chunk, const XT* __restrict__ x,
+                                                  unsigned long long nvec, const SharedRcp& k, float o) {
+  constexpr int EPT = 16 / sizeof(XT);
+  constexpr int VPW = CV / (T / 32);
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int G = gridDim.x;
+  for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
+    const unsigned long long w0 = (unsigned long long)c * CV + warp * VPW;   // warp's first vector
+    const bool keep = c == blockIdx.x;
+    unsigned long long row0 = 0;
+    unsigned int rem0 = 0;
+    if (ROWS != 0) { row0 = (w0 * EPT) / a.row_len; rem0 = (unsigned int)(w0 * EPT - row0 * a.row_len); }
+    int sum = 0;
+    unsigned int cur = ~0u;                  // row (relative to row0) the running sum belongs to
+#pragma unroll
+    for (int ub = 0; ub < VPW / 32; ub += CQ_U) {
+      Vec<XT, EPT> xv[CQ_U];
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned long long v = w0 + (ub + u) * 32 + lane;
+        if (v < nvec) {
+          if (keep) *reinterpret_cast<uint4*>(&xv[u]) = s_chunk[warp * VPW + (ub + u) * 32 + lane];
+          else xv[u] = ld_stream<XT, EPT>(x + v * EPT);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned long long v = w0 + (ub + u) * 32 + lane;
+        if (w0 + (ub + u) * 32 >= nvec) break;           // the whole warp is past the end
+        const bool live = v < nvec;
+        int vs = 0;
+        if (live) {
+          uint32_t packed[EPT / 4];
+          if constexpr (MODE == 0) calq_vec_fast<XT, EPT, true>(xv[u], k, o, 0, 0, packed, vs);
+          else if constexpr (MODE == 1) calq_vec_fast<XT, EPT, false>(xv[u], k, o, (int)a.lo, (int)a.hi, packed, vs);
+          else calq_vec<XT, EPT>(xv[u], k, o, a.lo, a.hi, a.sat8 != 0, packed, vs);
+          calq_store<EPT>(a.q + v * EPT, packed);
+        }
+        if constexpr (ROWS == 1) {
+          sum += vs;                       // the warp's whole span lies in one row: one atomic per chunk
+        } else if constexpr (ROWS == 2) {
+          const unsigned int r = fast_div(rem0 + ((ub + u) * 32 + lane) * EPT, a.rdiv);
+          const unsigned int r_first = __shfl_sync(0xffffffffu, r, 0);
+          const unsigned int r_last = __shfl_sync(0xffffffffu, r, 31);
+          if (r_first != cur || r_last != cur) {
+            if (cur != ~0u) {
+              const int tot = __reduce_add_sync(0xffffffffu, sum);
+              if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
+            }
+            sum = 0;
+            cur = (r_first == r_last) ? r_first : ~0u;
+          }
+          if (cur != ~0u) sum += vs;
+          else if (live) atomicAdd(&a.rowsum[row0 + r], vs);
+        }
+      }
+    }
+    if constexpr (ROWS == 1) {
+      if (w0 < nvec) {
+        const int tot = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) atomicAdd(&a.rowsum[row0], tot);
+      }
+    } else if constexpr (ROWS == 2) {
+      if (cur != ~0u) {
+        const int tot = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -914,71 +1016,26 @@ __global__ void __launch_bounds__(T, (T >= 1024 ? 1 : 4)) calq_tensor_kernel(con
   const float s = s_par[0], o = rintf(s_par[1]);
   const SharedRcp k = make_shared_rcp(s);
   const bool fast = calq_fast_ok(k, s_par[2], s_par[3]);
+  // ---- phase 3: quantize.  The per-element variant (fast / saturating pack) and the row-sum bookkeeping are chosen
+  // ONCE, outside the unrolled loops: interleaved inside them they made a 5 000-instruction body whose executed part
+  // was scattered (ncu: 4.4 warps per issue slot waiting for instructions) ----
   // rows that are a whole number of warp spans (VPW vectors): a warp never straddles two rows
   const bool simple_rows = a.rowsum != nullptr && (a.row_len % (VPW * EPT)) == 0;
-  // ---- phase 3: quantize; a warp owns VPW contiguous vectors, so its codes fall in few rows ----
-  for (unsigned int c = blockIdx.x; c < a.nchunks; c += G) {
-    const unsigned long long w0 = (unsigned long long)c * CV + warp * VPW;   // warp's first vector
-    const bool keep = c == blockIdx.x;
-    unsigned long long row0 = 0;
-    unsigned int rem0 = 0;
-    if (a.rowsum) { row0 = (w0 * EPT) / a.row_len; rem0 = (unsigned int)(w0 * EPT - row0 * a.row_len); }
-    int sum = 0;
-    unsigned int cur = ~0u;                  // row (relative to row0) the running sum belongs to
-#pragma unroll
-    for (int ub = 0; ub < VPW / 32; ub += CQ_U) {
-      Vec<XT, EPT> xv[CQ_U];
-#pragma unroll
-      for (int u = 0; u < CQ_U; ++u) {
-        const unsigned long long v = w0 + (ub + u) * 32 + lane;
-        if (v < nvec) {
-          if (keep) *reinterpret_cast<uint4*>(&xv[u]) = s_chunk[warp * VPW + (ub + u) * 32 + lane];
-          else xv[u] = ld_stream<XT, EPT>(x + v * EPT);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < CQ_U; ++u) {
-        const unsigned long long v = w0 + (ub + u) * 32 + lane;
-        if (w0 + (ub + u) * 32 >= nvec) break;           // the whole warp is past the end
-        const bool live = v < nvec;
-        int vs = 0;
-        if (live) {
-          uint32_t packed[EPT / 4];
-          calq_vec_any<XT, EPT>(xv[u], k, o, a, fast, packed, vs);
-          calq_store<EPT>(a.q + v * EPT, packed);
-        }
-        if (simple_rows) {
-          sum += vs;                       // the warp's whole span lies in one row: one atomic per chunk
-        } else if (a.rowsum) {
-          // one atomic per (warp, row): sums are carried while the whole warp stays in one row
-          const unsigned int r = fast_div(rem0 + ((ub + u) * 32 + lane) * EPT, a.rdiv);
-          const unsigned int r_first = __shfl_sync(0xffffffffu, r, 0);
-          const unsigned int r_last = __shfl_sync(0xffffffffu, r, 31);
-          if (r_first != cur || r_last != cur) {
-            if (cur != ~0u) {
-              const int tot = __reduce_add_sync(0xffffffffu, sum);
-              if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
-            }
-            sum = 0;
-            cur = (r_first == r_last) ? r_first : ~0u;
-          }
-          if (cur != ~0u) sum += vs;
-          else if (live) atomicAdd(&a.rowsum[row0 + r], vs);
-        }
-      }
-    }
-    if (simple_rows) {
-      if (w0 < nvec) {
-        const int tot = __reduce_add_sync(0xffffffffu, sum);
-        if (lane == 0) atomicAdd(&a.rowsum[row0], tot);
-      }
-      continue;
-    }
-    if (a.rowsum && cur != ~0u) {
-      const int tot = __reduce_add_sync(0xffffffffu, sum);
-      if (lane == 0) atomicAdd(&a.rowsum[row0 + cur], tot);
-    }
+  const int mode = fast ? (a.sat8 ? 0 : 1) : 2;
+  const int rows = a.rowsum == nullptr ? 0 : (simple_rows ? 1 : 2);
+#define FFQ_PASS3(M, R) calq_tensor_pass3<XT, T, CV, M, R>(a, s_chunk, x, nvec, k, o)
+  switch (mode * 3 + rows) {
+    case 0: FFQ_PASS3(0, 0); break;
+    case 1: FFQ_PASS3(0, 1); break;
+    case 2: FFQ_PASS3(0, 2); break;
+    case 3: FFQ_PASS3(1, 0); break;
+    case 4: FFQ_PASS3(1, 1); break;
+    case 5: FFQ_PASS3(1, 2); break;
+    case 6: FFQ_PASS3(2, 0); break;
+    case 7: FFQ_PASS3(2, 1); break;
+    default: FFQ_PASS3(2, 2); break;
   }
+#undef FFQ_PASS3
   __syncthreads();
   stamp(4);
 }
