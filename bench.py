@@ -50,6 +50,10 @@ def parse_args():
     ap.add_argument("--memoize-parameters", action="store_true",
                     help="headline with the estimator's default memoisation of unchanged weights ON (default: OFF, so that every "
                          "timed step re-quantizes every weight exactly as the reference's step does)")
+    ap.add_argument("--overlap-parameters", type=int, default=0,
+                    help="estimator option overlap_parameters: launch each weight's fused calibration step this many weight "
+                         "quantizers ahead of its use on a side stream (0: in line on the step's stream)")
+    ap.add_argument("--overlap-sweep", default="", help="comma-separated overlap_parameters values timed as extra ablations")
     ap.add_argument("--workload", default="calib", choices=["calib", "w4a16-calib", "wq4", "cfg5"],
                     help="calib: configs[1] (default, W8A8 8B-shape).  w4a16-calib: configs[4] recipe (W4 g=128 / A16) on "
                          "--shape.  wq4: configs[2], W4 g=128 weight fake-quant of all linears sharded by layer")
@@ -554,17 +558,18 @@ def run_ours(args):
     dev_tokens = [t.to(dev) for t in host_tokens]
     static_tokens = torch.empty_like(dev_tokens[0])
 
-    def make_estimator(memoize):
-        return ff.range_setting.running_minmax(sync_ranges=world > 1, memoize_parameters=memoize)
+    def make_estimator(memoize, overlap=None):
+        return ff.range_setting.running_minmax(sync_ranges=world > 1, memoize_parameters=memoize,
+                                               overlap_parameters=args.overlap_parameters if overlap is None else overlap)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    def region(steps, tokens_src, e2e, graph, memoize=False, dedupe=True, align_ranks_before_exit=False):
+    def region(steps, tokens_src, e2e, graph, memoize=False, dedupe=True, align_ranks_before_exit=False, overlap=None):
         """Enter estimate_ranges, warm up, time `steps` steps + block exit.  Returns seconds (device)."""
         out_host = torch.empty(max(steps, 1), dtype=torch.float32).pin_memory()    # one pinned slot per step
-        estimator = make_estimator(memoize)
+        estimator = make_estimator(memoize, overlap)
         estimator.dedupe = dedupe
         estimator._state.dedupe = dedupe
         with torch.no_grad(), ff.estimate_ranges(model, estimator):
@@ -645,9 +650,13 @@ def run_ours(args):
     # ---- the same steps under other schedules (context, each its own estimate_ranges block) -----------------
     ablation = {}
     short = max(3, min(args.steps, 5))
-    for name, kw in (("eager_no_cuda_graph", dict(graph=False, memoize=memo)),
+    sweep = [int(v) for v in args.overlap_sweep.split(",") if v.strip()]
+    if args.overlap_parameters and 0 not in sweep:
+        sweep.insert(0, 0)
+    for name, kw in [("eager_no_cuda_graph", dict(graph=False, memoize=memo)),
                      ("memoize_parameters_on" if not memo else "memoize_parameters_off", dict(graph=use_graph, memoize=not memo)),
-                     ("no_dedupe_no_memoize", dict(graph=use_graph, memoize=False, dedupe=False))):
+                     ("no_dedupe_no_memoize", dict(graph=use_graph, memoize=False, dedupe=False))] + \
+            [(f"overlap_parameters_{v}", dict(graph=use_graph, memoize=False, overlap=v)) for v in sweep]:
         reset_quantizers()
         d, _ = region(short, dev_tokens, e2e=False, **kw)
         d = allmax_value(d, dev, world)
@@ -749,6 +758,7 @@ def run_ours(args):
                 drop_in = br.gpu_calibration(sh, seq, layers, dev, cfg1=cfg1_ref, compiled=not args.skip_compiled_baseline)
         config = workload_config(sh, layers, seq, world)
         schedule = {"cuda_graph": use_graph, "dedupe_shared_inputs": True, "memoize_parameters": memo,
+                    "overlap_parameters": args.overlap_parameters,
                     "note": "how THIS arm runs the config's steps; every timed step re-quantizes every weight unless "
                             "memoize_parameters is true"}
         line = {

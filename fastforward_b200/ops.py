@@ -428,9 +428,17 @@ def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor,
     """``parameters_for_range_`` for many quantizers in ONE launch.  ``min_buf`` / ``max_buf``: contiguous buffers
     holding every quantizer's running range; ``entries``: ``(start, length, num_bits, symmetric, allow_one_sided,
     scale, offset_or_None)`` with fp32 contiguous CUDA ``scale`` / ``offset`` of ``length`` elements."""
+    parameters_for_ranges_batched_prepare(min_buf, max_buf, entries, reciprocal_scalar_division)()
+
+
+def parameters_for_ranges_batched_prepare(min_buf: torch.Tensor, max_buf: torch.Tensor, entries,
+                                          reciprocal_scalar_division: bool = False):
+    """Validation and the descriptor table (host work + one small H2D copy) of ``parameters_for_ranges_batched_``
+    now, the launch when the returned callable is called: the data-parallel block exit prepares before its host
+    sync and launches after the ranges were all-reduced."""
     C.require_cuda(min_buf, "min_buf")
     if not entries:
-        return
+        return lambda: None
     if min_buf.dtype != max_buf.dtype or not min_buf.is_contiguous() or not max_buf.is_contiguous():
         raise RuntimeError("parameters_for_ranges_batched_: range buffers must be contiguous and of one dtype")
     words = (ctypes.c_int64 * 3)()
@@ -448,9 +456,16 @@ def parameters_for_ranges_batched_(min_buf: torch.Tensor, max_buf: torch.Tensor,
             enc[key] = (int(words[0]), int(words[1]), int(words[2]))
         w = enc[key]
         rows.append((int(start), int(length), scale.data_ptr(), 0 if offset is None else offset.data_ptr(), w[0], w[1], w[2], 0))
-    desc = torch.tensor(rows, dtype=torch.int64).to(min_buf.device, non_blocking=False)
-    C.check(C.lib.ffq_params_for_ranges_batched(min_buf.data_ptr(), max_buf.data_ptr(), C.dtype_tag(min_buf.dtype),
-                                                desc.data_ptr(), len(rows), C.current_stream(min_buf.device)))
+    desc = torch.tensor(rows, dtype=torch.int64).pin_memory().to(min_buf.device, non_blocking=True)
+    keep = [t for e in entries for t in (e[5], e[6]) if t is not None]      # the table holds raw pointers
+
+    def launch() -> None:
+        with (C.device_of(min_buf.device) if min_buf.is_cuda else C._NO_GUARD):
+            C.check(C.lib.ffq_params_for_ranges_batched(min_buf.data_ptr(), max_buf.data_ptr(), C.dtype_tag(min_buf.dtype),
+                                                        desc.data_ptr(), len(rows), C.current_stream(min_buf.device)))
+        del keep[:]
+
+    return launch
 
 
 def calibrate_quantize_mode(shape: Sequence[int], tile_size, dtype: torch.dtype) -> int:
@@ -479,6 +494,7 @@ def calibrate_quantize_(
     symmetric: bool, allow_one_sided: bool, scale_out: torch.Tensor, offset_out: Optional[torch.Tensor],
     flags: Optional[torch.Tensor] = None, settled: Optional[torch.Tensor] = None, rowsum: bool = False,
     run_fixup: bool = True, workspace: Optional[torch.Tensor] = None, reciprocal_scalar_division: bool = False,
+    stream: Optional["torch.cuda.Stream"] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """One RunningMinMax calibration step in one pass over ``data``: updates ``run_min``/``run_max`` in place
     (range_setting/minmax.py:229-237), writes the quantizer's ``scale``/``offset`` for the updated range in place
@@ -488,7 +504,9 @@ def calibrate_quantize_(
     ``settled`` / ``run_fixup``: see include/ffq_b200.h -- only a caller that has read ``settled != 0`` may pass
     ``run_fixup=False``.  ``workspace``: zero-initialised uint8 buffer of ``_CALQ_WS`` bytes for the per-tensor
     kernel's grid barrier, owned by the caller and used by one stream at a time (default: a cached per-(device,
-    stream) buffer).
+    stream) buffer).  ``stream``: launch on this stream instead of the current one; the outputs are still allocated
+    on the CURRENT stream, so the caller orders ``stream`` after the current stream before the call and the current
+    stream after ``stream`` before the outputs are used (the estimator's overlapped parameter steps).
     Raises NotImplementedError for layouts the fused kernels do not cover (see calibrate_quantize_mode)."""
     x, shape, tile, layout = _prep(data, tile_size)
     _bitwidth_guard(torch.int8, num_bits)
@@ -513,7 +531,7 @@ def calibrate_quantize_(
         x.data_ptr(), C.dtype_tag(x.dtype), q.data_ptr(), run_min.data_ptr(), run_max.data_ptr(), C.dtype_tag(run_min.dtype),
         scale_out.data_ptr(), C.ptr(offset_out), C.ptr(rs), row_len, C.ptr(flags), C.ptr(settled), int(bool(run_fixup)),
         layout.ref, float(num_bits), int(bool(symmetric)), _flags(allow_one_sided, reciprocal_scalar_division),
-        ws.data_ptr(), ws.numel(), C.current_stream(x.device)))
+        ws.data_ptr(), ws.numel(), C.current_stream(x.device) if stream is None else stream.cuda_stream))
     return q, rs
 
 

@@ -74,13 +74,25 @@ def estimate_ranges(model_or_layers, estimator, *args: Any, **kwargs: Any) -> Ge
         for part in estimator.split_module(module):
             prepared.append((part, estimator.prepare(part)))
     failed = True
+    cleaned = []
+
+    def cleanup_all() -> None:
+        if not cleaned:
+            cleaned.append(True)
+            for module, metadata in prepared:
+                estimator.cleanup(module, metadata)
+
     try:
         yield
         failed = False
     finally:
         try:
             if not failed and hasattr(estimator, "finalize"):
-                estimator.finalize(prepared)
+                if getattr(estimator, "finalize_runs_cleanup", False):
+                    # the estimator removes the overrides itself, BEFORE its one host sync: host work that needs nothing
+                    # from the device belongs in front of the wait, not behind it
+                    estimator.finalize(prepared, cleanup=cleanup_all)
+                else:
+                    estimator.finalize(prepared)
         finally:
-            for module, metadata in prepared:
-                estimator.cleanup(module, metadata)
+            cleanup_all()

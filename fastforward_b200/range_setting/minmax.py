@@ -165,13 +165,42 @@ class _BlockState:
     """What the steps of one block share: the arenas (activations apart from parameters: only the former differ
     between data-parallel ranks), the most recent fused outputs by input tensor (dedupe) and the counters."""
 
-    def __init__(self, dedupe: bool, memoize: bool) -> None:
+    def __init__(self, dedupe: bool, memoize: bool, overlap: int = 0) -> None:
         self.act = _RangeArena(chunk=1 << 14)
         self.param = _RangeArena()
         self.recent: dict = {}        # (data_ptr, shape, dtype) -> _Recent
         self.aliases: List["RunningMinMaxEstimator"] = []
         self.dedupe, self.memoize = dedupe, memoize
-        self.stats = {"fused": 0, "deduped": 0, "memoized": 0, "separate": 0}
+        self.stats = {"fused": 0, "deduped": 0, "memoized": 0, "separate": 0, "overlapped": 0}
+        # overlapped parameter steps: the fused step of a weight does not depend on the activations, so it is launched
+        # ``overlap`` parameter quantizers AHEAD of its use on a side stream (a parallel branch of a captured graph):
+        # an HBM-bound kernel under the tensor-bound GEMMs of the layers before it
+        self.overlap = 0 if memoize else int(overlap)
+        self.porder: List["RunningMinMaxEstimator"] = []     # parameter steps in the order they first ran
+        self.side: dict = {}                                  # device -> side stream
+
+    def side_stream(self, device: torch.device):
+        if device not in self.side:
+            self.side[device] = torch.cuda.Stream(device=device)
+        return self.side[device]
+
+    def side_workspace(self, device: torch.device) -> torch.Tensor:
+        key = ("ws", device)
+        if key not in self.side:
+            self.side[key] = torch.zeros(ops._CALQ_WS, dtype=torch.uint8, device=device)
+        return self.side[key]
+
+    def launch_ahead(self, step: "RunningMinMaxEstimator") -> None:
+        """After ``step`` has been served: make sure the next ``overlap`` parameter steps are in flight."""
+        order = self.porder
+        for j in range(step._pidx + 1, min(len(order), step._pidx + 1 + self.overlap)):
+            if order[j]._ahead is None:
+                order[j]._issue_ahead()
+
+    def drain(self) -> None:
+        """Join every parameter step still in flight into the current stream (block exit, failed block)."""
+        for s in self.porder:
+            s._drop_ahead()
 
     def flag(self, device):
         return self.param.flag(device)        # one flag word per device for the whole block
@@ -207,6 +236,9 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         self._nsteps = 0
         self._alias_of: Optional["RunningMinMaxEstimator"] = None
         self._memo = None             # (weakref(data), version, output) of the previous fused step on a Parameter
+        self._ahead = None            # (event, weakref(data), version, output) of a step launched ahead on the side stream
+        self._pidx = None             # position among the block's parameter steps (``_BlockState.porder``)
+        self._pdata = None            # (weakref(data), version, mode) of this step's most recent launch on a Parameter
         self._slot = None             # (arena, chunk index, offset, n) of the running range when it lives in an arena
         self._param_data = False      # the data this quantizer sees is an nn.Parameter (identical on every DP rank)
         lo, hi = quantizer.quantization_range       # continues from an existing range (minmax.py:198-200)
@@ -342,6 +374,17 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
                 st.stats["memoized"] += 1
                 return out
             self._memo = None
+        # (1b) this step was launched ahead on the side stream (overlapped parameter steps)
+        if self._ahead is not None:
+            result = self._take_ahead(data)
+            if result is not None:
+                codes, rowsum = result
+                self._nsteps += 1
+                st.stats["overlapped"] += 1
+                if st.dedupe:
+                    st.recent[(data.data_ptr(), data.shape, data.dtype)] = _Recent(data, self, codes, rowsum)
+                st.launch_ahead(self)
+                return self._wrap(quantizer, codes, rowsum, data.dtype)
         # (2) another quantizer of the same configuration has just processed this very tensor
         key = None
         if st is not None and st.dedupe:
@@ -359,6 +402,24 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
                     self._nsteps += 1
                     st.stats["deduped"] += 1
                     return self._wrap(quantizer, ent.codes, ent.rowsum, data.dtype)
+        codes, rowsum = self._launch(quantizer, data, mode)
+        out = self._wrap(quantizer, codes, rowsum, data.dtype)
+        if st is not None:
+            st.stats["fused"] += 1
+            if key is not None:
+                st.recent[key] = _Recent(data, self, codes, rowsum)
+            if st.memoize and isinstance(data, torch.nn.Parameter):
+                self._memo = (weakref.ref(data), data._version, out)
+            if st.overlap and mode in (1, 3) and isinstance(data, torch.nn.Parameter):
+                if self._pidx is None:
+                    self._pidx = len(st.porder)
+                    st.porder.append(self)
+                self._pdata = (weakref.ref(data), data._version, mode)
+                st.launch_ahead(self)
+        return out
+
+    def _launch(self, quantizer, data: torch.Tensor, mode: int, stream=None):
+        """The fused kernel itself (on ``stream`` when given, else on the current stream) -> (codes, rowsum)."""
         self._unalias()
         self.initialize_parameters(quantizer, data)
         if quantizer.has_uninitialized_params:
@@ -380,24 +441,65 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         if mode in (2, 3):
             arena = self._arena_for(data)
             ws = arena.barrier_workspace(data.device) if arena is not None else None
+            if stream is not None:            # the side stream's launches keep their flag words apart from the main stream's
+                ws = self._state.side_workspace(data.device)
         codes, rowsum = ops.calibrate_quantize_(
             self.min, self.max, data.detach(), tile, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
             quantizer.scale.data, None if quantizer.offset is None else quantizer.offset.data,
             self.flags, self._settled if mode == 1 else None, rowsum=want_rowsum, run_fixup=not self._settled_seen,
-            workspace=ws, reciprocal_scalar_division=_host_of(quantizer).rcp)
+            workspace=ws, reciprocal_scalar_division=_host_of(quantizer).rcp, stream=stream)
         if self._settled_host is not None and not self._settled_seen:
-            self._settled_host.copy_(self._settled, non_blocking=True)
-        if self._eager:
-            self.check_finite()
-        self._nsteps += 1
-        out = self._wrap(quantizer, codes, rowsum, data.dtype)
-        if st is not None:
-            st.stats["fused"] += 1
-            if key is not None:
-                st.recent[key] = _Recent(data, self, codes, rowsum)
-            if st.memoize and isinstance(data, torch.nn.Parameter):
-                self._memo = (weakref.ref(data), data._version, out)
-        return out
+            if stream is None:
+                self._settled_host.copy_(self._settled, non_blocking=True)
+            else:
+                with torch.cuda.stream(stream):
+                    self._settled_host.copy_(self._settled, non_blocking=True)
+        if stream is None:
+            if self._eager:
+                self.check_finite()
+            self._nsteps += 1
+        return codes, rowsum
+
+    # ---- overlapped parameter steps -------------------------------------------------------------------------
+    def _issue_ahead(self) -> None:
+        """Launch this step's fused kernel on the block's side stream, ahead of the call that will use it.  Only for
+        a Parameter that has not changed since this step's previous launch: the running range already covers those
+        values, so the update is idempotent whatever happens to the result -- if the tensor is modified before the
+        result is used, the result is dropped and the step runs again in line."""
+        st, quantizer = self._state, self._quantizer_ref()
+        if st is None or quantizer is None or self._pdata is None or torch.is_grad_enabled():
+            return
+        ref, version, mode = self._pdata
+        data = ref()
+        if data is None or data._version != version or self._alias_of is not None or self.min is None \
+                or quantizer.has_uninitialized_params or self._eager or _host_of(quantizer).get_export_mode():
+            return
+        cur = torch.cuda.current_stream(data.device)
+        side = st.side_stream(data.device)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side.wait_event(fork)
+        codes, rowsum = self._launch(quantizer, data, mode, stream=side)
+        done = torch.cuda.Event()
+        done.record(side)
+        self._ahead = (done, ref, version, (codes, rowsum))
+
+    def _take_ahead(self, data: torch.Tensor):
+        """(codes, rowsum) of the launch in flight for ``data`` -- the current stream now waits for it -- or None."""
+        if self._ahead is None:
+            return None
+        done, ref, version, result = self._ahead
+        self._ahead = None
+        torch.cuda.current_stream(data.device if isinstance(data, torch.Tensor) and data.is_cuda else None).wait_event(done)
+        if ref() is not data or data._version != version:
+            return None
+        return result
+
+    def _drop_ahead(self) -> None:
+        if self._ahead is not None:
+            done = self._ahead[0]
+            self._ahead = None
+            torch.cuda.current_stream(self.min.device if self.min is not None else None).wait_event(done)
 
     def forward(self, quantizer, callback, args: tuple, kwargs: dict):
         data = args[0] if args else kwargs.get("data", next(iter(kwargs.values()), None))
@@ -406,6 +508,7 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
                 (self.min.device != data.device or torch.promote_types(self.min.dtype, data.dtype) != self.min.dtype):
             mode = 0     # a continued range on another device / in a narrower dtype: the plain path converts it
         if not mode:
+            self._drop_ahead()
             return super().forward(quantizer, callback, args, kwargs)
         if not self._initialized:
             self.setup_estimator(data)
@@ -416,36 +519,47 @@ class RunningMinMaxEstimator(SimpleEstimatorStep, torch.nn.Module):
         return f"min={self.min}, max={self.max}"
 
 
-def _unalias_all(steps) -> None:
-    """``_unalias`` for many estimators at once: every aliased range / parameter tensor gets its own copy with ONE
-    multi-tensor launch per dtype (x * 1 is exact, keeps the sign of zero and NaN) instead of four clones per quantizer."""
-    todo = []          # (owner object, attribute, source tensor)
+def _unalias_prepare(steps):
+    """First half of giving aliased quantizers their own parameter storage back when the block ends: the new tensors
+    are allocated and installed (host work that needs nothing from the device), the values follow with
+    ``_unalias_finish`` -- after whatever still writes the shared storage (the re-derivation from merged ranges).
+    The running ranges stay shared views: the steps end with the block."""
+    dsts, srcs = [], []
     for s in steps:
         if s._alias_of is None:
             continue
         s._alias_of = None
-        todo.append((s, "min", s.min))
-        todo.append((s, "max", s.max))
         q = s._quantizer_ref()
-        if q is not None:
-            todo.append((q.scale, "data", q.scale.data))
-            if q.offset is not None:
-                todo.append((q.offset, "data", q.offset.data))
+        if q is None:
+            continue
+        with torch.no_grad():
+            for p in (q.scale, q.offset):
+                if p is not None:
+                    src = p.data
+                    dst = torch.empty_like(src)
+                    p.data = dst
+                    dsts.append(dst)
+                    srcs.append(src)
+    return dsts, srcs
+
+
+def _unalias_finish(plan) -> None:
+    """Second half: ONE multi-tensor copy per (device, dtype) fills the storage ``_unalias_prepare`` installed."""
+    dsts, srcs = plan
+    if not dsts:
+        return
     groups: dict = {}
-    for ent in todo:
-        groups.setdefault((ent[2].device, ent[2].dtype), []).append(ent)
+    for d, s_ in zip(dsts, srcs):
+        groups.setdefault((d.device, d.dtype), ([], []))
+        groups[(d.device, d.dtype)][0].append(d)
+        groups[(d.device, d.dtype)][1].append(s_)
     with torch.no_grad():
-        for ents in groups.values():
-            srcs = [e[2] for e in ents]
-            if srcs[0].is_floating_point() and len(srcs) > 1:
-                copies = torch._foreach_mul(srcs, 1)
-            else:
-                copies = [t.clone() for t in srcs]
-            for (owner, attr, _), c in zip(ents, copies):
-                if attr == "data":
-                    owner.data = c
-                else:
-                    owner._buffers[attr] = c          # a registered buffer: skip Module.__setattr__'s bookkeeping
+        for d, s_ in groups.values():
+            torch._foreach_copy_(d, s_)
+
+
+def _unalias_all(steps) -> None:
+    _unalias_finish(_unalias_prepare(steps))
 
 
 def _raise_for_flags(value: int) -> None:
@@ -523,11 +637,17 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
     fused               one kernel per quantizer per forward where the layout allows (default True)
     dedupe              identically configured quantizers fed the same tensor object share one launch (default True)
     memoize_parameters  an unchanged ``nn.Parameter`` is not re-quantized on later steps (default True)
+    overlap_parameters  N > 0 (and ``memoize_parameters=False``): from the second step on, the fused step of a weight is
+                        launched N weight quantizers ahead of its use on a side stream, so the HBM-bound kernel runs
+                        under the tensor-bound linears of the layers before it (a parallel branch when the step is
+                        captured in a CUDA graph).  Same work per step, same results: only an unchanged Parameter
+                        is launched ahead, for which the running-range update is idempotent
     """
 
     def __init__(self, disable_quantization: bool = False, skip_unsupported_quantizers: bool = False, *,
                  eager_checks: bool = False, sync_ranges: bool = False, process_group=None, fused: bool = True,
-                 dedupe: bool = True, memoize_parameters: bool = True, sync_parameters: bool = False) -> None:
+                 dedupe: bool = True, memoize_parameters: bool = True, sync_parameters: bool = False,
+                 overlap_parameters: int = 0) -> None:
         self.disable_quantization = disable_quantization
         self.skip_unsupported_quantizers = skip_unsupported_quantizers
         self.eager_checks = eager_checks
@@ -535,8 +655,9 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
         self.process_group = process_group
         self.fused = fused
         self.dedupe, self.memoize_parameters, self.sync_parameters = dedupe, memoize_parameters, sync_parameters
+        self.overlap_parameters = int(overlap_parameters)
         self._steps: list = []
-        self._state = _BlockState(dedupe, memoize_parameters)
+        self._state = _BlockState(dedupe, memoize_parameters, overlap_parameters)
         self.last_stats: dict = {}
         self.last_exit: dict = {}
 
@@ -554,62 +675,89 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
             if sys.exc_info()[0] is None:
                 self.finalize(())
             else:                                # the block failed: drop its half-finished state
+                self._state.drain()
                 for s in self._state.aliases:
                     s._unalias()
-                self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters)
+                self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters, self.overlap_parameters)
         super().cleanup(module, metadata)
 
     # ---- block exit -------------------------------------------------------------------------------------
-    def finalize(self, prepared: Sequence[tuple]) -> None:
+    finalize_runs_cleanup = True      # estimate_ranges hands its cleanup loop to finalize(), see below
+
+    def finalize(self, prepared: Sequence[tuple], cleanup=None) -> None:
+        """The block ends.  ONE host sync, and everything the host can do without the device's answer happens BEFORE
+        it, while the device is still working through the queued steps: the slot signature and its all-reduce, the
+        descriptor table of the batched range -> parameters launch, fresh storage for the de-duplicated quantizers,
+        and (``cleanup``, passed by this package's ``estimate_ranges``) the removal of the overrides.  After the sync:
+        two all-reduces, one parameters launch, one multi-tensor copy."""
         del prepared
         import time
 
         steps, state = self._steps, self._state
-        self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters)
+        self._steps, self._state = [], _BlockState(self.dedupe, self.memoize_parameters, self.overlap_parameters)
         t0 = time.perf_counter()
+        state.drain()
+        exchange = None
+        unalias = ([], [])
         flags_value = None
+        detail: dict = {}
         try:
             if self.sync_ranges:
-                flags_value = self._sync(steps, state)
-        finally:
-            t1 = time.perf_counter()
-            _unalias_all(state.aliases)         # aliased quantizers get their own parameter storage back
+                exchange = self._sync_begin(steps, state)
+            unalias = _unalias_prepare(state.aliases)
+            if exchange is None:
+                _unalias_finish(unalias)        # nothing will rewrite the shared storage: copy now, before the sync
+                unalias = ([], [])
             state.recent.clear()
-        t2 = time.perf_counter()
-        self.last_stats = dict(state.stats)
-        # ONE host sync for all quantizers: the reference's per-step `isinf().any()` checks.  A data-parallel exit has
-        # already read the (rank-merged) flags of the block's arenas together with the slot signature.
-        flags = [s.flags for _, s in steps if s.flags is not None and s._state is None]
-        if flags_value is None:
-            flags = state.all_flags() + flags
+            # the reference's per-step `isinf().any()` checks, folded into one read; a data-parallel exit carries the
+            # flags of the block's arenas inside the signature message instead
+            flags = [s.flags for _, s in steps if s.flags is not None and s._state is None]
+            if exchange is None:
+                flags = state.all_flags() + flags
+            stacked = None
+            if flags and not self.eager_checks:
+                stacked = torch.stack([f.reshape(()) for f in {id(f): f for f in flags}.values()])
+                if stacked.is_cuda:
+                    host = torch.empty(stacked.shape, dtype=stacked.dtype).pin_memory()
+                    host.copy_(stacked, non_blocking=True)
+                    stacked = (host, stacked.device)
+            if cleanup is not None:
+                cleanup()
+            t1 = time.perf_counter()
+            # ---- the exit's one host sync -----------------------------------------------------------------
+            if exchange is not None:
+                flags_value = self._sync_finish(exchange, state, detail)
+            t2 = time.perf_counter()
+        finally:
+            _unalias_finish(unalias)
         value = flags_value or 0
-        if flags and not self.eager_checks:
-            for v in torch.stack([f.reshape(()) for f in {id(f): f for f in flags}.values()]).tolist():
+        if isinstance(stacked, tuple):
+            # single process: THE host sync of the exit; data parallel: the signature read has drained this stream already
+            torch.cuda.current_stream(stacked[1]).synchronize()
+            stacked = stacked[0]
+        if stacked is not None:
+            for v in stacked.tolist():
                 value |= int(v)
         t3 = time.perf_counter()
-        self.last_exit = {"sync_ms": (t1 - t0) * 1e3, "unalias_ms": (t2 - t1) * 1e3, "flags_ms": (t3 - t2) * 1e3,
-                          "aliased": len(state.aliases), **getattr(self, "_exit_detail", {})}
+        self.last_stats = dict(state.stats)
+        self.last_exit = {"before_sync_ms": (t1 - t0) * 1e3, "sync_and_exchange_ms": (t2 - t1) * 1e3,
+                          "flags_ms": (t3 - t2) * 1e3, "aliased": len(state.aliases), **detail}
         if not self.eager_checks or flags_value is not None:
             _raise_for_flags(value)
 
-    def _sync(self, steps, state) -> Optional[int]:
-        """Merge the running ranges across the data-parallel ranks and re-derive (scale, offset) from them.
-        Slots of the activation arena are handed out in the order quantizers first see data, which control flow that
-        depends on the data (experts without tokens on one shard) can make rank dependent: the ranks first agree on
-        the slot layout (one small MAX all-reduce of a signature vector, which also carries the block's +-inf flags so
-        that the exit has ONE host sync); identical layouts all-reduce the arena in place (one MIN + one MAX
-        collective per dtype, asynchronous), anything else is packed per quantizer in ``prepare`` order with neutral
-        fill for quantizers a rank did not see.  Returns the flags merged over the ranks (None: nothing exchanged)."""
-        import time
-
+    def _sync_begin(self, steps, state):
+        """Data-parallel exit, the part before the host sync.  Slots of the activation arena are handed out in the
+        order quantizers first see data, which control flow that depends on the data (experts without tokens on one
+        shard) can make rank dependent: the ranks first agree on the slot layout with one small MAX all-reduce of a
+        signature vector, which also carries the block's +-inf flags.  Issued here, read in ``_sync_finish``; in
+        between the host prepares the batched parameters launch for the common case of identical layouts."""
         import torch.distributed as dist
 
-        from ..distributed import _active, all_reduce_minmax_buffers
+        from ..distributed import _active
 
         group = self.process_group
         if not _active(group):
             return None
-        t0 = time.perf_counter()
         todo = [(i, q, s) for i, (q, s) in enumerate(steps)
                 if s._alias_of is None and (self.sync_parameters or not s._param_data)]
         device = None
@@ -631,14 +779,34 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
                 sig.append(-2)
         n = len(sig)
         # [sig | -sig | flag bit 0 | flag bit 1]: MAX over the ranks gives max(sig), -min(sig) and the OR of each flag bit
-        msg = torch.tensor(sig + [-v for v in sig] + [0, 0], dtype=torch.int64).to(device, non_blocking=True)
+        msg = torch.tensor(sig + [-v for v in sig] + [0, 0], dtype=torch.int64)
+        if device.type == "cuda":
+            msg = msg.pin_memory()
+        msg = msg.to(device, non_blocking=True)
         flags = [f for f in state.all_flags() if f.device == device]
-        for f in flags:
-            f64 = f.reshape(()).to(torch.int64)
-            msg[2 * n] |= f64 & 1
-            msg[2 * n + 1] |= (f64 >> 1) & 1
+        if flags:
+            f64 = torch.stack([f.reshape(()) for f in flags]).to(torch.int64)
+            msg[2 * n:] |= torch.stack([(f64 & 1).amax(), ((f64 >> 1) & 1).amax()])
         dist.all_reduce(msg, op=dist.ReduceOp.MAX, group=group)
-        got = msg.tolist()                       # the exit's one host sync
+        if msg.is_cuda:
+            got = torch.empty(msg.shape, dtype=msg.dtype).pin_memory()
+            got.copy_(msg, non_blocking=True)
+        else:
+            got = msg
+        live = [(q, s) for _, q, s in todo if s.min is not None]
+        launches = self._prepare_parameters_from_ranges(live, state) if -2 not in sig else None
+        return {"todo": todo, "sig": sig, "device": device, "group": group, "got": got, "live": live, "launches": launches}
+
+    def _sync_finish(self, ex, state, detail: dict) -> int:
+        import time
+
+        from ..distributed import all_reduce_minmax_buffers
+
+        t0 = time.perf_counter()
+        device, group, sig, n = ex["device"], ex["group"], ex["sig"], len(ex["sig"])
+        if device.type == "cuda":
+            torch.cuda.current_stream(device).synchronize()     # the exit's one host sync
+        got = ex["got"].tolist()
         t1 = time.perf_counter()
         same = all(a == -b for a, b in zip(got[:n], got[n:2 * n])) and -2 not in sig
         flags_value = int(got[2 * n]) | (int(got[2 * n + 1]) << 1)
@@ -648,16 +816,26 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
             if self.sync_parameters:
                 all_reduce_minmax_buffers(list(state.param.buffers()), None, group=group)
         else:
-            self._sync_packed(todo, device, group)
+            self._sync_packed(ex["todo"], device, group)
             all_reduce_minmax_buffers([], other_flags, group=group)
         for f in other_flags:
             flags_value |= int(f.item())
         t2 = time.perf_counter()
-        self._reset_parameters_from_ranges([(q, s) for _, q, s in todo if s.min is not None], state)
+        if same and ex["launches"] is not None:
+            for launch in ex["launches"]:
+                launch()
+        else:
+            for launch in self._prepare_parameters_from_ranges([(q, s) for q, s in ex["live"] if s.min is not None], state):
+                launch()
         t3 = time.perf_counter()
-        self._exit_detail = {"signature_ms": (t1 - t0) * 1e3, "allreduce_issue_ms": (t2 - t1) * 1e3,
-                             "params_ms": (t3 - t2) * 1e3, "exchanged_quantizers": n, "same_layout": same}
+        detail.update({"wait_ms": (t1 - t0) * 1e3, "allreduce_issue_ms": (t2 - t1) * 1e3, "params_ms": (t3 - t2) * 1e3,
+                       "exchanged_quantizers": n, "same_layout": same})
         return flags_value
+
+    def _sync(self, steps, state) -> Optional[int]:
+        """Both halves back to back (tests; the block exit interleaves its other host work between them)."""
+        ex = self._sync_begin(steps, state)
+        return None if ex is None else self._sync_finish(ex, state, {})
 
     def _sync_packed(self, todo, device, group) -> None:
         import torch.distributed as dist
@@ -698,11 +876,21 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
                 s.min = None            # already applied
             pos += n
 
-    def _reset_parameters_from_ranges(self, steps, state) -> None:
-        """After the ranges were merged across ranks: every quantizer's (scale, offset) from its merged range.  The
-        quantizers whose running range lives in an arena chunk and whose parameters are materialised fp32 tensors of
-        the right size are done with ONE launch per chunk; the rest go through the ``quantization_range`` setter."""
+    def _prepare_parameters_from_ranges(self, steps, state) -> list:
+        """After the ranges were merged across ranks every quantizer's (scale, offset) follows from its merged range.
+        Returns the launches as closures, so that the tables can be built before the exit's host sync and fired
+        after the all-reduces were issued: quantizers whose running range lives in an arena chunk and whose
+        parameters are materialised fp32 tensors of the right size share ONE launch per chunk (descriptor table
+        already on the device); the rest go through the ``quantization_range`` setter."""
         per_chunk: dict = {}
+        launches: list = []
+
+        def through_setter(quantizer, step):
+            def run():
+                if step.min is not None and not _set_range_direct(quantizer, step.min, step.max):
+                    quantizer.quantization_range = (step.min, step.max)
+            return run
+
         for quantizer, step in steps:
             slot = step._slot
             entry = None
@@ -714,14 +902,14 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
                     entry = (slot[2], n, quantizer.num_bits, quantizer.symmetric, quantizer.allow_one_sided,
                              scale.data, None if offset is None else offset.data)
             if entry is None:
-                if not _set_range_direct(quantizer, step.min, step.max):
-                    quantizer.quantization_range = (step.min, step.max)
+                launches.append(through_setter(quantizer, step))
                 continue
             per_chunk.setdefault((id(slot[0]), slot[1], step.min.device, step.min.dtype, _host_of(quantizer).rcp),
                                  (slot, []))[1].append(entry)
         for (_, ci, dev, dt, rcp), (slot, entries) in per_chunk.items():
             mn, mx, used = slot[0].chunks[(dev, dt)][ci]
-            ops.parameters_for_ranges_batched_(mn, mx, entries, reciprocal_scalar_division=rcp)
+            launches.append(ops.parameters_for_ranges_batched_prepare(mn, mx, entries, reciprocal_scalar_division=rcp))
+        return launches
 
 
 class SmoothedMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):

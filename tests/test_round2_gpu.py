@@ -65,6 +65,85 @@ def test_dedupe_and_memoisation_are_bit_identical():
                 assert torch.equal(par[name][1], base_par[name][1]), (kw, name)
 
 
+@pytest.mark.parametrize("ahead", [1, 3, 64])
+def test_overlapped_parameter_steps_are_bit_identical(ahead):
+    """Weights calibrated `ahead` quantizers early on the side stream: outputs and parameters equal the in-line run."""
+    g = torch.Generator().manual_seed(6)
+    batches = [torch.randint(0, 1024, (1, 64), generator=g).to(DEV) for _ in range(4)]
+    base_out, base_par, _ = _run(_tiny(), batches, dedupe=True, memoize_parameters=False)
+    out, par, stats = _run(_tiny(), batches, dedupe=True, memoize_parameters=False, overlap_parameters=ahead)
+    # 7 weights x 2 layers; the first step records the order, afterwards all but the first weight of a step run ahead
+    assert stats["overlapped"] == (7 * 2 - 1) * (len(batches) - 1), stats
+    for a, b in zip(out, base_out):
+        assert torch.equal(a, b)
+    for name in par:
+        assert torch.equal(par[name][0], base_par[name][0]), name
+        if par[name][1] is not None:
+            assert torch.equal(par[name][1], base_par[name][1]), name
+
+
+def test_overlapped_parameter_steps_under_graph_capture():
+    """The side stream joins the capture as a parallel branch; replays equal eager steps on the same inputs."""
+    g = torch.Generator().manual_seed(7)
+    batches = [torch.randint(0, 1024, (1, 64), generator=g).to(DEV) for _ in range(5)]
+    base_out, base_par, _ = _run(_tiny(), batches, memoize_parameters=False)
+    model = _tiny()
+    est = ff.range_setting.running_minmax(memoize_parameters=False, overlap_parameters=4)
+    static = torch.empty_like(batches[0])
+    outs = []
+    with torch.no_grad(), ff.estimate_ranges(model, est):
+        for b in batches[:2]:
+            static.copy_(b)
+            outs.append(model(static).clone())
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        static.copy_(batches[2])
+        with torch.cuda.graph(cg):
+            y = model(static)
+        # capture does not execute: replay for batch 2, then the remaining batches
+        for b in batches[2:]:
+            static.copy_(b)
+            cg.replay()
+            outs.append(y.clone())
+    assert est.last_stats["overlapped"] > 0
+    for a, b in zip(outs, base_out):
+        assert torch.equal(a, b)
+    for name, q in ff.nn.named_quantizers(model):
+        assert torch.equal(q.scale.detach(), base_par[name][0]), name
+
+
+def test_overlapped_step_is_dropped_when_the_parameter_changes():
+    torch.manual_seed(1)
+    lins = torch.nn.Sequential(*[torch.nn.Linear(256, 256, dtype=torch.bfloat16, device=DEV) for _ in range(3)])
+    ff.quantize_model(lins)
+    for lin in lins:
+        lin.weight_quantizer = ff.nn.LinearQuantizer(8, granularity=ff.PerChannel(0), quantized_dtype=torch.int8).to(DEV)
+        lin.input_quantizer = ff.nn.LinearQuantizer(8, symmetric=False, quantized_dtype=torch.int8).to(DEV)
+    qlinear.install()
+    x = torch.randn(4, 16, 256, device=DEV, dtype=torch.bfloat16)
+    est = ff.range_setting.running_minmax(memoize_parameters=False, overlap_parameters=2)
+    w0 = lins[2].weight.detach().clone()
+    hook = lins[1].register_forward_hook(lambda *a: lins[2].weight.mul_(1.5) if hook.live else None)
+    hook.live = False
+    with torch.no_grad(), ff.strict_quantization(False), ff.estimate_ranges(lins, est):
+        lins(x); lins(x)
+        hook.live = True                  # the last weight changes AFTER its step was launched ahead
+        y = lins(x)
+        hook.live = False
+    hook.remove()
+    w1 = lins[2].weight.detach()
+    mn = torch.minimum(w0.min(1).values, w1.min(1).values).cpu()
+    mx = torch.maximum(w0.max(1).values, w1.max(1).values).cpu()
+    ws, _ = R.parameters_for_range(mn, mx, 8, True, True)
+    assert torch.equal(lins[2].weight_quantizer.scale.detach().cpu(), ws)
+    # the output used codes of the CHANGED weight: equal to an in-line estimator continuing from the same state
+    want = R.quantize_by_tile(w1.cpu(), ws, (1, 256), 8, torch.int8, None)
+    with torch.no_grad():
+        got = lins[2].weight_quantizer(lins[2].weight).raw_data.cpu()
+    assert torch.equal(got, want)
+    assert torch.isfinite(y).all()
+
+
 def test_aliased_quantizers_own_their_parameters_after_the_block():
     model = _tiny()
     batches = [torch.randint(0, 1024, (1, 64)).to(DEV) for _ in range(2)]
