@@ -39,5 +39,13 @@ from .range_setting import estimate_ranges as estimate_ranges
 from .quantization import fuse as _fuse  # noqa: E402  (after nn: it needs LinearQuantizer)
 from .quantization import view_ops as _view_ops  # noqa: E402,F401  (registers the per-tensor view ops with the dispatcher)
 from .quantization.fuse import fuse_qdq_weights as fuse_qdq_weights
+from .quantization import save_load as _save_load  # noqa: E402  (after nn: it walks the quantizers of a model)
+
+# on-disk formats (reference quantization/__init__.py:16-19, nn/quantized_module.py:357-363): functions of the
+# ``quantization`` namespace and, equivalently, methods of every QuantizedModule
+for _name in ("save_quantization_state", "load_quantization_state", "save_quantized_model", "load_quantized_model"):
+    setattr(quantization, _name, getattr(_save_load, _name))
+    setattr(nn.QuantizedModule, _name, getattr(_save_load, _name))
+del _name
 
 __version__ = "0.1.0"

@@ -142,6 +142,7 @@ def _load() -> ctypes.CDLL:
         "ffq_debug_gemm_profile": (None, [vp]),
         "ffq_calibrate_fakequant_batched": (i32, [vp, vp, i64, i64, i32, i64, dbl, i32, i32, i32, vp, sz, vp]),
         "ffq_gptq_block": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i64, vp, i32, vp, i32, vp, i64, i64, i64, dbl, i32, vp]),
+        "ffq_lpbq_encode": (i32, [vp, i64, i64, i32, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
@@ -159,7 +160,7 @@ EXPORTED = (
     "ffq_dequantize ffq_fakequant_fwd ffq_quantize_bwd ffq_minmax ffq_params_for_range "
     "ffq_dynamic_quantize ffq_qlinear_w8a8 ffq_rowsum_i8 ffq_fakequant_fwd_bwd_host ffq_selftest_shared_div ffq_grid_mse ffq_grid_mse_workspace_bytes ffq_qlinear_w4a16 "
     "ffq_calibrate_quantize ffq_calibrate_quantize_mode ffq_calibrate_quantize_workspace_bytes ffq_gptq_block "
-    "ffq_params_for_ranges_batched ffq_params_for_ranges_encode ffq_calibrate_fakequant ffq_debug_gemm_profile ffq_calibrate_fakequant_batched"
+    "ffq_params_for_ranges_batched ffq_params_for_ranges_encode ffq_calibrate_fakequant ffq_debug_gemm_profile ffq_calibrate_fakequant_batched ffq_lpbq_encode"
 ).split()
 
 

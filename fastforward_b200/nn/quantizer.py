@@ -9,6 +9,7 @@ from typing import Any, Callable, Dict, Iterator, Optional
 import torch
 
 from .. import forward_override as override
+from ..serialization import remember_init_args
 
 
 class Tag:
@@ -118,6 +119,10 @@ class QuantizerMetadata:
         return f"QuantizerMetadata(tags={self._tags}, {', '.join(f'{k}={v}' for k, v in self._kwargs.items())})"
 
 
+_MODULE_INTERNALS = frozenset(torch.nn.Module().__dict__) | {"_ffq_init_args", "quant_metadata", "_quantizer_overrides"}
+
+
+@remember_init_args
 class Quantizer(torch.nn.Module):
     """``forward`` = the override stack wrapped around ``quantize`` (nn/quantizer.py:413-416)."""
 
@@ -170,6 +175,17 @@ class Quantizer(torch.nn.Module):
         if self._quantizer_overrides:
             raise RuntimeError("quantizer_overrides can not be serialized. Please remove all overrides before serialization.")
         return super().__getstate__()
+
+    # ---- config.yaml form (serialization.py; reference nn/quantizer.py:300-339): the constructor arguments plus the
+    # plain attributes; tensors travel in the safetensors file, the metadata is assigned when the quantizer is attached
+    def _yaml_state(self) -> dict:
+        if self._quantizer_overrides:
+            raise RuntimeError("quantizer_overrides can not be serialized. Please remove all overrides before serialization.")
+        return {k: v for k, v in self.__dict__.items() if k not in _MODULE_INTERNALS and not isinstance(v, torch.Tensor)}
+
+    def _yaml_setstate(self, state: dict) -> None:
+        for key, value in state.items():
+            setattr(self, key, value)
 
     def __deepcopy__(self, memo):
         if id(self) in memo:

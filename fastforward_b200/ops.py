@@ -567,3 +567,26 @@ def grid_mse(
         x.data_ptr(), C.dtype_tag(x.dtype), cand_scale.data_ptr(), C.ptr(cand_offset), ncand, err.data_ptr(),
         layout.ref, float(num_bits), C.ptr(ws), ws_bytes, C.current_stream(x.device)))
     return err
+
+
+# ------------------------------------------------------------------------------------------
+# LPBQ scale compression (export/_lpbq.py:131-160)
+# ------------------------------------------------------------------------------------------
+@_on_device
+def lpbq_encode(scale_2d: torch.Tensor, channel_axis: int, bitwidth: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``LPBQProcessor.grouped_dynamic_quantize`` in one kernel: for every channel of the 2-D per-block scale tensor
+    (``channel_axis`` 0: a channel is a row, 1: a column) ``float_scale = max(scale) / 2**bitwidth`` and
+    ``int_scale = clamp(round(scale / float_scale), 1, 2**bitwidth)``.  Returns ``(int_scale int32 like scale_2d,
+    float_scale fp32 [channels])``, bit-identical to the reference's aten chain."""
+    C.require_cuda(scale_2d, "scale_2d")
+    if scale_2d.dim() != 2 or scale_2d.dtype != torch.float32:
+        raise NotImplementedError("lpbq_encode: a 2-D float32 scale tensor is required")
+    if scale_2d.numel() == 0:
+        raise ValueError("lpbq_encode: empty scale tensor")
+    s = scale_2d if scale_2d.is_contiguous() else scale_2d.contiguous()
+    rows, cols = s.shape
+    iq = torch.empty((rows, cols), dtype=torch.int32, device=s.device)
+    fs = torch.empty(rows if channel_axis == 0 else cols, dtype=torch.float32, device=s.device)
+    C.check(C.lib.ffq_lpbq_encode(s.data_ptr(), rows, cols, int(channel_axis), int(bitwidth), iq.data_ptr(), fs.data_ptr(),
+                                  C.current_stream(s.device)))
+    return iq, fs

@@ -10,6 +10,7 @@ from typing import Any, Sequence
 
 import torch
 
+from ..serialization import remember_init_args
 from .tiled_tensor import check_tile_compatibility
 
 logger = logging.getLogger(__name__)
@@ -19,6 +20,7 @@ def _tuple(v) -> tuple:
     return (v,) if isinstance(v, int) else tuple(v)
 
 
+@remember_init_args
 class Granularity(abc.ABC):
     _fields: tuple = ()
 

@@ -344,6 +344,17 @@ FFQ_API int ffq_gptq_block(float* w, int64_t ldw, float* q, int64_t ldq, float* 
                    const int32_t* orig_col, int64_t row_block, int64_t col_block, int64_t num_col_blocks,
                    double num_bits, int code_dtype, void* stream);
 
+/* ---- f4: LPBQ scale compression (on-disk encodings of per-block weights) --------------------
+ * scale: fp32 [rows, cols] per-block scales of ONE weight.  channel_axis = 0: a channel is a row (the scales of
+ * PerBlock(block_dims=1, per_channel_dims=0), [out_channels, blocks]); 1: a channel is a column
+ * (PerBlock(block_dims=0, per_channel_dims=1), [blocks, in_channels]).  For every channel c
+ *     float_scale[c]  = max over the channel's blocks of scale / 2^bitwidth
+ *     int_scale[., .] = clamp(rint(scale / float_scale[c]), 1, 2^bitwidth)      (same shape as scale, int32)
+ * with aten's roundings (IEEE fp32 division, half-to-even), bit-identical to the reference on the same input.
+ * replaces: export/_lpbq.py:131-160 (LPBQProcessor.grouped_dynamic_quantize: amax, 2x div, round, clamp, cast). */
+FFQ_API int ffq_lpbq_encode(const float* scale, int64_t rows, int64_t cols, int channel_axis, int bitwidth,
+                            int32_t* int_scale, float* float_scale, void* stream);
+
 /* ---- test hook ---------------------------------------------------------------------------
  * Sweeps the kernels' shared-reciprocal division against __fdiv_rn over n pseudo-random
  * (dividend, scale) pairs.  counts_dev: uint64[4], zero-initialised by the caller:

@@ -441,3 +441,18 @@ def mse_grid_select(cumulative_error: Tensor, lo: Tensor, hi: Tensor) -> Tuple[T
     best = cumulative_error.min(dim=0).indices
     idx = torch.arange(lo.shape[1])
     return lo[best, idx], hi[best, idx]
+
+
+# --------------------------------------------------------------------------------------
+# f4  LPBQ scale compression                           export/_lpbq.py:131-160
+# --------------------------------------------------------------------------------------
+def lpbq_grouped_dynamic_quantize(scale_2d: Tensor, channel_axis: int, bitwidth: int) -> Tuple[Tensor, Tensor]:
+    """``LPBQProcessor.grouped_dynamic_quantize`` restated: per channel (``channel_axis`` 0: a row of ``scale_2d``,
+    1: a column) the float scale is the channel's largest block scale divided by ``2**bitwidth`` (:149-150) and every
+    block scale becomes ``clamp(round(scale / float_scale), 1, 2**bitwidth)`` (:153-155).  Returns (integers as
+    int64 shaped like ``scale_2d``, float scale with the reduced dimension kept)."""
+    reduce_dim = 1 if channel_axis == 0 else 0
+    max_scale = torch.amax(scale_2d, dim=reduce_dim, keepdim=True)
+    dynamic_scale = max_scale / max_scale.new_tensor(2 ** bitwidth)
+    q = torch.clamp(torch.round(scale_2d / dynamic_scale), 1, 2 ** bitwidth)
+    return q.to(torch.int64), dynamic_scale

@@ -290,3 +290,19 @@ def test_mse_grid(i):
     scale, offset = R.parameters_for_range(best_lo, best_hi, c["num_bits"], c["symmetric"], True)
     assert bits_equal(scale, c["scale"])
     assert bits_equal(offset if offset is not None else torch.zeros_like(scale), c["offset"])
+
+
+def test_lpbq_oracle_matches_reference():
+    """oracle.lpbq_grouped_dynamic_quantize against the reference's LPBQProcessor on both block orientations."""
+    from conftest import load_golden
+    cases = load_golden("lpbq")
+    assert len(cases) == 15
+    for c in cases:
+        rows, cols = c["data_shape"]
+        block = c["tile_size"][1] if c["orientation"] == "rows" else c["tile_size"][0]
+        shape2d = (rows, cols // block) if c["orientation"] == "rows" else (rows // block, cols)
+        q, f = R.lpbq_grouped_dynamic_quantize(c["scale"].reshape(shape2d), 0 if c["orientation"] == "rows" else 1,
+                                               c["compressed_bw"])
+        assert torch.equal(q, c["int_scale"]) and torch.equal(f.flatten(), c["float_scale"].flatten())
+        assert c["encoding"]["per_block_int_scale"] == q.flatten().tolist()
+        assert c["encoding"]["scale"] == f.flatten().tolist()

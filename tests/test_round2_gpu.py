@@ -572,3 +572,62 @@ def test_whole_model_batched_fake_quant_equals_per_weight():
     g.replay(); torch.cuda.synchronize()
     for (na, pa), (nb, pb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(pa, pb), na
+
+
+# ------------------------------------------------------------------------------------------------------------
+# LPBQ scale compression (export/_lpbq.py:131-160): kernel vs the reference's recorded outputs and the oracle
+# ------------------------------------------------------------------------------------------------------------
+def test_lpbq_encode_matches_reference_goldens():
+    from conftest import load_golden
+    from fastforward_b200.quantization.lpbq import LPBQProcessor
+    for c in load_golden("lpbq"):
+        proc = LPBQProcessor(compressed_bw=c["compressed_bw"], decompressed_bw=c["decompressed_bw"])
+        enc = proc.generate_lpbq_encoding("w", c["scale"].to(DEV), c["data_shape"], c["tile_size"], c["compressed_bw"])
+        assert enc == c["encoding"], (c["data_shape"], c["tile_size"], c["compressed_bw"])
+        rows, cols = c["data_shape"]
+        block = c["tile_size"][1] if c["orientation"] == "rows" else c["tile_size"][0]
+        shape2d = (rows, cols // block) if c["orientation"] == "rows" else (rows // block, cols)
+        q, f = proc.grouped_dynamic_quantize(c["scale"].reshape(shape2d).to(DEV), c["grouping"], c["compressed_bw"])
+        assert torch.equal(q.cpu().long(), c["int_scale"]) and torch.equal(f.cpu().flatten(), c["float_scale"].flatten())
+
+
+@pytest.mark.parametrize("shape,axis", [((4096, 32), 0), ((4096, 112), 0), ((32, 4096), 1), ((3, 1), 0), ((1, 5), 1),
+                                        ((14336, 32), 0)])
+@pytest.mark.parametrize("bw", [4, 7])
+def test_lpbq_encode_matches_oracle(shape, axis, bw):
+    g = torch.Generator().manual_seed(shape[0] * 31 + shape[1] + bw)
+    s = torch.rand(shape, generator=g) * torch.logspace(-4, 1, shape[1]).reshape(1, -1) + 1e-8
+    s[0, 0] = 0.0                                           # a zero scale clamps to 1
+    iq, fs = ops.lpbq_encode(s.to(DEV), axis, bw)
+    q, f = R.lpbq_grouped_dynamic_quantize(s, axis, bw)
+    assert iq.dtype == torch.int32 and torch.equal(iq.cpu().long(), q)
+    assert bits_equal_f32(fs.cpu(), f.flatten())
+
+
+def bits_equal_f32(a, b):
+    return a.shape == b.shape and torch.equal(a.view(torch.int32), b.contiguous().view(torch.int32))
+
+
+def test_lpbq_argument_checks():
+    from fastforward_b200.quantization.lpbq import LPBQProcessor
+    for kw in (dict(compressed_bw=8), dict(compressed_bw=16, decompressed_bw=8), dict(compressed_bw=0), dict(decompressed_bw=0)):
+        with pytest.raises(ValueError):
+            LPBQProcessor(**{"compressed_bw": 4, "decompressed_bw": 8, **kw})
+    proc = LPBQProcessor()
+    s = torch.rand(64 * 128, device=DEV)
+    for data_shape, tile, bits in (((64, 128), (1, 1), 4), ((64, 128), (4, 128), 4)):
+        with pytest.raises(ValueError, match="not suitable for LPBQ"):
+            proc.generate_lpbq_encoding("w", s, data_shape, tile, bits)
+    with pytest.raises(ValueError, match="not suitable for LPBQ"):
+        LPBQProcessor(8, 16).generate_lpbq_encoding("w", s[:64 * 32], (64, 128), (4, 1), 4)
+    with pytest.raises(ValueError, match="not suitable for LPBQ"):
+        proc.generate_lpbq_encoding("w", s[:64 * 32], (64, 128), (4, 1), 4, is_symmetric=False)
+    with pytest.raises(RuntimeError):
+        ops.lpbq_encode(torch.rand(4, 4), 0, 4)                 # host tensor: no CPU path
+    q = ff.nn.LinearQuantizer(4, granularity=ff.PerBlock(block_dims=1, block_sizes=16, per_channel_dims=0)).to(DEV)
+    w = torch.randn(32, 64, device=DEV)
+    with torch.no_grad(), ff.estimate_ranges(q, ff.range_setting.running_minmax):
+        q(w)
+    enc = proc.encode_quantizer("w", q, w.shape)
+    assert enc["block_size"] == 16 and len(enc["scale"]) == 32 and len(enc["per_block_int_scale"]) == 32 * 4
+    assert all(1 <= v <= 16 for v in enc["per_block_int_scale"]) and enc["offset"] == [-128.0] * 32
