@@ -1098,6 +1098,193 @@ static int run_tensor_any(CalqArgs& a, unsigned long long nvec, cudaStream_t st)
   return run_tensor<XT, CQ_T, CQ_CHUNK_VECS>(a, nvec, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// per-tensor, optimistic: ONE pass in the common case that the batch does not move the running range
+// ------------------------------------------------------------------------------------------
+// The two-pass structure of the kernel above (extrema -> grid barrier -> quantize) is the reference's; a 16 MB
+// activation tensor spends 3-5 of its 16 us in the barrier and runs its two passes one after the other.  But a running
+// range only ever widens, and after the first few batches most batches do not widen it (the chance that batch t sets
+// a new extreme is ~2/t).  So:
+//   kernel A (calq_tensor_opt_kernel<.., false>): every CTA derives (scale, offset) from the OLD running range and, in
+//     one pass, takes the batch's extrema AND writes codes + row sums for those parameters.  No barrier: the CTAs leave
+//     their partial extrema in the workspace and take a ticket; the LAST CTA merges them into the running range,
+//     writes the parameters of the merged range and records whether the merged range differs from the old one
+//     in any bit (`redo`);
+//   kernel B (<.., true>): returns after one load unless `redo` is set; then it writes codes + row sums again with the
+//     parameters of the merged range (the tensor is still in L2).
+// Result: codes = quantize(x, parameters(merged range)) in every case, exactly what the two-pass kernel produces (when
+// the merged range equals the old one bit for bit, so do the parameters and therefore the codes).  The first batch of a
+// block (no range yet) and every batch that widens the range cost two passes, as before, without the barrier.
+// Work is assigned by rows (a warp per row of the row-sum layout, or per 512 vectors when no row sums are wanted), so
+// a row's sum is one plain store: no atomics, no zero-initialisation.
+constexpr int CQO_T = 256;
+constexpr unsigned int CQO_SPAN = 512;                 // vectors per warp task when there are no rows
+
+// MODE 0: fast exact division + saturating 8-bit pack, 1: fast, 2: guarded division, 3: no codes (extrema only)
+template <typename XT, int MODE, bool MINMAX>
+__device__ __forceinline__ void calq_opt_pass(const CalqArgs& a, const XT* __restrict__ x, unsigned long long nvec,
+                                              unsigned int span, unsigned long long ntasks, const SharedRcp& k, float o,
+                                              float& mn, float& mx) {
+  constexpr int EPT = 16 / sizeof(XT);
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long nwarps = (unsigned long long)gridDim.x * (CQO_T / 32);
+  for (unsigned long long task = (unsigned long long)blockIdx.x * (CQO_T / 32) + warp; task < ntasks; task += nwarps) {
+    const unsigned long long v0 = task * span;
+    const unsigned int n = (unsigned int)((nvec - v0) < span ? (nvec - v0) : span);
+    int sum = 0;
+    for (unsigned int b = 0; b < n; b += 32 * CQ_U) {
+      Vec<XT, EPT> xv[CQ_U];
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned int i = b + u * 32 + lane;
+        if (i < n) xv[u] = ld_stream<XT, EPT>(x + (v0 + i) * EPT);
+      }
+#pragma unroll
+      for (int u = 0; u < CQ_U; ++u) {
+        const unsigned int i = b + u * 32 + lane;
+        if (i < n) {
+          if constexpr (MINMAX) {
+            float vmn, vmx;
+            vec_minmax<XT, EPT>(xv[u], vmn, vmx);
+            mn = nan_min(mn, vmn);
+            mx = nan_max(mx, vmx);
+          }
+          if constexpr (MODE != 3) {
+            uint32_t packed[EPT / 4];
+            if constexpr (MODE == 0) calq_vec_fast<XT, EPT, true>(xv[u], k, o, 0, 0, packed, sum);
+            else if constexpr (MODE == 1) calq_vec_fast<XT, EPT, false>(xv[u], k, o, (int)a.lo, (int)a.hi, packed, sum);
+            else calq_vec<XT, EPT>(xv[u], k, o, a.lo, a.hi, a.sat8 != 0, packed, sum);
+            calq_store<EPT>(a.q + (v0 + i) * EPT, packed);
+          }
+        }
+      }
+    }
+    if constexpr (MODE != 3) {
+      if (a.rowsum) {
+        const int tot = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) a.rowsum[task] = tot;
+      }
+    }
+  }
+}
+
+template <typename XT, bool REDO>
+__global__ void __launch_bounds__(CQO_T, 4) calq_tensor_opt_kernel(const CalqArgs a) {
+  constexpr int EPT = 16 / sizeof(XT);
+  __shared__ float s_f[64];
+  __shared__ float s_par[4];
+  __shared__ int s_flag;
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int G = gridDim.x;
+  const unsigned long long nvec = a.numel / EPT;
+  const unsigned int span = a.rowsum ? a.row_len / EPT : CQO_SPAN;
+  const unsigned long long ntasks = (nvec + span - 1) / span;
+  const XT* __restrict__ x = static_cast<const XT*>(a.x);
+  unsigned int* redo = a.bar + 2;                        // workspace word 2: written by A's last CTA, read by B
+
+  if (threadIdx.x == 0) {
+    float rmn, rmx;
+    int go;
+    if constexpr (REDO) {
+      go = (int)__ldcg(redo);
+      rmn = load_as_float(a.run_min, a.run_dt, 0);       // the merged range and its parameters, written by kernel A
+      rmx = load_as_float(a.run_max, a.run_dt, 0);
+      s_par[0] = go ? __ldcg(a.scale) : 1.f;
+      s_par[1] = (go && a.offset) ? __ldcg(a.offset) : 0.f;
+    } else {
+      rmn = load_as_float(a.run_min, a.run_dt, 0);       // the OLD range: never trust the stored parameters to match it
+      rmx = load_as_float(a.run_max, a.run_dt, 0);
+      go = (rmn <= rmx) && !isinf(rmn) && !isinf(rmx);   // a usable range (false for the +-inf start and for NaN)
+      float sc = 1.f, off = 0.f;
+      if (go) calq_params(a, rmn, rmx, a.symmetric && a.allow_one_sided && (rmn >= 0.f), sc, off);
+      s_par[0] = sc; s_par[1] = off;
+    }
+    s_par[2] = rmn; s_par[3] = rmx;
+    s_flag = go;
+  }
+  __syncthreads();
+  const bool go = s_flag != 0;
+  if (REDO && !go) return;
+  const float s = s_par[0], o = rintf(s_par[1]);
+  const float old_mn = s_par[2], old_mx = s_par[3];
+  const SharedRcp k = make_shared_rcp(s);
+  // the fast variants are exact only for elements inside the range the guard was settled from; a speculative pass may
+  // meet elements outside it -- then the range widens and kernel B rewrites everything
+  const bool fast = calq_fast_ok(k, old_mn, old_mx);
+  const int mode = !go ? 3 : (fast ? (a.sat8 ? 0 : 1) : 2);
+  float mn = INFINITY, mx = -INFINITY;
+  switch (mode) {
+    case 0: calq_opt_pass<XT, 0, !REDO>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
+    case 1: calq_opt_pass<XT, 1, !REDO>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
+    case 2: calq_opt_pass<XT, 2, !REDO>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
+    default:
+      if constexpr (!REDO) calq_opt_pass<XT, 3, true>(a, x, nvec, span, ntasks, k, o, mn, mx);
+      break;
+  }
+  if constexpr (!REDO) {
+    block_minmax(mn, mx, s_f);
+    if (threadIdx.x == 0) {
+      a.part[blockIdx.x] = mn;
+      a.part[G + blockIdx.x] = mx;
+      __threadfence();
+      const unsigned int ticket = atomicInc(a.bar, G - 1);     // wraps to 0 with the last arrival: nothing to reset
+      s_flag = ticket == G - 1;
+    }
+    __syncthreads();
+    if (s_flag && warp == 0) {
+      __threadfence();
+      mn = INFINITY; mx = -INFINITY;
+      for (unsigned int i = lane; i < G; i += 32) {
+        mn = nan_min(mn, __ldcg(&a.part[i]));
+        mx = nan_max(mx, __ldcg(&a.part[G + i]));
+      }
+      mn = group_min<32>(mn);
+      mx = group_max<32>(mx);
+      if (lane == 0) {
+        const float rmn = nan_min(old_mn, mn);
+        const float rmx = nan_max(old_mx, mx);
+        float sc, off;
+        calq_params(a, rmn, rmx, a.symmetric && a.allow_one_sided && (rmn >= 0.f), sc, off);
+        store_from_float(a.run_min, a.run_dt, 0, rmn);
+        store_from_float(a.run_max, a.run_dt, 0, rmx);
+        if (a.flags && (isinf(mn) || isinf(mx))) atomicOr(a.flags, 1);
+        a.scale[0] = sc;
+        if (a.offset) a.offset[0] = off;
+        const bool same = go && __float_as_uint(rmn) == __float_as_uint(old_mn) && __float_as_uint(rmx) == __float_as_uint(old_mx);
+        *redo = same ? 0u : 1u;
+      }
+    }
+  }
+}
+
+template <typename XT>
+static int run_tensor_opt(CalqArgs& a, unsigned long long nvec, cudaStream_t st) {
+  constexpr int EPT = 16 / sizeof(XT);
+  const unsigned int span = a.rowsum ? a.row_len / EPT : CQO_SPAN;
+  const unsigned long long ntasks = (nvec + span - 1) / span;
+  const unsigned long long want = (ntasks + CQO_T / 32 - 1) / (CQO_T / 32);
+  unsigned long long cap = (unsigned long long)sm_count() * 8;
+  if (cap > 4096) cap = 4096;              // partial extrema of at most 4096 CTAs fit the workspace
+  const unsigned int grid = (unsigned int)(want < cap ? want : cap);
+  calq_tensor_opt_kernel<XT, false><<<grid, CQO_T, 0, st>>>(a);
+  FFQ_LAUNCH_CHECK();
+  calq_tensor_opt_kernel<XT, true><<<grid, CQO_T, 0, st>>>(a);
+  FFQ_LAUNCH_CHECK();
+  return FFQ_OK;
+}
+
+// the optimistic pair serves tensors of at least 256 KB whose row-sum rows (if any) are 32 .. 8192 vectors long;
+// FFQ_CALQ_OPTIMISTIC=0 keeps the two-pass kernel everywhere (A/B switch)
+static bool tensor_opt_applies(const CalqArgs& a, unsigned long long nvec, int ept) {
+  static const bool off = []() { const char* e = getenv("FFQ_CALQ_OPTIMISTIC"); return e && e[0] == '0'; }();
+  if (off || a.prof || nvec < 16384) return false;
+  if (a.rowsum) {
+    const unsigned int rv = a.row_len / (unsigned int)ept;
+    if (a.row_len % (unsigned int)ept != 0 || rv < 32 || rv > 8192) return false;
+  }
+  return true;
+}
+
 template <typename XT>
 static cudaError_t launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_t st) {
   // one CTA per row, sized to the row (no idle slots beyond the last warp); 8 vectors (128 B) per thread in
@@ -1331,6 +1518,13 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
   a.part = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16);
   a.bar_groups = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 16 + (size_t)2 * 4096 * sizeof(float));
   const unsigned long long nvec = a.numel / ept;
+  if (tensor_opt_applies(a, nvec, ept)) {
+    switch (x_dtype) {
+      case FFQ_F32: return run_tensor_opt<float>(a, nvec, st);
+      case FFQ_BF16: return run_tensor_opt<__nv_bfloat16>(a, nvec, st);
+      default: return run_tensor_opt<__half>(a, nvec, st);
+    }
+  }
   switch (x_dtype) {
     case FFQ_F32: return run_tensor_any<float>(a, nvec, st);
     case FFQ_BF16: return run_tensor_any<__nv_bfloat16>(a, nvec, st);

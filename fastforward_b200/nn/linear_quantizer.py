@@ -36,7 +36,11 @@ class AbstractAffineQuantizer(Quantizer, abc.ABC):
 
     @property
     def has_uninitialized_params(self) -> bool:
-        return any(isinstance(p, torch.nn.parameter.UninitializedParameter) for p in self.parameters())
+        # own parameters only (a quantizer has no submodules): this sits on every calibration step's host path
+        for p in self._parameters.values():
+            if isinstance(p, torch.nn.parameter.UninitializedParameter):
+                return True
+        return False
 
     def extra_repr(self) -> str:
         own = f"num_bits={self.num_bits}, granularity={self.granularity}"

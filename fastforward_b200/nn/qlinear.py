@@ -84,6 +84,11 @@ def build(host) -> types.SimpleNamespace:
     # W8A8
     # --------------------------------------------------------------------------------------------------------
     def accepts_w8a8(input=None, weight=None, bias=None, output_quantizer=None, strict_quantization=None) -> bool:
+        # the predicate reads a dozen attributes of QuantizedTensors: each would be a __torch_function__ round trip
+        with torch._C.DisableTorchFunctionSubclass():
+            return _accepts_w8a8(input, weight, bias, output_quantizer, strict_quantization)
+
+    def _accepts_w8a8(input, weight, bias, output_quantizer, strict_quantization) -> bool:
         px, pw = params(input), params(weight)
         if px is None or pw is None or not input.is_cuda or not weight.is_cuda:
             return False
@@ -343,9 +348,11 @@ def build(host) -> types.SimpleNamespace:
 
 def register_all(kernels, register, Predicate) -> list:
     """Register one host's kernels with that host's dispatcher; returns the registration hooks."""
+    # the dispatcher tries the newest registration first: W8A8 goes last so that an int8 x int8 call is decided by
+    # ONE predicate (accepts_w4a16 would evaluate accepts_w8a8 a second time before declining)
     return [
-        register("linear", Predicate(kernels.accepts_w8a8), kernels.w8a8_linear),
         register("linear", Predicate(kernels.accepts_w4a16), kernels.w4a16_linear),
+        register("linear", Predicate(kernels.accepts_w8a8), kernels.w8a8_linear),
         register("matmul", Predicate(kernels.accepts_matmul), kernels.int8_matmul),
         register("mm", Predicate(kernels.accepts_mm), kernels.int8_mm),
         register("bmm", Predicate(kernels.accepts_bmm), kernels.int8_mm),

@@ -134,6 +134,94 @@ def test_tensor_vs_oracle(shape, dtype, symmetric, one_sided, variant):
     assert _check_against_oracle(xs, tuple(shape), 8, symmetric, one_sided) == 0
 
 
+OPT_SHAPES = [((512, 1024), torch.bfloat16), ((2048, 4096), torch.bfloat16), ((300, 14336), torch.bfloat16), ((4, 128, 1024), torch.float16),
+              ((1000, 1004), torch.float32), ((64, 65536), torch.bfloat16), ((3, 70000 * 8), torch.bfloat16), ((40000, 8), torch.float32)]
+
+
+@pytest.mark.parametrize("shape,dtype", OPT_SHAPES)
+@pytest.mark.parametrize("symmetric,one_sided,bits", [(True, True, 8), (True, False, 8), (False, True, 8), (False, True, 4)])
+@pytest.mark.parametrize("rowsum", [True, False])
+def test_tensor_sequences_that_do_and_do_not_widen_the_range(shape, dtype, symmetric, one_sided, bits, rowsum):
+    """The optimistic per-tensor pair (codes speculatively from the old range, rewritten only when the batch widens it)
+    over a sequence of batches: fresh range, the same batch again, a narrower batch, a wider one, a narrower one again,
+    a batch that moves only the minimum.  Every step's range, parameters, codes and row sums equal the oracle's.  The
+    last three shapes have rows outside the pair's row-sum window and stay on the two-pass kernel."""
+    g = torch.Generator().manual_seed(sum(shape) + symmetric * 4 + one_sided * 2 + bits)
+    x0 = torch.randn(shape, generator=g) * 0.5 + 0.1
+    x1 = torch.randn(shape, generator=g) * 2.0
+    low = x0.clone()
+    low.view(-1)[17] = -9.0
+    xs = [t.to(dtype) for t in (x0, x0, x0 * 0.5, x1, x1 * 0.9, low, x0)]
+    tile = tuple(shape)
+    outs, flags, _ = _run_fused(xs, tile, bits, symmetric, one_sided, rowsum=rowsum)
+    assert flags == 0
+    mn = mx = None
+    for i, (x, (q, rs, scale, offset, rmn, rmx)) in enumerate(zip(xs, outs)):
+        mn, mx, s, o, rq = _oracle_step(mn, mx, x, tile, bits, symmetric, one_sided)
+        assert bits_equal(rmn, mn) and bits_equal(rmx, mx), i
+        assert bits_equal(scale, s), i
+        if offset is not None:
+            assert bits_equal(offset, o if o is not None else torch.zeros_like(s)), i
+        assert bits_equal(q, rq), i
+        if rowsum:
+            assert torch.equal(rs, rq.reshape(-1, rq.shape[-1]).int().sum(1).to(torch.int32)), i
+        else:
+            assert rs is None
+
+
+def test_tensor_sequence_with_special_values_and_stale_parameters():
+    """NaN and +-inf inside a sequence (the range turns NaN / infinite and stays so: every later batch is rewritten), and
+    parameters that do not match the running range when a step starts (the pair derives its own from the range)."""
+    g = torch.Generator().manual_seed(3)
+    shape = (256, 2048)
+    x = (torch.randn(shape, generator=g)).bfloat16()
+    bad = x.clone(); bad[7, 9] = float("nan")
+    inf = x.clone(); inf[1, 1] = float("inf")
+    for seq, want_flag in (([x, x, bad, x], 0), ([x, inf, x], 1)):
+        outs, flags, _ = _run_fused(seq, shape, 8, False, True)
+        assert (flags & 1) == want_flag
+        mn = mx = None
+        for i, (b, (q, rs, scale, offset, rmn, rmx)) in enumerate(zip(seq, outs)):
+            if bool(torch.isinf(b.float()).any()):
+                break                       # the reference raises at this batch (minmax.py:233-234): ours sets the flag
+            mn, mx, s, o, rq = _oracle_step(mn, mx, b, shape, 8, False, True)
+            assert bits_equal(rmn, mn) and bits_equal(rmx, mx) and bits_equal(scale, s) and bits_equal(offset, o), i
+            assert bits_equal(q, rq), i
+    # stale parameters: overwrite scale/offset between two steps on the same data
+    mn = torch.full((1,), float("inf"), dtype=torch.bfloat16, device=DEV); mx = -mn
+    scale, offset = torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    xd = x.to(DEV)
+    q1, rs1 = ops.calibrate_quantize_(mn, mx, xd, shape, 8, False, True, scale, offset, rowsum=True)
+    s1, o1 = scale.clone(), offset.clone()
+    scale.fill_(123.0); offset.fill_(-7.0)
+    q2, rs2 = ops.calibrate_quantize_(mn, mx, xd, shape, 8, False, True, scale, offset, rowsum=True)
+    assert torch.equal(q1, q2) and torch.equal(rs1, rs2) and torch.equal(scale, s1) and torch.equal(offset, o1)
+
+
+def test_tensor_pair_under_graph_replay():
+    """Captured once, replayed over changing inputs: the rewrite kernel's work depends on the data, its launch does not."""
+    g = torch.Generator().manual_seed(9)
+    shape = (1024, 1024)
+    xs = [(torch.randn(shape, generator=g) * sc).bfloat16() for sc in (1.0, 0.5, 3.0, 0.1, 3.5)]
+    mn = torch.full((1,), float("inf"), dtype=torch.bfloat16, device=DEV); mx = -mn
+    scale, offset = torch.empty(1, device=DEV), torch.empty(1, device=DEV)
+    ws = torch.zeros(ops._CALQ_WS, dtype=torch.uint8, device=DEV)
+    static = xs[0].to(DEV).clone()
+    ops.calibrate_quantize_(mn, mx, static, shape, 8, False, True, scale, offset, rowsum=True, workspace=ws)   # warm-up
+    mn.fill_(float("inf")); mx.fill_(float("-inf"))
+    torch.cuda.synchronize()
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        q, rs = ops.calibrate_quantize_(mn, mx, static, shape, 8, False, True, scale, offset, rowsum=True, workspace=ws)
+    omn = omx = None
+    for x in xs:
+        static.copy_(x)
+        cg.replay()
+        omn, omx, s, o, rq = _oracle_step(omn, omx, x, shape, 8, False, True)
+        assert bits_equal(q.cpu(), rq) and bits_equal(scale.cpu(), s) and bits_equal(offset.cpu(), o)
+        assert torch.equal(rs.cpu(), rq.int().sum(1).to(torch.int32))
+
+
 @pytest.mark.parametrize("bits", [2, 4, 7])
 def test_low_bit_widths(bits):
     g = torch.Generator().manual_seed(bits)

@@ -28,7 +28,9 @@ def time_graph(fn, n, reps=5):
     return e0.elapsed_time(e1) * 1e-3 / (reps * n)
 
 
-def run(shape, tile, symmetric, nbuf, dtype=torch.bfloat16):
+def run(shape, tile, symmetric, nbuf, dtype=torch.bfloat16, reset=False):
+    """reset=True: the running range is reset to (+inf, -inf) before every step (two fill kernels, timed apart and
+    subtracted), so every step is a 'the batch widens the range' step -- the slow case of the optimistic per-tensor pair."""
     xs = [(torch.randn(shape, device=dev) * 0.02).to(dtype) for _ in range(nbuf)]
     nt = (shape[0] // tile[0]) * (shape[1] // tile[1])
     mn = torch.full((nt,), float("inf"), dtype=dtype, device=dev); mx = -mn
@@ -36,7 +38,12 @@ def run(shape, tile, symmetric, nbuf, dtype=torch.bfloat16):
     settled = torch.zeros(1, dtype=torch.int32, device=dev)
     keep = []
 
+    def fills(i):
+        mn.fill_(float("inf")); mx.fill_(float("-inf"))
+
     def fused(i):
+        if reset:
+            fills(i)
         keep.append(ops.calibrate_quantize_(mn, mx, xs[i % nbuf], tile, 8, symmetric, True, scale, offset, None, settled, rowsum=True))
 
     def unfused(i):
@@ -50,11 +57,13 @@ def run(shape, tile, symmetric, nbuf, dtype=torch.bfloat16):
         keep.append((q, rs))
     n = max(8, nbuf)
     tf = time_graph(fused, n)
+    if reset:
+        tf -= time_graph(fills, n)
     keep.clear()
     tu = time_graph(unfused, n)
     keep.clear()
     by = xs[0].numel() * (xs[0].element_size() + 1)
-    print(f"{str(shape):>16} tile={str(tile):>14} sym={symmetric!s:5} fused {tf * 1e6:7.1f} us ({by / tf / 1e9:6.0f} GB/s)   "
+    print(("range reset every step: " if reset else "") + f"{str(shape):>16} tile={str(tile):>14} sym={symmetric!s:5} fused {tf * 1e6:7.1f} us ({by / tf / 1e9:6.0f} GB/s)   "
           f"unfused {tu * 1e6:7.1f} us ({by / tu / 1e9:6.0f} GB/s)", flush=True)
 
 
@@ -66,4 +75,6 @@ if __name__ == "__main__":
     run((2048, 4096), (2048, 4096), False, 1)
     run((2048, 14336), (2048, 14336), False, 1)
     run((8192, 4096), (8192, 4096), False, 1)
+    run((2048, 4096), (2048, 4096), False, 1, reset=True)
+    run((2048, 14336), (2048, 14336), False, 1, reset=True)
     run((4096, 4096), (1, 4096), True, 4, torch.float32)
