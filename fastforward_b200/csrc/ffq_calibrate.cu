@@ -1121,7 +1121,7 @@ constexpr int CQO_T = 256;
 constexpr unsigned int CQO_SPAN = 512;                 // vectors per warp task when there are no rows
 
 // MODE 0: fast exact division + saturating 8-bit pack, 1: fast, 2: guarded division, 3: no codes (extrema only)
-template <typename XT, int MODE, bool MINMAX>
+template <typename XT, int MODE, bool MINMAX, int U>
 __device__ __forceinline__ void calq_opt_pass(const CalqArgs& a, const XT* __restrict__ x, unsigned long long nvec,
                                               unsigned int span, unsigned long long ntasks, const SharedRcp& k, float o,
                                               float& mn, float& mx) {
@@ -1132,15 +1132,15 @@ __device__ __forceinline__ void calq_opt_pass(const CalqArgs& a, const XT* __res
     const unsigned long long v0 = task * span;
     const unsigned int n = (unsigned int)((nvec - v0) < span ? (nvec - v0) : span);
     int sum = 0;
-    for (unsigned int b = 0; b < n; b += 32 * CQ_U) {
-      Vec<XT, EPT> xv[CQ_U];
+    for (unsigned int b = 0; b < n; b += 32 * U) {
+      Vec<XT, EPT> xv[U];
 #pragma unroll
-      for (int u = 0; u < CQ_U; ++u) {
+      for (int u = 0; u < U; ++u) {
         const unsigned int i = b + u * 32 + lane;
         if (i < n) xv[u] = ld_stream<XT, EPT>(x + (v0 + i) * EPT);
       }
 #pragma unroll
-      for (int u = 0; u < CQ_U; ++u) {
+      for (int u = 0; u < U; ++u) {
         const unsigned int i = b + u * 32 + lane;
         if (i < n) {
           if constexpr (MINMAX) {
@@ -1168,8 +1168,8 @@ __device__ __forceinline__ void calq_opt_pass(const CalqArgs& a, const XT* __res
   }
 }
 
-template <typename XT, bool REDO>
-__global__ void __launch_bounds__(CQO_T, 4) calq_tensor_opt_kernel(const CalqArgs a) {
+template <typename XT, bool REDO, int U>
+__global__ void __launch_bounds__(CQO_T, (U > 4 ? 2 : 4)) calq_tensor_opt_kernel(const CalqArgs a) {
   constexpr int EPT = 16 / sizeof(XT);
   __shared__ float s_f[64];
   __shared__ float s_par[4];
@@ -1214,11 +1214,11 @@ __global__ void __launch_bounds__(CQO_T, 4) calq_tensor_opt_kernel(const CalqArg
   const int mode = !go ? 3 : (fast ? (a.sat8 ? 0 : 1) : 2);
   float mn = INFINITY, mx = -INFINITY;
   switch (mode) {
-    case 0: calq_opt_pass<XT, 0, !REDO>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
-    case 1: calq_opt_pass<XT, 1, !REDO>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
-    case 2: calq_opt_pass<XT, 2, !REDO>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
+    case 0: calq_opt_pass<XT, 0, !REDO, U>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
+    case 1: calq_opt_pass<XT, 1, !REDO, U>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
+    case 2: calq_opt_pass<XT, 2, !REDO, U>(a, x, nvec, span, ntasks, k, o, mn, mx); break;
     default:
-      if constexpr (!REDO) calq_opt_pass<XT, 3, true>(a, x, nvec, span, ntasks, k, o, mn, mx);
+      if constexpr (!REDO) calq_opt_pass<XT, 3, true, U>(a, x, nvec, span, ntasks, k, o, mn, mx);
       break;
   }
   if constexpr (!REDO) {
@@ -1266,9 +1266,19 @@ static int run_tensor_opt(CalqArgs& a, unsigned long long nvec, cudaStream_t st)
   unsigned long long cap = (unsigned long long)sm_count() * 8;
   if (cap > 4096) cap = 4096;              // partial extrema of at most 4096 CTAs fit the workspace
   const unsigned int grid = (unsigned int)(want < cap ? want : cap);
-  calq_tensor_opt_kernel<XT, false><<<grid, CQO_T, 0, st>>>(a);
-  FFQ_LAUNCH_CHECK();
-  calq_tensor_opt_kernel<XT, true><<<grid, CQO_T, 0, st>>>(a);
+  // 16-byte loads in flight per lane: 8 while the whole tensor is one wave at two CTAs per SM (a 4096-element bf16 row
+  // is two L2 round trips per lane: 2048x4096 12.8 -> 12.1 us), else 4 (four CTAs per SM: 8192x4096 26.3 us against
+  // 34.3 with 8); FFQ_CALQ_OPT_U=4 forces the latter (A/B)
+  static const bool u4 = []() { const char* e = getenv("FFQ_CALQ_OPT_U"); return e && e[0] == '4'; }();
+  if (u4 || want > (unsigned long long)sm_count() * 2) {
+    calq_tensor_opt_kernel<XT, false, 4><<<grid, CQO_T, 0, st>>>(a);
+    FFQ_LAUNCH_CHECK();
+    calq_tensor_opt_kernel<XT, true, 4><<<grid, CQO_T, 0, st>>>(a);
+  } else {
+    calq_tensor_opt_kernel<XT, false, 8><<<grid, CQO_T, 0, st>>>(a);
+    FFQ_LAUNCH_CHECK();
+    calq_tensor_opt_kernel<XT, true, 8><<<grid, CQO_T, 0, st>>>(a);
+  }
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
 }

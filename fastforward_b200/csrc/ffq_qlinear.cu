@@ -108,14 +108,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   return v;
 }
 
-// barrier over the 4 epilogue warps that also ORs a predicate (the tile's "wide constants" decision)
+// barrier over the NT epilogue threads that also ORs a predicate (the tile's "wide constants" decision)
+template <int NT = 128>
 __device__ __forceinline__ bool epilogue_bar_or(bool pred) {
   uint32_t r;
   asm volatile(
       "{\n\t.reg .pred p, q;\n\t"
       "setp.ne.b32 p, %1, 0;\n\t"
-      "barrier.cta.red.or.pred q, 1, 128, p;\n\t"
-      "selp.b32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"((uint32_t)pred) : "memory");
+      "barrier.cta.red.or.pred q, 1, %2, p;\n\t"
+      "selp.b32 %0, 1, 0, q;\n\t}" : "=r"(r) : "r"((uint32_t)pred), "n"(NT) : "memory");
   return r != 0;
 }
 
@@ -240,21 +241,24 @@ template <typename OutT>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& g, const CUtensorMap* map_y, uint32_t taddr, int bn, int row,
                                               int row0_warp, int n_tile0, bool wide, int32_t rx, float* col_params,
                                               const int32_t* col_ints, uint8_t* stage, float rq_s, float rq_o, bool& pending,
-                                              long long* pt = nullptr) {
+                                              long long* pt = nullptr, int c_begin = 0, int c_end = -1) {
+  // [c_begin, c_end): this warp's share of the tile's columns (the pair kernel splits a lane quadrant between two warps);
+  // both bounds are multiples of a staged box
   // pt (test hook, one thread): [0] tcgen05.ld, [1] waiting for the staging box to be free, [2] arithmetic + staging,
   // [3] fence + TMA store issue
   const int lane = threadIdx.x & 31;
   constexpr int COLS_PER_BOX = 128 / (int)sizeof(OutT);       // 64 (16-bit) or 32 (fp32) columns per staged box
   int rq_sum = 0;
+  if (c_end < 0) c_end = bn;
 #pragma unroll 1
-  for (int c0 = 0; c0 < ((g.dbg & 1) ? 0 : bn); c0 += 32) {
+  for (int c0 = c_begin; c0 < ((g.dbg & 1) ? 0 : c_end); c0 += 32) {
     uint32_t acc[32];
     long long q0 = pt ? clock64() : 0;
     tmem_ld32(taddr + (uint32_t)c0, acc);
     if (pt) { const long long q1 = clock64(); pt[0] += q1 - q0; q0 = q1; }
     // a lone trailing 32-column chunk of a 16-bit tile (bn = 224) cannot fill a box: direct stores
     const bool box_first = (c0 % COLS_PER_BOX) == 0;
-    const bool staged = stage != nullptr && (sizeof(OutT) == 4 || !box_first || c0 + 32 < bn);
+    const bool staged = stage != nullptr && (sizeof(OutT) == 4 || !box_first || c0 + 32 < c_end);
     if (staged && box_first && pending) {
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous box has been read
       __syncwarp();
@@ -415,20 +419,32 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // into every other pair's stage (tcgen05.commit multicast to the whole cluster, "empty" barriers count P);
 // "tile ready" goes to the pair only, and the pair's 8 epilogue warps release the accumulator on the leader.
 // ================================================================================================
-constexpr int STAGES2 = 6;
+// Epilogue warps per CTA: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each taking half of the tile's columns:
+// the drain of a tile -- all of it exposed after a launch's last wave -- takes half as long).  Eight warps need eight
+// staging boxes (32 KB), which fit beside five ring stages instead of six.  -DFFQ_GEMM2_EPW=4 builds the former shape.
+#ifndef FFQ_GEMM2_EPW
+#define FFQ_GEMM2_EPW 8
+#endif
+constexpr int EP2_WARPS = FFQ_GEMM2_EPW;
+static_assert(EP2_WARPS == 4 || EP2_WARPS == 8, "FFQ_GEMM2_EPW must be 4 or 8");
+constexpr int EP2_THREADS = 32 * EP2_WARPS;
+constexpr int GEMM2_THREADS = 64 + EP2_THREADS;    // TMA producer warp + MMA warp + epilogue warps
+constexpr int STAGES2 = EP2_WARPS == 8 ? 5 : 6;
 constexpr int HALF_STAGE = A_STAGE + BM * BK;      // A 128x128B + B half 128x128B = 32 KB
-constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + OUT_STAGE_BYTES + COL_BYTES + 256 + 1024;
+constexpr int OUT_STAGE2_BYTES = EP2_WARPS * 32 * 128;
+constexpr int SMEM2_BYTES = STAGES2 * HALF_STAGE + OUT_STAGE2_BYTES + COL_BYTES + 256 + 1024;
+static_assert(SMEM2_BYTES <= 232448, "pair kernel: shared memory over the 227 KB limit");
 template <typename OutT, int P>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM2_THREADS, 1)
 w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_y, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint8_t* out_stage = smem + STAGES2 * HALF_STAGE;                                // [4 warps][32 rows][128 B], swizzled
-  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE + OUT_STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES2 * HALF_STAGE;                                // [EP2_WARPS][32 rows][128 B], swizzled
+  float* col_params = reinterpret_cast<float*>(smem + STAGES2 * HALF_STAGE + OUT_STAGE2_BYTES);
   int32_t* col_ints = reinterpret_cast<int32_t*>(col_params);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + OUT_STAGE_BYTES + COL_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * HALF_STAGE + OUT_STAGE2_BYTES + COL_BYTES);
   uint64_t* full_bar = bars;                  // [STAGES2]  (the pair leader's copy is the one in use)
   uint64_t* empty_bar = bars + STAGES2;       // [STAGES2]  (each CTA waits on its own copy; P arrivals)
   uint64_t* tmem_full = bars + 2 * STAGES2;   // [2]        (each CTA waits on its own copy)
@@ -451,7 +467,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES2; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], P); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * EP2_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -539,9 +555,13 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       }
     }
   } else {
-    // ===== epilogue (warps 2..5 of every CTA): this CTA's 128 rows =====
+    // ===== epilogue (warps 2.. of every CTA): this CTA's 128 rows; with eight warps, warps 2..5 take the first half of
+    // a tile's 32-column chunks and warps 6..9 the second (TMEM lane quadrant = warp % 4 either way) =====
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int ep_tid = threadIdx.x - 64;
+    const int split = EP2_WARPS == 8 ? (((bn >> 5) + 1) >> 1) << 5 : bn;     // first column of the second half
+    const int c_begin = half ? split : 0, c_end = half ? bn : split;
     const float rq_s = g.rq_codes ? g.rq_scale[0] : 1.f;
     const float rq_o = (g.rq_codes && g.rq_offset) ? rintf(g.rq_offset[0]) : 0.f;
     int it = 0;
@@ -555,8 +575,8 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const long long c0t = prof ? clock64() : 0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const bool wide = epilogue_bar_or(stage_col_params(g, tn * bn, bn, ep_tid, 128, col_params, col_ints));
+      asm volatile("bar.sync 1, %0;" ::"n"(EP2_THREADS) : "memory");
+      const bool wide = epilogue_bar_or<EP2_THREADS>(stage_col_params(g, tn * bn, bn, ep_tid, EP2_THREADS, col_params, col_ints));
       if (prof) t_cols += clock64() - c0t;
       const int row = tm * TM + (int)cta * BM + quad * 32 + lane;
       const int32_t rx = (g.ow && row < g.M) ? g.rowsum_x[row] : 0;
@@ -567,11 +587,11 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
       epilogue_tile<OutT>(g, &map_y, taddr, bn, row, tm * TM + (int)cta * BM + quad * 32, tn * bn, wide, rx, col_params,
-                          col_ints, g.tma_store ? out_stage + quad * 4096 : nullptr, rq_s, rq_o, store_pending,
-                          prof ? pt : nullptr);
+                          col_ints, g.tma_store ? out_stage + (half * 4 + quad) * 4096 : nullptr, rq_s, rq_o, store_pending,
+                          prof ? pt : nullptr, c_begin, c_end);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);   // 8 arrivals (4 warps x 2 CTAs) free the accumulator
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[buf]);   // EP2_WARPS x 2 CTAs arrivals free the accumulator
     }
     if (store_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (prof) {
@@ -678,7 +698,7 @@ static int launch_pairs(const CUtensorMap& map_a, const CUtensorMap& map_b, cons
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2 * P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.blockDim = dim3(GEMM2_THREADS); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
   const cudaError_t e = once_per_device(attr_done, [&]() -> cudaError_t {

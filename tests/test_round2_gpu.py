@@ -597,7 +597,8 @@ def test_lpbq_encode_matches_reference_goldens():
 def test_lpbq_encode_matches_oracle(shape, axis, bw):
     g = torch.Generator().manual_seed(shape[0] * 31 + shape[1] + bw)
     s = torch.rand(shape, generator=g) * torch.logspace(-4, 1, shape[1]).reshape(1, -1) + 1e-8
-    s[0, 0] = 0.0                                           # a zero scale clamps to 1
+    if shape[1 - axis] > 1:
+        s[0, 0] = 0.0                                       # a zero scale clamps to 1 (an all-zero channel is 0 / 0: undefined)
     iq, fs = ops.lpbq_encode(s.to(DEV), axis, bw)
     q, f = R.lpbq_grouped_dynamic_quantize(s, axis, bw)
     assert iq.dtype == torch.int32 and torch.equal(iq.cpu().long(), q)
