@@ -77,5 +77,14 @@ for rows, ncols in [(5, 128), (1000, 37), (33, 64)]:
     sc = torch.rand(rows * 2, device=dev) * 0.02 + 1e-3; of = torch.randn(rows * 2, device=dev)
     G.gptq_block_(blk, q[:, 64:64 + ncols], e[:, 64:64 + ncols], hinv[64:64 + ncols, 64:64 + ncols], sc, of,
                   torch.arange(64, 64 + ncols, dtype=torch.int32, device=dev), 1, 128, 2, 4)
+# optimistic per-tensor pair without row sums (ragged last task) and with rows at the window's edges; LPBQ scale compression
+for shape, rowsum in [((1000, 1004), True), ((333, 1000), False), ((64, 65536), True), ((9000, 256), True)]:
+    x = torch.randn(shape, device=dev).bfloat16() if shape[1] % 8 == 0 else torch.randn(shape, device=dev)
+    mn = torch.full((1,), float("inf"), dtype=x.dtype, device=dev); mx = -mn
+    s = torch.empty(1, device=dev); o = torch.empty(1, device=dev)
+    for scale in (1.0, 0.5, 2.0):
+        ops.calibrate_quantize_(mn, mx, x * scale, shape, 8, False, True, s, o, None, None, rowsum=rowsum)
+for shape, axis in [((300, 7), 0), ((5, 1000), 1), ((1, 1), 0), ((4096, 32), 0)]:
+    ops.lpbq_encode(torch.rand(shape, device=dev) + 1e-3, axis, 4)
 torch.cuda.synchronize()
 print("sanitize pass done")
