@@ -592,6 +592,7 @@ def run_ours(args):
             barrier(); torch.cuda.synchronize()
             t0, t1, tmid = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             wall0 = time.perf_counter()
+            lc_timed0 = _cabi.launch_count()
             t0.record()
             for i in range(steps):
                 static_tokens.copy_(tokens_src[args.warmup + i], non_blocking=True)
@@ -604,6 +605,7 @@ def run_ours(args):
                     # D2H read of the step's result into that step's pinned slot; asynchronous like the H2D copy of the
                     # inputs, all of them complete before the region's closing synchronize
                     out_host[i:i + 1].copy_(metric, non_blocking=True)
+            region.launches_per_timed_step = (_cabi.launch_count() - lc_timed0) / max(steps, 1)   # eager regions only
             if align_ranks_before_exit:      # diagnostic regions only: take the ranks' skew out of the exit time
                 torch.cuda.synchronize(); barrier()
             tmid.record()
@@ -668,9 +670,11 @@ def run_ours(args):
     exit_aligned_wall_ms = allmax_value(region.exit_wall_ms, dev, world)
     # ---- instrumented eager pass for the roofline of the dominant kernel ------------------------
     reset_quantizers()
-    lc0 = _cabi.launch_count()
-    region(1, dev_tokens, e2e=False, graph=False, memoize=memo)
-    launches_per_step = (_cabi.launch_count() - lc0) / (1 + args.warmup)
+    # launches of this library per STEADY-STATE step: the timed steps of an eager region (its warm-up steps still issue
+    # the fix-up launches of weights whose `settled` flag the host has not seen yet; a replayed graph does not pass
+    # through the library's counter at all)
+    region(2, dev_tokens, e2e=False, graph=False, memoize=memo)
+    launches_per_step = region.launches_per_timed_step
     reset_quantizers()
     census = KernelCensus(ff)
     with torch.no_grad(), ff.estimate_ranges(model, make_estimator(memo)):
@@ -727,9 +731,12 @@ def run_ours(args):
                 continue
 
         def traffic_of(kind):
-            key = "w8a8_gemm2_kernel" if kind.startswith("w8a8") else None
-            ent = ncu_traffic.get(key) if key else None
-            return ent["dram_bytes_per_launch"] if ent and layers == sh.layers and seq == SEQ and args.shape == "8b" else None
+            # the layer's 7 linears run on two kernels (CTA pairs; single CTAs for the k / v projections): launch-weighted mean
+            ents = [v for k, v in ncu_traffic.items() if kind.startswith("w8a8") and k.startswith("w8a8_gemm") and isinstance(v, dict)]
+            n = sum(e["launches_in_capture"] for e in ents)
+            if not n or not (layers == sh.layers and seq == SEQ and args.shape == "8b"):
+                return None
+            return int(sum(e["dram_bytes_per_launch"] * e["launches_in_capture"] for e in ents) / n)
         roofline = None
         if dominant[0]:
             d = dominant[1]

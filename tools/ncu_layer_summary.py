@@ -2,7 +2,10 @@
 """Condense `ncu --page raw --csv --print-units base` of tools/prof_layer.py into a per-kernel table (markdown) and the
 DRAM traffic per launch bench.py reports as `roofline.traffic` (json).  Only the launches of the LAST step are used.
 
-    python tools/ncu_layer_summary.py raw.csv out.md out.json [steps=3]"""
+    python tools/ncu_layer_summary.py raw.csv out.md out.json [steps=3] [launches of the last step]
+
+The steady-state step of one decoder layer is 22 launches (4 per-tensor pairs, 7 per-channel weight launches, 7 linears);
+earlier steps add fix-up launches, so the last step is taken by count when it is given."""
 import csv
 import json
 import re
@@ -11,6 +14,7 @@ from collections import OrderedDict
 
 raw, out_md, out_json = sys.argv[1:4]
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+last_n = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 rows = list(csv.reader(open(raw, newline="")))
 start = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 header = rows[start]
@@ -33,7 +37,7 @@ def short(name):
     return m.group(3) if m else name[:40]
 
 
-last = data[len(data) - len(data) // steps:]
+last = data[-last_n:] if last_n else data[len(data) - len(data) // steps:]
 METRICS = [
     ("gpu__time_duration.sum", "us", 1e-3),
     ("dram__bytes_read.sum", "DRAM read MB", 1e-6),
