@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(512, 2) calq_rows_kernel(const CalqArgs a) {
   const unsigned int nvec = a.row_len / EPT;
   const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   const XT* __restrict__ x = static_cast<const XT*>(a.x) + row * a.row_len;
+  pdl_wait();                    // programmatic dependent launch (ffq_common.cuh): no-ops unless FFQ_PDL=1
+  pdl_trigger();
 
   Vec<XT, EPT> xin[VPT];
 #pragma unroll
@@ -1181,6 +1183,8 @@ __global__ void __launch_bounds__(CQO_T, (U > 4 ? 2 : 4)) calq_tensor_opt_kernel
   const unsigned long long ntasks = (nvec + span - 1) / span;
   const XT* __restrict__ x = static_cast<const XT*>(a.x);
   unsigned int* redo = a.bar + 2;                        // workspace word 2: written by A's last CTA, read by B
+  pdl_wait();
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     float rmn, rmx;
@@ -1271,13 +1275,13 @@ static int run_tensor_opt(CalqArgs& a, unsigned long long nvec, cudaStream_t st)
   // 34.3 with 8); FFQ_CALQ_OPT_U=4 forces the latter (A/B)
   static const bool u4 = []() { const char* e = getenv("FFQ_CALQ_OPT_U"); return e && e[0] == '4'; }();
   if (u4 || want > (unsigned long long)sm_count() * 2) {
-    calq_tensor_opt_kernel<XT, false, 4><<<grid, CQO_T, 0, st>>>(a);
+    launch_pdl(calq_tensor_opt_kernel<XT, false, 4>, dim3(grid), dim3(CQO_T), 0, st, a);
     FFQ_LAUNCH_CHECK();
-    calq_tensor_opt_kernel<XT, true, 4><<<grid, CQO_T, 0, st>>>(a);
+    launch_pdl(calq_tensor_opt_kernel<XT, true, 4>, dim3(grid), dim3(CQO_T), 0, st, a);
   } else {
-    calq_tensor_opt_kernel<XT, false, 8><<<grid, CQO_T, 0, st>>>(a);
+    launch_pdl(calq_tensor_opt_kernel<XT, false, 8>, dim3(grid), dim3(CQO_T), 0, st, a);
     FFQ_LAUNCH_CHECK();
-    calq_tensor_opt_kernel<XT, true, 8><<<grid, CQO_T, 0, st>>>(a);
+    launch_pdl(calq_tensor_opt_kernel<XT, true, 8>, dim3(grid), dim3(CQO_T), 0, st, a);
   }
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
@@ -1308,8 +1312,8 @@ static cudaError_t launch_rows(const CalqArgs& a, unsigned int nvec, cudaStream_
   const bool full = threads * (unsigned int)vpt == nvec;
 #define FFQ_ROWS_LAUNCH(V)                                                                    \
   do {                                                                                        \
-    if (full) calq_rows_kernel<XT, V, true><<<grid, threads, 0, st>>>(a);                     \
-    else calq_rows_kernel<XT, V, false><<<grid, threads, 0, st>>>(a);                         \
+    if (full) launch_pdl(calq_rows_kernel<XT, V, true>, dim3(grid), dim3(threads), 0, st, a);  \
+    else launch_pdl(calq_rows_kernel<XT, V, false>, dim3(grid), dim3(threads), 0, st, a);      \
   } while (0)
   switch (vpt) {
     case 1: FFQ_ROWS_LAUNCH(1); break;

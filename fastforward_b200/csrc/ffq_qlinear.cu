@@ -318,6 +318,8 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();                   // barriers and TMEM are set up while the previous kernel drains (no-ops unless FFQ_PDL=1)
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -479,6 +481,8 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   cluster_sync_all();                         // barriers of ALL CTAs are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();                   // barriers and TMEM are set up while the previous kernel drains (no-ops unless FFQ_PDL=1)
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer (every CTA; completions count on the pair leaders' full barriers) =====
@@ -695,10 +699,13 @@ static int launch_pairs(const CUtensorMap& map_a, const CUtensorMap& map_b, cons
   static int max_clusters[64] = {0};
   auto kern = w8a8_gemm2_kernel<OutT, P>;
   cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2 * P; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(GEMM2_THREADS); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.blockDim = dim3(GEMM2_THREADS); cfg.dynamicSmemBytes = SMEM2_BYTES; cfg.stream = st; cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
   const cudaError_t e = once_per_device(attr_done, [&]() -> cudaError_t {
@@ -841,9 +848,9 @@ int ffq_qlinear_w8a8(const int8_t* qx, const int8_t* qw, void* y, int y_dtype, i
   const long long tiles1 = ((M + BM - 1) / BM) * ((N + g.bn - 1) / g.bn);
   const int grid1 = (int)(tiles1 < sm_count() ? tiles1 : sm_count());
   switch (y_dtype) {
-    case FFQ_F32: w8a8_gemm_kernel<float><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, map_y, g); break;
-    case FFQ_BF16: w8a8_gemm_kernel<__nv_bfloat16><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, map_y, g); break;
-    default: w8a8_gemm_kernel<__half><<<grid1, GEMM_THREADS, SMEM_BYTES, st>>>(map_a, map_b1, map_y, g); break;
+    case FFQ_F32: launch_pdl(w8a8_gemm_kernel<float>, dim3(grid1), dim3(GEMM_THREADS), SMEM_BYTES, st, map_a, map_b1, map_y, g); break;
+    case FFQ_BF16: launch_pdl(w8a8_gemm_kernel<__nv_bfloat16>, dim3(grid1), dim3(GEMM_THREADS), SMEM_BYTES, st, map_a, map_b1, map_y, g); break;
+    default: launch_pdl(w8a8_gemm_kernel<__half>, dim3(grid1), dim3(GEMM_THREADS), SMEM_BYTES, st, map_a, map_b1, map_y, g); break;
   }
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
