@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(512, 2) calq_rows_kernel(const CalqArgs a) {
   const unsigned int nvec = a.row_len / EPT;
   const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   const XT* __restrict__ x = static_cast<const XT*>(a.x) + row * a.row_len;
-  pdl_wait();                    // programmatic dependent launch (ffq_common.cuh): no-ops unless FFQ_PDL=1
+  pdl_wait();                    // programmatic dependent launch (ffq_common.cuh): no-ops under FFQ_PDL=0
   pdl_trigger();
 
   Vec<XT, EPT> xin[VPT];
@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(512, 2) calq_rows_kernel(const CalqArgs a) {
 // over ALL running mins and quantizes those rows, streaming them from HBM/L2.  Grid: a few CTAs per SM.
 template <typename XT>
 __global__ void __launch_bounds__(CQ_T) calq_rows_fixup_kernel(const CalqArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = 16 / sizeof(XT);
   __shared__ float s_f[64];
   __shared__ int s_i[32];
@@ -383,6 +385,8 @@ constexpr float CQ_DEFERRED = -1.0f;    // scale sentinel: a legitimate scale is
 // Deferred tiles (symmetric one-sided candidates) get the sentinel scale and are finished by calq_sentinel_fixup.
 template <typename XT, typename RT, int LANES, bool FQ>
 __global__ void __launch_bounds__(256) calq_group_kernel(const CalqArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = 16 / sizeof(XT);
   constexpr int U = 4;
   const unsigned long long nvec = a.numel / EPT;
@@ -632,6 +636,8 @@ __device__ __forceinline__ void calq_tile_thread_body(const CalqArgs& a, unsigne
 
 template <typename XT, typename RT, int NV, bool FQ, bool ZOFF>
 __global__ void __launch_bounds__(256) calq_tile_thread_kernel(const CalqArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   calq_tile_thread_body<XT, RT, NV, FQ, ZOFF>(a, (unsigned long long)blockIdx.x * 256ull + threadIdx.x);
 }
 
@@ -653,6 +659,8 @@ template <typename XT, int NV, bool ZOFF>
 __global__ void __launch_bounds__(256) calq_tile_thread_batched_kernel(CalqArgs a, const FqItem* __restrict__ items,
                                                                        const unsigned int* __restrict__ block_start, int n,
                                                                        unsigned int* flags_base) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   const int t = find_item(block_start, n, blockIdx.x);
   const FqItem it = items[t];
   a.x = it.x; a.y = it.y; a.scale = it.scale; a.offset = it.offset; a.numel = (unsigned long long)it.numel;
@@ -664,6 +672,8 @@ __global__ void __launch_bounds__(256) calq_tile_thread_batched_kernel(CalqArgs 
 // deferred rows, optional running range.
 template <typename XT, int VPT>
 __global__ void __launch_bounds__(512) calq_rows_fq_kernel(const CalqArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = 16 / sizeof(XT);
   __shared__ float s_mn[16], s_mx[16];
   const unsigned long long row = blockIdx.x;
@@ -785,6 +795,8 @@ __device__ __forceinline__ void calq_sentinel_fixup_body(const CalqArgs& a, unsi
 
 template <typename XT, bool FQ>
 __global__ void __launch_bounds__(256) calq_sentinel_fixup_kernel(const CalqArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   calq_sentinel_fixup_body<XT, FQ>(a, ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5,
                                    ((unsigned long long)gridDim.x * blockDim.x) >> 5);
 }
@@ -793,6 +805,8 @@ constexpr int FQ_FIXUP_BLOCKS = 8;      // CTAs per tensor of the batched fix-up
 template <typename XT>
 __global__ void __launch_bounds__(256) calq_sentinel_fixup_batched_kernel(CalqArgs a, const FqItem* __restrict__ items,
                                                                           unsigned int* flags_base) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   const int t = blockIdx.x / FQ_FIXUP_BLOCKS;
   const FqItem it = items[t];
   a.x = it.x; a.y = it.y; a.scale = it.scale; a.offset = it.offset; a.numel = (unsigned long long)it.numel;
@@ -1340,8 +1354,8 @@ static void launch_group_rt(const CalqArgs& a, cudaStream_t st) {
       const bool z = a.symmetric != 0;
 #define FFQ_TT(NV)                                                                                              \
       do {                                                                                                        \
-        if (z) calq_tile_thread_kernel<XT, RT, NV, FQ, true><<<grid, 256, 0, st>>>(a);                            \
-        else calq_tile_thread_kernel<XT, RT, NV, FQ, false><<<grid, 256, 0, st>>>(a);                             \
+        if (z) launch_pdl(calq_tile_thread_kernel<XT, RT, NV, FQ, true>, dim3(grid), dim3(256), 0, st, a);                            \
+        else launch_pdl(calq_tile_thread_kernel<XT, RT, NV, FQ, false>, dim3(grid), dim3(256), 0, st, a);                             \
       } while (0)
       if (a.lanes == 8) FFQ_TT(8); else FFQ_TT(16);
 #undef FFQ_TT
@@ -1350,12 +1364,12 @@ static void launch_group_rt(const CalqArgs& a, cudaStream_t st) {
   }
   const unsigned int grid = (unsigned int)((nvec + 256 * 4 - 1) / (256 * 4));
   switch (a.lanes) {
-    case 1: calq_group_kernel<XT, RT, 1, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 2: calq_group_kernel<XT, RT, 2, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 4: calq_group_kernel<XT, RT, 4, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 8: calq_group_kernel<XT, RT, 8, FQ><<<grid, 256, 0, st>>>(a); break;
-    case 16: calq_group_kernel<XT, RT, 16, FQ><<<grid, 256, 0, st>>>(a); break;
-    default: calq_group_kernel<XT, RT, 32, FQ><<<grid, 256, 0, st>>>(a); break;
+    case 1: launch_pdl(calq_group_kernel<XT, RT, 1, FQ>, dim3(grid), dim3(256), 0, st, a); break;
+    case 2: launch_pdl(calq_group_kernel<XT, RT, 2, FQ>, dim3(grid), dim3(256), 0, st, a); break;
+    case 4: launch_pdl(calq_group_kernel<XT, RT, 4, FQ>, dim3(grid), dim3(256), 0, st, a); break;
+    case 8: launch_pdl(calq_group_kernel<XT, RT, 8, FQ>, dim3(grid), dim3(256), 0, st, a); break;
+    case 16: launch_pdl(calq_group_kernel<XT, RT, 16, FQ>, dim3(grid), dim3(256), 0, st, a); break;
+    default: launch_pdl(calq_group_kernel<XT, RT, 32, FQ>, dim3(grid), dim3(256), 0, st, a); break;
   }
 }
 
@@ -1373,10 +1387,10 @@ static void launch_rows_fq(const CalqArgs& a, unsigned int nvec, cudaStream_t st
   const unsigned int threads = ((nvec + vpt - 1) / vpt + 31) / 32 * 32;
   const unsigned int grid = (unsigned int)a.rows;
   switch (vpt) {
-    case 1: calq_rows_fq_kernel<XT, 1><<<grid, threads, 0, st>>>(a); break;
-    case 2: calq_rows_fq_kernel<XT, 2><<<grid, threads, 0, st>>>(a); break;
-    case 4: calq_rows_fq_kernel<XT, 4><<<grid, threads, 0, st>>>(a); break;
-    default: calq_rows_fq_kernel<XT, 8><<<grid, threads, 0, st>>>(a); break;
+    case 1: launch_pdl(calq_rows_fq_kernel<XT, 1>, dim3(grid), dim3(threads), 0, st, a); break;
+    case 2: launch_pdl(calq_rows_fq_kernel<XT, 2>, dim3(grid), dim3(threads), 0, st, a); break;
+    case 4: launch_pdl(calq_rows_fq_kernel<XT, 4>, dim3(grid), dim3(threads), 0, st, a); break;
+    default: launch_pdl(calq_rows_fq_kernel<XT, 8>, dim3(grid), dim3(threads), 0, st, a); break;
   }
 }
 
@@ -1386,7 +1400,7 @@ static void launch_sentinel_fixup(const CalqArgs& a, cudaStream_t st) {
   unsigned long long blocks = (warps_wanted + 7) / 8;
   const unsigned long long cap = (unsigned long long)4 * sm_count();
   if (blocks > cap) blocks = cap;
-  calq_sentinel_fixup_kernel<XT, FQ><<<(unsigned int)blocks, 256, 0, st>>>(a);
+  launch_pdl(calq_sentinel_fixup_kernel<XT, FQ>, dim3((unsigned int)blocks), dim3(256), 0, st, a);
 }
 
 }  // namespace ffq
@@ -1502,9 +1516,9 @@ int ffq_calibrate_quantize(const void* x, int x_dtype, int8_t* q, void* run_min,
     if (symmetric && allow_one_sided && run_fixup) {
       unsigned int grid = (unsigned int)(a.rows < (unsigned long long)sm_count() ? a.rows : sm_count());
       switch (x_dtype) {
-        case FFQ_F32: calq_rows_fixup_kernel<float><<<grid, CQ_T, 0, st>>>(a); break;
-        case FFQ_BF16: calq_rows_fixup_kernel<__nv_bfloat16><<<grid, CQ_T, 0, st>>>(a); break;
-        default: calq_rows_fixup_kernel<__half><<<grid, CQ_T, 0, st>>>(a); break;
+        case FFQ_F32: launch_pdl(calq_rows_fixup_kernel<float>, dim3(grid), dim3(CQ_T), 0, st, a); break;
+        case FFQ_BF16: launch_pdl(calq_rows_fixup_kernel<__nv_bfloat16>, dim3(grid), dim3(CQ_T), 0, st, a); break;
+        default: launch_pdl(calq_rows_fixup_kernel<__half>, dim3(grid), dim3(CQ_T), 0, st, a); break;
       }
       FFQ_LAUNCH_CHECK();
     }
@@ -1669,8 +1683,8 @@ int ffq_calibrate_fakequant_batched(const ffq_fq_item_t* items_dev, const uint32
   const int n = (int)num_items;
 #define FFQ_TTB(XT, NV)                                                                                                 \
   do {                                                                                                                \
-    if (symmetric) calq_tile_thread_batched_kernel<XT, NV, true><<<grid, 256, 0, st>>>(a, items, block_start_dev, n, flags_base);   \
-    else calq_tile_thread_batched_kernel<XT, NV, false><<<grid, 256, 0, st>>>(a, items, block_start_dev, n, flags_base);            \
+    if (symmetric) launch_pdl(calq_tile_thread_batched_kernel<XT, NV, true>, dim3(grid), dim3(256), 0, st, a, items, block_start_dev, n, flags_base);   \
+    else launch_pdl(calq_tile_thread_batched_kernel<XT, NV, false>, dim3(grid), dim3(256), 0, st, a, items, block_start_dev, n, flags_base);            \
   } while (0)
   if (x_dtype == FFQ_BF16) { if (tile_len == 64) FFQ_TTB(__nv_bfloat16, 8); else FFQ_TTB(__nv_bfloat16, 16); }
   else { if (tile_len == 64) FFQ_TTB(__half, 8); else FFQ_TTB(__half, 16); }
@@ -1678,8 +1692,8 @@ int ffq_calibrate_fakequant_batched(const ffq_fq_item_t* items_dev, const uint32
   FFQ_LAUNCH_CHECK();
   if (decide) {
     const unsigned int fgrid = (unsigned int)(num_items * FQ_FIXUP_BLOCKS);
-    if (x_dtype == FFQ_BF16) calq_sentinel_fixup_batched_kernel<__nv_bfloat16><<<fgrid, 256, 0, st>>>(a, items, flags_base);
-    else calq_sentinel_fixup_batched_kernel<__half><<<fgrid, 256, 0, st>>>(a, items, flags_base);
+    if (x_dtype == FFQ_BF16) launch_pdl(calq_sentinel_fixup_batched_kernel<__nv_bfloat16>, dim3(fgrid), dim3(256), 0, st, a, items, flags_base);
+    else launch_pdl(calq_sentinel_fixup_batched_kernel<__half>, dim3(fgrid), dim3(256), 0, st, a, items, flags_base);
     FFQ_LAUNCH_CHECK();
   }
   return FFQ_OK;

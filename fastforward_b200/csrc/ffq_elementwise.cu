@@ -102,6 +102,8 @@ template <typename InT, typename OutT> struct EwEpt {
 
 template <int OP, typename InT, typename OutT, int RM>
 __global__ void __launch_bounds__(EW_THREADS, 4) ew_row_kernel(const EwArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = EwEpt<InT, OutT>::value;
   constexpr bool FLOAT_OUT = std::is_same<OutT, float>::value || std::is_same<OutT, __half>::value ||
                              std::is_same<OutT, __nv_bfloat16>::value;
@@ -265,6 +267,8 @@ __device__ __forceinline__ void ew_vector_exact(const float (&x)[EPT], float (&y
 
 template <int OP, typename InT, typename OutT, int RM>
 __global__ void __launch_bounds__(EW_THREADS, 4) ew_tile_kernel(const EwArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = EwEpt<InT, OutT>::value;
   constexpr int U = EW_UNROLL;
   constexpr bool FLOAT_OUT = std::is_same<OutT, float>::value || std::is_same<OutT, __half>::value ||
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(256) ew_generic_kernel(const EwArgs a) {
 template <int OP, typename InT, typename OutT, int RM>
 static void launch_tile(const EwArgs& a, cudaStream_t st) {
   const unsigned long long blocks = (a.total_segs + EW_THREADS / 32 - 1) / (EW_THREADS / 32);
-  ew_tile_kernel<OP, InT, OutT, RM><<<(unsigned int)blocks, EW_THREADS, 0, st>>>(a);
+  launch_pdl(ew_tile_kernel<OP, InT, OutT, RM>, dim3((unsigned int)blocks), dim3(EW_THREADS), 0, st, a);
   count_launch();
 }
 
@@ -394,7 +398,7 @@ static void launch_row(const EwArgs& a, cudaStream_t st) {
   const unsigned long long nvec = a.numel / EPT;
   unsigned long long blocks = (nvec + EW_THREADS * EW_UNROLL - 1) / (EW_THREADS * EW_UNROLL);
   if (blocks == 0) blocks = 1;
-  ew_row_kernel<OP, InT, OutT, RM><<<(unsigned int)blocks, EW_THREADS, 0, st>>>(a);
+  launch_pdl(ew_row_kernel<OP, InT, OutT, RM>, dim3((unsigned int)blocks), dim3(EW_THREADS), 0, st, a);
   count_launch();
 }
 

@@ -318,7 +318,7 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  pdl_wait();                   // barriers and TMEM are set up while the previous kernel drains (no-ops unless FFQ_PDL=1)
+  pdl_wait();                   // barriers and TMEM are set up while the previous kernel drains (no-ops under FFQ_PDL=0)
   pdl_trigger();
 
   if (warp == 0) {
@@ -481,7 +481,7 @@ w8a8_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   cluster_sync_all();                         // barriers of ALL CTAs are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  pdl_wait();                   // barriers and TMEM are set up while the previous kernel drains (no-ops unless FFQ_PDL=1)
+  pdl_wait();                   // barriers and TMEM are set up while the previous kernel drains (no-ops under FFQ_PDL=0)
   pdl_trigger();
 
   if (warp == 0) {

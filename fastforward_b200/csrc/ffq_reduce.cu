@@ -207,6 +207,8 @@ template <> struct RParamT<RM_F16> { using type = __half; };
 
 template <typename T, int LANES, int RM>
 __global__ void __launch_bounds__(RD_THREADS, 3) bwd_row_group_kernel(const BwdArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = 16 / sizeof(T);
   constexpr int U = BwdUnroll<T>::value;
   using PT = typename RParamT<RM>::type;      // the fast path requires scale/offset stored in the chain's dtype
@@ -305,6 +307,8 @@ __device__ __forceinline__ void bwd_stream(const T* __restrict__ x, const T* __r
 // fp32 data fits 64 registers without spills (4 CTAs per SM: cfg1 55 -> 50 us); the 16-bit variants would spill
 template <typename T, int EPT, int RM>
 __global__ void __launch_bounds__(RD_THREADS, 4) bwd_row_warp_kernel(const BwdArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   const unsigned long long tile = (unsigned long long)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
   if (tile >= a.num_tiles) return;
   const unsigned int lane = threadIdx.x & 31;
@@ -326,6 +330,8 @@ __global__ void __launch_bounds__(RD_THREADS, 4) bwd_row_warp_kernel(const BwdAr
 // --- large / few tiles: one CTA per tile segment ---------------------------------------------
 template <typename T, int EPT, int RM>
 __global__ void __launch_bounds__(RD_THREADS, 4) bwd_row_cta_kernel(const BwdArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   __shared__ float smem[32];
   const unsigned long long tile = blockIdx.x / a.S;
   const unsigned int seg = blockIdx.x % a.S;
@@ -353,6 +359,8 @@ __global__ void __launch_bounds__(RD_THREADS, 4) bwd_row_cta_kernel(const BwdArg
 
 // second stage: one warp per tile folds the S partials in a fixed order
 __global__ void __launch_bounds__(RD_THREADS) bwd_finalize_kernel(const BwdArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   const unsigned long long tile = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tile >= a.num_tiles) return;
@@ -457,20 +465,20 @@ static void launch_bwd_row(const BwdArgs& a, const Plan& plan, bool vec_ok, cuda
     constexpr int U = BwdUnroll<T>::value;
     const unsigned int blocks = (unsigned int)((nvec + RD_THREADS * U - 1) / (RD_THREADS * U));
     switch (lanes) {
-      case 1: bwd_row_group_kernel<T, 1, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 2: bwd_row_group_kernel<T, 2, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 4: bwd_row_group_kernel<T, 4, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 8: bwd_row_group_kernel<T, 8, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 16: bwd_row_group_kernel<T, 16, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      default: bwd_row_group_kernel<T, 32, RM><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 1: launch_pdl(bwd_row_group_kernel<T, 1, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 2: launch_pdl(bwd_row_group_kernel<T, 2, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 4: launch_pdl(bwd_row_group_kernel<T, 4, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 8: launch_pdl(bwd_row_group_kernel<T, 8, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 16: launch_pdl(bwd_row_group_kernel<T, 16, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      default: launch_pdl(bwd_row_group_kernel<T, 32, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
     }
     return;
   }
   const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
   if (a.S == 1 && use_warp_per_tile(plan, EPT)) {
     const unsigned int blocks = (unsigned int)((a.num_tiles + RD_THREADS / 32 - 1) / (RD_THREADS / 32));
-    if (ept == EPT) bwd_row_warp_kernel<T, EPT, RM><<<blocks, RD_THREADS, 0, st>>>(a);
-    else bwd_row_warp_kernel<T, 1, RM><<<blocks, RD_THREADS, 0, st>>>(a);
+    if (ept == EPT) launch_pdl(bwd_row_warp_kernel<T, EPT, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a);
+    else launch_pdl(bwd_row_warp_kernel<T, 1, RM>, dim3(blocks), dim3(RD_THREADS), 0, st, a);
     return;
   }
   const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
@@ -478,8 +486,8 @@ static void launch_bwd_row(const BwdArgs& a, const Plan& plan, bool vec_ok, cuda
   unsigned long long per_seg = (a.seg_len + ept - 1) / ept;
   int threads = RD_THREADS;
   while (threads > 32 && (unsigned long long)threads / 2 >= per_seg) threads /= 2;
-  if (ept == EPT) bwd_row_cta_kernel<T, EPT, RM><<<blocks, threads, 0, st>>>(a);
-  else bwd_row_cta_kernel<T, 1, RM><<<blocks, threads, 0, st>>>(a);
+  if (ept == EPT) launch_pdl(bwd_row_cta_kernel<T, EPT, RM>, dim3(blocks), dim3(threads), 0, st, a);
+  else launch_pdl(bwd_row_cta_kernel<T, 1, RM>, dim3(blocks), dim3(threads), 0, st, a);
 }
 
 // fast kernels exist for x.dtype == g.dtype with a single promoted dtype for the whole chain
@@ -532,6 +540,8 @@ __device__ __forceinline__ void mm_emit(const MmArgs& a, unsigned long long tile
 
 template <typename XT, int LANES>
 __global__ void __launch_bounds__(RD_THREADS) mm_row_group_kernel(const MmArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   constexpr int EPT = 16 / sizeof(XT);
   const XT* __restrict__ x = static_cast<const XT*>(a.x);
   const unsigned long long nvec = a.numel / EPT;
@@ -584,6 +594,8 @@ __device__ __forceinline__ void mm_stream(const XT* __restrict__ x, unsigned int
 
 template <typename XT, int EPT>
 __global__ void __launch_bounds__(RD_THREADS) mm_row_warp_kernel(const MmArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   const unsigned long long tile = (unsigned long long)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
   if (tile >= a.num_tiles) return;
   const unsigned int lane = threadIdx.x & 31;
@@ -598,6 +610,8 @@ __global__ void __launch_bounds__(RD_THREADS) mm_row_warp_kernel(const MmArgs a)
 
 template <typename XT, int EPT>
 __global__ void __launch_bounds__(RD_THREADS) mm_row_cta_kernel(const MmArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   __shared__ float smem[64];
   const unsigned long long tile = blockIdx.x / a.S;
   const unsigned int seg = blockIdx.x % a.S;
@@ -615,6 +629,8 @@ __global__ void __launch_bounds__(RD_THREADS) mm_row_cta_kernel(const MmArgs a) 
 }
 
 __global__ void __launch_bounds__(RD_THREADS) mm_finalize_kernel(const MmArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   const unsigned long long tile = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (tile >= a.num_tiles) return;
@@ -651,28 +667,28 @@ static void launch_mm_row(const MmArgs& a, const Plan& plan, bool vec_ok, cudaSt
     const unsigned long long nvec = a.numel / EPT;
     const unsigned int blocks = (unsigned int)((nvec + RD_THREADS * RD_UNROLL - 1) / (RD_THREADS * RD_UNROLL));
     switch (lanes) {
-      case 1: mm_row_group_kernel<XT, 1><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 2: mm_row_group_kernel<XT, 2><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 4: mm_row_group_kernel<XT, 4><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 8: mm_row_group_kernel<XT, 8><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      case 16: mm_row_group_kernel<XT, 16><<<blocks, RD_THREADS, 0, st>>>(a); break;
-      default: mm_row_group_kernel<XT, 32><<<blocks, RD_THREADS, 0, st>>>(a); break;
+      case 1: launch_pdl(mm_row_group_kernel<XT, 1>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 2: launch_pdl(mm_row_group_kernel<XT, 2>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 4: launch_pdl(mm_row_group_kernel<XT, 4>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 8: launch_pdl(mm_row_group_kernel<XT, 8>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      case 16: launch_pdl(mm_row_group_kernel<XT, 16>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
+      default: launch_pdl(mm_row_group_kernel<XT, 32>, dim3(blocks), dim3(RD_THREADS), 0, st, a); break;
     }
     return;
   }
   const int ept = (vec_ok && plan.tile_numel % EPT == 0) ? EPT : 1;
   if (a.S == 1 && use_warp_per_tile(plan, EPT)) {
     const unsigned int blocks = (unsigned int)((a.num_tiles + RD_THREADS / 32 - 1) / (RD_THREADS / 32));
-    if (ept == EPT) mm_row_warp_kernel<XT, EPT><<<blocks, RD_THREADS, 0, st>>>(a);
-    else mm_row_warp_kernel<XT, 1><<<blocks, RD_THREADS, 0, st>>>(a);
+    if (ept == EPT) launch_pdl(mm_row_warp_kernel<XT, EPT>, dim3(blocks), dim3(RD_THREADS), 0, st, a);
+    else launch_pdl(mm_row_warp_kernel<XT, 1>, dim3(blocks), dim3(RD_THREADS), 0, st, a);
     return;
   }
   const unsigned int blocks = (unsigned int)(a.num_tiles * a.S);
   unsigned long long per_seg = (a.seg_len + ept - 1) / ept;
   int threads = RD_THREADS;
   while (threads > 32 && (unsigned long long)threads / 2 >= per_seg) threads /= 2;
-  if (ept == EPT) mm_row_cta_kernel<XT, EPT><<<blocks, threads, 0, st>>>(a);
-  else mm_row_cta_kernel<XT, 1><<<blocks, threads, 0, st>>>(a);
+  if (ept == EPT) launch_pdl(mm_row_cta_kernel<XT, EPT>, dim3(blocks), dim3(threads), 0, st, a);
+  else launch_pdl(mm_row_cta_kernel<XT, 1>, dim3(blocks), dim3(threads), 0, st, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -689,6 +705,8 @@ struct PrArgs {
 
 // stage A (only when the one-sided decision is live): per-block min of min_range -> part[]
 __global__ void __launch_bounds__(RD_THREADS) pr_min_kernel(const PrArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   __shared__ float smem[64];
   float mn = INFINITY, dummy = 0.f;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n;
@@ -699,6 +717,8 @@ __global__ void __launch_bounds__(RD_THREADS) pr_min_kernel(const PrArgs a) {
 }
 
 __global__ void __launch_bounds__(RD_THREADS) pr_apply_kernel(const PrArgs a) {
+  pdl_wait();                    // programmatic dependent launch: no-ops unless launched that way
+  pdl_trigger();
   __shared__ float smem[64];
   __shared__ int s_one_sided;
   bool one_sided = false;
@@ -866,7 +886,7 @@ int ffq_quantize_bwd(const void* x, int x_dtype, const void* g, int g_dtype, voi
     FFQ_LAUNCH_CHECK();
     if (a.S > 1) {
       const unsigned long long threads = a.num_tiles * 32;
-      bwd_finalize_kernel<<<(unsigned int)((threads + RD_THREADS - 1) / RD_THREADS), RD_THREADS, 0, st>>>(a);
+      launch_pdl(bwd_finalize_kernel, dim3((unsigned int)((threads + RD_THREADS - 1) / RD_THREADS)), dim3(RD_THREADS), 0, st, a);
       FFQ_LAUNCH_CHECK();
     }
     return FFQ_OK;
@@ -921,7 +941,7 @@ int ffq_minmax(const void* x, int x_dtype, void* tile_min, void* tile_max, void*
     FFQ_LAUNCH_CHECK();
     if (a.S > 1) {
       const unsigned long long threads = a.num_tiles * 32;
-      mm_finalize_kernel<<<(unsigned int)((threads + RD_THREADS - 1) / RD_THREADS), RD_THREADS, 0, st>>>(a);
+      launch_pdl(mm_finalize_kernel, dim3((unsigned int)((threads + RD_THREADS - 1) / RD_THREADS)), dim3(RD_THREADS), 0, st, a);
       FFQ_LAUNCH_CHECK();
     }
     return FFQ_OK;
@@ -965,10 +985,10 @@ int ffq_params_for_range(const void* min_range, const void* max_range, int range
       return FFQ_ERR_WORKSPACE;
     }
     a.nparts = (unsigned int)nb;
-    pr_min_kernel<<<(unsigned int)nb, RD_THREADS, 0, st>>>(a);
+    launch_pdl(pr_min_kernel, dim3((unsigned int)nb), dim3(RD_THREADS), 0, st, a);
     FFQ_LAUNCH_CHECK();
   }
-  pr_apply_kernel<<<(unsigned int)(((unsigned long long)n + RD_THREADS - 1) / RD_THREADS), RD_THREADS, 0, st>>>(a);
+  launch_pdl(pr_apply_kernel, dim3((unsigned int)(((unsigned long long)n + RD_THREADS - 1) / RD_THREADS)), dim3(RD_THREADS), 0, st, a);
   FFQ_LAUNCH_CHECK();
   return FFQ_OK;
 }

@@ -10,10 +10,12 @@ nvidia-smi -L
 (time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r3f_bench_reference.json 2> gpurun_out/r3f_bench_reference.err; cut -c1-400 gpurun_out/r3f_bench_reference.json)
 (time timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize.py > gpurun_out/r3f_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/r3f_sanitizer_memcheck.log)
 (time timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1800 --csv --log-file gpurun_out/r3f_launches.csv python bench.py --steps 2 --warmup 1 --layers 2 --skip-extras --skip-cpu-baseline --skip-drop-in --skip-compiled-baseline > gpurun_out/r3f_launches_bench.log 2>&1; tail -2 gpurun_out/r3f_launches_bench.log | cut -c1-300)
+if [ "${FULL_NCU:-0}" = 1 ]; then
 (time timeout 900 ncu --set full --clock-control none -k regex:'ffq|calq|w8a8' -o gpurun_out/r3f_layer -f python tools/prof_layer.py 2 > gpurun_out/r3f_ncu_layer.log 2>&1; tail -3 gpurun_out/r3f_ncu_layer.log)
 ncu -i gpurun_out/r3f_layer.ncu-rep --page raw --csv --print-units base > gpurun_out/r3f_layer_raw.csv 2>/dev/null
 ls -la gpurun_out/r3f_layer.ncu-rep gpurun_out/r3f_layer_raw.csv
 rm -f gpurun_out/r3f_layer.ncu-rep          # the report itself is over the 64 MiB that travel back; the raw page is what the summary reads
+fi
 python - <<'PY'
 import json
 d=json.loads([l for l in open('gpurun_out/r3f_bench.json').read().splitlines() if l.startswith('{')][-1])
