@@ -714,13 +714,19 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
             flags = [s.flags for _, s in steps if s.flags is not None and s._state is None]
             if exchange is None:
                 flags = state.all_flags() + flags
-            stacked = None
+            pending = []                        # (host-visible tensor, device to synchronise or None), one per device
             if flags and not self.eager_checks:
-                stacked = torch.stack([f.reshape(()) for f in {id(f): f for f in flags}.values()])
-                if stacked.is_cuda:
-                    host = torch.empty(stacked.shape, dtype=stacked.dtype).pin_memory()
-                    host.copy_(stacked, non_blocking=True)
-                    stacked = (host, stacked.device)
+                by_device: dict = {}
+                for f in {id(f): f for f in flags}.values():
+                    by_device.setdefault(f.device, []).append(f.reshape(()))
+                for device, fs in by_device.items():
+                    stacked = torch.stack(fs)
+                    if stacked.is_cuda:
+                        host = torch.empty(stacked.shape, dtype=stacked.dtype).pin_memory()
+                        host.copy_(stacked, non_blocking=True)
+                        pending.append((host, device))
+                    else:
+                        pending.append((stacked, None))
             if cleanup is not None:
                 cleanup()
             t1 = time.perf_counter()
@@ -730,13 +736,13 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
             t2 = time.perf_counter()
         finally:
             _unalias_finish(unalias)
+            _unalias_all(state.aliases)         # only after a failure above: whoever is still aliased gets its own storage
         value = flags_value or 0
-        if isinstance(stacked, tuple):
-            # single process: THE host sync of the exit; data parallel: the signature read has drained this stream already
-            torch.cuda.current_stream(stacked[1]).synchronize()
-            stacked = stacked[0]
-        if stacked is not None:
-            for v in stacked.tolist():
+        for host, device in pending:
+            if device is not None:
+                # single process: THE host sync of the exit; data parallel: the signature read has drained this stream already
+                torch.cuda.current_stream(device).synchronize()
+            for v in host.tolist():
                 value |= int(v)
         t3 = time.perf_counter()
         self.last_stats = dict(state.stats)
