@@ -419,7 +419,7 @@ w8a8_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // Barriers: TMA completions of a pair (its own A loads and every B slice multicast into it) land on the pair
 // leader's "full" barrier; a stage is refilled only after ALL P pairs have consumed it, because every pair writes
 // into every other pair's stage (tcgen05.commit multicast to the whole cluster, "empty" barriers count P);
-// "tile ready" goes to the pair only, and the pair's 8 epilogue warps release the accumulator on the leader.
+// "tile ready" goes to the pair only, and the pair's epilogue warps (EP2_WARPS per CTA) release the accumulator on the leader.
 // ================================================================================================
 // Epilogue warps per CTA: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each taking half of the tile's columns:
 // the drain of a tile -- all of it exposed after a launch's last wave -- takes half as long).  Eight warps need eight
