@@ -307,3 +307,71 @@ def test_gptq_argument_checks_need_no_gpu():
         Gq.gptq(layer, [])
     with pytest.raises(TypeError, match="Unsupported granularity"):     # gptq.py:219-221
         Gq._check_granularity(G.PerChannel(2))
+
+
+# ---- estimate_ranges: block exit protocol (range_setting/common.py) ----------------------------------------------
+class _RecordingEstimator:
+    """Minimal RangeEstimator: records the order of the calls estimate_ranges makes when the block ends."""
+
+    def __init__(self, runs_cleanup: bool, fail_in_finalize: bool = False):
+        self.log = []
+        self.finalize_runs_cleanup = runs_cleanup
+        self.fail = fail_in_finalize
+
+    def split_module(self, module):
+        yield from (m for m in module.modules() if isinstance(m, torch.nn.Linear))
+
+    def prepare(self, module):
+        self.log.append(("prepare", id(module)))
+        return id(module)
+
+    def cleanup(self, module, metadata):
+        assert metadata == id(module)
+        self.log.append(("cleanup", id(module)))
+
+    def finalize(self, prepared, cleanup=None):
+        self.log.append(("finalize-begin", len(prepared)))
+        if cleanup is not None:
+            cleanup()                      # host work that needs nothing from the device goes in front of the sync
+        if self.fail:
+            raise RuntimeError("boom")
+        self.log.append(("finalize-end", None))
+
+
+@pytest.mark.parametrize("runs_cleanup", [True, False])
+def test_estimate_ranges_exit_protocol(runs_cleanup):
+    model = torch.nn.Sequential(torch.nn.Linear(2, 2), torch.nn.Linear(2, 2))
+    est = _RecordingEstimator(runs_cleanup)
+    with ff.estimate_ranges(model, est):
+        pass
+    kinds = [k for k, _ in est.log]
+    assert kinds.count("cleanup") == 2 and kinds.count("prepare") == 2            # every module cleaned exactly once
+    if runs_cleanup:                                                              # ... inside finalize, before it returns
+        assert kinds.index("finalize-end") > max(i for i, k in enumerate(kinds) if k == "cleanup")
+    else:                                                                         # ... after finalize (the reference's order)
+        assert kinds.index("finalize-end") < min(i for i, k in enumerate(kinds) if k == "cleanup")
+
+
+def test_estimate_ranges_cleans_up_when_the_block_or_the_exit_fails():
+    model = torch.nn.Sequential(torch.nn.Linear(2, 2))
+    est = _RecordingEstimator(True)
+    with pytest.raises(ValueError):
+        with ff.estimate_ranges(model, est):
+            raise ValueError("user code failed")
+    kinds = [k for k, _ in est.log]
+    assert "finalize-begin" not in kinds and kinds.count("cleanup") == 1          # a failed block is not finalized
+    for runs_cleanup in (True, False):
+        est = _RecordingEstimator(runs_cleanup, fail_in_finalize=True)
+        with pytest.raises(RuntimeError, match="boom"):
+            with ff.estimate_ranges(model, est):
+                pass
+        assert [k for k, _ in est.log].count("cleanup") == 1                      # once, whoever ran it
+
+
+def test_estimate_ranges_argument_contract():
+    model = torch.nn.Linear(2, 2)
+    with pytest.raises(ValueError, match="already initialized"):
+        with ff.estimate_ranges(model, _RecordingEstimator(True), 1):
+            pass
+    with ff.estimate_ranges([model, model], _RecordingEstimator, True) :        # a class + its arguments, a list of modules
+        pass
