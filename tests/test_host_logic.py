@@ -375,3 +375,66 @@ def test_estimate_ranges_argument_contract():
             pass
     with ff.estimate_ranges([model, model], _RecordingEstimator, True) :        # a class + its arguments, a list of modules
         pass
+
+
+# ---- overlapped parameter steps: the scheduling logic, with the device replaced by recorders -----------------------
+def test_overlapped_parameter_steps_schedule(monkeypatch):
+    from fastforward_b200 import ops
+    from fastforward_b200.range_setting import minmax as M
+
+    class _Event:
+        def record(self, stream=None):
+            pass
+
+    class _Stream:
+        cuda_stream = 0
+        waited = 0
+
+        def wait_event(self, event):
+            type(self).waited += 1
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: _Stream())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    where = []
+
+    def fake_calibrate(run_min, run_max, data, tile, *a, stream=None, **k):
+        where.append("side" if stream is not None else "main")
+        return torch.zeros(data.shape, dtype=torch.int8), None
+
+    monkeypatch.setattr(ops, "calibrate_quantize_", fake_calibrate)
+    est = M.RunningMinMaxRangeEstimator(memoize_parameters=False, overlap_parameters=2)
+    weights = [torch.nn.Parameter(torch.randn(8, 16)) for _ in range(5)]
+    quantizers = [ff.nn.LinearQuantizer(8, granularity=ff.PerChannel(0), quantized_dtype=torch.int8) for _ in weights]
+    steps = [M.RunningMinMaxEstimator(q, state=est._state) for q in quantizers]
+    with torch.no_grad():
+        for s, q, w in zip(steps, quantizers, weights):          # step 1 records the order: everything in line
+            s._fused_step(q, w, 1)
+        assert where == ["main"] * 5 and est._state.stats["overlapped"] == 0
+        where.clear()
+        for s, q, w in zip(steps, quantizers, weights):          # step 2: the first in line, the rest launched ahead
+            s._fused_step(q, w, 1)
+        assert where == ["main", "side", "side", "side", "side"] and est._state.stats["overlapped"] == 4
+        assert all(s._ahead is None for s in steps)              # nothing left in flight at the end of a step
+        # a weight that changes after its step was launched ahead: the result is dropped, the step re-runs in line
+        where.clear()
+        steps[0]._fused_step(quantizers[0], weights[0], 1)       # launches 1 and 2 ahead
+        assert steps[1]._ahead is not None and steps[2]._ahead is not None
+        weights[2].mul_(2.0)                                     # bumps the version counter
+        steps[1]._fused_step(quantizers[1], weights[1], 1)
+        steps[2]._fused_step(quantizers[2], weights[2], 1)
+        assert where == ["main", "side", "side", "side", "main", "side"]     # 0 | 1, 2 ahead | 3 ahead | 2 again | 4 ahead
+        # the block ends with launches in flight: drain joins them
+        assert steps[3]._ahead is not None and steps[4]._ahead is not None
+        est._state.drain()
+        assert all(s._ahead is None for s in steps)
+    # memoisation makes overlap pointless: it is switched off
+    assert M._BlockState(True, True, overlap=4).overlap == 0
