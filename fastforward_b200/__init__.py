@@ -48,4 +48,21 @@ for _name in ("save_quantization_state", "load_quantization_state", "save_quanti
     setattr(nn.QuantizedModule, _name, getattr(_save_load, _name))
 del _name
 
+# the rest of the reference's `fastforward.quantization` namespace (quantization/__init__.py:6-19) and the two module
+# aliases of the top level (__init__.py:33-34); bound here because these modules need `nn` to be importable first
+from .quantization import freeze as _freeze  # noqa: E402
+from .quantization import gptq as _gptq  # noqa: E402,F401  (ff.quantization.gptq is the module AND callable, see its end)
+from .quantization.affine import dynamic as _dynamic, static as _static  # noqa: E402
+from .quantization.function import create_quantization_function as _create_quantization_function  # noqa: E402
+
+quantization.static, quantization.dynamic = _static, _dynamic
+quantization.freeze_parameters = _freeze.freeze_parameters
+quantization.create_quantization_function = _create_quantization_function
+quantization.QuantizationConfig, quantization.QuantizerCollection = QuantizationConfig, QuantizerCollection
+for _name in ("fuse_qdq_weights", "find_weight_quantizers", "stub_weight_quantizers", "ConventionDiscovery",
+              "WeightQuantizerDiscovery"):
+    setattr(quantization, _name, getattr(_fuse, _name))
+del _name
+affine, granularity = quantization.affine, quantization.granularity
+
 __version__ = "0.1.0"

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import abc
 import dataclasses
+import inspect
 from typing import Any, Callable, Generic, TypeVar
 
 import torch
@@ -84,3 +85,59 @@ class QuantizationContext(Generic[P]):
         from ..quantized_tensor import QuantizedTensor
 
         return QuantizedTensor(data, self)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a QuantizationFunction from a pair of plain functions (reference: quantization/function.py:209-330)
+# ---------------------------------------------------------------------------------------------------------------
+_NO_DEFAULT = inspect.Parameter.empty
+
+
+def _keyword_parameters(fn: Callable[..., torch.Tensor]) -> dict:
+    """name -> (annotation, default) of every parameter after the data tensor; all must be passable by keyword."""
+    params = list(inspect.signature(fn).parameters.values())[1:]
+    out = {}
+    for p in params:
+        if p.kind not in (p.KEYWORD_ONLY, p.POSITIONAL_OR_KEYWORD):
+            raise TypeError(f"All parameters must be keyword only or positional or keyword parameters {p.name} is "
+                            f"{p.kind.description}")
+        out[p.name] = (Any if p.annotation is _NO_DEFAULT else p.annotation, p.default)
+    return out
+
+
+def create_quantization_function(cls_name: str, quantize: Callable[..., torch.Tensor],
+                                 dequantize: Callable[..., torch.Tensor]):
+    """``(ParamsType, FunctionType, helper)`` for a custom quantizer given as two plain functions
+    ``quantize(data, **p) -> Tensor`` and ``dequantize(data, **p) -> Tensor``.  ``ParamsType`` is a dataclass holding
+    the union of their keyword parameters (a parameter both share must agree in annotation and default),
+    ``FunctionType`` a ``QuantizationFunction`` whose ``quantize`` wraps the codes in a ``QuantizedTensor`` carrying
+    those parameters, and ``helper(data, **p)`` builds the parameters and quantizes in one call."""
+    q_params, d_params = _keyword_parameters(quantize), _keyword_parameters(dequantize)
+    for name in q_params.keys() & d_params.keys():
+        if q_params[name][0] != d_params[name][0]:
+            raise TypeError(f"The type annotation for '{name}' must be the same in both the quantize and dequantize function")
+        if q_params[name][1] != d_params[name][1]:
+            raise ValueError(f"The default value for '{name}' must be the same in both the quantize and dequantize function")
+    merged = {**q_params, **d_params}
+    fields = [(name, annotation, dataclasses.field() if default is _NO_DEFAULT else dataclasses.field(default=default))
+              for name, (annotation, default) in merged.items()]
+    params_type = dataclasses.make_dataclass(
+        f"{cls_name}Params", fields, bases=(QuantizationParameters,),
+        namespace={"quantize_params": lambda self: {n: getattr(self, n) for n in q_params},
+                   "dequantize_params": lambda self: {n: getattr(self, n) for n in d_params}})
+
+    def _quantize(cls, data: torch.Tensor, params):
+        from ..quantized_tensor import QuantizedTensor
+
+        return QuantizedTensor(quantize(data, **params.quantize_params()), QuantizationContext(cls, params))
+
+    def _dequantize(cls, data: torch.Tensor, params) -> torch.Tensor:
+        return dequantize(data, **params.dequantize_params())
+
+    function_type = type(cls_name, (QuantizationFunction,), {"quantize": classmethod(_quantize),
+                                                               "dequantize": classmethod(_dequantize)})
+
+    def helper(data: torch.Tensor, **kwargs: Any):
+        return function_type.quantize(data, params_type(**kwargs))
+
+    return params_type, function_type, helper

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import weakref
-from typing import Iterator, List, Optional, Tuple
+from typing import Iterator, List, Optional, Protocol, Tuple, runtime_checkable
 
 import torch
 
@@ -24,6 +24,14 @@ from ..nn.quantizer import Quantizer, QuantizerStub
 from ..quant_init import find_quantizers
 
 WeightQuantizerTarget = Tuple[torch.nn.Module, str, Quantizer]
+
+
+@runtime_checkable
+class WeightQuantizerDiscovery(Protocol):
+    """Anything callable as ``discovery(model) -> iterator of (module, weight_attr, quantizer)`` (fuse.py:36-50)."""
+
+    def __call__(self, model: torch.nn.Module) -> Iterator[WeightQuantizerTarget]:
+        ...
 
 
 class ConventionDiscovery:
@@ -89,6 +97,24 @@ def _fuse_target(module: torch.nn.Module, weight_attr: str, quantizer: Quantizer
         for name, child in list(module.named_children()):
             if child is quantizer:
                 setattr(module, name, QuantizerStub(_metadata=quantizer.quant_metadata))
+
+
+def find_weight_quantizers(model: torch.nn.Module, *, discovery=None) -> List[WeightQuantizerTarget]:
+    """The ``(module, weight_attr, quantizer)`` targets a fuse or stub pass would act on, without performing it
+    (fuse.py:244-264)."""
+    discovery = ConventionDiscovery() if discovery is None else discovery
+    return list(discovery(model))
+
+
+def stub_weight_quantizers(model: torch.nn.Module, *, discovery=None) -> None:
+    """Replace the discovered weight quantizers by stubs carrying their metadata; weights are neither read nor written
+    (fuse.py:267-300).  For models whose saved weights are already grid-snapped: the forward pass must not quantize
+    them a second time."""
+    for module, _, quantizer in find_weight_quantizers(model, discovery=discovery):
+        for name, child in list(module.named_children()):
+            if child is quantizer:
+                setattr(module, name, QuantizerStub(_metadata=quantizer.quant_metadata))
+                break
 
 
 def fuse_qdq_weights(model: torch.nn.Module, *, stub_quantizers: bool = False, discovery=None,

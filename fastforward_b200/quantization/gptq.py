@@ -10,6 +10,8 @@ Hessian accumulation, the Cholesky inversion and the trailing update between blo
 
 from __future__ import annotations
 
+import sys
+
 import logging
 import math
 from typing import Any, Callable, Iterable, Optional
@@ -205,3 +207,13 @@ def invert_hessian(hessian: torch.Tensor, perc_damp: float) -> torch.Tensor:
     hessian = torch.cholesky_inverse(hessian)
     hessian = torch.linalg.cholesky(hessian, upper=True)
     return hessian
+
+
+# ``ff.quantization.gptq(module, dataset, ...)`` is a function in the reference (quantization/__init__.py:15) and a
+# submodule here (its helpers -- gptq_block_ and friends -- are imported from it): the module itself is callable.
+class _CallableModule(type(sys)):
+    def __call__(self, *args, **kwargs):
+        return self.gptq(*args, **kwargs)
+
+
+sys.modules[__name__].__class__ = _CallableModule

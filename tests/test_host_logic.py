@@ -438,3 +438,70 @@ def test_overlapped_parameter_steps_schedule(monkeypatch):
         assert all(s._ahead is None for s in steps)
     # memoisation makes overlap pointless: it is switched off
     assert M._BlockState(True, True, overlap=4).overlap == 0
+
+
+# ---- the rest of the `quantization` namespace -----------------------------------------------------------------------
+def test_create_quantization_function():
+    """reference tests/quantization/test_function.py:116-152."""
+    import dataclasses
+
+    data = torch.randn(3, 3)
+
+    def _quantize(data: torch.Tensor, scale: float) -> torch.Tensor:
+        return data * scale
+
+    def _dequantize(data: torch.Tensor, rescale: float = 3.5) -> torch.Tensor:
+        return data * rescale
+
+    Params, Function, custom = ff.quantization.create_quantization_function("CustomQuantizer", _quantize, _dequantize)
+    assert {f.name for f in dataclasses.fields(Params)} == {"scale", "rescale"}
+    with ff.strict_quantization(False):
+        quantized = custom(data, scale=2.0)
+        assert torch.equal(quantized.raw_data, data * 2.0)
+        assert torch.equal(quantized.dequantize(), data * 2.0 * 3.5)
+    assert quantized.quant_func is Function and isinstance(quantized.quant_args(), Params)
+    assert quantized.quant_args().scale == 2.0 and quantized.quant_args().rescale == 3.5
+
+    def _bad_default(data: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        return data
+
+    def _bad_annotation(data: torch.Tensor, scale: int) -> torch.Tensor:
+        return data
+
+    def _varargs(data: torch.Tensor, *scales: float) -> torch.Tensor:
+        return data
+
+    with pytest.raises(ValueError, match="default value"):
+        ff.quantization.create_quantization_function("X", _quantize, _bad_default)
+    with pytest.raises(TypeError, match="type annotation"):
+        ff.quantization.create_quantization_function("X", _quantize, _bad_annotation)
+    with pytest.raises(TypeError, match="keyword"):
+        ff.quantization.create_quantization_function("X", _varargs, _dequantize)
+
+
+def test_quantization_namespace_matches_the_reference():
+    """Every public name of the reference's `fastforward.quantization` and the two top-level module aliases."""
+    for name in ("dynamic", "static", "freeze_parameters", "create_quantization_function", "ConventionDiscovery",
+                 "WeightQuantizerDiscovery", "find_weight_quantizers", "fuse_qdq_weights", "stub_weight_quantizers", "gptq",
+                 "QuantizationConfig", "QuantizerCollection", "load_quantization_state", "load_quantized_model",
+                 "save_quantization_state", "save_quantized_model"):
+        assert hasattr(ff.quantization, name), name
+    assert ff.affine is ff.quantization.affine and ff.granularity is ff.quantization.granularity
+
+
+def test_find_and_stub_weight_quantizers():
+    model = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    ff.quantize_model(model)
+    ff.find_quantizers(model, "**/[quantizer:parameter/weight]").initialize(ff.nn.LinearQuantizer, num_bits=4)
+    ff.find_quantizers(model, "**/[quantizer:activation/input]").initialize(ff.nn.LinearQuantizer, num_bits=8)
+    targets = ff.quantization.find_weight_quantizers(model)
+    assert [(m is model[i], attr) for i, (m, attr, _) in enumerate(targets)] == [(True, "weight"), (True, "weight")]
+    assert all(q is m.weight_quantizer for m, _, q in targets)
+    assert isinstance(ff.quantization.ConventionDiscovery(), ff.quantization.WeightQuantizerDiscovery)
+    before = [m.weight.detach().clone() for m in model]
+    meta = model[0].weight_quantizer.quant_metadata
+    ff.quantization.stub_weight_quantizers(model)
+    assert all(m.weight_quantizer.is_stub() and not m.input_quantizer.is_stub() for m in model)
+    assert model[0].weight_quantizer.quant_metadata is meta                  # the slot's metadata survives
+    assert all(torch.equal(m.weight, w) for m, w in zip(model, before))      # weights untouched
+    assert ff.quantization.find_weight_quantizers(model) == []
