@@ -8,7 +8,7 @@ dictionary with the reference's keys.  There is no CPU path: scales that live on
 
 from __future__ import annotations
 
-from typing import Any, Dict, Optional, Tuple
+from typing import Any, Dict, Tuple
 
 import torch
 

@@ -16,7 +16,6 @@ import torch
 
 import fastforward_b200 as ff
 from fastforward_b200 import serialization
-from fastforward_b200.quantization import save_load as SL
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FORMATS = os.path.join(ROOT, "tests", "golden", "formats")
