@@ -632,3 +632,27 @@ def test_lpbq_argument_checks():
     enc = proc.encode_quantizer("w", q, w.shape)
     assert enc["block_size"] == 16 and len(enc["scale"]) == 32 and len(enc["per_block_int_scale"]) == 32 * 4
     assert all(1 <= v <= 16 for v in enc["per_block_int_scale"]) and enc["offset"] == [-128.0] * 32
+
+
+# ------------------------------------------------------------------------------------------------------------
+# on-disk formats with parameters that live on the device (tests/test_save_load.py covers the formats on the CPU)
+# ------------------------------------------------------------------------------------------------------------
+def test_save_and_load_a_calibrated_model_from_the_device(tmp_path):
+    model = _tiny()
+    batches = [torch.randint(0, 1024, (1, 64)).to(DEV) for _ in range(2)]
+    _run(model, batches, memoize_parameters=False)
+    path = ff.quantization.save_quantized_model(model, tmp_path / "artifact", name_or_path="tiny")
+    fresh = _tiny(seed=9)                              # other weights, other (uncalibrated) quantizers
+    ff.quantization.stub_weight_quantizers(fresh)      # some slots hold stubs, some initialised quantizers: both get replaced
+    ff.quantization.load_quantized_model(fresh, path, expected_name="tiny", overwrite_policy="overwrite")
+    fresh.to(DEV)
+    want, got = dict(ff.nn.named_quantizers(model)), dict(ff.nn.named_quantizers(fresh))
+    assert want.keys() == got.keys() and len(want) == 28
+    for name, q in want.items():
+        assert torch.equal(got[name].scale.detach().to(DEV), q.scale.detach()), name
+        assert (q.offset is None) == (got[name].offset is None)
+        if q.offset is not None:
+            assert torch.equal(got[name].offset.detach().to(DEV), q.offset.detach()), name
+    x = batches[0]
+    with torch.no_grad():
+        assert torch.equal(model(x), fresh(x))
