@@ -565,7 +565,31 @@ def _unalias_finish(plan) -> None:
 
 
 def _unalias_all(steps) -> None:
-    _unalias_finish(_unalias_prepare(steps))
+    """Both halves at once, for when nothing will rewrite the shared storage any more: the copies are allocated AND
+    filled by one multi-tensor op per (device, dtype) (``x * 1`` is exact and keeps the sign of zero and NaN) instead
+    of one Python-level allocation per tensor."""
+    owners, srcs = [], []
+    for s in steps:
+        if s._alias_of is None:
+            continue
+        s._alias_of = None
+        q = s._quantizer_ref()
+        if q is None:
+            continue
+        for p in (q.scale, q.offset):
+            if p is not None:
+                owners.append(p)
+                srcs.append(p.data)
+    groups: dict = {}
+    for owner, src in zip(owners, srcs):
+        groups.setdefault((src.device, src.dtype), []).append((owner, src))
+    with torch.no_grad():
+        for ents in groups.values():
+            tensors = [src for _, src in ents]
+            copies = torch._foreach_mul(tensors, 1) if tensors[0].is_floating_point() and len(tensors) > 1 \
+                else [t.clone() for t in tensors]
+            for (owner, _), c in zip(ents, copies):
+                owner.data = c
 
 
 def _raise_for_flags(value: int) -> None:
@@ -710,10 +734,10 @@ class RunningMinMaxRangeEstimator(_MinMaxRangeEstimatorBase):
         try:
             if self.sync_ranges:
                 exchange = self._sync_begin(steps, state)
-            unalias = _unalias_prepare(state.aliases)
             if exchange is None:
-                _unalias_finish(unalias)        # nothing will rewrite the shared storage: copy now, before the sync
-                unalias = ([], [])
+                _unalias_all(state.aliases)     # nothing will rewrite the shared storage: copy now, before the sync
+            else:
+                unalias = _unalias_prepare(state.aliases)
             state.recent.clear()
             # the reference's per-step `isinf().any()` checks, folded into one read; a data-parallel exit carries the
             # flags of the block's arenas inside the signature message instead
