@@ -104,6 +104,14 @@ class QuantizedTensor(torch.Tensor):
     def int_repr(self) -> torch.Tensor:
         return self.raw_data
 
+    # In-place operators are declined (quantized_tensor.py:488-507): the result of an arithmetic operator does not lie
+    # on the quantization grid, so ``qt += x`` must not write into the codes; Python then evaluates ``qt = qt + x``.
+    def _declined(self, *args: Any, **kwargs: Any):
+        return NotImplemented
+
+    __iadd__ = __isub__ = __imul__ = __imatmul__ = __itruediv__ = __ifloordiv__ = __imod__ = _declined
+    __ilshift__ = __irshift__ = __iand__ = __ixor__ = __ior__ = __ipow__ = _declined
+
     def quant_args(self):
         return self._quantization_context.quantization_params
 

@@ -505,3 +505,12 @@ def test_find_and_stub_weight_quantizers():
     assert model[0].weight_quantizer.quant_metadata is meta                  # the slot's metadata survives
     assert all(torch.equal(m.weight, w) for m, w in zip(model, before))      # weights untouched
     assert ff.quantization.find_weight_quantizers(model) == []
+
+
+def test_quantized_tensor_declines_in_place_operators():
+    """reference quantized_tensor.py:488-507: `qt += x` must not write into the codes."""
+    from fastforward_b200.quantization.function import QuantizationContext, QuantizationParameters
+    qt = ff.QuantizedTensor(torch.zeros(2, 2), QuantizationContext(object, QuantizationParameters()))
+    for op in ("__iadd__", "__isub__", "__imul__", "__imatmul__", "__itruediv__", "__ifloordiv__", "__imod__", "__ilshift__",
+               "__irshift__", "__iand__", "__ixor__", "__ior__", "__ipow__"):
+        assert getattr(qt, op)(1) is NotImplemented, op
